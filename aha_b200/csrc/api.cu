@@ -1,0 +1,599 @@
+// api.cu -- extern "C" entry points of libaha_b200.so (see include/aha_b200.h for the contract and the
+// reference items each entry replaces).  Host side = the C++ mirror of aha's model structs:
+// Qwen3Model (/root/reference/src/models/qwen3/model.rs:94-214), Qwen3VLModel (qwen3vl/model.rs:837-1324),
+// Qwen3ASRModel (qwen3_asr/model.rs:308-425) and generate_generic (common/generate.rs:115-159).
+#include <array>
+#include <chrono>
+#include <mutex>
+
+#include "audio_model.cuh"
+#include "text_model.cuh"
+#include "vision_model.cuh"
+
+using namespace aha;
+
+namespace {
+std::mutex g_err_mu;
+std::string g_create_error;
+}  // namespace
+
+struct aha_model {
+    enum Kind { QWEN3, QWEN3VL, QWEN3_ASR } kind = QWEN3;
+    Ctx ctx;
+    TextModel text;
+    VisionModel vision;
+    AudioModel audio;
+    std::vector<uint32_t> stop_ids;
+    std::string last_error;
+    // Qwen3-VL state / config
+    int image_token_id = -1, video_token_id = -1, vision_start_token_id = -1;
+    bool have_rope_delta = false;  // rope_deltas: Option<Tensor>, qwen3vl/model.rs:842
+    int rope_delta = 0;
+    int audio_token_id = -1;
+    int* d_scatter_idx = nullptr;
+    int max_scatter = 0;
+    double last_vision_secs = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // pinned staging for the host<->device scalars of a step
+    uint32_t* h_pin = nullptr;
+};
+
+namespace {
+
+void bind(aha_model* m) { AHA_CUDA_CHECK(cudaSetDevice(m->ctx.device)); }
+
+template <typename F>
+int guarded(aha_model* m, F&& f) {
+    try {
+        if (!m) throw std::runtime_error("null model handle");
+        bind(m);
+        f();
+        return 0;
+    } catch (const std::exception& e) {
+        if (m) m->last_error = e.what();
+        else { std::lock_guard<std::mutex> lk(g_err_mu); g_create_error = e.what(); }
+        // leave the stream usable: drop a dangling capture, clear sticky launch errors
+        if (m && m->ctx.stream) {
+            cudaStreamCaptureStatus cs;
+            if (cudaStreamIsCapturing(m->ctx.stream, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) {
+                cudaGraph_t g = nullptr; cudaStreamEndCapture(m->ctx.stream, &g); if (g) cudaGraphDestroy(g);
+            }
+        }
+        cudaGetLastError();
+        return 1;
+    }
+}
+
+const aha_tensor_desc* mm_entry(const aha_mm* mm, size_t i) {
+    if (!mm || i >= mm->n) return nullptr;
+    const aha_tensor_desc* d = &mm->data_vec[i];
+    return d->data ? d : nullptr;
+}
+
+std::vector<float> desc_to_f32(const aha_tensor_desc& d) {
+    const size_t n = WeightTable::numel(d);
+    std::vector<float> v(n);
+    if (d.dtype == AHA_F32) std::memcpy(v.data(), d.data, n * sizeof(float));
+    else for (size_t i = 0; i < n; ++i) v[i] = WeightTable::at(d, i);
+    return v;
+}
+std::vector<int64_t> desc_to_i64(const aha_tensor_desc& d) {
+    const size_t n = WeightTable::numel(d);
+    std::vector<int64_t> v(n);
+    for (size_t i = 0; i < n; ++i) {
+        switch (d.dtype) {
+            case AHA_U32: v[i] = reinterpret_cast<const uint32_t*>(d.data)[i]; break;
+            case AHA_I64: v[i] = reinterpret_cast<const int64_t*>(d.data)[i]; break;
+            case AHA_U8: v[i] = reinterpret_cast<const uint8_t*>(d.data)[i]; break;
+            default: throw std::runtime_error("integer tensor expected");
+        }
+    }
+    return v;
+}
+
+// Qwen3VLModel::get_rope_index, image branch (/root/reference/src/models/qwen3vl/model.rs:901-1071,1072-1090):
+// text runs get equal t/h/w ids; an image of merged grid (t,h',w') gets t_idx = base, h_idx = base+0..h'-1,
+// w_idx = base+0..w'-1; the next run starts at max+1; rope_delta = max+1-S.  pos3 is [3][S].
+void get_rope_index(const uint32_t* ids, int S, const std::vector<std::array<int, 3>>& grid, int merge, int image_tok, int vstart_tok,
+                    std::vector<int>& pos3, int& delta) {
+    pos3.assign((size_t)3 * S, 0);
+    if (grid.empty()) {
+        for (int r = 0; r < 3; ++r) for (int i = 0; i < S; ++i) pos3[(size_t)r * S + i] = i;
+        delta = 0;
+        return;
+    }
+    int out = 0;            // tokens emitted so far
+    int last_max = -1;      // max of the last pushed chunk
+    bool any = false;
+    int text_start = 0, text_end = 0;
+    size_t image_index = 0;
+    std::array<int, 3> thw{0, 0, 0};
+    bool have_thw = false;
+    auto push_text = [&](int len) {
+        const int start = any ? last_max + 1 : 0;
+        for (int i = 0; i < len; ++i) for (int r = 0; r < 3; ++r) pos3[(size_t)r * S + out + i] = start + i;
+        if (len > 0) last_max = start + len - 1;
+        // an empty chunk has no max in the reference either; it only matters that `any` flips
+        any = true;
+        out += len;
+        return start + len;
+    };
+    for (int j0 = 0; j0 < S; ++j0) {
+        if ((int)ids[j0] != vstart_tok) continue;
+        const int j = j0 + 1;
+        if (j >= S) throw std::runtime_error("vision_start token at the end of the prompt");
+        if ((int)ids[j] == image_tok) {
+            if (image_index >= grid.size()) throw std::runtime_error("more image placeholders than image_grid_thw rows");
+            thw = grid[image_index++];
+            have_thw = true;
+            text_end = j;
+        }
+        if (!have_thw) throw std::runtime_error("vision_start not followed by an image token (video is out of scope)");
+        const int gt = thw[0], gh = thw[1] / merge, gw = thw[2] / merge;
+        const int text_len = text_end - text_start;
+        if (out + text_len + gt * gh * gw > S) throw std::runtime_error("image placeholders exceed the prompt length");
+        const int base = push_text(text_len);
+        for (int t = 0; t < gt; ++t)
+            for (int h = 0; h < gh; ++h)
+                for (int w = 0; w < gw; ++w) {
+                    const int i = out + (t * gh + h) * gw + w;
+                    pos3[i] = base + t; pos3[(size_t)S + i] = base + h; pos3[(size_t)2 * S + i] = base + w;
+                }
+        last_max = base + std::max(gt, std::max(gh, gw)) - 1;
+        out += gt * gh * gw;
+        text_start = text_end + gt * gh * gw;
+    }
+    if (text_start < S) push_text(S - text_start);
+    if (out != S) throw std::runtime_error("get_rope_index: placeholder layout does not cover the prompt");
+    int mx = 0;
+    for (int v : pos3) mx = std::max(mx, v);
+    delta = mx + 1 - S;
+}
+
+void upload_ids(aha_model* m, const uint32_t* ids, size_t S) {
+    TextModel& T = m->text;
+    AHA_REQUIRE(S >= 1, "empty input_ids");
+    AHA_REQUIRE((int)S <= T.max_prefill, "prompt of " + std::to_string(S) + " tokens exceeds max_prefill " + std::to_string(T.max_prefill));
+    for (size_t i = 0; i < S; ++i) AHA_REQUIRE(ids[i] < (uint32_t)T.cfg.V, "token id out of range");
+    AHA_CUDA_CHECK(cudaMemcpyAsync(T.d_ids, ids, S * sizeof(uint32_t), cudaMemcpyHostToDevice, m->ctx.stream));
+}
+void upload_pos(aha_model* m, const std::vector<int>& pos3) {
+    AHA_CUDA_CHECK(cudaMemcpyAsync(m->text.d_pos3, pos3.data(), pos3.size() * sizeof(int), cudaMemcpyHostToDevice, m->ctx.stream));
+    AHA_CUDA_CHECK(cudaStreamSynchronize(m->ctx.stream));  // pos3 may be a temporary
+}
+void upload_scatter_idx(aha_model* m, const std::vector<int>& idx) {
+    AHA_REQUIRE((int)idx.size() <= m->max_scatter, "too many placeholder tokens");
+    AHA_CUDA_CHECK(cudaMemcpyAsync(m->d_scatter_idx, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice, m->ctx.stream));
+    AHA_CUDA_CHECK(cudaStreamSynchronize(m->ctx.stream));
+}
+
+void fetch_outputs(aha_model* m, float* logits_out, uint32_t* argmax_out) {
+    TextModel& T = m->text;
+    if (logits_out) AHA_CUDA_CHECK(cudaMemcpyAsync(logits_out, T.logits, (size_t)T.cfg.V * sizeof(float), cudaMemcpyDeviceToHost, m->ctx.stream));
+    if (argmax_out) AHA_CUDA_CHECK(cudaMemcpyAsync(m->h_pin, T.d_argmax, sizeof(uint32_t), cudaMemcpyDeviceToHost, m->ctx.stream));
+    AHA_CUDA_CHECK(cudaStreamSynchronize(m->ctx.stream));
+    if (argmax_out) *argmax_out = m->h_pin[0];
+}
+
+// The multi-token forward (prefill).  Mirrors Qwen3Model::forward / Qwen3VLModel::forward / Qwen3ASRThinker::forward.
+void forward_prefill(aha_model* m, const uint32_t* ids, size_t S, size_t offset, const aha_mm* mm, bool initial) {
+    TextModel& T = m->text;
+    Ctx& c = m->ctx;
+    upload_ids(m, ids, S);
+    std::vector<int> pos3((size_t)3 * S);
+    std::vector<const float*> deepstack;
+    int n_visual = 0;
+    bool embeds_ready = false;
+    m->last_vision_secs = 0;
+    if (m->kind == aha_model::QWEN3VL) {
+        if (initial) AHA_REQUIRE(mm && mm->n == 5, "Qwen3VL process data error, must have pixel_values, image_grid_thw, pixel_values_video, video_grid_thw, cache_position");
+        const aha_tensor_desc* pv = initial ? mm_entry(mm, 0) : nullptr;
+        const aha_tensor_desc* thw = initial ? mm_entry(mm, 1) : nullptr;
+        if (initial) AHA_REQUIRE(!mm_entry(mm, 2) && !mm_entry(mm, 3), "video inputs are out of scope of this build (SURVEY.md section 8)");
+        std::vector<std::array<int, 3>> grid;
+        if (pv && thw) {
+            auto g = desc_to_i64(*thw);
+            AHA_REQUIRE(g.size() % 3 == 0 && !g.empty(), "image_grid_thw must be (n, 3)");
+            int N = 0;
+            for (size_t i = 0; i < g.size(); i += 3) { grid.push_back({(int)g[i], (int)g[i + 1], (int)g[i + 2]}); N += (int)(g[i] * g[i + 1] * g[i + 2]); }
+            AHA_REQUIRE(pv->rank == 2 && pv->shape[0] == N && pv->shape[1] == m->vision.patch_dim, "pixel_values shape does not match image_grid_thw");
+            AHA_REQUIRE(N <= m->vision.max_patches, "image needs " + std::to_string(N) + " patches, max_patches is " + std::to_string(m->vision.max_patches));
+            // placeholder positions + count check (model.rs:1158-1164)
+            std::vector<int> idx;
+            for (size_t i = 0; i < S; ++i) if ((int)ids[i] == m->image_token_id) idx.push_back((int)i);
+            const int n_embed = N / (m->vision.cfg.merge * m->vision.cfg.merge);
+            if ((int)idx.size() != n_embed)
+                throw std::runtime_error("n_image_token num: " + std::to_string(idx.size()) + " not equal to image_embed len: " + std::to_string(n_embed));
+            // pixel_values -> HBM, ViT
+            if (pv->dtype == AHA_F32) AHA_CUDA_CHECK(cudaMemcpyAsync(m->vision.pix, pv->data, (size_t)N * m->vision.patch_dim * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+            else { auto f = desc_to_f32(*pv); AHA_CUDA_CHECK(cudaMemcpyAsync(m->vision.pix, f.data(), f.size() * sizeof(float), cudaMemcpyHostToDevice, c.stream)); AHA_CUDA_CHECK(cudaStreamSynchronize(c.stream)); }
+            AHA_CUDA_CHECK(cudaEventRecord(m->ev0, c.stream));
+            m->vision.forward(N, grid);
+            AHA_CUDA_CHECK(cudaEventRecord(m->ev1, c.stream));
+            upload_scatter_idx(m, idx);
+            embed_gather_kernel<<<(unsigned)S, 256, 0, c.stream>>>(T.d_ids, T.embed, T.x, (int)S, T.cfg.H, T.cfg.V); c.cnt.kernels++;
+            scatter_rows_kernel<<<n_embed, 256, 0, c.stream>>>(m->d_scatter_idx, m->vision.image_embeds, T.x, T.cfg.H, 0); c.cnt.kernels++;
+            embeds_ready = true;
+            n_visual = n_embed;
+            for (float* p : m->vision.ds_out) deepstack.push_back(p);
+        }
+        // positions: first call -> get_rope_index, later -> arange + offset + rope_deltas (model.rs:1226-1264)
+        if (!m->have_rope_delta) {
+            int delta = 0;
+            get_rope_index(ids, (int)S, grid, m->vision.cfg.merge, m->image_token_id, m->vision_start_token_id, pos3, delta);
+            m->rope_delta = delta; m->have_rope_delta = true;
+        } else {
+            for (int r = 0; r < 3; ++r) for (size_t i = 0; i < S; ++i) pos3[(size_t)r * S + i] = (int)(i + offset) + m->rope_delta;
+        }
+    } else if (m->kind == aha_model::QWEN3_ASR) {
+        if (initial) AHA_REQUIRE(mm && mm->n == 1, "Qwen3 asr process data error, must have input_features");
+        const aha_tensor_desc* feat = initial ? mm_entry(mm, 0) : nullptr;
+        if (feat) {
+            AHA_REQUIRE(feat->rank == 2 && feat->shape[0] == m->audio.cfg.mel, "input_features must be (num_mel_bins, frames)");
+            const int Tm = (int)feat->shape[1];
+            AHA_REQUIRE(Tm <= m->audio.max_frames, "input_features longer than max_frames");
+            auto f = desc_to_f32(*feat);
+            AHA_CUDA_CHECK(cudaMemcpyAsync(m->audio.d_mel, f.data(), f.size() * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+            AHA_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+            AHA_CUDA_CHECK(cudaEventRecord(m->ev0, c.stream));
+            const int n_tok = m->audio.forward(m->audio.d_mel, Tm);
+            AHA_CUDA_CHECK(cudaEventRecord(m->ev1, c.stream));
+            std::vector<int> idx;
+            for (size_t i = 0; i < S; ++i) if ((int)ids[i] == m->audio_token_id) idx.push_back((int)i);
+            if ((int)idx.size() != n_tok)  // qwen3_asr/model.rs:348-354
+                throw std::runtime_error("n_audio_tokens num: " + std::to_string(idx.size()) + " not equal to audio_feature len: " + std::to_string(n_tok));
+            upload_scatter_idx(m, idx);
+            embed_gather_kernel<<<(unsigned)S, 256, 0, c.stream>>>(T.d_ids, T.embed, T.x, (int)S, T.cfg.H, T.cfg.V); c.cnt.kernels++;
+            scatter_rows_kernel<<<n_tok, 256, 0, c.stream>>>(m->d_scatter_idx, m->audio.audio_embeds, T.x, T.cfg.H, 0); c.cnt.kernels++;
+            embeds_ready = true;
+        }
+        for (int r = 0; r < 3; ++r) for (size_t i = 0; i < S; ++i) pos3[(size_t)r * S + i] = (int)(i + offset);
+    } else {
+        for (int r = 0; r < 3; ++r) for (size_t i = 0; i < S; ++i) pos3[(size_t)r * S + i] = (int)(i + offset);
+    }
+    upload_pos(m, pos3);
+    T.prefill((int)S, (int)offset, embeds_ready, m->d_scatter_idx, n_visual, deepstack);
+}
+
+void forward_any(aha_model* m, const uint32_t* ids, size_t S, size_t offset, const aha_mm* mm, bool initial, float* logits_out, uint32_t* argmax_out) {
+    TextModel& T = m->text;
+    AHA_REQUIRE(ids != nullptr && S >= 1, "input_ids must hold at least one token");
+    AHA_REQUIRE(offset + S <= (size_t)T.max_ctx, "context exceeds max_ctx");
+    const bool has_mm = initial && mm && ((m->kind == aha_model::QWEN3VL && (mm_entry(mm, 0) || mm_entry(mm, 2))) || (m->kind == aha_model::QWEN3_ASR && mm_entry(mm, 0)));
+    if (initial && m->kind == aha_model::QWEN3VL) AHA_REQUIRE(mm && mm->n == 5, "Qwen3VL process data error, must have pixel_values, image_grid_thw, pixel_values_video, video_grid_thw, cache_position");
+    if (initial && m->kind == aha_model::QWEN3_ASR) AHA_REQUIRE(mm && mm->n == 1, "Qwen3 asr process data error, must have input_features");
+    if (S == 1 && !has_mm && (m->kind != aha_model::QWEN3VL || m->have_rope_delta)) {
+        // decode step: single token against the cache
+        AHA_REQUIRE(ids[0] < (uint32_t)T.cfg.V, "token id out of range");
+        T.ensure_tokens((int)offset + 1);
+        T.set_state(ids[0], (int)offset, m->kind == aha_model::QWEN3VL ? m->rope_delta : 0, 0);
+        T.decode_step();
+    } else {
+        // The reference builds an (S,S) causal mask with offset 0 for every multi-token call
+        // (qwen3/model.rs:164-175); with a non-empty cache its broadcast_add against (S, off+S) scores fails.
+        AHA_REQUIRE(offset == 0, "seq_len > 1 with seqlen_offset > 0 is not supported (the reference's mask shape rejects it too)");
+        forward_prefill(m, ids, S, offset, mm, initial);
+        T.finish_argmax(0);
+    }
+    fetch_outputs(m, logits_out, argmax_out);
+    if (m->kind != aha_model::QWEN3 && has_mm) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, m->ev0, m->ev1) == cudaSuccess) m->last_vision_secs = ms * 1e-3;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int aha_b200_abi_version(void) { return AHA_B200_ABI_VERSION; }
+
+int aha_b200_create(const char* kind, const char* config_json, const aha_tensor_desc* weights, size_t n_weights, const uint32_t* eos_ids,
+                    size_t n_eos, const aha_options* opts, aha_model** out) {
+    if (!out) return 1;
+    *out = nullptr;
+    aha_model* m = nullptr;
+    try {
+        AHA_REQUIRE(kind && config_json && weights, "kind, config_json and weights are required");
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+            throw std::runtime_error("no CUDA device visible: libaha_b200 has no CPU fallback");
+        aha_options o{};
+        if (opts) o = *opts;
+        o.use_graph = opts ? opts->use_graph : 1;
+        AHA_REQUIRE(o.device >= 0 && o.device < ndev, "invalid device ordinal");
+        cudaDeviceProp prop;
+        AHA_CUDA_CHECK(cudaGetDeviceProperties(&prop, o.device));
+        AHA_REQUIRE(prop.major == 10, std::string("device '") + prop.name + "' is not sm_100-class (this library is built for sm_100a only)");
+        m = new aha_model();
+        m->ctx.device = o.device;
+        m->ctx.num_sms = prop.multiProcessorCount;
+        AHA_CUDA_CHECK(cudaSetDevice(o.device));
+        AHA_CUDA_CHECK(cudaStreamCreateWithFlags(&m->ctx.stream, cudaStreamNonBlocking));
+        AHA_CUDA_CHECK(cudaEventCreate(&m->ev0));
+        AHA_CUDA_CHECK(cudaEventCreate(&m->ev1));
+        AHA_CUDA_CHECK(cudaMallocHost(&m->h_pin, 64));
+        gemv_init();
+        const std::string k = kind;
+        const std::string cfg_text = config_json;
+        Json root = JsonParser(cfg_text).parse();
+        WeightTable wt(weights, n_weights);
+        const int tp_rank = o.tp_world > 1 ? o.tp_rank : 0, tp_world = o.tp_world > 1 ? o.tp_world : 1;
+        const int max_ctx = o.max_ctx > 0 ? o.max_ctx : 8192;
+        const int max_prefill = o.max_prefill > 0 ? o.max_prefill : max_ctx;
+        TextCfg tc;
+        if (k == "qwen3") {
+            m->kind = aha_model::QWEN3;
+            tc = TextCfg::from_json(root);
+            const std::string prefix = wt.has("model.embed_tokens.weight") ? "model." : "";  // qwen3/model.rs:105-109
+            m->text.load(m->ctx, tc, wt, prefix, "lm_head.weight", tp_rank, tp_world);
+        } else if (k == "qwen3vl") {
+            m->kind = aha_model::QWEN3VL;
+            tc = TextCfg::from_json(root.at("text_config"));
+            tc.tie = root.boolean_or("tie_word_embeddings", false);  // lm_head tying follows the TOP-LEVEL flag (model.rs:853-861)
+            AHA_REQUIRE(tc.mrope, "text_config.rope_scaling.mrope_section is required for Qwen3-VL");
+            m->image_token_id = root.integer("image_token_id"); m->video_token_id = root.integer_or("video_token_id", -1);
+            m->vision_start_token_id = root.integer("vision_start_token_id");
+            m->text.load(m->ctx, tc, wt, "model.language_model.", "lm_head.weight", tp_rank, tp_world);
+            m->vision.load(m->ctx, VisionCfg::from_json(root.at("vision_config")), wt, "model.visual.", o.max_patches > 0 ? o.max_patches : 16384);
+            AHA_REQUIRE(m->vision.cfg.out_hidden == tc.H, "vision out_hidden_size must equal the text hidden_size");
+        } else if (k == "qwen3_asr") {
+            m->kind = aha_model::QWEN3_ASR;
+            const Json& tk = root.at("thinker_config");
+            tc = TextCfg::from_json(tk.at("text_config"));
+            tc.mrope_asr = true;  // apply_interleaved_mrope_asr index rule (rope.rs:478-500); rows are identical so it is numerically a no-op
+            m->audio_token_id = tk.integer("audio_token_id");
+            m->text.load(m->ctx, tc, wt, "thinker.model.", "thinker.lm_head.weight", tp_rank, tp_world);
+            m->audio.load(m->ctx, AudioCfg::from_json(tk.at("audio_config")), wt, "thinker.audio_tower.", o.max_frames > 0 ? o.max_frames : 3000);
+            AHA_REQUIRE(m->audio.cfg.out_dim == tc.H, "audio output_dim must equal the text hidden_size");
+        } else {
+            throw std::runtime_error("unknown model kind '" + k + "' (expected qwen3 | qwen3vl | qwen3_asr)");
+        }
+        m->text.alloc_runtime(max_ctx, max_prefill, o.use_graph != 0);
+        m->max_scatter = max_prefill;
+        m->d_scatter_idx = m->ctx.alloc<int>(max_prefill);
+        for (size_t i = 0; i < n_eos; ++i) m->stop_ids.push_back(eos_ids[i]);
+        AHA_CUDA_CHECK(cudaStreamSynchronize(m->ctx.stream));
+        AHA_CUDA_CHECK(cudaDeviceSynchronize());
+        *out = m;
+        return 0;
+    } catch (const std::exception& e) {
+        {
+            std::lock_guard<std::mutex> lk(g_err_mu);
+            g_create_error = e.what();
+        }
+        cudaGetLastError();
+        if (m) aha_b200_destroy(m);
+        return 1;
+    }
+}
+
+int aha_b200_forward_initial(aha_model* m, const uint32_t* ids, size_t seq_len, size_t seqlen_offset, const aha_mm* mm, float* logits_out,
+                             uint32_t* argmax_out) {
+    return guarded(m, [&] { forward_any(m, ids, seq_len, seqlen_offset, mm, true, logits_out, argmax_out); });
+}
+
+int aha_b200_forward_step(aha_model* m, const uint32_t* ids, size_t seq_len, size_t seqlen_offset, float* logits_out, uint32_t* argmax_out) {
+    return guarded(m, [&] { forward_any(m, ids, seq_len, seqlen_offset, nullptr, false, logits_out, argmax_out); });
+}
+
+int aha_b200_clear_cache(aha_model* m) {
+    return guarded(m, [&] {
+        AHA_CUDA_CHECK(cudaStreamSynchronize(m->ctx.stream));
+        m->text.reset_pages();
+        m->have_rope_delta = false;  // qwen3vl/model.rs:1279-1282
+        m->rope_delta = 0;
+    });
+}
+
+size_t aha_b200_stop_token_ids(aha_model* m, uint32_t* out, size_t cap) {
+    if (!m) return 0;
+    for (size_t i = 0; i < m->stop_ids.size() && i < cap && out; ++i) out[i] = m->stop_ids[i];
+    return m->stop_ids.size();
+}
+
+int aha_b200_generate(aha_model* m, const uint32_t* ids, size_t seq_len, const aha_mm* mm, const aha_gen_params* params, uint32_t* out_tokens,
+                      size_t cap, size_t* n_out, aha_usage* usage) {
+    return guarded(m, [&] {
+        AHA_REQUIRE(params && out_tokens && n_out, "params, out_tokens and n_out are required");
+        AHA_REQUIRE(params->temperature < 1e-7f, "only the ArgMax sampler (temperature < 1e-7) is implemented");
+        AHA_REQUIRE(params->repeat_penalty == 1.0f || params->repeat_penalty == 0.0f || params->repeat_last_n == 0,
+                    "repeat_penalty != 1.0 is not implemented on the device loop");
+        TextModel& T = m->text;
+        const size_t sample_len = params->max_tokens ? params->max_tokens : 1024;
+        AHA_REQUIRE(cap >= sample_len, "out_tokens capacity is smaller than max_tokens");
+        AHA_REQUIRE(seq_len + sample_len <= (size_t)T.max_ctx, "prompt + max_tokens exceeds max_ctx");
+        using clk = std::chrono::steady_clock;
+        std::vector<uint32_t> generated;
+        const auto t0 = clk::now();
+        uint32_t tok = 0;
+        forward_any(m, ids, seq_len, 0, mm, true, nullptr, &tok);   // forward_initial + sample (first token never EOS-checked)
+        generated.push_back(tok);
+        const auto t1 = clk::now();
+        const double vision_secs = m->last_vision_secs;
+        // decode loop on the device: token feedback through DecodeState, EOS inspected on the host once per burst
+        size_t done = 1;
+        bool stop = false;
+        if (sample_len > 1) {
+            T.ensure_tokens((int)(seq_len + sample_len));
+            T.set_state(tok, (int)seq_len, m->kind == aha_model::QWEN3VL ? m->rope_delta : 0, 0);
+            std::vector<uint32_t> burst;
+            while (done < sample_len && !stop) {
+                const size_t n = std::min<size_t>(32, sample_len - done);
+                for (size_t i = 0; i < n; ++i) T.decode_step();
+                burst.resize(n);
+                AHA_CUDA_CHECK(cudaMemcpyAsync(burst.data(), T.d_history + (done - 1), n * sizeof(uint32_t), cudaMemcpyDeviceToHost, m->ctx.stream));
+                AHA_CUDA_CHECK(cudaStreamSynchronize(m->ctx.stream));
+                for (size_t i = 0; i < n; ++i) {
+                    generated.push_back(burst[i]);
+                    ++done;
+                    bool is_eos = false;
+                    for (uint32_t e : m->stop_ids) is_eos |= (e == burst[i]);
+                    if (is_eos) { stop = true; break; }  // EOS is pushed before the break (generate.rs:139-141)
+                }
+            }
+        }
+        const auto t2 = clk::now();
+        for (size_t i = 0; i < generated.size(); ++i) out_tokens[i] = generated[i];
+        *n_out = generated.size();
+        if (usage) {
+            usage->prompt_tokens = (uint32_t)seq_len;
+            usage->completion_tokens = (uint32_t)generated.size();
+            usage->prompt_secs = std::chrono::duration<double>(t1 - t0).count();
+            usage->completion_secs = std::chrono::duration<double>(t2 - t1).count();
+            usage->vision_secs = vision_secs;
+        }
+        // model.clear_cache() (generate.rs:147)
+        m->text.reset_pages();
+        m->have_rope_delta = false;
+        m->rope_delta = 0;
+    });
+}
+
+int aha_b200_decode_steps(aha_model* m, uint32_t first_token, size_t seqlen_offset, size_t n_steps, uint32_t* out_tokens) {
+    return guarded(m, [&] {
+        TextModel& T = m->text;
+        AHA_REQUIRE(first_token < (uint32_t)T.cfg.V, "token id out of range");
+        AHA_REQUIRE(seqlen_offset + n_steps <= (size_t)T.max_ctx, "context exceeds max_ctx");
+        T.ensure_tokens((int)(seqlen_offset + n_steps));
+        T.set_state(first_token, (int)seqlen_offset, m->kind == aha_model::QWEN3VL ? m->rope_delta : 0, 0);
+        for (size_t i = 0; i < n_steps; ++i) T.decode_step();
+        if (out_tokens) AHA_CUDA_CHECK(cudaMemcpyAsync(out_tokens, T.d_history, n_steps * sizeof(uint32_t), cudaMemcpyDeviceToHost, m->ctx.stream));
+        AHA_CUDA_CHECK(cudaStreamSynchronize(m->ctx.stream));
+    });
+}
+
+int aha_b200_mel_spectrogram(aha_model* m, const float* wave, size_t n_samples, float* mel_out, size_t mel_cap, size_t* n_frames) {
+    return guarded(m, [&] {
+        AHA_REQUIRE(m->kind == aha_model::QWEN3_ASR, "mel_spectrogram needs a qwen3_asr handle");
+        AHA_REQUIRE(wave && mel_out && n_frames, "wave, mel_out and n_frames are required");
+        const int frames = m->audio.mel_from_host(wave, n_samples);
+        AHA_REQUIRE((size_t)frames * m->audio.cfg.mel <= mel_cap, "mel_out too small");
+        AHA_CUDA_CHECK(cudaMemcpyAsync(mel_out, m->audio.d_mel, (size_t)frames * m->audio.cfg.mel * sizeof(float), cudaMemcpyDeviceToHost, m->ctx.stream));
+        AHA_CUDA_CHECK(cudaStreamSynchronize(m->ctx.stream));
+        *n_frames = (size_t)frames;
+    });
+}
+
+// u8 HWC -> normalised, frame-duplicated, merge-block-ordered patches.
+__global__ void patchify_kernel(const uint8_t* __restrict__ img, int H, int W, int patch, int merge, int tpatch, float* __restrict__ out) {
+    const int gw = W / patch, gh = H / patch;
+    const int p = blockIdx.x;  // patch in merge-block order (single temporal group)
+    const int mw = gw / merge;
+    const int blk = p / (merge * merge), in = p % (merge * merge);
+    const int row = (blk / mw) * merge + in / merge, col = (blk % mw) * merge + in % merge;
+    (void)gh;
+    const int feat = 3 * tpatch * patch * patch;
+    for (int f = threadIdx.x; f < feat; f += blockDim.x) {
+        const int c = f / (tpatch * patch * patch), rem = f % (patch * patch), py = rem / patch, px = rem % patch;
+        const uint8_t v = img[((size_t)(row * patch + py) * W + (col * patch + px)) * 3 + c];
+        // img_transform: f32(v) * (1/255), (x - 0.5) / 0.5   (img_utils.rs:272-294 with mean = std = 0.5)
+        const float x = (float)v * (1.0f / 255.0f);
+        out[(size_t)p * feat + f] = (x - 0.5f) / 0.5f;
+    }
+}
+
+int aha_b200_image_patchify(aha_model* m, const uint8_t* img_hwc, size_t h, size_t w, float* pixel_values_out, size_t cap, uint32_t grid_thw_out[3]) {
+    return guarded(m, [&] {
+        AHA_REQUIRE(m->kind == aha_model::QWEN3VL, "image_patchify needs a qwen3vl handle");
+        VisionModel& V = m->vision;
+        const int ps = V.cfg.patch, mg = V.cfg.merge;
+        AHA_REQUIRE(h % (ps * mg) == 0 && w % (ps * mg) == 0, "image size must already be a multiple of patch_size*merge_size (img_smart_resize output)");
+        const int gh = (int)h / ps, gw = (int)w / ps, N = gh * gw;
+        AHA_REQUIRE(N <= V.max_patches, "image exceeds max_patches");
+        AHA_REQUIRE((size_t)N * V.patch_dim <= cap, "pixel_values_out too small");
+        uint8_t* d_img = nullptr;
+        AHA_CUDA_CHECK(cudaMalloc(&d_img, h * w * 3));
+        try {
+            AHA_CUDA_CHECK(cudaMemcpyAsync(d_img, img_hwc, h * w * 3, cudaMemcpyHostToDevice, m->ctx.stream));
+            patchify_kernel<<<N, 256, 0, m->ctx.stream>>>(d_img, (int)h, (int)w, ps, mg, V.cfg.tpatch, V.pix);
+            m->ctx.cnt.kernels++;
+            AHA_CUDA_CHECK(cudaMemcpyAsync(pixel_values_out, V.pix, (size_t)N * V.patch_dim * sizeof(float), cudaMemcpyDeviceToHost, m->ctx.stream));
+            AHA_CUDA_CHECK(cudaStreamSynchronize(m->ctx.stream));
+        } catch (...) { cudaFree(d_img); throw; }
+        cudaFree(d_img);
+        grid_thw_out[0] = 1; grid_thw_out[1] = (uint32_t)gh; grid_thw_out[2] = (uint32_t)gw;
+    });
+}
+
+void aha_b200_destroy(aha_model* m) {
+    if (!m) return;
+    cudaSetDevice(m->ctx.device);
+    if (m->ctx.stream) cudaStreamSynchronize(m->ctx.stream);
+    m->text.destroy();
+    m->ctx.free_all();
+    if (m->h_pin) cudaFreeHost(m->h_pin);
+    if (m->ev0) cudaEventDestroy(m->ev0);
+    if (m->ev1) cudaEventDestroy(m->ev1);
+    if (m->ctx.stream) cudaStreamDestroy(m->ctx.stream);
+    delete m;
+}
+
+const char* aha_b200_last_error(aha_model* m) {
+    if (m) return m->last_error.c_str();
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    static thread_local std::string copy;
+    copy = g_create_error;
+    return copy.c_str();
+}
+
+void* aha_b200_stream(aha_model* m) { return m ? (void*)m->ctx.stream : nullptr; }
+
+int aha_b200_get_stats(aha_model* m, aha_stats* out) {
+    return guarded(m, [&] {
+        AHA_REQUIRE(out, "out is required");
+        out->kernel_launches = m->ctx.cnt.kernels;
+        out->graph_launches = m->ctx.cnt.graphs;
+        out->kernels_per_decode_step = m->text.step_graph_kernels;
+        out->weight_bytes = m->ctx.alloc_bytes;
+        out->kv_bytes_per_token = (uint64_t)m->text.cfg.L * 2 * m->text.nkv_l * m->text.cfg.hd * sizeof(float);
+        out->decode_bytes_per_step_fixed = m->text.decode_weight_bytes;
+    });
+}
+int aha_b200_reset_stats(aha_model* m) {
+    return guarded(m, [&] { m->ctx.cnt = Counters{}; });
+}
+int aha_b200_set_trace(aha_model* m, int on) {
+    return guarded(m, [&] {
+        m->text.set_trace(on != 0);
+        if (m->kind == aha_model::QWEN3VL) m->vision.set_trace(on != 0);
+        if (m->kind == aha_model::QWEN3_ASR) m->audio.set_trace(on != 0);
+    });
+}
+int aha_b200_debug_read(aha_model* m, const char* what, int index, float* out, size_t cap, size_t* n) {
+    return guarded(m, [&] {
+        AHA_REQUIRE(what && out && n, "what, out and n are required");
+        const std::string w = what;
+        const float* src = nullptr;
+        size_t cnt = 0;
+        TextModel& T = m->text;
+        if (w == "hidden") {
+            AHA_REQUIRE(T.trace_buf && index >= 0 && index < T.cfg.L, "hidden trace not available");
+            src = T.trace_buf + (size_t)index * T.max_prefill * T.cfg.H; cnt = (size_t)T.trace_S * T.cfg.H;
+        } else if (w == "vit") {
+            AHA_REQUIRE(m->kind == aha_model::QWEN3VL && m->vision.trace_buf && index >= 0 && index <= m->vision.cfg.depth, "vit trace not available");
+            src = m->vision.trace_buf + (size_t)index * m->vision.max_patches * m->vision.cfg.H; cnt = (size_t)m->vision.last_N * m->vision.cfg.H;
+        } else if (w == "image_embeds") {
+            AHA_REQUIRE(m->kind == aha_model::QWEN3VL, "image_embeds needs a qwen3vl handle");
+            const int ne = m->vision.last_N / (m->vision.cfg.merge * m->vision.cfg.merge);
+            src = index <= 0 ? m->vision.image_embeds : m->vision.ds_out.at(index - 1); cnt = (size_t)ne * m->vision.cfg.out_hidden;
+        } else if (w == "audio") {
+            AHA_REQUIRE(m->kind == aha_model::QWEN3_ASR && m->audio.trace_buf && index >= 0 && index <= m->audio.cfg.layers, "audio trace not available");
+            src = m->audio.trace_buf + (size_t)index * m->audio.max_tokens * m->audio.cfg.d_model; cnt = (size_t)m->audio.last_tokens * m->audio.cfg.d_model;
+        } else if (w == "audio_embeds") {
+            AHA_REQUIRE(m->kind == aha_model::QWEN3_ASR, "audio_embeds needs a qwen3_asr handle");
+            src = m->audio.audio_embeds; cnt = (size_t)m->audio.last_tokens * m->audio.cfg.out_dim;
+        } else if (w == "rope_delta") {
+            AHA_REQUIRE(cap >= 1, "out too small");
+            out[0] = (float)m->rope_delta; *n = 1; return;
+        } else {
+            throw std::runtime_error("unknown debug tensor '" + w + "'");
+        }
+        AHA_REQUIRE(cnt <= cap, "out too small");
+        AHA_CUDA_CHECK(cudaMemcpyAsync(out, src, cnt * sizeof(float), cudaMemcpyDeviceToHost, m->ctx.stream));
+        AHA_CUDA_CHECK(cudaStreamSynchronize(m->ctx.stream));
+        *n = cnt;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,502 @@
+// text_model.cuh -- the Qwen3 decoder stack shared by Qwen3, Qwen3-VL (text) and Qwen3-ASR (thinker):
+// weights in HBM, paged KV cache, prefill orchestration and the per-token decode step (CUDA graph).
+// Reference: Qwen3Model / Qwen3DecoderLayer (/root/reference/src/models/qwen3/model.rs:19-214),
+// Qwen3VLTextModel (qwen3vl/model.rs:743-835), Qwen3ASRThinkerTextModel (qwen3_asr/model.rs:229-306).
+#pragma once
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/aha_b200.h"
+#include "attention.cuh"
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "gemv.cuh"
+#include "json.hpp"
+#include "kernels_common.cuh"
+
+namespace aha {
+
+// ---------------------------------------------------------------------------------------------------
+struct Counters {
+    uint64_t kernels = 0, graphs = 0;
+};
+
+struct Ctx {  // per-handle launch context
+    cudaStream_t stream = nullptr;
+    int device = 0;
+    int num_sms = 148;
+    Counters cnt;
+    bool capturing = false;
+    std::vector<void*> allocs;
+    size_t alloc_bytes = 0;
+
+    template <typename T>
+    T* alloc(size_t n) {
+        void* p = nullptr;
+        AHA_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+        allocs.push_back(p);
+        alloc_bytes += n * sizeof(T);
+        return reinterpret_cast<T*>(p);
+    }
+    void free_all() {
+        for (void* p : allocs) cudaFree(p);
+        allocs.clear();
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Host-side weight table (descs by name) + dtype conversion.
+inline float half_bits_to_float(uint16_t h) {
+    const uint32_t sign = (h >> 15) & 1, exp = (h >> 10) & 0x1f, man = h & 0x3ff;
+    uint32_t f;
+    if (exp == 0) {
+        if (man == 0) f = sign << 31;
+        else {
+            int e = -1; uint32_t m = man;
+            do { ++e; m <<= 1; } while (!(m & 0x400));
+            f = (sign << 31) | ((uint32_t)(127 - 15 - e) << 23) | ((m & 0x3ff) << 13);
+        }
+    } else if (exp == 31) f = (sign << 31) | 0x7f800000u | (man << 13);
+    else f = (sign << 31) | ((exp + 112) << 23) | (man << 13);
+    float r; std::memcpy(&r, &f, 4); return r;
+}
+inline float bf16_bits_to_float(uint16_t b) { uint32_t f = (uint32_t)b << 16; float r; std::memcpy(&r, &f, 4); return r; }
+
+struct WeightTable {
+    std::map<std::string, const aha_tensor_desc*> by_name;
+    explicit WeightTable(const aha_tensor_desc* w, size_t n) {
+        for (size_t i = 0; i < n; ++i)
+            if (w[i].name) by_name[w[i].name] = &w[i];
+    }
+    bool has(const std::string& n) const { return by_name.count(n) != 0; }
+    const aha_tensor_desc& get(const std::string& n) const {
+        auto it = by_name.find(n);
+        if (it == by_name.end()) throw std::runtime_error("missing weight tensor '" + n + "'");
+        return *it->second;
+    }
+    static size_t numel(const aha_tensor_desc& d) { size_t n = 1; for (int i = 0; i < d.rank; ++i) n *= (size_t)d.shape[i]; return n; }
+    // element i as float
+    static float at(const aha_tensor_desc& d, size_t i) {
+        switch (d.dtype) {
+            case AHA_F32: return reinterpret_cast<const float*>(d.data)[i];
+            case AHA_F16: return half_bits_to_float(reinterpret_cast<const uint16_t*>(d.data)[i]);
+            case AHA_BF16: return bf16_bits_to_float(reinterpret_cast<const uint16_t*>(d.data)[i]);
+            default: throw std::runtime_error(std::string("weight '") + (d.name ? d.name : "?") + "': unsupported dtype");
+        }
+    }
+    void expect(const std::string& n, std::initializer_list<int64_t> shape) const {
+        const aha_tensor_desc& d = get(n);
+        size_t want = 1; for (auto s : shape) want *= (size_t)s;
+        if (numel(d) != want) throw std::runtime_error("weight '" + n + "' has " + std::to_string(numel(d)) + " elements, expected " + std::to_string(want));
+    }
+    // rows [r0, r0+nr) of a [R, C] matrix -> fp16 staging (cols [c0, c0+nc))
+    void rows_to_half(const std::string& n, int64_t R, int64_t C, int64_t r0, int64_t nr, int64_t c0, int64_t nc, __half* dst, int64_t dst_ld) const {
+        const aha_tensor_desc& d = get(n);
+        if ((int64_t)numel(d) != R * C) throw std::runtime_error("weight '" + n + "': unexpected size");
+        if (d.dtype == AHA_F16) {
+            const uint16_t* s = reinterpret_cast<const uint16_t*>(d.data);
+            for (int64_t r = 0; r < nr; ++r) std::memcpy(reinterpret_cast<uint16_t*>(dst) + r * dst_ld, s + (r0 + r) * C + c0, (size_t)nc * 2);
+        } else {
+            for (int64_t r = 0; r < nr; ++r)
+                for (int64_t c = 0; c < nc; ++c) dst[r * dst_ld + c] = __float2half_rn(at(d, (size_t)((r0 + r) * C + c0 + c)));
+        }
+    }
+    std::vector<float> vec_f32(const std::string& n, size_t expect_n) const {
+        const aha_tensor_desc& d = get(n);
+        if (numel(d) != expect_n) throw std::runtime_error("weight '" + n + "': unexpected size");
+        std::vector<float> v(expect_n);
+        for (size_t i = 0; i < expect_n; ++i) v[i] = at(d, i);
+        return v;
+    }
+};
+
+template <typename T>
+inline T* upload(Ctx& c, const std::vector<T>& h) {
+    T* d = c.alloc<T>(h.size());
+    AHA_CUDA_CHECK(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return d;
+}
+inline float* upload_vec(Ctx& c, const WeightTable& wt, const std::string& name, size_t n) { return upload(c, wt.vec_f32(name, n)); }
+
+struct LinearW {
+    __half* w = nullptr;  // [N, K]
+    float* b = nullptr;   // [N] or nullptr
+    int N = 0, K = 0;
+};
+
+// Upload `names` stacked along the output dimension ([sum N_i, K]); optional row interleave of two
+// equally-sized matrices (gate/up -> rows g0,u0,g1,u1,...).  Row/col slices implement tensor parallelism.
+struct RowSrc { std::string name; int64_t rows_total; int64_t r0; int64_t nr; };
+inline LinearW upload_linear(Ctx& c, const WeightTable& wt, const std::vector<RowSrc>& parts, int64_t K_total, int64_t c0, int64_t nc,
+                             bool interleave2, const std::vector<std::string>& bias_names) {
+    int64_t N = 0;
+    for (auto& p : parts) N += p.nr;
+    std::vector<__half> stage((size_t)N * nc);
+    if (interleave2) {
+        AHA_REQUIRE(parts.size() == 2 && parts[0].nr == parts[1].nr, "interleave needs two equal parts");
+        for (int k = 0; k < 2; ++k)
+            wt.rows_to_half(parts[k].name, parts[k].rows_total, K_total, parts[k].r0, parts[k].nr, c0, nc, stage.data() + (size_t)k * nc, 2 * nc);
+    } else {
+        int64_t r = 0;
+        for (auto& p : parts) {
+            wt.rows_to_half(p.name, p.rows_total, K_total, p.r0, p.nr, c0, nc, stage.data() + (size_t)r * nc, nc);
+            r += p.nr;
+        }
+    }
+    LinearW L;
+    L.N = (int)N; L.K = (int)nc;
+    L.w = upload(c, stage);
+    if (!bias_names.empty()) {
+        std::vector<float> b;
+        for (size_t i = 0; i < bias_names.size(); ++i) {
+            auto v = wt.vec_f32(bias_names[i], (size_t)parts[i].rows_total);
+            b.insert(b.end(), v.begin() + parts[i].r0, v.begin() + parts[i].r0 + parts[i].nr);
+        }
+        if (interleave2) {
+            std::vector<float> bi(b.size());
+            const size_t h = b.size() / 2;
+            for (size_t i = 0; i < h; ++i) { bi[2 * i] = b[i]; bi[2 * i + 1] = b[h + i]; }
+            b.swap(bi);
+        }
+        L.b = upload(c, b);
+    }
+    return L;
+}
+
+// ---------------------------------------------------------------------------------------------------
+struct TextCfg {
+    int H = 0, I = 0, L = 0, nh = 0, nkv = 0, hd = 0, V = 0;
+    float eps = 1e-6f, theta = 1e6f;
+    bool tie = false, attn_bias = false;
+    bool mrope = false, mrope_asr = false;
+    int mrope_section[3] = {0, 0, 0};
+    static TextCfg from_json(const Json& j) {
+        TextCfg c;
+        c.H = j.integer("hidden_size"); c.I = j.integer("intermediate_size"); c.L = j.integer("num_hidden_layers");
+        c.nh = j.integer("num_attention_heads"); c.nkv = j.integer_or("num_key_value_heads", c.nh);
+        c.hd = j.integer_or("head_dim", c.H / c.nh); c.V = j.integer("vocab_size");
+        c.eps = (float)j.number_or("rms_norm_eps", 1e-6); c.theta = (float)j.number_or("rope_theta", 1e6);
+        c.tie = j.boolean_or("tie_word_embeddings", false); c.attn_bias = j.boolean_or("attention_bias", false);
+        const std::string act = j.string_or("hidden_act", "silu");
+        AHA_REQUIRE(act == "silu", "hidden_act '" + act + "' is not supported (Qwen3 family uses silu)");
+        if (j.has("rope_scaling") && j.at("rope_scaling").has("mrope_section")) {
+            auto s = j.at("rope_scaling").int_array("mrope_section");
+            AHA_REQUIRE(s.size() == 3, "mrope_section must have 3 entries");
+            for (int i = 0; i < 3; ++i) c.mrope_section[i] = s[i];
+            c.mrope = true;
+        }
+        return c;
+    }
+};
+
+struct TextLayer {
+    LinearW qkv, o, gu, down;
+    float *ln1 = nullptr, *ln2 = nullptr, *qn = nullptr, *kn = nullptr;
+};
+
+constexpr int kPageShift = 5;            // 32-token KV pages
+constexpr int kPage = 1 << kPageShift;
+constexpr int kDecodeSplits = 16;        // split-KV factor of the decode attention
+
+struct TextModel {
+    TextCfg cfg;
+    Ctx* ctx = nullptr;
+    int tp_rank = 0, tp_world = 1;
+    int nh_l = 0, nkv_l = 0, I_l = 0, qkv_dim = 0;  // per-rank (tensor-parallel) sizes
+    __half* embed = nullptr;
+    __half* lm_head = nullptr;
+    float* norm = nullptr;
+    std::vector<TextLayer> layers;
+    float* inv_freq = nullptr;
+    uint8_t* mrope_sel = nullptr;
+    uint64_t weight_bytes = 0, decode_weight_bytes = 0;
+
+    // paged KV
+    int max_ctx = 0, num_pages = 0;
+    float* kv_pool = nullptr;
+    size_t layer_stride = 0, page_stride = 0;
+    int* d_page_table = nullptr;
+    std::vector<int> h_page_table, free_pages;
+    int pages_mapped = 0;
+
+    // prefill workspaces
+    int max_prefill = 0;
+    float *x = nullptr, *xn = nullptr, *qkv = nullptr, *attn = nullptr, *hbuf = nullptr;
+    uint32_t* d_ids = nullptr;
+    int* d_pos3 = nullptr;
+    // decode workspaces
+    float *x1 = nullptr, *qkv1 = nullptr, *attn1 = nullptr, *h1 = nullptr, *logits = nullptr, *partial = nullptr;
+    int* counters = nullptr;
+    float* pmax = nullptr; int* pidx = nullptr; int n_pcand = 0;
+    DecodeState* d_state = nullptr;
+    uint32_t* d_history = nullptr; int hist_cap = 0;
+    uint32_t* d_argmax = nullptr;
+    cudaGraphExec_t step_graph = nullptr;
+    uint64_t step_graph_kernels = 0;
+    bool use_graph = true;
+
+    // tracing (tests)
+    bool trace = false;
+    float* trace_buf = nullptr;  // [L][max_prefill][H]
+    int trace_S = 0;
+
+    // ---------------------------------------------------------------------------------------------
+    void load(Ctx& c, const TextCfg& cf, const WeightTable& wt, const std::string& prefix, const std::string& lm_head_name,
+              int rank, int world) {
+        ctx = &c; cfg = cf; tp_rank = rank; tp_world = world;
+        AHA_REQUIRE(cfg.hd == 128, "head_dim must be 128 (Qwen3 family)");
+        AHA_REQUIRE(cfg.nh % cfg.nkv == 0, "num_attention_heads must be a multiple of num_key_value_heads");
+        AHA_REQUIRE(cfg.nkv % world == 0 && cfg.I % world == 0, "tensor-parallel world must divide num_key_value_heads and intermediate_size");
+        const int G = cfg.nh / cfg.nkv;
+        AHA_REQUIRE(G == 1 || G == 2 || G == 4 || G == 6, "unsupported GQA group size");
+        nkv_l = cfg.nkv / world; nh_l = nkv_l * G; I_l = cfg.I / world;
+        qkv_dim = (nh_l + 2 * nkv_l) * cfg.hd;
+        AHA_REQUIRE(cfg.H % 16 == 0 && I_l % 16 == 0, "hidden/intermediate sizes must be multiples of 16");
+        const int H = cfg.H, hd = cfg.hd;
+        const size_t before = c.alloc_bytes;
+        {
+            std::vector<__half> st((size_t)cfg.V * H);
+            wt.rows_to_half(prefix + "embed_tokens.weight", cfg.V, H, 0, cfg.V, 0, H, st.data(), H);
+            embed = upload(c, st);
+            if (cfg.tie) lm_head = embed;
+            else {
+                wt.rows_to_half(lm_head_name, cfg.V, H, 0, cfg.V, 0, H, st.data(), H);
+                lm_head = upload(c, st);
+            }
+        }
+        norm = upload_vec(c, wt, prefix + "norm.weight", H);
+        layers.resize(cfg.L);
+        for (int l = 0; l < cfg.L; ++l) {
+            const std::string p = prefix + "layers." + std::to_string(l) + ".";
+            TextLayer& T = layers[l];
+            std::vector<std::string> qb, ob;
+            if (cfg.attn_bias) { qb = {p + "self_attn.q_proj.bias", p + "self_attn.k_proj.bias", p + "self_attn.v_proj.bias"}; ob = {p + "self_attn.o_proj.bias"}; }
+            T.qkv = upload_linear(c, wt,
+                                  {{p + "self_attn.q_proj.weight", (int64_t)cfg.nh * hd, (int64_t)rank * nh_l * hd, (int64_t)nh_l * hd},
+                                   {p + "self_attn.k_proj.weight", (int64_t)cfg.nkv * hd, (int64_t)rank * nkv_l * hd, (int64_t)nkv_l * hd},
+                                   {p + "self_attn.v_proj.weight", (int64_t)cfg.nkv * hd, (int64_t)rank * nkv_l * hd, (int64_t)nkv_l * hd}},
+                                  H, 0, H, false, qb);
+            T.o = upload_linear(c, wt, {{p + "self_attn.o_proj.weight", H, 0, H}}, (int64_t)cfg.nh * hd, (int64_t)rank * nh_l * hd, (int64_t)nh_l * hd, false,
+                                (rank == 0 ? ob : std::vector<std::string>{}));
+            T.gu = upload_linear(c, wt, {{p + "mlp.gate_proj.weight", cfg.I, (int64_t)rank * I_l, I_l}, {p + "mlp.up_proj.weight", cfg.I, (int64_t)rank * I_l, I_l}},
+                                 H, 0, H, true, {});
+            T.down = upload_linear(c, wt, {{p + "mlp.down_proj.weight", H, 0, H}}, cfg.I, (int64_t)rank * I_l, I_l, false, {});
+            T.ln1 = upload_vec(c, wt, p + "input_layernorm.weight", H);
+            T.ln2 = upload_vec(c, wt, p + "post_attention_layernorm.weight", H);
+            T.qn = upload_vec(c, wt, p + "self_attn.q_norm.weight", hd);
+            T.kn = upload_vec(c, wt, p + "self_attn.k_norm.weight", hd);
+        }
+        weight_bytes = c.alloc_bytes - before;
+        decode_weight_bytes = 0;
+        for (auto& T : layers)
+            decode_weight_bytes += 2ull * ((size_t)T.qkv.N * T.qkv.K + (size_t)T.o.N * T.o.K + (size_t)T.gu.N * T.gu.K + (size_t)T.down.N * T.down.K) +
+                                   4ull * (2 * H + 2 * hd);
+        decode_weight_bytes += 4ull * H + 2ull * (size_t)cfg.V * H;
+        // RoPE tables: inv_freq in f32 powf like rope.rs:7-13; M-RoPE row selector per frequency (rope.rs:454-476 / 478-500)
+        std::vector<float> inv(hd / 2);
+        for (int j = 0; j < hd / 2; ++j) inv[j] = 1.0f / powf(cfg.theta, (float)(2 * j) / (float)hd);
+        inv_freq = upload(c, inv);
+        std::vector<uint8_t> sel(hd / 2, 0);
+        if (cfg.mrope) {
+            for (int dim = 1; dim < 3; ++dim) {
+                const int length = cfg.mrope_asr ? cfg.mrope_section[dim] : cfg.mrope_section[dim] * 3;
+                for (int idx = dim; idx < length && idx < hd / 2; idx += 3) sel[idx] = (uint8_t)dim;
+            }
+        }
+        mrope_sel = upload(c, sel);
+    }
+
+    void alloc_runtime(int max_ctx_, int max_prefill_, bool graph) {
+        Ctx& c = *ctx;
+        max_ctx = max_ctx_; max_prefill = max_prefill_; use_graph = graph;
+        num_pages = ceil_div(max_ctx, kPage);
+        page_stride = (size_t)2 * nkv_l * kPage * cfg.hd;
+        layer_stride = page_stride * num_pages;
+        kv_pool = c.alloc<float>(layer_stride * cfg.L);
+        d_page_table = c.alloc<int>(num_pages);
+        h_page_table.assign(num_pages, 0);
+        reset_pages();
+        const size_t S = max_prefill;
+        x = c.alloc<float>(S * cfg.H); xn = c.alloc<float>(S * cfg.H);
+        qkv = c.alloc<float>(S * qkv_dim); attn = c.alloc<float>(S * nh_l * cfg.hd); hbuf = c.alloc<float>(S * I_l);
+        d_ids = c.alloc<uint32_t>(S); d_pos3 = c.alloc<int>(3 * S);
+        x1 = c.alloc<float>(cfg.H); qkv1 = c.alloc<float>(qkv_dim); attn1 = c.alloc<float>((size_t)nh_l * cfg.hd); h1 = c.alloc<float>(I_l);
+        logits = c.alloc<float>(cfg.V);
+        partial = c.alloc<float>((size_t)nh_l * kDecodeSplits * (cfg.hd + 2));
+        counters = c.alloc<int>(nkv_l);
+        AHA_CUDA_CHECK(cudaMemset(counters, 0, nkv_l * sizeof(int)));
+        n_pcand = gemv_grid(cfg.V, GEPI_ARGMAX);
+        pmax = c.alloc<float>(n_pcand); pidx = c.alloc<int>(n_pcand);
+        d_state = c.alloc<DecodeState>(1);
+        AHA_CUDA_CHECK(cudaMemset(d_state, 0, sizeof(DecodeState)));
+        hist_cap = max_ctx;
+        d_history = c.alloc<uint32_t>(hist_cap);
+        d_argmax = c.alloc<uint32_t>(1);
+    }
+
+    void set_trace(bool on) {
+        if (on && !trace_buf) trace_buf = ctx->alloc<float>((size_t)cfg.L * max_prefill * cfg.H);
+        trace = on;
+    }
+
+    // ---- paged KV management (host side).  Physical pages are handed out from the END of the pool so the
+    // logical->physical mapping is never the identity (the indirection is always exercised).
+    void reset_pages() {
+        free_pages.clear();
+        for (int p = 0; p < num_pages; ++p) free_pages.push_back(p);
+        pages_mapped = 0;
+    }
+    void ensure_tokens(int n_tokens) {
+        AHA_REQUIRE(n_tokens <= max_ctx, "context of " + std::to_string(n_tokens) + " tokens exceeds max_ctx " + std::to_string(max_ctx));
+        const int need = ceil_div(n_tokens, kPage);
+        if (need <= pages_mapped) return;
+        const int first = pages_mapped;
+        while (pages_mapped < need) {
+            h_page_table[pages_mapped++] = free_pages.back();
+            free_pages.pop_back();
+        }
+        AHA_CUDA_CHECK(cudaMemcpyAsync(d_page_table + first, h_page_table.data() + first, (size_t)(pages_mapped - first) * sizeof(int),
+                                       cudaMemcpyHostToDevice, ctx->stream));
+    }
+    KVSrc kv_src(int layer) const {
+        KVSrc s;
+        s.k = kv_pool + (size_t)layer * layer_stride;
+        s.v = s.k + (size_t)nkv_l * kPage * cfg.hd;
+        s.page_table = d_page_table; s.page_shift = kPageShift; s.page_stride = page_stride;
+        s.tok_stride = cfg.hd; s.head_stride = (size_t)kPage * cfg.hd;
+        return s;
+    }
+
+    // ---- GEMM dispatch (SIMT exact path; the tcgen05 path plugs in here)
+    void gemm(int epi, const float* A, int lda, const LinearW& W, const float* resid, int ldr, float* C, int ldc, int M, int act = ACT_NONE) {
+        GemmArgs g;
+        g.A = A; g.lda = lda; g.W = W.w; g.bias = W.b; g.resid = resid; g.ldr = ldr; g.C = C; g.ldc = ldc; g.M = M; g.N = W.N; g.K = W.K; g.act = act;
+        gemm_simt(ctx->stream, epi, g);
+        ctx->cnt.kernels++;
+    }
+
+    // ---- prefill: ids already on device in d_ids (or embeddings already in x when embeds_ready), pos3 in d_pos3.
+    // visual_idx/deepstack: Qwen3-VL deepstack injection (qwen3vl/model.rs:815-824).
+    void prefill(int S, int pos0, bool embeds_ready, const int* d_visual_idx, int n_visual, const std::vector<const float*>& deepstack) {
+        Ctx& c = *ctx;
+        cudaStream_t st = c.stream;
+        const int H = cfg.H, hd = cfg.hd;
+        AHA_REQUIRE(S <= max_prefill, "prompt of " + std::to_string(S) + " tokens exceeds max_prefill " + std::to_string(max_prefill));
+        AHA_REQUIRE(tp_world == 1, "tensor-parallel prefill is not implemented in this build");
+        ensure_tokens(pos0 + S);
+        if (!embeds_ready) { embed_gather_kernel<<<S, 256, 0, st>>>(d_ids, embed, x, S, H, cfg.V); c.cnt.kernels++; }
+        RopeArgs rp{inv_freq, mrope_sel, d_pos3, S};
+        const float scaling = (float)(1.0 / std::sqrt((double)hd));
+        for (int l = 0; l < cfg.L; ++l) {
+            TextLayer& T = layers[l];
+            rmsnorm_kernel<<<S, 256, 0, st>>>(x, T.ln1, cfg.eps, xn, H); c.cnt.kernels++;
+            gemm(EPI_STORE, xn, H, T.qkv, nullptr, 0, qkv, qkv_dim, S);
+            KVSrc kv = kv_src(l);
+            qk_norm_rope_kv_kernel<128><<<dim3(S, nh_l + 2 * nkv_l), 128, 0, st>>>(qkv, T.qn, T.kn, cfg.eps, rp, const_cast<float*>(kv.k), const_cast<float*>(kv.v), kv, nh_l, nkv_l, pos0);
+            c.cnt.kernels++;
+            FlashArgs fa;
+            fa.q = qkv; fa.q_tok_stride = qkv_dim; fa.q_head_stride = hd; fa.kv = kv;
+            fa.out = attn; fa.o_tok_stride = (size_t)nh_l * hd; fa.o_head_stride = hd;
+            fa.Sq = S; fa.Skv = pos0 + S; fa.q0 = 0; fa.kv0 = 0; fa.groups = nh_l / nkv_l; fa.scaling = scaling;
+            flash_attn<128>(st, fa, nh_l, true); c.cnt.kernels++;
+            gemm(EPI_RESID, attn, nh_l * hd, T.o, x, H, x, H, S);
+            rmsnorm_kernel<<<S, 256, 0, st>>>(x, T.ln2, cfg.eps, xn, H); c.cnt.kernels++;
+            gemm(EPI_SWIGLU, xn, H, T.gu, nullptr, 0, hbuf, I_l, S);
+            gemm(EPI_RESID, hbuf, I_l, T.down, x, H, x, H, S);
+            if (l < (int)deepstack.size() && n_visual > 0) {
+                scatter_rows_kernel<<<n_visual, 256, 0, st>>>(d_visual_idx, deepstack[l], x, H, 1); c.cnt.kernels++;
+            }
+            if (trace) AHA_CUDA_CHECK(cudaMemcpyAsync(trace_buf + (size_t)l * max_prefill * H, x, (size_t)S * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        }
+        trace_S = S;
+        AHA_CUDA_CHECK(cudaGetLastError());
+        // last-token logits: final RMSNorm fused into the lm_head GEMV (qwen3/model.rs:186-187,142)
+        head(x + (size_t)(S - 1) * H);
+    }
+
+    void head(const float* xrow) {
+        GemvArgs a{};
+        a.W = lm_head; a.x = xrow; a.norm_w = norm; a.eps = cfg.eps; a.out = logits; a.pmax = pmax; a.pidx = pidx; a.N = cfg.V; a.K = cfg.H;
+        gemv(ctx->stream, PRO_RMSNORM, GEPI_ARGMAX, a); ctx->cnt.kernels++;
+    }
+    // publish argmax; advance != 0 also feeds the token back into the decode state
+    void finish_argmax(int advance) {
+        argmax_final_kernel<<<1, 32, 0, ctx->stream>>>(pmax, pidx, n_pcand, d_argmax, d_state, d_history, hist_cap, advance);
+        ctx->cnt.kernels++;
+    }
+
+    // ---- one decode step, all inputs taken from d_state (token, pos, rope_delta)
+    template <int G>
+    void launch_decode_attn(const DecodeAttnArgs& a) {
+        decode_attn_kernel<128, G><<<dim3(kDecodeSplits, nkv_l), 256, 0, ctx->stream>>>(a);
+    }
+    void decode_step_launches() {
+        Ctx& c = *ctx;
+        cudaStream_t st = c.stream;
+        const int H = cfg.H, hd = cfg.hd;
+        AHA_REQUIRE(tp_world == 1, "tensor-parallel decode is not implemented in this build");
+        embed_gather_kernel<<<1, 256, 0, st>>>(&d_state->token, embed, x1, 1, H, cfg.V); c.cnt.kernels++;
+        const float scaling = (float)(1.0 / std::sqrt((double)hd));
+        for (int l = 0; l < cfg.L; ++l) {
+            TextLayer& T = layers[l];
+            GemvArgs a{};
+            a.W = T.qkv.w; a.bias = T.qkv.b; a.x = x1; a.norm_w = T.ln1; a.eps = cfg.eps; a.out = qkv1; a.N = T.qkv.N; a.K = T.qkv.K;
+            gemv(st, PRO_RMSNORM, GEPI_STORE, a); c.cnt.kernels++;
+            KVSrc kv = kv_src(l);
+            DecodeAttnArgs d{};
+            d.qkv = qkv1; d.qw = T.qn; d.kw = T.kn; d.eps = cfg.eps; d.inv_freq = inv_freq; d.st = d_state;
+            d.kbase = const_cast<float*>(kv.k); d.vbase = const_cast<float*>(kv.v); d.kv = kv;
+            d.partial = partial; d.counters = counters; d.out = attn1; d.nh = nh_l; d.nkv = nkv_l; d.nsplit = kDecodeSplits; d.scaling = scaling;
+            switch (nh_l / nkv_l) {
+                case 1: launch_decode_attn<1>(d); break;
+                case 2: launch_decode_attn<2>(d); break;
+                case 4: launch_decode_attn<4>(d); break;
+                default: launch_decode_attn<6>(d); break;
+            }
+            c.cnt.kernels++;
+            GemvArgs o{};
+            o.W = T.o.w; o.bias = T.o.b; o.x = attn1; o.resid = x1; o.out = x1; o.N = T.o.N; o.K = T.o.K;
+            gemv(st, PRO_NONE, GEPI_RESID, o); c.cnt.kernels++;
+            GemvArgs g{};
+            g.W = T.gu.w; g.x = x1; g.norm_w = T.ln2; g.eps = cfg.eps; g.out = h1; g.N = T.gu.N; g.K = T.gu.K;
+            gemv(st, PRO_RMSNORM, GEPI_SWIGLU, g); c.cnt.kernels++;
+            GemvArgs dn{};
+            dn.W = T.down.w; dn.x = h1; dn.resid = x1; dn.out = x1; dn.N = T.down.N; dn.K = T.down.K;
+            gemv(st, PRO_NONE, GEPI_RESID, dn); c.cnt.kernels++;
+        }
+        head(x1);
+        finish_argmax(1);
+        AHA_CUDA_CHECK(cudaGetLastError());
+    }
+    void decode_step() {
+        Ctx& c = *ctx;
+        if (!use_graph) { decode_step_launches(); return; }
+        if (!step_graph) {
+            const uint64_t k0 = c.cnt.kernels;
+            cudaGraph_t g = nullptr;
+            AHA_CUDA_CHECK(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal));
+            try { decode_step_launches(); } catch (...) { cudaStreamEndCapture(c.stream, &g); if (g) cudaGraphDestroy(g); throw; }
+            AHA_CUDA_CHECK(cudaStreamEndCapture(c.stream, &g));
+            step_graph_kernels = c.cnt.kernels - k0;
+            c.cnt.kernels = k0;
+            AHA_CUDA_CHECK(cudaGraphInstantiate(&step_graph, g, 0));
+            AHA_CUDA_CHECK(cudaGraphDestroy(g));
+        }
+        AHA_CUDA_CHECK(cudaGraphLaunch(step_graph, c.stream));
+        c.cnt.graphs++;
+        c.cnt.kernels += step_graph_kernels;
+    }
+    void set_state(uint32_t token, int pos, int rope_delta, int n_hist) {
+        DecodeState s{token, pos, rope_delta, n_hist};
+        AHA_CUDA_CHECK(cudaMemcpyAsync(d_state, &s, sizeof(s), cudaMemcpyHostToDevice, ctx->stream));
+        AHA_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // `s` is a stack temporary
+    }
+    void destroy() {
+        if (step_graph) { cudaGraphExecDestroy(step_graph); step_graph = nullptr; }
+    }
+};
+
+}  // namespace aha

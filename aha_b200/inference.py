@@ -1,0 +1,190 @@
+"""Host-side mirror of aha's model-executor seam for the B200 path.
+
+`B200Model` has the methods of `trait InferenceModel`
+(/root/reference/src/models/common/mod.rs:25-45): forward_initial, forward_step, clear_cache,
+stop_token_ids -- same names, argument meaning and error behaviour (errors are raised, never
+swallowed) -- and `generate` = generate_generic (/root/reference/src/models/common/generate.rs:115-159).
+Everything here is plumbing around libaha_b200.so; no arithmetic happens in Python."""
+import ctypes as C
+import json
+
+import numpy as np
+
+from . import _lib as L
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+class MultiModalData:
+    """common/mod.rs:14-22 -- positional list of optional tensors."""
+
+    def __init__(self, data_vec):
+        self.data_vec = list(data_vec)
+
+
+class B200Model:
+    def __init__(self, kind, config, weights, eos_ids=(), device=0, max_ctx=8192, max_prefill=0, max_patches=0,
+                 max_frames=0, use_graph=True, decode_impl=0, gemm_impl=0, tp_rank=0, tp_world=1):
+        self._lib = L.load()
+        self.kind = kind
+        self.config = config
+        cfg_json = json.dumps(config).encode()
+        names = list(weights.keys())
+        arrs = [np.ascontiguousarray(weights[n]) for n in names]
+        descs = (L.TensorDesc * len(names))(*[L.make_desc(a, n) for a, n in zip(arrs, names)])
+        eos = np.asarray(list(eos_ids), dtype=np.uint32)
+        opts = L.Options(device=device, tp_rank=tp_rank, tp_world=tp_world, max_ctx=max_ctx, max_prefill=max_prefill,
+                         max_patches=max_patches, max_frames=max_frames, use_graph=1 if use_graph else 0,
+                         decode_impl=decode_impl, gemm_impl=gemm_impl)
+        h = C.c_void_p()
+        rc = self._lib.aha_b200_create(kind.encode(), cfg_json, descs, len(names),
+                                       eos.ctypes.data_as(C.POINTER(C.c_uint32)), len(eos), C.byref(opts), C.byref(h))
+        if rc != 0:
+            raise B200Error(self._lib.aha_b200_last_error(None).decode())
+        self._h = h
+        tc = config if kind == "qwen3" else (config["text_config"] if kind == "qwen3vl" else config["thinker_config"]["text_config"])
+        self.vocab_size = tc["vocab_size"]
+        self.hidden_size = tc["hidden_size"]
+
+    # ------------------------------------------------------------------ helpers
+    def _check(self, rc):
+        if rc != 0:
+            raise B200Error(self._lib.aha_b200_last_error(self._h).decode())
+
+    def _mm(self, data):
+        if data is None:
+            return None, None
+        vec = data.data_vec if isinstance(data, MultiModalData) else list(data)
+        keep, descs = [], []
+        for t in vec:
+            if t is None:
+                d = L.TensorDesc()
+                d.data = None
+            else:
+                a = np.ascontiguousarray(t)
+                if a.dtype == np.int32:
+                    a = a.astype(np.int64)
+                keep.append(a)
+                d = L.make_desc(a)
+            descs.append(d)
+        arr = (L.TensorDesc * len(descs))(*descs)
+        mm = L.MM(arr, len(descs))
+        return mm, (keep, arr)
+
+    @staticmethod
+    def _ids(input_ids):
+        return np.ascontiguousarray(np.asarray(input_ids, dtype=np.uint32).reshape(-1))
+
+    # ------------------------------------------------------------------ InferenceModel
+    def forward_initial(self, input_ids, seqlen_offset, data=None, want_logits=True):
+        """-> logits (1,1,V) float32 (like the reference's Tensor) and sets self.last_argmax."""
+        ids = self._ids(input_ids)
+        mm, _keep = self._mm(data)
+        logits = np.empty(self.vocab_size, np.float32) if want_logits else None
+        am = C.c_uint32(0)
+        self._check(self._lib.aha_b200_forward_initial(
+            self._h, ids.ctypes.data_as(C.POINTER(C.c_uint32)), ids.size, int(seqlen_offset),
+            C.byref(mm) if mm is not None else None,
+            logits.ctypes.data_as(C.POINTER(C.c_float)) if want_logits else None, C.byref(am)))
+        self.last_argmax = int(am.value)
+        return logits.reshape(1, 1, -1) if want_logits else None
+
+    def forward_step(self, input_ids, seqlen_offset, want_logits=True):
+        ids = self._ids(input_ids)
+        logits = np.empty(self.vocab_size, np.float32) if want_logits else None
+        am = C.c_uint32(0)
+        self._check(self._lib.aha_b200_forward_step(
+            self._h, ids.ctypes.data_as(C.POINTER(C.c_uint32)), ids.size, int(seqlen_offset),
+            logits.ctypes.data_as(C.POINTER(C.c_float)) if want_logits else None, C.byref(am)))
+        self.last_argmax = int(am.value)
+        return logits.reshape(1, 1, -1) if want_logits else None
+
+    def clear_cache(self):
+        self._check(self._lib.aha_b200_clear_cache(self._h))
+
+    def stop_token_ids(self):
+        n = self._lib.aha_b200_stop_token_ids(self._h, None, 0)
+        out = (C.c_uint32 * max(n, 1))()
+        self._lib.aha_b200_stop_token_ids(self._h, out, n)
+        return [int(out[i]) for i in range(n)]
+
+    # ------------------------------------------------------------------ generate_generic
+    def generate(self, input_ids, data=None, max_tokens=1024, temperature=0.0, repeat_penalty=1.0, repeat_last_n=64,
+                 seed=299792458):
+        """-> (generated ids, usage dict).  Greedy (ArgMax) only, like `temperature: 0` requests."""
+        ids = self._ids(input_ids)
+        mm, _keep = self._mm(data)
+        p = L.GenParams(temperature=temperature, repeat_penalty=repeat_penalty, repeat_last_n=repeat_last_n,
+                        max_tokens=max_tokens, seed=seed)
+        out = (C.c_uint32 * max_tokens)()
+        n = C.c_size_t(0)
+        u = L.Usage()
+        self._check(self._lib.aha_b200_generate(self._h, ids.ctypes.data_as(C.POINTER(C.c_uint32)), ids.size,
+                                                C.byref(mm) if mm is not None else None, C.byref(p), out, max_tokens,
+                                                C.byref(n), C.byref(u)))
+        usage = dict(prompt_tokens=u.prompt_tokens, completion_tokens=u.completion_tokens, prompt_secs=u.prompt_secs,
+                     completion_secs=u.completion_secs, vision_secs=u.vision_secs)
+        return [int(out[i]) for i in range(n.value)], usage
+
+    # ------------------------------------------------------------------ frontends
+    def mel_spectrogram(self, wave):
+        wave = np.ascontiguousarray(wave, dtype=np.float32).reshape(-1)
+        n_mels = self.config["thinker_config"]["audio_config"]["num_mel_bins"]
+        cap = n_mels * (wave.size // 160 + 2)
+        out = np.empty(cap, np.float32)
+        nf = C.c_size_t(0)
+        self._check(self._lib.aha_b200_mel_spectrogram(self._h, wave.ctypes.data_as(C.POINTER(C.c_float)), wave.size,
+                                                       out.ctypes.data_as(C.POINTER(C.c_float)), cap, C.byref(nf)))
+        return out[: n_mels * nf.value].reshape(n_mels, nf.value).copy()
+
+    def image_patchify(self, img_u8_hwc):
+        img = np.ascontiguousarray(img_u8_hwc, dtype=np.uint8)
+        h, w, _ = img.shape
+        vc = self.config["vision_config"]
+        feat = vc["in_channels"] * vc["temporal_patch_size"] * vc["patch_size"] ** 2
+        n = (h // vc["patch_size"]) * (w // vc["patch_size"])
+        out = np.empty((n, feat), np.float32)
+        grid = (C.c_uint32 * 3)()
+        self._check(self._lib.aha_b200_image_patchify(self._h, img.ctypes.data_as(C.POINTER(C.c_uint8)), h, w,
+                                                      out.ctypes.data_as(C.POINTER(C.c_float)), out.size, grid))
+        return out, np.array([[grid[0], grid[1], grid[2]]], dtype=np.uint32)
+
+    # ------------------------------------------------------------------ introspection (tests / bench)
+    def decode_steps(self, first_token, seqlen_offset, n_steps, want_tokens=True):
+        out = (C.c_uint32 * n_steps)() if want_tokens else None
+        self._check(self._lib.aha_b200_decode_steps(self._h, int(first_token), int(seqlen_offset), int(n_steps), out))
+        return [int(out[i]) for i in range(n_steps)] if want_tokens else None
+
+    def stream_ptr(self):
+        return int(self._lib.aha_b200_stream(self._h) or 0)
+
+    def stats(self):
+        s = L.Stats()
+        self._check(self._lib.aha_b200_get_stats(self._h, C.byref(s)))
+        return {k: int(getattr(s, k)) for k, _ in L.Stats._fields_}
+
+    def reset_stats(self):
+        self._check(self._lib.aha_b200_reset_stats(self._h))
+
+    def set_trace(self, on=True):
+        self._check(self._lib.aha_b200_set_trace(self._h, 1 if on else 0))
+
+    def debug_read(self, what, index, cap):
+        out = np.empty(cap, np.float32)
+        n = C.c_size_t(0)
+        self._check(self._lib.aha_b200_debug_read(self._h, what.encode(), int(index),
+                                                  out.ctypes.data_as(C.POINTER(C.c_float)), cap, C.byref(n)))
+        return out[: n.value].copy()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.aha_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

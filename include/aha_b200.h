@@ -1,0 +1,168 @@
+/*
+ * aha_b200.h -- C ABI of libaha_b200.so: a B200-native (sm_100a) prefill + decode path for
+ * Qwen3 / Qwen3-VL / Qwen3-ASR that drops in behind jhqxxx/aha's model-executor seam.
+ *
+ * The reference has no FFI; its seam is the Rust trait
+ *     trait InferenceModel { forward_initial, forward_step, clear_cache, stop_token_ids }
+ *     (/root/reference/src/models/common/mod.rs:25-45)
+ * consumed by generate_generic* (/root/reference/src/models/common/generate.rs:87-368) and, for ASR,
+ * the inherent `forward` (/root/reference/src/models/qwen3_asr/generate.rs:153-155).
+ * Each entry point below names the reference item it replaces.  INTEGRATION.md shows the Rust shim
+ * (`impl InferenceModel for B200Model`) a maintainer would add.
+ *
+ * Rules of the ABI:
+ *   - plain C types only; every call returns 0 on success, non-zero on error; the message is
+ *     available from aha_b200_last_error(); nothing throws or aborts across the boundary;
+ *   - the library owns all device memory (weights, paged KV pool, workspaces, CUDA graphs) behind the
+ *     opaque handle; the caller owns every host buffer it passes; no host pointer is retained past
+ *     a call (weights are copied to HBM during aha_b200_create);
+ *   - a handle is NOT re-entrant (aha serialises requests behind a write lock,
+ *     /root/reference/src/server/api.rs:31,117,131) but IS thread-migratable: every entry binds
+ *     the CUDA device itself, no thread-local state;
+ *   - there is no CPU fallback: if no sm_100 device is present, create fails.
+ */
+#ifndef AHA_B200_H
+#define AHA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AHA_B200_ABI_VERSION 1
+
+typedef struct aha_model aha_model;
+
+/* candle DType subset carried across the boundary */
+enum { AHA_F32 = 0, AHA_F16 = 1, AHA_BF16 = 2, AHA_U32 = 3, AHA_I64 = 4, AHA_U8 = 5 };
+
+/* A contiguous row-major host tensor (what a candle Tensor flattens to). */
+typedef struct aha_tensor_desc {
+    const char* name;      /* checkpoint tensor name (weights) or NULL */
+    int32_t dtype;         /* AHA_* */
+    int32_t rank;
+    int64_t shape[8];
+    const void* data;      /* host pointer */
+} aha_tensor_desc;
+
+/* MultiModalData (/root/reference/src/models/common/mod.rs:14-22), positional like data_vec:
+ * Qwen3-VL: [pixel_values, image_grid_thw, pixel_values_video, video_grid_thw, cache_position]
+ *           (/root/reference/src/models/qwen3vl/generate.rs:88-94; length checked model.rs:1292-1296)
+ * Qwen3-ASR: [input_features]  (/root/reference/src/models/qwen3_asr/model.rs:405-411)
+ * An absent entry is a desc with data == NULL.  n must be 5 (VL) or 1 (ASR). */
+typedef struct aha_mm {
+    const aha_tensor_desc* data_vec;
+    size_t n;
+} aha_mm;
+
+typedef struct aha_options {
+    int32_t device;        /* CUDA ordinal (reference: Device::new_cuda(0), src/utils/mod.rs:36) */
+    int32_t tp_rank;       /* tensor-parallel rank / world (new design); 0/1 = single GPU */
+    int32_t tp_world;
+    int32_t max_ctx;       /* KV capacity in tokens (0 = 8192) */
+    int32_t max_prefill;   /* largest S accepted by forward_initial (0 = max_ctx) */
+    int32_t max_patches;   /* largest ViT patch count (0 = 16384); Qwen3-VL only */
+    int32_t max_frames;    /* largest mel frame count (0 = 3000); Qwen3-ASR only */
+    int32_t use_graph;     /* 1 = replay the decode step from a CUDA graph (default), 0 = eager launches */
+    int32_t decode_impl;   /* 0 = auto, 1 = per-op kernels, 2 = persistent fused step kernel */
+    int32_t gemm_impl;     /* 0 = auto, 1 = SIMT fp32, 2 = tcgen05 (split-fp16, fp32-exact) */
+    const void* tp_comm;   /* opaque: ncclUniqueId bytes (128) when tp_world > 1, else NULL */
+    int32_t reserved[8];
+} aha_options;
+
+typedef struct aha_gen_params {      /* ChatCompletionParameters subset used by generate_generic */
+    float temperature;     /* < 1e-7 => ArgMax (sample.rs:13).  Non-greedy is not implemented: error. */
+    float repeat_penalty;  /* 1.0 = off (sample.rs:46) */
+    int32_t repeat_last_n; /* default 64 (generate.rs:47) */
+    uint32_t max_tokens;   /* sample_len (default 1024, generate.rs:408-409) */
+    uint64_t seed;         /* unused for ArgMax */
+} aha_gen_params;
+
+typedef struct aha_usage {           /* Usage timing split (generate.rs:126-145) */
+    uint32_t prompt_tokens;
+    uint32_t completion_tokens;
+    double prompt_secs;              /* forward_initial + first sample */
+    double completion_secs;          /* the decode loop */
+    double vision_secs;              /* device time of the ViT / audio tower inside prompt_secs */
+} aha_usage;
+
+typedef struct aha_stats {
+    uint64_t kernel_launches;        /* kernels launched by this handle since create / last reset */
+    uint64_t graph_launches;
+    uint64_t kernels_per_decode_step;/* kernel nodes inside one decode-step graph */
+    uint64_t weight_bytes;           /* bytes of weights resident in HBM */
+    uint64_t kv_bytes_per_token;
+    uint64_t decode_bytes_per_step_fixed; /* algorithmic weight bytes read per decode step */
+} aha_stats;
+
+/* XModel::new(cfg, VarBuilder, eos_ids) inside XGenerateModel::init
+ * (/root/reference/src/models/qwen3/generate.rs:22-50, qwen3vl/generate.rs:33-63,
+ *  qwen3_asr/generate.rs:51-87).  kind = "qwen3" | "qwen3vl" | "qwen3_asr"; config_json is the
+ * checkpoint's config.json text; weights are the safetensors tensors by name. */
+int aha_b200_create(const char* kind, const char* config_json,
+                    const aha_tensor_desc* weights, size_t n_weights,
+                    const uint32_t* eos_ids, size_t n_eos,
+                    const aha_options* opts, aha_model** out);
+
+/* InferenceModel::forward_initial (/root/reference/src/models/common/mod.rs:28-35;
+ * Qwen3-VL model.rs:1285-1311; Qwen3-ASR model.rs:394-411).  ids: (1,S) u32.
+ * logits_out: V floats or NULL; argmax_out: first-max index or NULL (ArgMax sampler on device). */
+int aha_b200_forward_initial(aha_model* m, const uint32_t* ids, size_t seq_len, size_t seqlen_offset,
+                             const aha_mm* mm, float* logits_out, uint32_t* argmax_out);
+
+/* InferenceModel::forward_step (/root/reference/src/models/common/mod.rs:37-38). */
+int aha_b200_forward_step(aha_model* m, const uint32_t* ids, size_t seq_len, size_t seqlen_offset,
+                          float* logits_out, uint32_t* argmax_out);
+
+/* InferenceModel::clear_cache (mod.rs:41; Qwen3-VL also resets rope_deltas, model.rs:1279-1282). */
+int aha_b200_clear_cache(aha_model* m);
+
+/* InferenceModel::stop_token_ids (mod.rs:44).  Returns the count; writes up to cap ids. */
+size_t aha_b200_stop_token_ids(aha_model* m, uint32_t* out, size_t cap);
+
+/* generate_generic (/root/reference/src/models/common/generate.rs:115-159) with the ArgMax sampler:
+ * prefill, then the decode loop entirely on the device (token feedback without host round trips),
+ * first token never EOS-checked, EOS token pushed before the break, cache cleared at the end. */
+int aha_b200_generate(aha_model* m, const uint32_t* ids, size_t seq_len, const aha_mm* mm,
+                      const aha_gen_params* params, uint32_t* out_tokens, size_t cap, size_t* n_out,
+                      aha_usage* usage);
+
+/* WhisperFeatureExtractor::call (/root/reference/src/models/feature_extractor/
+ * feature_extraction_whisper.rs:65-115): wave (n) f32 host -> log-mel (n_mels, n_frames) f32 host.
+ * Returns frames through *n_frames.  Qwen3-ASR handles only. */
+int aha_b200_mel_spectrogram(aha_model* m, const float* wave, size_t n_samples,
+                             float* mel_out, size_t mel_cap, size_t* n_frames);
+
+/* img_transform + process_vision_tensor (/root/reference/src/utils/img_utils.rs:272-294,
+ * src/models/qwen3vl/processor.rs:174-251): u8 HWC image whose size already satisfies
+ * img_smart_resize -> pixel_values (grid_t*grid_h*grid_w, 3*2*16*16) f32 host + grid_thw[3]. */
+int aha_b200_image_patchify(aha_model* m, const uint8_t* img_hwc, size_t h, size_t w,
+                            float* pixel_values_out, size_t cap, uint32_t grid_thw_out[3]);
+
+void aha_b200_destroy(aha_model* m);
+
+/* Last error message of the handle (or of the failed create when m == NULL). */
+const char* aha_b200_last_error(aha_model* m);
+
+/* --- introspection used by tests / bench (not part of the reference seam) --- */
+int aha_b200_abi_version(void);
+/* cudaStream_t the handle launches on (for CUDA-event timing on the launching stream). */
+void* aha_b200_stream(aha_model* m);
+int aha_b200_get_stats(aha_model* m, aha_stats* out);
+int aha_b200_reset_stats(aha_model* m);
+/* Copy an internal activation to the host: what = "hidden" (text hidden states after layer `index`
+ * of the last forward_initial, S*H floats; requires aha_b200_set_trace(m,1)), "vit" (ViT hidden after
+ * block `index`), "image_embeds", "audio_embeds", "rope_delta" (1 float). */
+int aha_b200_set_trace(aha_model* m, int on);
+int aha_b200_debug_read(aha_model* m, const char* what, int index, float* out, size_t cap, size_t* n);
+/* Run n decode steps back to back on the device (graph replays, token feedback on device) without any
+ * host synchronisation inside; used by bench.py to time the device-resident `value`. */
+int aha_b200_decode_steps(aha_model* m, uint32_t first_token, size_t seqlen_offset, size_t n_steps,
+                          uint32_t* out_tokens /* n_steps, host, may be NULL */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AHA_B200_H */

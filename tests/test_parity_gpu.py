@@ -1,0 +1,282 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+Tolerance: max |logit difference| <= 1e-3 (north_star), greedy ids bit-exact wherever the oracle's
+top-1/top-2 gap exceeds the measured error."""
+import numpy as np
+import pytest
+
+from conftest import TOL, make_model, make_oracle, top2_gap
+
+pytestmark = pytest.mark.gpu
+
+
+def _ids(n, vocab, seed):
+    from aha_b200 import synth
+    return synth.synth_text_ids(n, vocab - 8, seed)
+
+
+@pytest.fixture(scope="module")
+def q3():
+    cfg, w, m = make_model("qwen3", "tiny", max_ctx=512)
+    yield cfg, w, m, make_oracle("qwen3", cfg, w)
+    m.close()
+
+
+@pytest.mark.parametrize("S", [1, 2, 31, 63, 64, 65, 130, 257])
+def test_qwen3_prefill_logits(q3, S):
+    cfg, w, m, o = q3
+    ids = _ids(S, cfg["vocab_size"], S)
+    m.clear_cache(); o.clear_cache()
+    got = m.forward_initial(ids, 0)[0, 0]
+    want = o.forward_initial(ids.reshape(1, -1), 0)[0, 0]
+    err = np.abs(got - want).max()
+    assert err <= TOL, err
+    if top2_gap(want) > 10 * err:
+        assert m.last_argmax == int(np.argmax(want))
+
+
+def test_qwen3_per_layer_hidden(q3):
+    cfg, w, m, o = q3
+    ids = _ids(40, cfg["vocab_size"], 11)
+    m.clear_cache(); o.clear_cache()
+    m.set_trace(True)
+    o.trace = []
+    m.forward_initial(ids, 0)
+    o.forward_initial(ids.reshape(1, -1), 0)
+    for l in range(cfg["num_hidden_layers"]):
+        got = m.debug_read("hidden", l, 40 * cfg["hidden_size"]).reshape(40, -1)
+        assert np.abs(got - o.trace[l][0]).max() <= 1e-4
+    m.set_trace(False)
+    o.trace = None
+
+
+def test_qwen3_teacher_forced_decode(q3):
+    cfg, w, m, o = q3
+    S, n = 37, 70  # crosses two 32-token page boundaries
+    ids = _ids(S + n, cfg["vocab_size"], 3)
+    m.clear_cache(); o.clear_cache()
+    m.forward_initial(ids[:S], 0)
+    o.forward_initial(ids[:S].reshape(1, -1), 0)
+    worst = 0.0
+    for i in range(n):
+        got = m.forward_step(ids[S + i:S + i + 1], S + i)[0, 0]
+        want = o.forward_step(ids[S + i:S + i + 1].reshape(1, 1), S + i)[0, 0]
+        err = np.abs(got - want).max()
+        worst = max(worst, err)
+        assert err <= TOL, (i, err)
+        if top2_gap(want) > 10 * max(err, 1e-6):
+            assert m.last_argmax == int(np.argmax(want)), i
+    print("teacher-forced worst abs logit err", worst)
+
+
+def test_qwen3_greedy_generate_matches_oracle(q3):
+    from oracle.generate import GenerationContext, generate_generic
+    cfg, w, m, o = q3
+    ids = _ids(21, cfg["vocab_size"], 5)
+    m.clear_cache(); o.clear_cache()
+    ctx = GenerationContext(temperature=0.0, initial_seq_len=21, max_tokens=40)
+    want, _, _ = generate_generic(o, ids.reshape(1, -1), None, ctx)
+    got, usage = m.generate(ids, max_tokens=40)
+    assert got == want
+    assert usage["prompt_tokens"] == 21 and usage["completion_tokens"] == len(want)
+
+
+def test_qwen3_graph_and_eager_agree(q3):
+    cfg, w, m, o = q3
+    cfg2, w2, m2 = make_model("qwen3", "tiny", max_ctx=512, use_graph=False)
+    try:
+        ids = _ids(50, cfg["vocab_size"], 8)
+        m.clear_cache()
+        m.forward_initial(ids, 0); m2.forward_initial(ids, 0)
+        a = m.decode_steps(5, 50, 20)
+        b = m2.decode_steps(5, 50, 20)
+        assert a == b
+        assert m.stats()["kernels_per_decode_step"] > 0
+    finally:
+        m2.close()
+
+
+def test_qwen3_untied_lm_head():
+    cfg, w, m = make_model("qwen3", "tiny-untied", max_ctx=128)
+    try:
+        o = make_oracle("qwen3", cfg, w)
+        ids = _ids(17, cfg["vocab_size"], 2)
+        got = m.forward_initial(ids, 0)[0, 0]
+        want = o.forward_initial(ids.reshape(1, -1), 0)[0, 0]
+        assert np.abs(got - want).max() <= TOL
+    finally:
+        m.close()
+
+
+def test_error_behaviour(q3):
+    from aha_b200 import B200Error
+    cfg, w, m, o = q3
+    m.clear_cache()
+    with pytest.raises(B200Error, match="token id out of range"):
+        m.forward_initial(np.array([cfg["vocab_size"]], np.uint32), 0)
+    with pytest.raises(B200Error, match="at least one token"):
+        m.forward_initial(np.array([], np.uint32), 0)
+    m.forward_initial(_ids(4, cfg["vocab_size"], 1), 0)
+    with pytest.raises(B200Error, match="seq_len > 1 with seqlen_offset > 0"):
+        m.forward_step(_ids(3, cfg["vocab_size"], 1), 4)
+    with pytest.raises(B200Error, match="max_ctx"):
+        m.forward_step(np.array([1], np.uint32), 512)
+    assert m.stop_token_ids() == [cfg["eos_token_id"]]
+    # the handle stays usable after an error
+    m.clear_cache()
+    assert m.forward_initial(_ids(4, cfg["vocab_size"], 1), 0).shape == (1, 1, cfg["vocab_size"])
+
+
+def test_clear_cache_resets_state(q3):
+    cfg, w, m, o = q3
+    ids = _ids(33, cfg["vocab_size"], 4)
+    m.clear_cache()
+    a = m.forward_initial(ids, 0)[0, 0].copy()
+    m.forward_step(np.array([3], np.uint32), 33)
+    m.clear_cache()
+    b = m.forward_initial(ids, 0)[0, 0]
+    assert np.array_equal(a, b)  # deterministic and independent of earlier requests
+
+
+# ----------------------------------------------------------------------------- Qwen3-VL
+@pytest.fixture(scope="module")
+def vl():
+    cfg, w, m = make_model("qwen3vl", "tiny", max_ctx=1024, max_patches=2048)
+    yield cfg, w, m, make_oracle("qwen3vl", cfg, w)
+    m.close()
+
+
+def _vl_inputs(cfg, sizes, n_text, seed=1):
+    from aha_b200 import synth
+    from oracle.qwen3vl import process_image
+    pvs, grids = [], []
+    for i, (h, w_) in enumerate(sizes):
+        pv, g = process_image(synth.synth_image(h, w_, seed + i))
+        pvs.append(pv); grids.append(g)
+    pv = np.concatenate(pvs, 0); grid = np.concatenate(grids, 0)
+    ids = np.concatenate([synth.synth_text_ids(3, 1000, 9), synth.vl_prompt_ids(cfg, grid, n_text)]).astype(np.uint32)
+    return pv, grid, ids
+
+
+@pytest.mark.parametrize("sizes", [[(256, 320)], [(256, 256), (320, 256)]])
+def test_vl_prefill_and_decode(vl, sizes):
+    cfg, w, m, o = vl
+    pv, grid, ids = _vl_inputs(cfg, sizes, 9)
+    m.clear_cache(); o.clear_cache()
+    got = m.forward_initial(ids, 0, [pv, grid, None, None, None])[0, 0]
+    want = o.forward_initial(ids.reshape(1, -1), 0, [pv, grid, None, None, None])[0, 0]
+    assert np.abs(got - want).max() <= TOL
+    assert int(m.debug_read("rope_delta", 0, 1)[0]) == o.rope_deltas
+    S = len(ids)
+    for i, t in enumerate([5, 17, 400]):
+        got = m.forward_step(np.array([t], np.uint32), S + i)[0, 0]
+        want = o.forward_step(np.array([[t]]), S + i)[0, 0]
+        assert np.abs(got - want).max() <= TOL
+
+
+def test_vl_vision_tower_blocks(vl):
+    cfg, w, m, o = vl
+    pv, grid, ids = _vl_inputs(cfg, [(256, 320)], 4)
+    m.clear_cache(); o.clear_cache()
+    m.set_trace(True)
+    o.visual.trace = []
+    m.forward_initial(ids, 0, [pv, grid, None, None, None])
+    emb, deep = o.visual.forward(pv, grid)
+    Hv, N = cfg["vision_config"]["hidden_size"], pv.shape[0]
+    for i, (name, x) in enumerate(o.visual.trace):
+        got = m.debug_read("vit", i, N * Hv).reshape(N, Hv)
+        assert np.abs(got - x).max() <= 1e-4, name
+    got = m.debug_read("image_embeds", 0, emb.size).reshape(emb.shape)
+    assert np.abs(got - emb).max() <= 1e-4
+    for k, d in enumerate(deep):
+        got = m.debug_read("image_embeds", k + 1, d.size).reshape(d.shape)
+        assert np.abs(got - d).max() <= 1e-4
+    m.set_trace(False)
+    o.visual.trace = None
+
+
+def test_vl_text_only_prompt(vl):
+    cfg, w, m, o = vl
+    ids = _ids(12, 1000, 3)
+    m.clear_cache(); o.clear_cache()
+    got = m.forward_initial(ids, 0, [None, None, None, None, None])[0, 0]
+    want = o.forward_initial(ids.reshape(1, -1), 0, [None, None, None, None, None])[0, 0]
+    assert np.abs(got - want).max() <= TOL
+
+
+def test_vl_errors(vl):
+    from aha_b200 import B200Error
+    cfg, w, m, o = vl
+    pv, grid, ids = _vl_inputs(cfg, [(256, 320)], 4)
+    m.clear_cache()
+    with pytest.raises(B200Error, match="must have pixel_values"):
+        m.forward_initial(ids, 0, [pv, grid])
+    bad = ids.copy(); bad[5] = 7  # one placeholder fewer
+    with pytest.raises(B200Error, match="not equal to image_embed len"):
+        m.forward_initial(bad, 0, [pv, grid, None, None, None])
+
+
+def test_vl_image_patchify(vl):
+    from aha_b200 import synth
+    from oracle.qwen3vl import process_image
+    cfg, w, m, o = vl
+    img = synth.synth_image(256, 320, 7)
+    pv, grid = m.image_patchify(img)
+    wpv, wgrid = process_image(img)
+    assert grid.tolist() == wgrid.tolist()
+    assert np.abs(pv - wpv).max() <= 1e-6
+
+
+# ----------------------------------------------------------------------------- Qwen3-ASR
+@pytest.fixture(scope="module")
+def asr():
+    cfg, w, m = make_model("qwen3_asr", "tiny", max_ctx=512, max_frames=600)
+    yield cfg, w, m, make_oracle("qwen3_asr", cfg, w)
+    m.close()
+
+
+@pytest.mark.parametrize("seconds", [1.0, 2.5, 3.07])
+def test_asr_mel_frontend(asr, seconds):
+    from aha_b200 import synth
+    from oracle.audio import WhisperFeatureExtractor
+    cfg, w, m, o = asr
+    wave = synth.synth_audio(seconds)
+    want = WhisperFeatureExtractor().call(wave[None], 16000)[0]
+    got = m.mel_spectrogram(wave)
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= 1e-3
+
+
+@pytest.mark.parametrize("seconds", [1.0, 2.5])
+def test_asr_prefill_and_decode(asr, seconds):
+    from aha_b200 import synth
+    from oracle.audio import WhisperFeatureExtractor, get_feat_extract_output_lengths
+    cfg, w, m, o = asr
+    mel = WhisperFeatureExtractor().call(synth.synth_audio(seconds)[None], 16000)[0]
+    ids = synth.asr_prompt_ids(cfg, get_feat_extract_output_lengths(mel.shape[1]))
+    m.clear_cache(); o.clear_cache()
+    m.set_trace(True)
+    o.audio.trace = []
+    got = m.forward_initial(ids, 0, [mel])[0, 0]
+    want = o.forward_initial(ids.reshape(1, -1), 0, [mel])[0, 0]
+    D = cfg["thinker_config"]["audio_config"]["d_model"]
+    for i, (name, x) in enumerate(o.audio.trace):
+        g = m.debug_read("audio", i, x.size).reshape(x.shape)
+        assert np.abs(g - x).max() <= 1e-4, name
+    assert np.abs(got - want).max() <= TOL
+    S = len(ids)
+    got = m.forward_step(np.array([9], np.uint32), S)[0, 0]
+    want = o.forward_step(np.array([[9]]), S)[0, 0]
+    assert np.abs(got - want).max() <= TOL
+    m.set_trace(False)
+    o.audio.trace = None
+
+
+def test_asr_errors(asr):
+    from aha_b200 import B200Error, synth
+    from oracle.audio import WhisperFeatureExtractor
+    cfg, w, m, o = asr
+    mel = WhisperFeatureExtractor().call(synth.synth_audio(1.0)[None], 16000)[0]
+    ids = synth.asr_prompt_ids(cfg, 5)
+    m.clear_cache()
+    with pytest.raises(B200Error, match="not equal to audio_feature len"):
+        m.forward_initial(ids, 0, [mel])
