@@ -450,16 +450,54 @@ int aha_b200_generate(aha_model* m, const uint32_t* ids, size_t seq_len, const a
     });
 }
 
-int aha_b200_decode_steps(aha_model* m, uint32_t first_token, size_t seqlen_offset, size_t n_steps, uint32_t* out_tokens) {
+int aha_b200_decode_steps(aha_model* m, uint32_t first_token, size_t seqlen_offset, size_t n_steps, uint32_t* out_tokens, double* device_ms) {
     return guarded(m, [&] {
         TextModel& T = m->text;
         AHA_REQUIRE(first_token < (uint32_t)T.cfg.V, "token id out of range");
         AHA_REQUIRE(seqlen_offset + n_steps <= (size_t)T.max_ctx, "context exceeds max_ctx");
         T.ensure_tokens((int)(seqlen_offset + n_steps));
         T.set_state(first_token, (int)seqlen_offset, m->kind == aha_model::QWEN3VL ? m->rope_delta : 0, 0);
+        if (n_steps > 0 && !T.step_graph && T.use_graph) {  // build the graph outside the timed region (pos is restored below)
+            T.decode_step();
+            T.set_state(first_token, (int)seqlen_offset, m->kind == aha_model::QWEN3VL ? m->rope_delta : 0, 0);
+        }
+        AHA_CUDA_CHECK(cudaEventRecord(m->ev0, m->ctx.stream));
         for (size_t i = 0; i < n_steps; ++i) T.decode_step();
+        AHA_CUDA_CHECK(cudaEventRecord(m->ev1, m->ctx.stream));
         if (out_tokens) AHA_CUDA_CHECK(cudaMemcpyAsync(out_tokens, T.d_history, n_steps * sizeof(uint32_t), cudaMemcpyDeviceToHost, m->ctx.stream));
         AHA_CUDA_CHECK(cudaStreamSynchronize(m->ctx.stream));
+        if (device_ms) { float ms = 0.f; AHA_CUDA_CHECK(cudaEventElapsedTime(&ms, m->ev0, m->ev1)); *device_ms = ms; }
+    });
+}
+
+int aha_b200_bench_kernel(aha_model* m, const char* which, int iters, double* avg_ms, uint64_t* bytes_per_launch) {
+    return guarded(m, [&] {
+        AHA_REQUIRE(which && iters > 0 && avg_ms && bytes_per_launch, "which, iters, avg_ms, bytes_per_launch are required");
+        TextModel& T = m->text;
+        const std::string w = which;
+        cudaStream_t st = m->ctx.stream;
+        const int L = T.cfg.L;
+        uint64_t bytes = 0;
+        auto launch = [&](int i) {
+            TextLayer& Y = T.layers[i % L];
+            GemvArgs a{};
+            if (w == "gemv_gate_up") { a.W = Y.gu.w; a.x = T.x1; a.norm_w = Y.ln2; a.eps = T.cfg.eps; a.out = T.h1; a.N = Y.gu.N; a.K = Y.gu.K; gemv(st, PRO_RMSNORM, GEPI_SWIGLU, a); bytes = 2ull * a.N * a.K; }
+            else if (w == "gemv_qkv") { a.W = Y.qkv.w; a.x = T.x1; a.norm_w = Y.ln1; a.eps = T.cfg.eps; a.out = T.qkv1; a.N = Y.qkv.N; a.K = Y.qkv.K; gemv(st, PRO_RMSNORM, GEPI_STORE, a); bytes = 2ull * a.N * a.K; }
+            else if (w == "gemv_down") { a.W = Y.down.w; a.x = T.h1; a.resid = T.x1; a.out = T.x1; a.N = Y.down.N; a.K = Y.down.K; gemv(st, PRO_NONE, GEPI_RESID, a); bytes = 2ull * a.N * a.K; }
+            else if (w == "gemv_o") { a.W = Y.o.w; a.x = T.attn1; a.resid = T.x1; a.out = T.x1; a.N = Y.o.N; a.K = Y.o.K; gemv(st, PRO_NONE, GEPI_RESID, a); bytes = 2ull * a.N * a.K; }
+            else if (w == "gemv_lm_head") { T.head(T.x1); bytes = 2ull * T.cfg.V * T.cfg.H; }
+            else throw std::runtime_error("unknown kernel '" + w + "'");
+            m->ctx.cnt.kernels++;
+        };
+        for (int i = 0; i < 3; ++i) launch(i);
+        AHA_CUDA_CHECK(cudaEventRecord(m->ev0, st));
+        for (int i = 0; i < iters; ++i) launch(i + 3);
+        AHA_CUDA_CHECK(cudaEventRecord(m->ev1, st));
+        AHA_CUDA_CHECK(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        AHA_CUDA_CHECK(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
+        *avg_ms = ms / iters;
+        *bytes_per_launch = bytes;
     });
 }
 

@@ -152,10 +152,20 @@ class B200Model:
         return out, np.array([[grid[0], grid[1], grid[2]]], dtype=np.uint32)
 
     # ------------------------------------------------------------------ introspection (tests / bench)
-    def decode_steps(self, first_token, seqlen_offset, n_steps, want_tokens=True):
-        out = (C.c_uint32 * n_steps)() if want_tokens else None
-        self._check(self._lib.aha_b200_decode_steps(self._h, int(first_token), int(seqlen_offset), int(n_steps), out))
-        return [int(out[i]) for i in range(n_steps)] if want_tokens else None
+    def decode_steps(self, first_token, seqlen_offset, n_steps, want_tokens=True, timed=False):
+        """n_steps graph replays with on-device token feedback; timed=True also returns the CUDA-event ms."""
+        out = (C.c_uint32 * max(n_steps, 1))() if want_tokens else None
+        ms = C.c_double(0.0)
+        self._check(self._lib.aha_b200_decode_steps(self._h, int(first_token), int(seqlen_offset), int(n_steps), out,
+                                                    C.byref(ms)))
+        toks = [int(out[i]) for i in range(n_steps)] if want_tokens else None
+        return (toks, ms.value) if timed else toks
+
+    def bench_kernel(self, which, iters=200):
+        ms = C.c_double(0.0)
+        nb = C.c_uint64(0)
+        self._check(self._lib.aha_b200_bench_kernel(self._h, which.encode(), int(iters), C.byref(ms), C.byref(nb)))
+        return ms.value, int(nb.value)
 
     def stream_ptr(self):
         return int(self._lib.aha_b200_stream(self._h) or 0)

@@ -160,7 +160,12 @@ int aha_b200_debug_read(aha_model* m, const char* what, int index, float* out, s
 /* Run n decode steps back to back on the device (graph replays, token feedback on device) without any
  * host synchronisation inside; used by bench.py to time the device-resident `value`. */
 int aha_b200_decode_steps(aha_model* m, uint32_t first_token, size_t seqlen_offset, size_t n_steps,
-                          uint32_t* out_tokens /* n_steps, host, may be NULL */);
+                          uint32_t* out_tokens /* n_steps, host, may be NULL */,
+                          double* device_ms /* CUDA-event time of the n_steps on the launching stream, may be NULL */);
+/* Time one kernel of the decode step in isolation (CUDA events on the launching stream), cycling over the
+ * layers' weights so that consecutive launches never hit L2.  which = "gemv_gate_up" | "gemv_qkv" |
+ * "gemv_down" | "gemv_o" | "gemv_lm_head" | "decode_attn".  bytes_per_launch = algorithmic bytes. */
+int aha_b200_bench_kernel(aha_model* m, const char* which, int iters, double* avg_ms, uint64_t* bytes_per_launch);
 
 #ifdef __cplusplus
 }
