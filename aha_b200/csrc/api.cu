@@ -349,7 +349,7 @@ int aha_b200_create(const char* kind, const char* config_json, const aha_tensor_
         } else {
             throw std::runtime_error("unknown model kind '" + k + "' (expected qwen3 | qwen3vl | qwen3_asr)");
         }
-        m->text.alloc_runtime(max_ctx, max_prefill, o.use_graph != 0);
+        m->text.alloc_runtime(max_ctx, max_prefill, o.use_graph != 0, o.decode_impl);
         m->max_scatter = max_prefill;
         m->d_scatter_idx = m->ctx.alloc<int>(max_prefill);
         for (size_t i = 0; i < n_eos; ++i) m->stop_ids.push_back(eos_ids[i]);

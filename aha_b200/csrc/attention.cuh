@@ -14,6 +14,9 @@
 
 namespace aha {
 
+constexpr int kPageShift = 5;            // 32-token KV pages
+constexpr int kPage = 1 << kPageShift;
+
 // ---------------------------------------------------------------------------------------------------
 // KV addressing.  Paged pool layout (fp32): [layer][page][K|V][kv_head][PAGE tokens][hd].
 // A contiguous source (ViT / audio encoder, no cache) sets page_table = nullptr.

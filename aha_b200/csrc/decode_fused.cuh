@@ -1,0 +1,611 @@
+// decode_fused.cuh -- the whole per-token decode step as ONE persistent, warp-specialised kernel.
+//
+// Why: at batch 1 the step is pure HBM streaming (3.4 GB of fp16 weights + the KV cache per token for
+// Qwen3-VL-2B, ~1 FLOP/byte) cut into ~140 dependent pieces of 8-50 MB; as separate launches every piece pays
+// launch + pipeline ramp and the memory system idles between them.  Here one CTA per SM stays resident for
+// the whole step:
+//   * warp 8 (one elected lane) is the PRODUCER: it walks this CTA's static schedule of transfers for all
+//     layers -- weight row slabs and paged-KV half pages -- and issues TMA bulk copies
+//     (cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes, SASS UBLKCP) into an 8 x 16 KB
+//     shared-memory ring guarded by full/empty mbarriers.  It never waits for activations, so weights for
+//     the next phases keep streaming while the consumers sit in a grid barrier;
+//   * warps 0-7 are CONSUMERS: per phase they load the activation vector slice they need into registers
+//     (each warp owns 1/8 of K), wait on the ring, form fp32 dot products (fp16 weights converted exactly),
+//     merge partial sums through shared memory and apply the fused epilogue (residual add, SwiGLU, argmax);
+//     attention is split-KV with per-warp online softmax, q/k RMSNorm + RoPE + KV append fused in;
+//   * phases are separated by a grid-wide barrier (atomic counter in L2) that only the consumers join.
+// Phases per layer: [rmsnorm+qkv] -> [attention] -> [o_proj+residual] -> [rmsnorm+gate/up+SwiGLU] ->
+// [down+residual]; then [final norm + lm_head + argmax] and the on-device token feedback.
+//
+// Reference semantics are those of Qwen3DecoderLayer::forward / QKNormAttention::forward / GateUpDownMLP
+// (/root/reference/src/models/qwen3/model.rs:71-87, src/models/common/modules.rs:81-87,530-579,757-813)
+// with seq_len = 1; arithmetic is fp32 throughout, identical to the per-op kernels in gemv.cuh/attention.cuh.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "attention.cuh"
+#include "common.cuh"
+#include "kernels_common.cuh"
+
+namespace aha {
+
+constexpr int kFusedStages = 8;
+constexpr int kFusedStageBytes = 16384;
+constexpr int kFusedConsumers = 8;                       // consumer warps
+constexpr int kFusedThreads = (kFusedConsumers + 1) * 32;
+constexpr int kFusedMaxRows = 8;                         // weight rows per stage (<= 16 KB)
+constexpr int kFusedMaxChunks = 4;                       // 8-element K chunks per lane => K <= 8192
+constexpr int kFusedPartRows = 128;                      // rows buffered between partial-sum flushes
+constexpr int kHalfPage = 16;                            // tokens per attention stage (K 8 KB + V 8 KB)
+
+struct FusedLayer {
+    const __half *qkv, *o, *gu, *down;
+    const float *qkv_b, *o_b;
+    const float *ln1, *ln2, *qn, *kn;
+};
+
+struct FusedArgs {
+    const FusedLayer* layers;   // device array [L]
+    int L, H, I, nh, nkv, hd, V, qkv_dim;
+    float eps, scaling;
+    const __half* embed;
+    const __half* lm_head;
+    const float* final_norm;
+    const float* inv_freq;
+    DecodeState* st;
+    float* x;          // [H]   residual stream
+    float* qkv1;       // [qkv_dim]
+    float* attn1;      // [nh*hd]
+    float* h1;         // [I]
+    float* logits;     // [V]
+    float* partial;    // [nh][nsplit][hd+2]
+    int* kv_counters;  // [nkv]      (zeroed by the host before launch)
+    unsigned* sync;    // [0] grid-barrier counter, [1] final ticket   (zeroed by the host before launch)
+    float* pmax; int* pidx;  // [grid] per-CTA argmax candidates
+    uint32_t* argmax_out;
+    uint32_t* history; int hist_cap;
+    float* kv_pool; size_t layer_stride, page_stride;
+    const int* page_table;
+    int nsplit;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+// TMA bulk copy global -> shared, completion signalled on an mbarrier (bytes % 16 == 0, 16-byte aligned).
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kFusedConsumers * 32) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Grid barrier joined by the consumer threads only.  `*seq` counts barriers passed by this CTA.
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& seq) {
+    consumer_bar_sync();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        const unsigned target = (seq + 1u) * gridDim.x;
+        while (ld_acquire_u32(counter) < target) {}
+        __threadfence();
+    }
+    seq += 1u;
+    consumer_bar_sync();
+}
+
+// ------------------------------------------------------------------------------------------------ schedule
+// Row slab of a [N,K] fp16 matrix owned by this CTA: contiguous rows [r0, r1); `unit` = 2 keeps SwiGLU pairs together.
+__device__ __forceinline__ void cta_rows(int N, int unit, int& r0, int& r1) {
+    const long long units = N / unit;
+    r0 = (int)((units * blockIdx.x) / gridDim.x) * unit;
+    r1 = (int)((units * (blockIdx.x + 1)) / gridDim.x) * unit;
+}
+__device__ __forceinline__ int rows_per_stage(int K) {
+    int r = kFusedStageBytes / (2 * K);
+    return r > kFusedMaxRows ? kFusedMaxRows : (r < 1 ? 1 : r);
+}
+// attention work item of this CTA: (kv head, [hp0, hp1) half pages); empty when the CTA has no item
+__device__ __forceinline__ bool attn_item(const FusedArgs& a, int ctx, int& kvh, int& split, int& hp0, int& hp1) {
+    const int items = a.nkv * a.nsplit;
+    if ((int)blockIdx.x >= items) { kvh = 0; split = 0; hp0 = hp1 = 0; return false; }
+    kvh = blockIdx.x / a.nsplit;
+    split = blockIdx.x % a.nsplit;
+    const int nhp = (ctx + kHalfPage - 1) / kHalfPage;
+    const int per = (nhp + a.nsplit - 1) / a.nsplit;
+    hp0 = split * per;
+    hp1 = min(nhp, hp0 + per);
+    if (hp1 < hp0) hp1 = hp0;
+    return true;
+}
+
+struct Ring {
+    uint8_t* buf;
+    uint64_t* full;
+    uint64_t* empty;
+};
+
+// ------------------------------------------------------------------------------------------------ producer
+struct Producer {
+    Ring ring;
+    unsigned it = 0;
+    __device__ __forceinline__ void acquire(int& slot) {
+        slot = it % kFusedStages;
+        mbar_wait(&ring.empty[slot], ((it / kFusedStages) & 1u) ^ 1u);
+    }
+    __device__ void rows(const __half* W, int N, int K, int unit) {
+        int r0, r1;
+        cta_rows(N, unit, r0, r1);
+        const int R = rows_per_stage(K);
+        for (int r = r0; r < r1; r += R) {
+            const int nr = min(R, r1 - r);
+            int slot;
+            acquire(slot);
+            const uint32_t bytes = (uint32_t)nr * K * 2u;
+            mbar_expect_tx(&ring.full[slot], bytes);
+            tma_bulk_g2s(ring.buf + (size_t)slot * kFusedStageBytes, W + (size_t)r * K, bytes, &ring.full[slot]);
+            ++it;
+        }
+    }
+    __device__ void attn(const FusedArgs& a, int layer, int ctx) {
+        int kvh, split, hp0, hp1;
+        if (!attn_item(a, ctx, kvh, split, hp0, hp1)) return;
+        const float* kbase = a.kv_pool + (size_t)layer * a.layer_stride;
+        const size_t vofs = (size_t)a.nkv * kPage * a.hd;
+        for (int hp = hp0; hp < hp1; ++hp) {
+            int slot;
+            acquire(slot);
+            const int page = a.page_table[(hp * kHalfPage) >> kPageShift];
+            const size_t off = (size_t)page * a.page_stride + (size_t)kvh * kPage * a.hd + (size_t)((hp * kHalfPage) & (kPage - 1)) * a.hd;
+            const uint32_t half_bytes = kHalfPage * a.hd * 4u;  // 8 KB for hd = 128
+            uint8_t* dst = ring.buf + (size_t)slot * kFusedStageBytes;
+            mbar_expect_tx(&ring.full[slot], 2u * half_bytes);
+            tma_bulk_g2s(dst, kbase + off, half_bytes, &ring.full[slot]);
+            tma_bulk_g2s(dst + half_bytes, kbase + vofs + off, half_bytes, &ring.full[slot]);
+            ++it;
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ consumer
+enum FusedEpi { FE_QKV = 0, FE_RESID = 1, FE_SWIGLU = 2, FE_LOGITS = 3 };
+
+struct Consumer {
+    Ring ring;
+    unsigned it = 0;
+    float* part;   // [kFusedPartRows][kFusedConsumers]
+    float* red;    // [32] scratch
+    int warp, lane;
+
+    __device__ __forceinline__ const uint8_t* wait_full(int& slot) {
+        slot = it % kFusedStages;
+        mbar_wait(&ring.full[slot], (it / kFusedStages) & 1u);
+        return ring.buf + (size_t)slot * kFusedStageBytes;
+    }
+    __device__ __forceinline__ void release(int slot) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ring.empty[slot]);
+        ++it;
+    }
+
+    // Load this lane's activation chunks for a [.,K] GEMV (warp w owns K-slice w), optional RMSNorm.
+    // src is fp32 global (read with ld.global.cg: other CTAs wrote it) or an fp16 embedding row.
+    __device__ void load_x(float (&xr)[kFusedMaxChunks][8], int K, const float* src32, const __half* src16, const float* norm_w, float eps) {
+        const int slice = K / kFusedConsumers;           // elements per warp
+        const int nch = slice / 8;                       // chunks per warp slice
+        float ss = 0.f;
+#pragma unroll
+        for (int j = 0; j < kFusedMaxChunks; ++j) {
+            const int c = lane + 32 * j;
+            if (c < nch) {
+                const int e = warp * slice + c * 8;
+                if (src16) {
+                    const uint4 u = *reinterpret_cast<const uint4*>(src16 + e);
+                    const float2 a = h2_to_f2(u.x), b = h2_to_f2(u.y), cc = h2_to_f2(u.z), d = h2_to_f2(u.w);
+                    xr[j][0] = a.x; xr[j][1] = a.y; xr[j][2] = b.x; xr[j][3] = b.y; xr[j][4] = cc.x; xr[j][5] = cc.y; xr[j][6] = d.x; xr[j][7] = d.y;
+                } else {
+                    const float4 v0 = __ldcg(reinterpret_cast<const float4*>(src32 + e));
+                    const float4 v1 = __ldcg(reinterpret_cast<const float4*>(src32 + e + 4));
+                    xr[j][0] = v0.x; xr[j][1] = v0.y; xr[j][2] = v0.z; xr[j][3] = v0.w; xr[j][4] = v1.x; xr[j][5] = v1.y; xr[j][6] = v1.z; xr[j][7] = v1.w;
+                }
+#pragma unroll
+                for (int e2 = 0; e2 < 8; ++e2) ss = fmaf(xr[j][e2], xr[j][e2], ss);
+            } else {
+#pragma unroll
+                for (int e2 = 0; e2 < 8; ++e2) xr[j][e2] = 0.f;
+            }
+        }
+        if (norm_w) {
+            ss = warp_sum(ss);
+            consumer_bar_sync();
+            if (lane == 0) red[warp] = ss;
+            consumer_bar_sync();
+            float tot = 0.f;
+#pragma unroll
+            for (int w = 0; w < kFusedConsumers; ++w) tot += red[w];
+            const float inv = 1.0f / sqrtf(tot / (float)K + eps);
+#pragma unroll
+            for (int j = 0; j < kFusedMaxChunks; ++j) {
+                const int c = lane + 32 * j;
+                if (c < nch) {
+                    const int e = warp * slice + c * 8;
+                    const float4 w0 = *reinterpret_cast<const float4*>(norm_w + e);
+                    const float4 w1 = *reinterpret_cast<const float4*>(norm_w + e + 4);
+                    xr[j][0] *= inv * w0.x; xr[j][1] *= inv * w0.y; xr[j][2] *= inv * w0.z; xr[j][3] *= inv * w0.w;
+                    xr[j][4] *= inv * w1.x; xr[j][5] *= inv * w1.y; xr[j][6] *= inv * w1.z; xr[j][7] *= inv * w1.w;
+                }
+            }
+        }
+    }
+
+    // flush buffered rows [rbase, rbase+n): sum the 8 warp partials, apply the epilogue
+    template <int EPI>
+    __device__ void flush(const FusedArgs& a, int rbase, int n, const float* bias, const float* resid32, const __half* resid16, float* out,
+                          float& best, int& bi) {
+        consumer_bar_sync();
+        const int tid = threadIdx.x;
+        if (EPI == FE_SWIGLU) {
+            for (int p = tid; p < n / 2; p += kFusedConsumers * 32) {
+                float g = 0.f, u = 0.f;
+#pragma unroll
+                for (int w = 0; w < kFusedConsumers; ++w) { g += part[(2 * p) * kFusedConsumers + w]; u += part[(2 * p + 1) * kFusedConsumers + w]; }
+                out[(rbase >> 1) + p] = silu_f(g) * u;
+            }
+        } else {
+            for (int r = tid; r < n; r += kFusedConsumers * 32) {
+                float v = 0.f;
+#pragma unroll
+                for (int w = 0; w < kFusedConsumers; ++w) v += part[r * kFusedConsumers + w];
+                const int row = rbase + r;
+                if (bias) v += bias[row];
+                if (EPI == FE_RESID) v += resid16 ? __half2float(resid16[row]) : __ldcg(resid32 + row);
+                out[row] = v;
+                if (EPI == FE_LOGITS && (v > best || (v == best && row < bi))) { best = v; bi = row; }
+            }
+        }
+        consumer_bar_sync();
+    }
+
+    // One GEMV phase: y[r0:r1) = W[r0:r1, :] . x  with the fused epilogue.
+    template <int EPI>
+    __device__ void gemv(const FusedArgs& a, const __half* W, int N, int K, const float (&xr)[kFusedMaxChunks][8], const float* bias,
+                         const float* resid32, const __half* resid16, float* out, float& best, int& bi) {
+        int r0, r1;
+        cta_rows(N, EPI == FE_SWIGLU ? 2 : 1, r0, r1);
+        const int R = rows_per_stage(K);
+        const int slice = K / kFusedConsumers, nch = slice / 8;
+        int buffered = 0, rbase = r0;
+        for (int r = r0; r < r1; r += R) {
+            const int nr = min(R, r1 - r);
+            int slot;
+            const uint8_t* st = wait_full(slot);
+            float acc[kFusedMaxRows];
+#pragma unroll
+            for (int i = 0; i < kFusedMaxRows; ++i) acc[i] = 0.f;
+#pragma unroll
+            for (int j = 0; j < kFusedMaxChunks; ++j) {
+                const int c = lane + 32 * j;
+                if (c < nch) {
+                    const uint8_t* p = st + ((size_t)warp * slice + (size_t)c * 8) * 2;
+#pragma unroll
+                    for (int i = 0; i < kFusedMaxRows; ++i) {
+                        if (i < nr) {
+                            const uint4 w = *reinterpret_cast<const uint4*>(p + (size_t)i * K * 2);
+                            acc[i] = dot8(w, make_float4(xr[j][0], xr[j][1], xr[j][2], xr[j][3]), make_float4(xr[j][4], xr[j][5], xr[j][6], xr[j][7]), acc[i]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < kFusedMaxRows; ++i) {
+                if (i < nr) {
+                    const float v = warp_sum(acc[i]);
+                    if (lane == 0) part[(buffered + i) * kFusedConsumers + warp] = v;
+                }
+            }
+            release(slot);
+            buffered += nr;
+            if (buffered + kFusedMaxRows > kFusedPartRows) {
+                flush<EPI>(a, rbase, buffered, bias, resid32, resid16, out, best, bi);
+                rbase += buffered;
+                buffered = 0;
+            }
+        }
+        if (buffered > 0) flush<EPI>(a, rbase, buffered, bias, resid32, resid16, out, best, bi);
+    }
+};
+
+// Attention scratch in shared memory (consumer side)
+template <int G>
+struct AttnSmem {
+    float qs[G][128];
+    float knew[128];
+    float vnew[128];
+    float m[kFusedConsumers][G];
+    float l[kFusedConsumers][G];
+    float acc[kFusedConsumers][G][128];
+    int last;
+};
+
+template <int G>
+__device__ void fused_attention(const FusedArgs& a, Consumer& c, AttnSmem<G>& s, int layer, const FusedLayer& Ly, int t_new, int rope_delta) {
+    constexpr int HD = 128;
+    const int ctx = t_new + 1;
+    const int lane = c.lane, warp = c.warp, tid = threadIdx.x;
+    int kvh, split, hp0, hp1;
+    const bool has_item = attn_item(a, ctx, kvh, split, hp0, hp1);
+    if (!has_item) return;  // this CTA's producer issued nothing for the phase either
+    const float rpos = (float)(t_new + rope_delta);
+    // ---- prologue: q heads (warps 0..G-1) and the new k (warp G): RMSNorm over hd then RoPE; v copy (warp G+1)
+    if (warp <= G) {
+        const bool is_q = warp < G;
+        const float* src = a.qkv1 + (size_t)(is_q ? (kvh * G + warp) : (a.nh + kvh)) * HD;
+        const float4 x = __ldcg(reinterpret_cast<const float4*>(src + lane * 4));
+        float ss = x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+        ss = warp_sum(ss);
+        const float inv = 1.0f / sqrtf(ss / (float)HD + a.eps);
+        const float4 w = *reinterpret_cast<const float4*>((is_q ? Ly.qn : Ly.kn) + lane * 4);
+        const float n[4] = {x.x * inv * w.x, x.y * inv * w.y, x.z * inv * w.z, x.w * inv * w.w};
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float partner = __shfl_xor_sync(0xffffffffu, n[e], 16);
+            const int d = lane * 4 + e;
+            const float ang = rpos * a.inv_freq[d & (HD / 2 - 1)];
+            const float rot = (d < HD / 2) ? -partner : partner;
+            o[e] = n[e] * cosf(ang) + rot * sinf(ang);
+        }
+        float* dst = is_q ? s.qs[warp] : s.knew;
+        *reinterpret_cast<float4*>(dst + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);
+    } else if (warp == G + 1) {
+        *reinterpret_cast<float4*>(s.vnew + lane * 4) = __ldcg(reinterpret_cast<const float4*>(a.qkv1 + (size_t)(a.nh + a.nkv + kvh) * HD + lane * 4));
+    }
+    consumer_bar_sync();
+    const int hp_new = t_new / kHalfPage;
+    if (hp_new >= hp0 && hp_new < hp1 && tid < HD) {  // append K,V of the current token to the paged cache
+        const int page = a.page_table[t_new >> kPageShift];
+        const size_t off = (size_t)layer * a.layer_stride + (size_t)page * a.page_stride + (size_t)kvh * kPage * HD + (size_t)(t_new & (kPage - 1)) * HD + tid;
+        a.kv_pool[off] = s.knew[tid];
+        a.kv_pool[off + (size_t)a.nkv * kPage * HD] = s.vnew[tid];
+    }
+    float4 q[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) q[g] = *reinterpret_cast<const float4*>(s.qs[g] + lane * 4);
+    float m[G], l[G];
+    float4 acc[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) { m[g] = -INFINITY; l[g] = 0.f; acc[g] = make_float4(0.f, 0.f, 0.f, 0.f); }
+
+    for (int hp = hp0; hp < hp1; ++hp) {
+        int slot;
+        const uint8_t* st = c.wait_full(slot);
+        const float* ks = reinterpret_cast<const float*>(st);
+        const float* vs = reinterpret_cast<const float*>(st + kHalfPage * HD * 4);
+        const int tA = hp * kHalfPage + 2 * warp, tB = tA + 1;     // two tokens per warp per stage
+        const bool hasA = tA < ctx, hasB = tB < ctx;
+        float4 k0 = make_float4(0.f, 0.f, 0.f, 0.f), v0 = k0, k1 = k0, v1 = k0;
+        if (hasA) {
+            if (tA == t_new) { k0 = *reinterpret_cast<const float4*>(s.knew + lane * 4); v0 = *reinterpret_cast<const float4*>(s.vnew + lane * 4); }
+            else { k0 = *reinterpret_cast<const float4*>(ks + (2 * warp) * HD + lane * 4); v0 = *reinterpret_cast<const float4*>(vs + (2 * warp) * HD + lane * 4); }
+        }
+        if (hasB) {
+            if (tB == t_new) { k1 = *reinterpret_cast<const float4*>(s.knew + lane * 4); v1 = *reinterpret_cast<const float4*>(s.vnew + lane * 4); }
+            else { k1 = *reinterpret_cast<const float4*>(ks + (2 * warp + 1) * HD + lane * 4); v1 = *reinterpret_cast<const float4*>(vs + (2 * warp + 1) * HD + lane * 4); }
+        }
+        if (hasA) {
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                float s0 = q[g].x * k0.x + q[g].y * k0.y + q[g].z * k0.z + q[g].w * k0.w;
+                float s1 = q[g].x * k1.x + q[g].y * k1.y + q[g].z * k1.z + q[g].w * k1.w;
+                s0 = warp_sum(s0) * a.scaling;
+                s1 = hasB ? warp_sum(s1) * a.scaling : -INFINITY;
+                const float mnew = fmaxf(m[g], fmaxf(s0, s1));
+                const float alpha = expf(m[g] - mnew);
+                const float p0 = expf(s0 - mnew), p1 = expf(s1 - mnew);
+                l[g] = l[g] * alpha + p0 + p1;
+                acc[g].x = acc[g].x * alpha + p0 * v0.x + p1 * v1.x;
+                acc[g].y = acc[g].y * alpha + p0 * v0.y + p1 * v1.y;
+                acc[g].z = acc[g].z * alpha + p0 * v0.z + p1 * v1.z;
+                acc[g].w = acc[g].w * alpha + p0 * v0.w + p1 * v1.w;
+                m[g] = mnew;
+            }
+        }
+        c.release(slot);  // after the math: every shared-memory read of this stage has been consumed
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        if (lane == 0) { s.m[warp][g] = m[g]; s.l[warp][g] = l[g]; }
+        *reinterpret_cast<float4*>(&s.acc[warp][g][lane * 4]) = acc[g];
+    }
+    consumer_bar_sync();
+    for (int idx = tid; idx < G * HD; idx += kFusedConsumers * 32) {
+        const int g = idx / HD, d = idx % HD;
+        float M = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < kFusedConsumers; ++w) M = fmaxf(M, s.m[w][g]);
+        float L = 0.f, O = 0.f;
+        if (M != -INFINITY) {
+#pragma unroll
+            for (int w = 0; w < kFusedConsumers; ++w) {
+                const float e = expf(s.m[w][g] - M);
+                L += s.l[w][g] * e;
+                O += s.acc[w][g][d] * e;
+            }
+        }
+        float* p = a.partial + ((size_t)(kvh * G + g) * a.nsplit + split) * (HD + 2);
+        p[d] = O;
+        if (d == 0) { p[HD] = M; p[HD + 1] = L; }
+    }
+    __threadfence();
+    consumer_bar_sync();
+    if (tid == 0) s.last = (atomicAdd(&a.kv_counters[kvh], 1) == a.nsplit - 1) ? 1 : 0;
+    consumer_bar_sync();
+    if (s.last) {  // last CTA of this kv head merges the split partials
+        __threadfence();
+        for (int idx = tid; idx < G * HD; idx += kFusedConsumers * 32) {
+            const int g = idx / HD, d = idx % HD;
+            const float* pb = a.partial + (size_t)(kvh * G + g) * a.nsplit * (HD + 2);
+            float M = -INFINITY;
+            for (int sp = 0; sp < a.nsplit; ++sp) M = fmaxf(M, __ldcg(pb + (size_t)sp * (HD + 2) + HD));
+            float L = 0.f, O = 0.f;
+            for (int sp = 0; sp < a.nsplit; ++sp) {
+                const float ms = __ldcg(pb + (size_t)sp * (HD + 2) + HD);
+                if (ms == -INFINITY) continue;
+                const float e = expf(ms - M);
+                L += __ldcg(pb + (size_t)sp * (HD + 2) + HD + 1) * e;
+                O += __ldcg(pb + (size_t)sp * (HD + 2) + d) * e;
+            }
+            a.attn1[(size_t)(kvh * G + g) * HD + d] = O / L;
+        }
+        if (tid == 0) a.kv_counters[kvh] = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+template <int G>
+__global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(FusedArgs a) {
+    extern __shared__ __align__(1024) uint8_t fused_smem_raw[];
+    uint8_t* ringbuf = fused_smem_raw;
+    uint64_t* full = reinterpret_cast<uint64_t*>(fused_smem_raw + (size_t)kFusedStages * kFusedStageBytes);
+    uint64_t* empty = full + kFusedStages;
+    float* part = reinterpret_cast<float*>(empty + kFusedStages);
+    float* red = part + kFusedPartRows * kFusedConsumers;
+    AttnSmem<G>* as = reinterpret_cast<AttnSmem<G>*>(red + 32);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int i = 0; i < kFusedStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kFusedConsumers); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int t_new = a.st->pos;
+    const int rope_delta = a.st->rope_delta;
+    const uint32_t token = a.st->token;
+    const int ctx = t_new + 1;
+    Ring ring{ringbuf, full, empty};
+
+    if (warp == kFusedConsumers) {
+        // =================================================== PRODUCER (one elected lane)
+        if (lane == 0) {
+            Producer p;
+            p.ring = ring;
+            for (int l = 0; l < a.L; ++l) {
+                const FusedLayer& Ly = a.layers[l];
+                p.rows(Ly.qkv, a.qkv_dim, a.H, 1);
+                p.attn(a, l, ctx);
+                p.rows(Ly.o, a.H, a.nh * a.hd, 1);
+                p.rows(Ly.gu, 2 * a.I, a.H, 2);
+                p.rows(Ly.down, a.H, a.I, 1);
+            }
+            p.rows(a.lm_head, a.V, a.H, 1);
+        }
+        return;
+    }
+    // ======================================================= CONSUMERS
+    Consumer c;
+    c.ring = ring; c.part = part; c.red = red; c.warp = warp; c.lane = lane;
+    unsigned seq = 0;
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    float xr[kFusedMaxChunks][8];
+    const __half* emb_row = a.embed + (size_t)token * a.H;
+    for (int l = 0; l < a.L; ++l) {
+        const FusedLayer& Ly = a.layers[l];
+        const bool first = (l == 0);
+        // P1: qkv = Wqkv . rmsnorm(x)      (layer 0 reads the embedding row directly: Embedding::forward)
+        c.load_x(xr, a.H, a.x, first ? emb_row : nullptr, Ly.ln1, a.eps);
+        c.template gemv<FE_QKV>(a, Ly.qkv, a.qkv_dim, a.H, xr, Ly.qkv_b, nullptr, nullptr, a.qkv1, best, bi);
+        grid_barrier(&a.sync[0], seq);
+        // P2: attention over the paged cache (+ q/k norm, RoPE, KV append)
+        fused_attention<G>(a, c, *as, l, Ly, t_new, rope_delta);
+        grid_barrier(&a.sync[0], seq);
+        // P3: x = resid + Wo . attn
+        c.load_x(xr, a.nh * a.hd, a.attn1, nullptr, nullptr, 0.f);
+        c.template gemv<FE_RESID>(a, Ly.o, a.H, a.nh * a.hd, xr, Ly.o_b, a.x, first ? emb_row : nullptr, a.x, best, bi);
+        grid_barrier(&a.sync[0], seq);
+        // P4: h = silu(gate) * up, gate/up rows interleaved, input rmsnorm(x)
+        c.load_x(xr, a.H, a.x, nullptr, Ly.ln2, a.eps);
+        c.template gemv<FE_SWIGLU>(a, Ly.gu, 2 * a.I, a.H, xr, nullptr, nullptr, nullptr, a.h1, best, bi);
+        grid_barrier(&a.sync[0], seq);
+        // P5: x = x + Wdown . h
+        c.load_x(xr, a.I, a.h1, nullptr, nullptr, 0.f);
+        c.template gemv<FE_RESID>(a, Ly.down, a.H, a.I, xr, nullptr, a.x, nullptr, a.x, best, bi);
+        grid_barrier(&a.sync[0], seq);
+    }
+    // final: logits = lm_head . rmsnorm(x), per-CTA argmax candidate
+    c.load_x(xr, a.H, a.x, nullptr, a.final_norm, a.eps);
+    best = -INFINITY; bi = 0x7fffffff;
+    c.template gemv<FE_LOGITS>(a, a.lm_head, a.V, a.H, xr, nullptr, nullptr, nullptr, a.logits, best, bi);
+    // CTA-level argmax (first maximal index), then the last CTA to arrive reduces across CTAs
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    consumer_bar_sync();
+    if (lane == 0) { red[warp] = best; reinterpret_cast<int*>(red)[8 + warp] = bi; }
+    consumer_bar_sync();
+    if (tid == 0) {
+        for (int w = 1; w < kFusedConsumers; ++w) {
+            const float ov = red[w];
+            const int oi = reinterpret_cast<int*>(red)[8 + w];
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        a.pmax[blockIdx.x] = best;
+        a.pidx[blockIdx.x] = bi;
+        __threadfence();
+        const unsigned ticket = atomicAdd(&a.sync[1], 1u);
+        if (ticket == gridDim.x - 1) {
+            __threadfence();
+            float gb = -INFINITY;
+            int gi = 0x7fffffff;
+            for (unsigned i = 0; i < gridDim.x; ++i) {
+                const float v = __ldcg(a.pmax + i);
+                const int id = __ldcg(a.pidx + i);
+                if (v > gb || (v == gb && id < gi)) { gb = v; gi = id; }
+            }
+            *a.argmax_out = (uint32_t)gi;
+            DecodeState* st = a.st;
+            st->token = (uint32_t)gi;
+            st->pos = t_new + 1;
+            if (st->n_hist < a.hist_cap) a.history[st->n_hist] = (uint32_t)gi;
+            st->n_hist += 1;
+        }
+    }
+}
+
+template <int G>
+inline size_t fused_smem_bytes() {
+    return (size_t)kFusedStages * kFusedStageBytes + 2 * kFusedStages * sizeof(uint64_t) + (size_t)kFusedPartRows * kFusedConsumers * sizeof(float) +
+           32 * sizeof(float) + sizeof(AttnSmem<G>) + 64;
+}
+
+}  // namespace aha

@@ -11,6 +11,7 @@
 
 #include "../../include/aha_b200.h"
 #include "attention.cuh"
+#include "decode_fused.cuh"
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemv.cuh"
@@ -197,8 +198,6 @@ struct TextLayer {
     float *ln1 = nullptr, *ln2 = nullptr, *qn = nullptr, *kn = nullptr;
 };
 
-constexpr int kPageShift = 5;            // 32-token KV pages
-constexpr int kPage = 1 << kPageShift;
 constexpr int kDecodeSplits = 16;        // split-KV factor of the decode attention
 
 struct TextModel {
@@ -237,6 +236,13 @@ struct TextModel {
     cudaGraphExec_t step_graph = nullptr;
     uint64_t step_graph_kernels = 0;
     bool use_graph = true;
+    // fused persistent decode kernel (decode_fused.cuh)
+    bool fused = false;
+    int decode_impl = 0;
+    FusedLayer* d_fused_layers = nullptr;
+    unsigned* d_sync = nullptr;   // [0] grid barrier, [1] final ticket, then kv tickets [nkv]
+    int fused_grid = 0, fused_nsplit = 0;
+    size_t fused_smem = 0;
 
     // tracing (tests)
     bool trace = false;
@@ -309,9 +315,35 @@ struct TextModel {
         mrope_sel = upload(c, sel);
     }
 
-    void alloc_runtime(int max_ctx_, int max_prefill_, bool graph) {
+    bool fused_supported(std::string* why) const {
+        auto no = [&](const char* m) { if (why) *why = m; return false; };
+        if (tp_world != 1) return no("tensor parallel");
+        if (cfg.hd != 128) return no("head_dim != 128");
+        if (cfg.H % 64 || I_l % 64 || (nh_l * cfg.hd) % 64) return no("K not a multiple of 64");
+        if (cfg.H > 8192 || I_l > 8192 || nh_l * cfg.hd > 8192) return no("K > 8192");
+        if (cfg.H > 4096 && rows_per_stage_host(cfg.H) % 2) return no("odd rows per stage for gate/up");
+        if (ctx->num_sms < nkv_l) return no("fewer SMs than kv heads");
+        if (cfg.attn_bias) return no("attention bias");
+        return true;
+    }
+    static int rows_per_stage_host(int K) { int r = kFusedStageBytes / (2 * K); return r > kFusedMaxRows ? kFusedMaxRows : (r < 1 ? 1 : r); }
+    template <int G>
+    void fused_prepare() {
+        fused_smem = fused_smem_bytes<G>();
+        AHA_CUDA_CHECK(cudaFuncSetAttribute(decode_step_fused_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem));
+        int nb = 0;
+        AHA_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, decode_step_fused_kernel<G>, kFusedThreads, fused_smem));
+        AHA_REQUIRE(nb >= 1, "fused decode kernel does not fit on an SM");
+    }
+    void alloc_runtime(int max_ctx_, int max_prefill_, bool graph, int decode_impl_ = 0) {
         Ctx& c = *ctx;
-        max_ctx = max_ctx_; max_prefill = max_prefill_; use_graph = graph;
+        max_ctx = max_ctx_; max_prefill = max_prefill_; use_graph = graph; decode_impl = decode_impl_;
+        {
+            std::string why;
+            const bool ok = fused_supported(&why);
+            AHA_REQUIRE(decode_impl != 2 || ok, "fused decode kernel unsupported for this model: " + why);
+            fused = ok && decode_impl != 1;
+        }
         num_pages = ceil_div(max_ctx, kPage);
         page_stride = (size_t)2 * nkv_l * kPage * cfg.hd;
         layer_stride = page_stride * num_pages;
@@ -325,11 +357,28 @@ struct TextModel {
         d_ids = c.alloc<uint32_t>(S); d_pos3 = c.alloc<int>(3 * S);
         x1 = c.alloc<float>(cfg.H); qkv1 = c.alloc<float>(qkv_dim); attn1 = c.alloc<float>((size_t)nh_l * cfg.hd); h1 = c.alloc<float>(I_l);
         logits = c.alloc<float>(cfg.V);
-        partial = c.alloc<float>((size_t)nh_l * kDecodeSplits * (cfg.hd + 2));
-        counters = c.alloc<int>(nkv_l);
-        AHA_CUDA_CHECK(cudaMemset(counters, 0, nkv_l * sizeof(int)));
+        fused_grid = c.num_sms;
+        fused_nsplit = std::max(1, std::min(32, fused_grid / std::max(1, nkv_l)));
+        partial = c.alloc<float>((size_t)nh_l * std::max(kDecodeSplits, fused_nsplit) * (cfg.hd + 2));
+        d_sync = c.alloc<unsigned>(2 + nkv_l);
+        AHA_CUDA_CHECK(cudaMemset(d_sync, 0, (2 + nkv_l) * sizeof(unsigned)));
+        counters = reinterpret_cast<int*>(d_sync + 2);
+        if (fused) {
+            std::vector<FusedLayer> fl(cfg.L);
+            for (int l = 0; l < cfg.L; ++l) {
+                TextLayer& T = layers[l];
+                fl[l] = FusedLayer{T.qkv.w, T.o.w, T.gu.w, T.down.w, T.qkv.b, T.o.b, T.ln1, T.ln2, T.qn, T.kn};
+            }
+            d_fused_layers = upload(c, fl);
+            switch (nh_l / nkv_l) {
+                case 1: fused_prepare<1>(); break;
+                case 2: fused_prepare<2>(); break;
+                case 4: fused_prepare<4>(); break;
+                default: fused_prepare<6>(); break;
+            }
+        }
         n_pcand = gemv_grid(cfg.V, GEPI_ARGMAX);
-        pmax = c.alloc<float>(n_pcand); pidx = c.alloc<int>(n_pcand);
+        pmax = c.alloc<float>(std::max(n_pcand, c.num_sms)); pidx = c.alloc<int>(std::max(n_pcand, c.num_sms));
         d_state = c.alloc<DecodeState>(1);
         AHA_CUDA_CHECK(cudaMemset(d_state, 0, sizeof(DecodeState)));
         hist_cap = max_ctx;
@@ -471,8 +520,35 @@ struct TextModel {
         finish_argmax(1);
         AHA_CUDA_CHECK(cudaGetLastError());
     }
+    template <int G>
+    void launch_fused(FusedArgs& fa) {
+        void* args[] = {&fa};
+        AHA_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)decode_step_fused_kernel<G>, dim3(fused_grid), dim3(kFusedThreads), args, fused_smem, ctx->stream));
+    }
+    void decode_step_fused() {
+        Ctx& c = *ctx;
+        FusedArgs fa{};
+        fa.layers = d_fused_layers; fa.L = cfg.L; fa.H = cfg.H; fa.I = I_l; fa.nh = nh_l; fa.nkv = nkv_l; fa.hd = cfg.hd; fa.V = cfg.V; fa.qkv_dim = qkv_dim;
+        fa.eps = cfg.eps; fa.scaling = (float)(1.0 / std::sqrt((double)cfg.hd));
+        fa.embed = embed; fa.lm_head = lm_head; fa.final_norm = norm; fa.inv_freq = inv_freq; fa.st = d_state;
+        fa.x = x1; fa.qkv1 = qkv1; fa.attn1 = attn1; fa.h1 = h1; fa.logits = logits; fa.partial = partial;
+        fa.kv_counters = counters; fa.sync = d_sync; fa.pmax = pmax; fa.pidx = pidx; fa.argmax_out = d_argmax;
+        fa.history = d_history; fa.hist_cap = hist_cap; fa.kv_pool = kv_pool; fa.layer_stride = layer_stride; fa.page_stride = page_stride;
+        fa.page_table = d_page_table; fa.nsplit = fused_nsplit;
+        AHA_REQUIRE(fused_grid <= n_pcand || true, "");
+        AHA_CUDA_CHECK(cudaMemsetAsync(d_sync, 0, (2 + nkv_l) * sizeof(unsigned), c.stream));
+        switch (nh_l / nkv_l) {
+            case 1: launch_fused<1>(fa); break;
+            case 2: launch_fused<2>(fa); break;
+            case 4: launch_fused<4>(fa); break;
+            default: launch_fused<6>(fa); break;
+        }
+        c.cnt.kernels++;
+        step_graph_kernels = 1;
+    }
     void decode_step() {
         Ctx& c = *ctx;
+        if (fused) { decode_step_fused(); return; }
         if (!use_graph) { decode_step_launches(); return; }
         if (!step_graph) {
             const uint64_t k0 = c.cnt.kernels;

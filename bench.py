@@ -125,6 +125,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--preset", default=os.environ.get("AHA_BENCH_PRESET", "vl2"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--decode-impl", type=int, default=int(os.environ.get("AHA_DECODE_IMPL", "0")))
     args = ap.parse_args()
     K, W = args.steps, max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -191,7 +192,7 @@ def main():
     log(f"[rank {rank}] weights generated in {time.time() - t0:.1f}s")
     t0 = time.time()
     m = B200Model(wl["kind"], cfg, wts, eos_ids=[], device=local_rank, max_ctx=wl["max_ctx"], max_prefill=wl["max_ctx"],
-                  max_patches=wl["max_patches"])
+                  max_patches=wl["max_patches"], decode_impl=args.decode_impl)
     log(f"[rank {rank}] model created in {time.time() - t0:.1f}s")
     img = synth.synth_image(h, w_, 1)
     pv, grid = m.image_patchify(img)
@@ -249,7 +250,7 @@ def main():
     for name in ("gemv_gate_up", "gemv_down", "gemv_qkv", "gemv_o", "gemv_lm_head"):
         kms, kb = m.bench_kernel(name, 280 if name != "gemv_lm_head" else 20)
         kernels[name] = {"avg_us": kms * 1e3, "bytes": kb, "gbps": kb / (kms * 1e-3) / 1e9}
-    dom = kernels["gemv_gate_up"]
+    fused = st["kernels_per_decode_step"] == 1
 
     ms_t = torch.tensor([best_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
     e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
@@ -285,14 +286,21 @@ def main():
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 16, "d2h_bytes_per_step": 4,
                         "with_logits_d2h_tokens_per_s": 1.0 / e2e_logits_s, "logits_bytes": 4 * tc["vocab_size"]},
-                "roofline": {"bound": "hbm", "kernel": "gemv_kernel<rmsnorm, swiglu> (gate/up projection)",
-                             "achieved": dom["gbps"], "peak": peak, "unit": "GB/s", "frac": dom["gbps"] / peak,
-                             "peak_source": peak_src, "traffic": None, "bytes_per_launch": dom["bytes"], "avg_launch_us": dom["avg_us"],
-                             "kernels": kernels,
+                "roofline": ({"bound": "hbm", "kernel": "decode_step_fused_kernel (the whole decode step: one launch per token)",
+                              "achieved": step_bytes / (step_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                              "frac": step_bytes / (step_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src, "traffic": None,
+                              "bytes_per_launch": step_bytes, "avg_launch_us": step_ms * 1e3, "per_op_kernels": kernels}
+                             if fused else
+                             {"bound": "hbm", "kernel": "gemv_kernel<rmsnorm, swiglu> (gate/up projection)",
+                              "achieved": kernels["gemv_gate_up"]["gbps"], "peak": peak, "unit": "GB/s",
+                              "frac": kernels["gemv_gate_up"]["gbps"] / peak, "peak_source": peak_src, "traffic": None,
+                              "bytes_per_launch": kernels["gemv_gate_up"]["bytes"], "avg_launch_us": kernels["gemv_gate_up"]["avg_us"],
+                              "per_op_kernels": kernels}) | {
                              "step": {"bytes": step_bytes, "gbps": step_bytes / (step_ms * 1e-3) / 1e9,
                                       "frac_full": step_bytes / (step_ms * 1e-3) / 1e9 / peak,
                                       "roofline_full_tok_s": peak * 1e9 / step_bytes,
                                       "roofline_kv_tok_s": peak * 1e9 / kv_read}},
+                "decode_impl": "fused persistent kernel" if fused else "per-op kernels (CUDA graph)",
                 "cpu_baseline": cpu_base}
         print(json.dumps(line), flush=True)
     m.close()

@@ -12,7 +12,14 @@ F32 = np.float32
 
 def linear(x, w, b=None):
     """candle_nn::Linear::forward: x @ W^T (+ b).  w: (out, in)."""
-    y = np.matmul(x.astype(F32, copy=False), w.T.astype(F32, copy=False))
+    x = x.astype(F32, copy=False)
+    w = w.astype(F32, copy=False)
+    rows = int(np.prod(x.shape[:-1])) if x.ndim > 1 else 1
+    if rows <= 8 and w.flags["C_CONTIGUOUS"]:
+        # decode (M ~ 1): W @ x^T is the same dot products without materialising W^T (a GEMV over contiguous W)
+        y = np.matmul(w, x.reshape(rows, -1).T).T.reshape(x.shape[:-1] + (w.shape[0],))
+    else:
+        y = np.matmul(x, w.T)
     if b is not None:
         y = y + b.astype(F32, copy=False)
     return y.astype(F32, copy=False)

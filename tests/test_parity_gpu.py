@@ -80,19 +80,47 @@ def test_qwen3_greedy_generate_matches_oracle(q3):
     assert usage["prompt_tokens"] == 21 and usage["completion_tokens"] == len(want)
 
 
-def test_qwen3_graph_and_eager_agree(q3):
+def test_qwen3_decode_implementations_agree(q3):
+    """fused persistent kernel (default) == per-op kernels under a CUDA graph == per-op eager launches."""
     cfg, w, m, o = q3
-    cfg2, w2, m2 = make_model("qwen3", "tiny", max_ctx=512, use_graph=False)
+    others = [make_model("qwen3", "tiny", max_ctx=512, decode_impl=1)[2],
+              make_model("qwen3", "tiny", max_ctx=512, decode_impl=1, use_graph=False)[2],
+              make_model("qwen3", "tiny", max_ctx=512, decode_impl=2)[2]]
     try:
         ids = _ids(50, cfg["vocab_size"], 8)
         m.clear_cache()
-        m.forward_initial(ids, 0); m2.forward_initial(ids, 0)
-        a = m.decode_steps(5, 50, 20)
-        b = m2.decode_steps(5, 50, 20)
-        assert a == b
-        assert m.stats()["kernels_per_decode_step"] > 0
+        m.forward_initial(ids, 0)
+        a = m.decode_steps(5, 50, 40)
+        la = m.forward_step(np.array([9], np.uint32), 90)[0, 0]
+        assert m.stats()["kernels_per_decode_step"] == 1          # the fused step is a single launch
+        for k, m2 in enumerate(others):
+            m2.forward_initial(ids, 0)
+            b = m2.decode_steps(5, 50, 40)
+            assert a == b, k
+            lb = m2.forward_step(np.array([9], np.uint32), 90)[0, 0]
+            assert np.abs(la - lb).max() <= 1e-5, k
+        assert others[0].stats()["kernels_per_decode_step"] > 100 or cfg["num_hidden_layers"] < 20
     finally:
-        m2.close()
+        for m2 in others:
+            m2.close()
+
+
+@pytest.mark.parametrize("impl", [1, 2])
+def test_qwen3_long_context_decode(impl):
+    """decode far past the prompt: many KV pages, every split of the attention busy."""
+    cfg, w, m = make_model("qwen3", "tiny", max_ctx=2048, decode_impl=impl)
+    try:
+        o = make_oracle("qwen3", cfg, w)
+        S = 700
+        ids = _ids(S + 3, cfg["vocab_size"], 21)
+        m.forward_initial(ids[:S], 0)
+        o.forward_initial(ids[:S].reshape(1, -1), 0)
+        for i in range(3):
+            got = m.forward_step(ids[S + i:S + i + 1], S + i)[0, 0]
+            want = o.forward_step(ids[S + i:S + i + 1].reshape(1, 1), S + i)[0, 0]
+            assert np.abs(got - want).max() <= TOL
+    finally:
+        m.close()
 
 
 def test_qwen3_untied_lm_head():
