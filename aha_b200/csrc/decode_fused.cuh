@@ -6,13 +6,14 @@
 // the whole step:
 //   * warp 8 (one elected lane) is the PRODUCER: it walks this CTA's static schedule of transfers for all
 //     layers -- weight row slabs and paged-KV half pages -- and issues TMA bulk copies
-//     (cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes, SASS UBLKCP) into an 8 x 16 KB
+//     (cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes, SASS UBLKCP) into a 12 x 16 KB
 //     shared-memory ring guarded by full/empty mbarriers.  It never waits for activations, so weights for
 //     the next phases keep streaming while the consumers sit in a grid barrier;
-//   * warps 0-7 are CONSUMERS: per phase they load the activation vector slice they need into registers
-//     (each warp owns 1/8 of K), wait on the ring, form fp32 dot products (fp16 weights converted exactly),
-//     merge partial sums through shared memory and apply the fused epilogue (residual add, SwiGLU, argmax);
-//     attention is split-KV with per-warp online softmax, q/k RMSNorm + RoPE + KV append fused in;
+//   * warps 0-7 are CONSUMERS: per phase they stage the activation vector in shared memory (RMSNorm fused),
+//     and each warp consumes the ring slots it owns (slot % 8): a whole stage of weight rows is reduced by one
+//     warp with fp32 dot products (fp16 weights converted exactly) and the fused epilogue (residual add,
+//     SwiGLU, argmax) is applied by its lanes; attention is split-KV with per-warp online softmax over the
+//     half pages the warp owns, q/k RMSNorm + RoPE + KV append fused in;
 //   * phases are separated by a grid-wide barrier (atomic counter in L2) that only the consumers join.
 // Phases per layer: [rmsnorm+qkv] -> [attention] -> [o_proj+residual] -> [rmsnorm+gate/up+SwiGLU] ->
 // [down+residual]; then [final norm + lm_head + argmax] and the on-device token feedback.
@@ -29,13 +30,12 @@
 
 namespace aha {
 
-constexpr int kFusedStages = 8;
+constexpr int kFusedStages = 12;
 constexpr int kFusedStageBytes = 16384;
 constexpr int kFusedConsumers = 8;                       // consumer warps
 constexpr int kFusedThreads = (kFusedConsumers + 1) * 32;
 constexpr int kFusedMaxRows = 8;                         // weight rows per stage (<= 16 KB)
-constexpr int kFusedMaxChunks = 4;                       // 8-element K chunks per lane => K <= 8192
-constexpr int kFusedPartRows = 128;                      // rows buffered between partial-sum flushes
+constexpr int kFusedMaxK = 8192;                         // activation vector staged in shared memory (32 KB)
 constexpr int kHalfPage = 16;                            // tokens per attention stage (K 8 KB + V 8 KB)
 
 struct FusedLayer {
@@ -67,6 +67,7 @@ struct FusedArgs {
     float* kv_pool; size_t layer_stride, page_stride;
     const int* page_table;
     int nsplit;
+    int dbg;           // timing experiments only: bit0 = skip grid barriers, bit1 = skip the GEMV math
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -101,20 +102,21 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
                  : "memory");
 }
 __device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kFusedConsumers * 32) : "memory"); }
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
     unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 
 // Grid barrier joined by the consumer threads only.  `*seq` counts barriers passed by this CTA.
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& seq) {
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& seq, int dbg = 0) {
+    if (dbg & 1) { consumer_bar_sync(); return; }
     consumer_bar_sync();
     if (threadIdx.x == 0) {
-        __threadfence();
+        __threadfence();                       // publish this CTA's writes (ordered after them by the bar.sync above)
         atomicAdd(counter, 1u);
         const unsigned target = (seq + 1u) * gridDim.x;
-        while (ld_acquire_u32(counter) < target) {}
+        while (ld_relaxed_u32(counter) < target) {}   // plain L2 polling; activations are read with ld.global.cg
         __threadfence();
     }
     seq += 1u;
@@ -130,7 +132,8 @@ __device__ __forceinline__ void cta_rows(int N, int unit, int& r0, int& r1) {
 }
 __device__ __forceinline__ int rows_per_stage(int K) {
     int r = kFusedStageBytes / (2 * K);
-    return r > kFusedMaxRows ? kFusedMaxRows : (r < 1 ? 1 : r);
+    r = r > kFusedMaxRows ? kFusedMaxRows : (r < 1 ? 1 : r);
+    return r > 1 ? (r & ~1) : r;   // even, so interleaved gate/up pairs never straddle a stage
 }
 // attention work item of this CTA: (kv head, [hp0, hp1) half pages); empty when the CTA has no item
 __device__ __forceinline__ bool attn_item(const FusedArgs& a, int ctx, int& kvh, int& split, int& hp0, int& hp1) {
@@ -195,154 +198,133 @@ struct Producer {
 };
 
 // ------------------------------------------------------------------------------------------------ consumer
+// Ring slots are OWNED by consumer warps: slot s is only ever consumed by warp s % 8, so each warp sees the uses
+// of its slots strictly in order (no cross-warp mbarrier phase hazards) and 8 stages are processed concurrently.
+// A GEMV stage (R rows x K fp16) is reduced entirely by its owner warp against the activation vector staged in
+// shared memory; the epilogue is applied by the lanes of that warp -- no cross-warp partial sums.
 enum FusedEpi { FE_QKV = 0, FE_RESID = 1, FE_SWIGLU = 2, FE_LOGITS = 3 };
 
 struct Consumer {
     Ring ring;
-    unsigned it = 0;
-    float* part;   // [kFusedPartRows][kFusedConsumers]
-    float* red;    // [32] scratch
+    unsigned it = 0;    // global stage counter (same sequence as the producer's)
+    float* xs;          // [K] activation vector (shared), also aliased by the attention scratch
+    float* red;         // [32] scratch
     int warp, lane;
 
-    __device__ __forceinline__ const uint8_t* wait_full(int& slot) {
-        slot = it % kFusedStages;
-        mbar_wait(&ring.full[slot], (it / kFusedStages) & 1u);
+    __device__ __forceinline__ bool owns(unsigned i) const { return (int)((i % kFusedStages) % kFusedConsumers) == warp; }
+    __device__ __forceinline__ const uint8_t* wait_full(unsigned i) {
+        const int slot = i % kFusedStages;
+        mbar_wait(&ring.full[slot], (i / kFusedStages) & 1u);
         return ring.buf + (size_t)slot * kFusedStageBytes;
     }
-    __device__ __forceinline__ void release(int slot) {
+    __device__ __forceinline__ void release(unsigned i) {
         __syncwarp();
-        if (lane == 0) mbar_arrive(&ring.empty[slot]);
-        ++it;
+        if (lane == 0) mbar_arrive(&ring.empty[i % kFusedStages]);
     }
 
-    // Load this lane's activation chunks for a [.,K] GEMV (warp w owns K-slice w), optional RMSNorm.
-    // src is fp32 global (read with ld.global.cg: other CTAs wrote it) or an fp16 embedding row.
-    __device__ void load_x(float (&xr)[kFusedMaxChunks][8], int K, const float* src32, const __half* src16, const float* norm_w, float eps) {
-        const int slice = K / kFusedConsumers;           // elements per warp
-        const int nch = slice / 8;                       // chunks per warp slice
+    // Stage the activation vector of a GEMV in shared memory (all consumer threads), optional RMSNorm.
+    // src is fp32 global written by other CTAs (ld.global.cg) or an fp16 embedding row.
+    __device__ void load_x(int K, const float* src32, const __half* src16, const float* norm_w, float eps) {
+        const int tid = threadIdx.x;
         float ss = 0.f;
-#pragma unroll
-        for (int j = 0; j < kFusedMaxChunks; ++j) {
-            const int c = lane + 32 * j;
-            if (c < nch) {
-                const int e = warp * slice + c * 8;
-                if (src16) {
-                    const uint4 u = *reinterpret_cast<const uint4*>(src16 + e);
-                    const float2 a = h2_to_f2(u.x), b = h2_to_f2(u.y), cc = h2_to_f2(u.z), d = h2_to_f2(u.w);
-                    xr[j][0] = a.x; xr[j][1] = a.y; xr[j][2] = b.x; xr[j][3] = b.y; xr[j][4] = cc.x; xr[j][5] = cc.y; xr[j][6] = d.x; xr[j][7] = d.y;
-                } else {
-                    const float4 v0 = __ldcg(reinterpret_cast<const float4*>(src32 + e));
-                    const float4 v1 = __ldcg(reinterpret_cast<const float4*>(src32 + e + 4));
-                    xr[j][0] = v0.x; xr[j][1] = v0.y; xr[j][2] = v0.z; xr[j][3] = v0.w; xr[j][4] = v1.x; xr[j][5] = v1.y; xr[j][6] = v1.z; xr[j][7] = v1.w;
-                }
-#pragma unroll
-                for (int e2 = 0; e2 < 8; ++e2) ss = fmaf(xr[j][e2], xr[j][e2], ss);
+        for (int e = tid * 4; e < K; e += kFusedConsumers * 32 * 4) {
+            float4 v;
+            if (src16) {
+                const uint2 u = *reinterpret_cast<const uint2*>(src16 + e);
+                const float2 a = h2_to_f2(u.x), b = h2_to_f2(u.y);
+                v = make_float4(a.x, a.y, b.x, b.y);
             } else {
-#pragma unroll
-                for (int e2 = 0; e2 < 8; ++e2) xr[j][e2] = 0.f;
+                v = __ldcg(reinterpret_cast<const float4*>(src32 + e));
             }
+            ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+            *reinterpret_cast<float4*>(xs + e) = v;
         }
         if (norm_w) {
             ss = warp_sum(ss);
-            consumer_bar_sync();
             if (lane == 0) red[warp] = ss;
             consumer_bar_sync();
             float tot = 0.f;
 #pragma unroll
             for (int w = 0; w < kFusedConsumers; ++w) tot += red[w];
             const float inv = 1.0f / sqrtf(tot / (float)K + eps);
-#pragma unroll
-            for (int j = 0; j < kFusedMaxChunks; ++j) {
-                const int c = lane + 32 * j;
-                if (c < nch) {
-                    const int e = warp * slice + c * 8;
-                    const float4 w0 = *reinterpret_cast<const float4*>(norm_w + e);
-                    const float4 w1 = *reinterpret_cast<const float4*>(norm_w + e + 4);
-                    xr[j][0] *= inv * w0.x; xr[j][1] *= inv * w0.y; xr[j][2] *= inv * w0.z; xr[j][3] *= inv * w0.w;
-                    xr[j][4] *= inv * w1.x; xr[j][5] *= inv * w1.y; xr[j][6] *= inv * w1.z; xr[j][7] *= inv * w1.w;
-                }
-            }
-        }
-    }
-
-    // flush buffered rows [rbase, rbase+n): sum the 8 warp partials, apply the epilogue
-    template <int EPI>
-    __device__ void flush(const FusedArgs& a, int rbase, int n, const float* bias, const float* resid32, const __half* resid16, float* out,
-                          float& best, int& bi) {
-        consumer_bar_sync();
-        const int tid = threadIdx.x;
-        if (EPI == FE_SWIGLU) {
-            for (int p = tid; p < n / 2; p += kFusedConsumers * 32) {
-                float g = 0.f, u = 0.f;
-#pragma unroll
-                for (int w = 0; w < kFusedConsumers; ++w) { g += part[(2 * p) * kFusedConsumers + w]; u += part[(2 * p + 1) * kFusedConsumers + w]; }
-                out[(rbase >> 1) + p] = silu_f(g) * u;
-            }
-        } else {
-            for (int r = tid; r < n; r += kFusedConsumers * 32) {
-                float v = 0.f;
-#pragma unroll
-                for (int w = 0; w < kFusedConsumers; ++w) v += part[r * kFusedConsumers + w];
-                const int row = rbase + r;
-                if (bias) v += bias[row];
-                if (EPI == FE_RESID) v += resid16 ? __half2float(resid16[row]) : __ldcg(resid32 + row);
-                out[row] = v;
-                if (EPI == FE_LOGITS && (v > best || (v == best && row < bi))) { best = v; bi = row; }
+            for (int e = tid * 4; e < K; e += kFusedConsumers * 32 * 4) {   // each thread rescales what it wrote
+                float4 v = *reinterpret_cast<float4*>(xs + e);
+                const float4 w = *reinterpret_cast<const float4*>(norm_w + e);
+                v.x *= inv * w.x; v.y *= inv * w.y; v.z *= inv * w.z; v.w *= inv * w.w;
+                *reinterpret_cast<float4*>(xs + e) = v;
             }
         }
         consumer_bar_sync();
     }
 
-    // One GEMV phase: y[r0:r1) = W[r0:r1, :] . x  with the fused epilogue.
+    // One GEMV phase: y[r0:r1) = W[r0:r1, :] . xs  with the fused epilogue.  Ends with a consumer barrier so
+    // that xs may be overwritten by the next phase.
     template <int EPI>
-    __device__ void gemv(const FusedArgs& a, const __half* W, int N, int K, const float (&xr)[kFusedMaxChunks][8], const float* bias,
-                         const float* resid32, const __half* resid16, float* out, float& best, int& bi) {
+    __device__ void gemv(const FusedArgs& a, int N, int K, const float* bias, const float* resid32, const __half* resid16, float* out,
+                         float& best, int& bi) {
         int r0, r1;
         cta_rows(N, EPI == FE_SWIGLU ? 2 : 1, r0, r1);
         const int R = rows_per_stage(K);
-        const int slice = K / kFusedConsumers, nch = slice / 8;
-        int buffered = 0, rbase = r0;
-        for (int r = r0; r < r1; r += R) {
+        const int nchunk = K >> 3;
+        unsigned i = it;
+        for (int r = r0; r < r1; r += R, ++i) {
+            if (!owns(i)) continue;
             const int nr = min(R, r1 - r);
-            int slot;
-            const uint8_t* st = wait_full(slot);
+            const uint8_t* st = wait_full(i);
             float acc[kFusedMaxRows];
 #pragma unroll
-            for (int i = 0; i < kFusedMaxRows; ++i) acc[i] = 0.f;
+            for (int q = 0; q < kFusedMaxRows; ++q) acc[q] = 0.f;
+            if (!(a.dbg & 2)) {
+                if (nr == R && R == 4) {            // hot shape (K = 2048): fully unrolled rows
+#pragma unroll 2
+                    for (int c = lane; c < nchunk; c += 32) {
+                        const float4 x0 = *reinterpret_cast<const float4*>(xs + c * 8);
+                        const float4 x1 = *reinterpret_cast<const float4*>(xs + c * 8 + 4);
+                        const uint8_t* p = st + (size_t)c * 16;
 #pragma unroll
-            for (int j = 0; j < kFusedMaxChunks; ++j) {
-                const int c = lane + 32 * j;
-                if (c < nch) {
-                    const uint8_t* p = st + ((size_t)warp * slice + (size_t)c * 8) * 2;
+                        for (int q = 0; q < 4; ++q) acc[q] = dot8(*reinterpret_cast<const uint4*>(p + (size_t)q * K * 2), x0, x1, acc[q]);
+                    }
+                } else {
+#pragma unroll 2
+                    for (int c = lane; c < nchunk; c += 32) {
+                        const float4 x0 = *reinterpret_cast<const float4*>(xs + c * 8);
+                        const float4 x1 = *reinterpret_cast<const float4*>(xs + c * 8 + 4);
+                        const uint8_t* p = st + (size_t)c * 16;
 #pragma unroll
-                    for (int i = 0; i < kFusedMaxRows; ++i) {
-                        if (i < nr) {
-                            const uint4 w = *reinterpret_cast<const uint4*>(p + (size_t)i * K * 2);
-                            acc[i] = dot8(w, make_float4(xr[j][0], xr[j][1], xr[j][2], xr[j][3]), make_float4(xr[j][4], xr[j][5], xr[j][6], xr[j][7]), acc[i]);
-                        }
+                        for (int q = 0; q < kFusedMaxRows; ++q)
+                            if (q < nr) acc[q] = dot8(*reinterpret_cast<const uint4*>(p + (size_t)q * K * 2), x0, x1, acc[q]);
                     }
                 }
             }
+            release(i);   // every shared-memory read of the stage feeds acc[] above; __syncwarp orders the lanes
+            float mine = 0.f, mate = 0.f;   // lane q keeps row q (and row q^1 for the SwiGLU pair)
 #pragma unroll
-            for (int i = 0; i < kFusedMaxRows; ++i) {
-                if (i < nr) {
-                    const float v = warp_sum(acc[i]);
-                    if (lane == 0) part[(buffered + i) * kFusedConsumers + warp] = v;
+            for (int q = 0; q < kFusedMaxRows; ++q) {
+                if (q < nr) {
+                    const float v = warp_sum(acc[q]);
+                    if (lane == q) mine = v;
+                    if (lane == (q ^ 1)) mate = v;
                 }
             }
-            release(slot);
-            buffered += nr;
-            if (buffered + kFusedMaxRows > kFusedPartRows) {
-                flush<EPI>(a, rbase, buffered, bias, resid32, resid16, out, best, bi);
-                rbase += buffered;
-                buffered = 0;
+            if (lane < nr) {
+                const int row = r + lane;
+                if (EPI == FE_SWIGLU) {
+                    if ((lane & 1) == 0) out[row >> 1] = silu_f(mine) * mate;   // rows (2i, 2i+1) = (gate_i, up_i)
+                } else {
+                    float v = mine;
+                    if (bias) v += bias[row];
+                    if (EPI == FE_RESID) v += resid16 ? __half2float(resid16[row]) : __ldcg(resid32 + row);
+                    out[row] = v;
+                    if (EPI == FE_LOGITS && (v > best || (v == best && row < bi))) { best = v; bi = row; }
+                }
             }
         }
-        if (buffered > 0) flush<EPI>(a, rbase, buffered, bias, resid32, resid16, out, best, bi);
+        it = i;
+        consumer_bar_sync();
     }
 };
 
-// Attention scratch in shared memory (consumer side)
+// Attention scratch in shared memory (consumer side; aliases the xs region, unused during this phase)
 template <int G>
 struct AttnSmem {
     float qs[G][128];
@@ -403,23 +385,25 @@ __device__ void fused_attention(const FusedArgs& a, Consumer& c, AttnSmem<G>& s,
 #pragma unroll
     for (int g = 0; g < G; ++g) { m[g] = -INFINITY; l[g] = 0.f; acc[g] = make_float4(0.f, 0.f, 0.f, 0.f); }
 
-    for (int hp = hp0; hp < hp1; ++hp) {
-        int slot;
-        const uint8_t* st = c.wait_full(slot);
+    unsigned i = c.it;
+    for (int hp = hp0; hp < hp1; ++hp, ++i) {
+        if (!c.owns(i)) continue;
+        const uint8_t* st = c.wait_full(i);
         const float* ks = reinterpret_cast<const float*>(st);
         const float* vs = reinterpret_cast<const float*>(st + kHalfPage * HD * 4);
-        const int tA = hp * kHalfPage + 2 * warp, tB = tA + 1;     // two tokens per warp per stage
-        const bool hasA = tA < ctx, hasB = tB < ctx;
-        float4 k0 = make_float4(0.f, 0.f, 0.f, 0.f), v0 = k0, k1 = k0, v1 = k0;
-        if (hasA) {
+        const int tbase = hp * kHalfPage;
+#pragma unroll 2
+        for (int tt = 0; tt < kHalfPage; tt += 2) {     // the owner warp walks the 16 tokens of the half page, two at a time
+            const int tA = tbase + tt, tB = tA + 1;
+            if (tA >= ctx) break;
+            const bool hasB = tB < ctx;
+            float4 k0, v0, k1 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = k1;
             if (tA == t_new) { k0 = *reinterpret_cast<const float4*>(s.knew + lane * 4); v0 = *reinterpret_cast<const float4*>(s.vnew + lane * 4); }
-            else { k0 = *reinterpret_cast<const float4*>(ks + (2 * warp) * HD + lane * 4); v0 = *reinterpret_cast<const float4*>(vs + (2 * warp) * HD + lane * 4); }
-        }
-        if (hasB) {
-            if (tB == t_new) { k1 = *reinterpret_cast<const float4*>(s.knew + lane * 4); v1 = *reinterpret_cast<const float4*>(s.vnew + lane * 4); }
-            else { k1 = *reinterpret_cast<const float4*>(ks + (2 * warp + 1) * HD + lane * 4); v1 = *reinterpret_cast<const float4*>(vs + (2 * warp + 1) * HD + lane * 4); }
-        }
-        if (hasA) {
+            else { k0 = *reinterpret_cast<const float4*>(ks + tt * HD + lane * 4); v0 = *reinterpret_cast<const float4*>(vs + tt * HD + lane * 4); }
+            if (hasB) {
+                if (tB == t_new) { k1 = *reinterpret_cast<const float4*>(s.knew + lane * 4); v1 = *reinterpret_cast<const float4*>(s.vnew + lane * 4); }
+                else { k1 = *reinterpret_cast<const float4*>(ks + (tt + 1) * HD + lane * 4); v1 = *reinterpret_cast<const float4*>(vs + (tt + 1) * HD + lane * 4); }
+            }
 #pragma unroll
             for (int g = 0; g < G; ++g) {
                 float s0 = q[g].x * k0.x + q[g].y * k0.y + q[g].z * k0.z + q[g].w * k0.w;
@@ -437,8 +421,9 @@ __device__ void fused_attention(const FusedArgs& a, Consumer& c, AttnSmem<G>& s,
                 m[g] = mnew;
             }
         }
-        c.release(slot);  // after the math: every shared-memory read of this stage has been consumed
+        c.release(i);  // after the math: every shared-memory read of this stage has been consumed
     }
+    c.it = i;
 #pragma unroll
     for (int g = 0; g < G; ++g) {
         if (lane == 0) { s.m[warp][g] = m[g]; s.l[warp][g] = l[g]; }
@@ -495,13 +480,14 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
     uint8_t* ringbuf = fused_smem_raw;
     uint64_t* full = reinterpret_cast<uint64_t*>(fused_smem_raw + (size_t)kFusedStages * kFusedStageBytes);
     uint64_t* empty = full + kFusedStages;
-    float* part = reinterpret_cast<float*>(empty + kFusedStages);
-    float* red = part + kFusedPartRows * kFusedConsumers;
-    AttnSmem<G>* as = reinterpret_cast<AttnSmem<G>*>(red + 32);
+    float* red = reinterpret_cast<float*>(empty + kFusedStages);
+    float* xs = red + 32;                                       // [kFusedMaxK] activations / attention scratch
+    AttnSmem<G>* as = reinterpret_cast<AttnSmem<G>*>(xs);
+    static_assert(sizeof(AttnSmem<G>) <= kFusedMaxK * sizeof(float), "attention scratch must fit in the xs region");
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int i = 0; i < kFusedStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kFusedConsumers); }
+        for (int i = 0; i < kFusedStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -531,46 +517,44 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
     }
     // ======================================================= CONSUMERS
     Consumer c;
-    c.ring = ring; c.part = part; c.red = red; c.warp = warp; c.lane = lane;
+    c.ring = ring; c.xs = xs; c.red = red; c.warp = warp; c.lane = lane;
     unsigned seq = 0;
     float best = -INFINITY;
     int bi = 0x7fffffff;
-    float xr[kFusedMaxChunks][8];
     const __half* emb_row = a.embed + (size_t)token * a.H;
     for (int l = 0; l < a.L; ++l) {
         const FusedLayer& Ly = a.layers[l];
         const bool first = (l == 0);
         // P1: qkv = Wqkv . rmsnorm(x)      (layer 0 reads the embedding row directly: Embedding::forward)
-        c.load_x(xr, a.H, a.x, first ? emb_row : nullptr, Ly.ln1, a.eps);
-        c.template gemv<FE_QKV>(a, Ly.qkv, a.qkv_dim, a.H, xr, Ly.qkv_b, nullptr, nullptr, a.qkv1, best, bi);
-        grid_barrier(&a.sync[0], seq);
+        c.load_x(a.H, a.x, first ? emb_row : nullptr, Ly.ln1, a.eps);
+        c.template gemv<FE_QKV>(a, a.qkv_dim, a.H, Ly.qkv_b, nullptr, nullptr, a.qkv1, best, bi);
+        grid_barrier(&a.sync[0], seq, a.dbg);
         // P2: attention over the paged cache (+ q/k norm, RoPE, KV append)
         fused_attention<G>(a, c, *as, l, Ly, t_new, rope_delta);
-        grid_barrier(&a.sync[0], seq);
+        grid_barrier(&a.sync[0], seq, a.dbg);
         // P3: x = resid + Wo . attn
-        c.load_x(xr, a.nh * a.hd, a.attn1, nullptr, nullptr, 0.f);
-        c.template gemv<FE_RESID>(a, Ly.o, a.H, a.nh * a.hd, xr, Ly.o_b, a.x, first ? emb_row : nullptr, a.x, best, bi);
-        grid_barrier(&a.sync[0], seq);
+        c.load_x(a.nh * a.hd, a.attn1, nullptr, nullptr, 0.f);
+        c.template gemv<FE_RESID>(a, a.H, a.nh * a.hd, Ly.o_b, a.x, first ? emb_row : nullptr, a.x, best, bi);
+        grid_barrier(&a.sync[0], seq, a.dbg);
         // P4: h = silu(gate) * up, gate/up rows interleaved, input rmsnorm(x)
-        c.load_x(xr, a.H, a.x, nullptr, Ly.ln2, a.eps);
-        c.template gemv<FE_SWIGLU>(a, Ly.gu, 2 * a.I, a.H, xr, nullptr, nullptr, nullptr, a.h1, best, bi);
-        grid_barrier(&a.sync[0], seq);
+        c.load_x(a.H, a.x, nullptr, Ly.ln2, a.eps);
+        c.template gemv<FE_SWIGLU>(a, 2 * a.I, a.H, nullptr, nullptr, nullptr, a.h1, best, bi);
+        grid_barrier(&a.sync[0], seq, a.dbg);
         // P5: x = x + Wdown . h
-        c.load_x(xr, a.I, a.h1, nullptr, nullptr, 0.f);
-        c.template gemv<FE_RESID>(a, Ly.down, a.H, a.I, xr, nullptr, a.x, nullptr, a.x, best, bi);
-        grid_barrier(&a.sync[0], seq);
+        c.load_x(a.I, a.h1, nullptr, nullptr, 0.f);
+        c.template gemv<FE_RESID>(a, a.H, a.I, nullptr, a.x, nullptr, a.x, best, bi);
+        grid_barrier(&a.sync[0], seq, a.dbg);
     }
     // final: logits = lm_head . rmsnorm(x), per-CTA argmax candidate
-    c.load_x(xr, a.H, a.x, nullptr, a.final_norm, a.eps);
+    c.load_x(a.H, a.x, nullptr, a.final_norm, a.eps);
     best = -INFINITY; bi = 0x7fffffff;
-    c.template gemv<FE_LOGITS>(a, a.lm_head, a.V, a.H, xr, nullptr, nullptr, nullptr, a.logits, best, bi);
+    c.template gemv<FE_LOGITS>(a, a.V, a.H, nullptr, nullptr, nullptr, a.logits, best, bi);
     // CTA-level argmax (first maximal index), then the last CTA to arrive reduces across CTAs
     for (int o = 16; o > 0; o >>= 1) {
         const float ov = __shfl_xor_sync(0xffffffffu, best, o);
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
     }
-    consumer_bar_sync();
     if (lane == 0) { red[warp] = best; reinterpret_cast<int*>(red)[8 + warp] = bi; }
     consumer_bar_sync();
     if (tid == 0) {
@@ -604,8 +588,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
 
 template <int G>
 inline size_t fused_smem_bytes() {
-    return (size_t)kFusedStages * kFusedStageBytes + 2 * kFusedStages * sizeof(uint64_t) + (size_t)kFusedPartRows * kFusedConsumers * sizeof(float) +
-           32 * sizeof(float) + sizeof(AttnSmem<G>) + 64;
+    return (size_t)kFusedStages * kFusedStageBytes + 2 * kFusedStages * sizeof(uint64_t) + 32 * sizeof(float) + (size_t)kFusedMaxK * sizeof(float) + 64;
 }
 
 }  // namespace aha

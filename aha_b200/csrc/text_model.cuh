@@ -319,14 +319,14 @@ struct TextModel {
         auto no = [&](const char* m) { if (why) *why = m; return false; };
         if (tp_world != 1) return no("tensor parallel");
         if (cfg.hd != 128) return no("head_dim != 128");
-        if (cfg.H % 64 || I_l % 64 || (nh_l * cfg.hd) % 64) return no("K not a multiple of 64");
-        if (cfg.H > 8192 || I_l > 8192 || nh_l * cfg.hd > 8192) return no("K > 8192");
-        if (cfg.H > 4096 && rows_per_stage_host(cfg.H) % 2) return no("odd rows per stage for gate/up");
+        if (cfg.H % 8 || I_l % 8) return no("K not a multiple of 8");
+        if (cfg.H > kFusedMaxK || I_l > kFusedMaxK || nh_l * cfg.hd > kFusedMaxK) return no("K > 8192");
+        if (rows_per_stage_host(cfg.H) % 2) return no("a gate/up row pair does not fit one 16 KB stage");
         if (ctx->num_sms < nkv_l) return no("fewer SMs than kv heads");
         if (cfg.attn_bias) return no("attention bias");
         return true;
     }
-    static int rows_per_stage_host(int K) { int r = kFusedStageBytes / (2 * K); return r > kFusedMaxRows ? kFusedMaxRows : (r < 1 ? 1 : r); }
+    static int rows_per_stage_host(int K) { int r = kFusedStageBytes / (2 * K); r = r > kFusedMaxRows ? kFusedMaxRows : (r < 1 ? 1 : r); return r > 1 ? (r & ~1) : r; }
     template <int G>
     void fused_prepare() {
         fused_smem = fused_smem_bytes<G>();
@@ -535,6 +535,7 @@ struct TextModel {
         fa.kv_counters = counters; fa.sync = d_sync; fa.pmax = pmax; fa.pidx = pidx; fa.argmax_out = d_argmax;
         fa.history = d_history; fa.hist_cap = hist_cap; fa.kv_pool = kv_pool; fa.layer_stride = layer_stride; fa.page_stride = page_stride;
         fa.page_table = d_page_table; fa.nsplit = fused_nsplit;
+        { const char* e = getenv("AHA_FUSED_DBG"); fa.dbg = e ? atoi(e) : 0; }
         AHA_REQUIRE(fused_grid <= n_pcand || true, "");
         AHA_CUDA_CHECK(cudaMemsetAsync(d_sync, 0, (2 + nkv_l) * sizeof(unsigned), c.stream));
         switch (nh_l / nkv_l) {
