@@ -621,6 +621,13 @@ int aha_b200_debug_read(aha_model* m, const char* what, int index, float* out, s
         } else if (w == "audio_embeds") {
             AHA_REQUIRE(m->kind == aha_model::QWEN3_ASR, "audio_embeds needs a qwen3_asr handle");
             src = m->audio.audio_embeds; cnt = (size_t)m->audio.last_tokens * m->audio.cfg.out_dim;
+        } else if (w == "fused_trace") {  // globaltimer stamps (ns, relative to the first) of CTA 0; index 0 = consumer, 1 = producer
+            AHA_REQUIRE(T.d_ftrace && (index == 0 || index == 1) && cap >= 4096, "fused trace not available");
+            std::vector<unsigned long long> h(4096);
+            AHA_CUDA_CHECK(cudaMemcpy(h.data(), T.d_ftrace + (size_t)index * 4096, 4096 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            size_t k = 0;
+            for (; k < 4096 && h[k]; ++k) out[k] = (float)(double)(h[k] - h[0]);
+            *n = k; return;
         } else if (w == "rope_delta") {
             AHA_REQUIRE(cap >= 1, "out too small");
             out[0] = (float)m->rope_delta; *n = 1; return;

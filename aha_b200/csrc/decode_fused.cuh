@@ -67,7 +67,8 @@ struct FusedArgs {
     float* kv_pool; size_t layer_stride, page_stride;
     const int* page_table;
     int nsplit;
-    int dbg;           // timing experiments only: bit0 = skip grid barriers, bit1 = skip the GEMV math
+    int dbg;           // timing experiments only: bit0 = skip grid barriers, bit1 = skip the GEMV math, bit2 = timestamps
+    unsigned long long* trace;  // [2][4096] globaltimer stamps of CTA 0 (consumer thread 0 / producer), dbg bit2
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -101,6 +102,8 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define AHA_STAMP(a, who, idx) do { if (((a).dbg & 4) && blockIdx.x == 0 && (idx) < 4096) (a).trace[(who) * 4096 + (idx)++] = gtime(); } while (0)
 __device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kFusedConsumers * 32) : "memory"); }
 __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
     unsigned v;
@@ -226,35 +229,80 @@ struct Consumer {
     // src is fp32 global written by other CTAs (ld.global.cg) or an fp16 embedding row.
     __device__ void load_x(int K, const float* src32, const __half* src16, const float* norm_w, float eps) {
         const int tid = threadIdx.x;
+        constexpr int kPer = kFusedMaxK / (kFusedConsumers * 32 * 4);   // float4 per thread (8 for K = 8192)
+        float4 v[kPer], w[kPer];
         float ss = 0.f;
-        for (int e = tid * 4; e < K; e += kFusedConsumers * 32 * 4) {
-            float4 v;
-            if (src16) {
-                const uint2 u = *reinterpret_cast<const uint2*>(src16 + e);
-                const float2 a = h2_to_f2(u.x), b = h2_to_f2(u.y);
-                v = make_float4(a.x, a.y, b.x, b.y);
-            } else {
-                v = __ldcg(reinterpret_cast<const float4*>(src32 + e));
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) {
+            const int e = (tid + j * kFusedConsumers * 32) * 4;
+            v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            w[j] = v[j];
+            if (e < K) {
+                if (norm_w) w[j] = *reinterpret_cast<const float4*>(norm_w + e);   // static data: in flight with x
+                if (src16) {
+                    const uint2 u = *reinterpret_cast<const uint2*>(src16 + e);
+                    const float2 a = h2_to_f2(u.x), b = h2_to_f2(u.y);
+                    v[j] = make_float4(a.x, a.y, b.x, b.y);
+                } else {
+                    v[j] = __ldcg(reinterpret_cast<const float4*>(src32 + e));
+                }
             }
-            ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-            *reinterpret_cast<float4*>(xs + e) = v;
         }
         if (norm_w) {
+#pragma unroll
+            for (int j = 0; j < kPer; ++j) ss += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
             ss = warp_sum(ss);
             if (lane == 0) red[warp] = ss;
             consumer_bar_sync();
             float tot = 0.f;
 #pragma unroll
-            for (int w = 0; w < kFusedConsumers; ++w) tot += red[w];
+            for (int q = 0; q < kFusedConsumers; ++q) tot += red[q];
             const float inv = 1.0f / sqrtf(tot / (float)K + eps);
-            for (int e = tid * 4; e < K; e += kFusedConsumers * 32 * 4) {   // each thread rescales what it wrote
-                float4 v = *reinterpret_cast<float4*>(xs + e);
-                const float4 w = *reinterpret_cast<const float4*>(norm_w + e);
-                v.x *= inv * w.x; v.y *= inv * w.y; v.z *= inv * w.z; v.w *= inv * w.w;
-                *reinterpret_cast<float4*>(xs + e) = v;
-            }
+#pragma unroll
+            for (int j = 0; j < kPer; ++j) { v[j].x *= inv * w[j].x; v[j].y *= inv * w[j].y; v[j].z *= inv * w[j].z; v[j].w *= inv * w[j].w; }
+        }
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) {
+            const int e = (tid + j * kFusedConsumers * 32) * 4;
+            if (e < K) *reinterpret_cast<float4*>(xs + e) = v[j];
         }
         consumer_bar_sync();
+    }
+
+    // dot products of a FULL stage of R rows against xs; NA independent accumulators per row break the FMA chain
+    template <int R, int NA>
+    __device__ __forceinline__ void stage_dots(const uint8_t* st, int K, float (&v)[kFusedMaxRows]) const {
+        float acc[R][NA];
+#pragma unroll
+        for (int q = 0; q < R; ++q)
+#pragma unroll
+            for (int n = 0; n < NA; ++n) acc[q][n] = 0.f;
+        const int nchunk = K >> 3;
+        int c = lane;
+        for (; c + 32 * (NA - 1) < nchunk; c += 32 * NA) {
+#pragma unroll
+            for (int n = 0; n < NA; ++n) {
+                const int cc = c + 32 * n;
+                const float4 x0 = *reinterpret_cast<const float4*>(xs + cc * 8);
+                const float4 x1 = *reinterpret_cast<const float4*>(xs + cc * 8 + 4);
+#pragma unroll
+                for (int q = 0; q < R; ++q)
+                    acc[q][n] = dot8(*reinterpret_cast<const uint4*>(st + (size_t)cc * 16 + (size_t)q * K * 2), x0, x1, acc[q][n]);
+            }
+        }
+        for (; c < nchunk; c += 32) {
+            const float4 x0 = *reinterpret_cast<const float4*>(xs + c * 8);
+            const float4 x1 = *reinterpret_cast<const float4*>(xs + c * 8 + 4);
+#pragma unroll
+            for (int q = 0; q < R; ++q) acc[q][0] = dot8(*reinterpret_cast<const uint4*>(st + (size_t)c * 16 + (size_t)q * K * 2), x0, x1, acc[q][0]);
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            float t = 0.f;
+#pragma unroll
+            for (int n = 0; n < NA; ++n) t += acc[q][n];
+            v[q] = t;
+        }
     }
 
     // One GEMV phase: y[r0:r1) = W[r0:r1, :] . xs  with the fused epilogue.  Ends with a consumer barrier so
@@ -265,45 +313,39 @@ struct Consumer {
         int r0, r1;
         cta_rows(N, EPI == FE_SWIGLU ? 2 : 1, r0, r1);
         const int R = rows_per_stage(K);
-        const int nchunk = K >> 3;
         unsigned i = it;
         for (int r = r0; r < r1; r += R, ++i) {
             if (!owns(i)) continue;
             const int nr = min(R, r1 - r);
             const uint8_t* st = wait_full(i);
-            float acc[kFusedMaxRows];
+            float v[kFusedMaxRows];
 #pragma unroll
-            for (int q = 0; q < kFusedMaxRows; ++q) acc[q] = 0.f;
+            for (int q = 0; q < kFusedMaxRows; ++q) v[q] = 0.f;
             if (!(a.dbg & 2)) {
-                if (nr == R && R == 4) {            // hot shape (K = 2048): fully unrolled rows
-#pragma unroll 2
-                    for (int c = lane; c < nchunk; c += 32) {
-                        const float4 x0 = *reinterpret_cast<const float4*>(xs + c * 8);
-                        const float4 x1 = *reinterpret_cast<const float4*>(xs + c * 8 + 4);
-                        const uint8_t* p = st + (size_t)c * 16;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) acc[q] = dot8(*reinterpret_cast<const uint4*>(p + (size_t)q * K * 2), x0, x1, acc[q]);
+                if (nr == R) {
+                    switch (R) {
+                        case 8: stage_dots<8, 1>(st, K, v); break;
+                        case 4: stage_dots<4, 2>(st, K, v); break;
+                        case 2: stage_dots<2, 2>(st, K, v); break;
+                        default: stage_dots<1, 4>(st, K, v); break;
                     }
-                } else {
-#pragma unroll 2
-                    for (int c = lane; c < nchunk; c += 32) {
-                        const float4 x0 = *reinterpret_cast<const float4*>(xs + c * 8);
-                        const float4 x1 = *reinterpret_cast<const float4*>(xs + c * 8 + 4);
-                        const uint8_t* p = st + (size_t)c * 16;
+                } else {   // tail stage of the slab: row by row
+                    for (int q = 0; q < nr; ++q) {
+                        float t[kFusedMaxRows];
+                        stage_dots<1, 4>(st + (size_t)q * K * 2, K, t);
 #pragma unroll
-                        for (int q = 0; q < kFusedMaxRows; ++q)
-                            if (q < nr) acc[q] = dot8(*reinterpret_cast<const uint4*>(p + (size_t)q * K * 2), x0, x1, acc[q]);
+                        for (int z = 0; z < kFusedMaxRows; ++z) if (z == q) v[z] = t[0];
                     }
                 }
             }
-            release(i);   // every shared-memory read of the stage feeds acc[] above; __syncwarp orders the lanes
+            release(i);   // every shared-memory read of the stage fed v[] above; __syncwarp orders the lanes
             float mine = 0.f, mate = 0.f;   // lane q keeps row q (and row q^1 for the SwiGLU pair)
 #pragma unroll
             for (int q = 0; q < kFusedMaxRows; ++q) {
                 if (q < nr) {
-                    const float v = warp_sum(acc[q]);
-                    if (lane == q) mine = v;
-                    if (lane == (q ^ 1)) mate = v;
+                    const float t = warp_sum(v[q]);
+                    if (lane == q) mine = t;
+                    if (lane == (q ^ 1)) mate = t;
                 }
             }
             if (lane < nr) {
@@ -311,11 +353,11 @@ struct Consumer {
                 if (EPI == FE_SWIGLU) {
                     if ((lane & 1) == 0) out[row >> 1] = silu_f(mine) * mate;   // rows (2i, 2i+1) = (gate_i, up_i)
                 } else {
-                    float v = mine;
-                    if (bias) v += bias[row];
-                    if (EPI == FE_RESID) v += resid16 ? __half2float(resid16[row]) : __ldcg(resid32 + row);
-                    out[row] = v;
-                    if (EPI == FE_LOGITS && (v > best || (v == best && row < bi))) { best = v; bi = row; }
+                    float y = mine;
+                    if (bias) y += bias[row];
+                    if (EPI == FE_RESID) y += resid16 ? __half2float(resid16[row]) : __ldcg(resid32 + row);
+                    out[row] = y;
+                    if (EPI == FE_LOGITS && (y > best || (y == best && row < bi))) { best = y; bi = row; }
                 }
             }
         }
@@ -377,13 +419,22 @@ __device__ void fused_attention(const FusedArgs& a, Consumer& c, AttnSmem<G>& s,
         a.kv_pool[off] = s.knew[tid];
         a.kv_pool[off + (size_t)a.nkv * kPage * HD] = s.vnew[tid];
     }
-    float4 q[G];
+    // Lane layout inside the owner warp: group = lane / 8 handles token (4*itr + group) of the half page,
+    // sub = lane % 8 handles dims {4*sub + 32*e + 0..3 : e = 0..3} (conflict-free 128-byte rows per quarter warp).
+    const int grp = lane >> 3, sub = lane & 7;
+    float4 q[G][4];
 #pragma unroll
-    for (int g = 0; g < G; ++g) q[g] = *reinterpret_cast<const float4*>(s.qs[g] + lane * 4);
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) q[g][e] = *reinterpret_cast<const float4*>(s.qs[g] + 4 * sub + 32 * e);
     float m[G], l[G];
-    float4 acc[G];
+    float4 acc[G][4];
 #pragma unroll
-    for (int g = 0; g < G; ++g) { m[g] = -INFINITY; l[g] = 0.f; acc[g] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    for (int g = 0; g < G; ++g) {
+        m[g] = -INFINITY; l[g] = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[g][e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 
     unsigned i = c.it;
     for (int hp = hp0; hp < hp1; ++hp, ++i) {
@@ -392,42 +443,66 @@ __device__ void fused_attention(const FusedArgs& a, Consumer& c, AttnSmem<G>& s,
         const float* ks = reinterpret_cast<const float*>(st);
         const float* vs = reinterpret_cast<const float*>(st + kHalfPage * HD * 4);
         const int tbase = hp * kHalfPage;
-#pragma unroll 2
-        for (int tt = 0; tt < kHalfPage; tt += 2) {     // the owner warp walks the 16 tokens of the half page, two at a time
-            const int tA = tbase + tt, tB = tA + 1;
-            if (tA >= ctx) break;
-            const bool hasB = tB < ctx;
-            float4 k0, v0, k1 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = k1;
-            if (tA == t_new) { k0 = *reinterpret_cast<const float4*>(s.knew + lane * 4); v0 = *reinterpret_cast<const float4*>(s.vnew + lane * 4); }
-            else { k0 = *reinterpret_cast<const float4*>(ks + tt * HD + lane * 4); v0 = *reinterpret_cast<const float4*>(vs + tt * HD + lane * 4); }
-            if (hasB) {
-                if (tB == t_new) { k1 = *reinterpret_cast<const float4*>(s.knew + lane * 4); v1 = *reinterpret_cast<const float4*>(s.vnew + lane * 4); }
-                else { k1 = *reinterpret_cast<const float4*>(ks + (tt + 1) * HD + lane * 4); v1 = *reinterpret_cast<const float4*>(vs + (tt + 1) * HD + lane * 4); }
+#pragma unroll
+        for (int itr = 0; itr < kHalfPage / 4; ++itr) {
+            const int tl = 4 * itr + grp;          // token inside the half page
+            const int t = tbase + tl;
+            const bool valid = t < ctx;
+            const float* kr = (t == t_new) ? s.knew : ks + tl * HD;
+            const float* vr = (t == t_new) ? s.vnew : vs + tl * HD;
+            float4 kk[4], vv[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                kk[e] = *reinterpret_cast<const float4*>(kr + 4 * sub + 32 * e);
+                vv[e] = *reinterpret_cast<const float4*>(vr + 4 * sub + 32 * e);
+                if (!valid) vv[e] = make_float4(0.f, 0.f, 0.f, 0.f);   // slots past ctx hold stale data: 0 * x must stay 0
             }
 #pragma unroll
             for (int g = 0; g < G; ++g) {
-                float s0 = q[g].x * k0.x + q[g].y * k0.y + q[g].z * k0.z + q[g].w * k0.w;
-                float s1 = q[g].x * k1.x + q[g].y * k1.y + q[g].z * k1.z + q[g].w * k1.w;
-                s0 = warp_sum(s0) * a.scaling;
-                s1 = hasB ? warp_sum(s1) * a.scaling : -INFINITY;
-                const float mnew = fmaxf(m[g], fmaxf(s0, s1));
-                const float alpha = expf(m[g] - mnew);
-                const float p0 = expf(s0 - mnew), p1 = expf(s1 - mnew);
-                l[g] = l[g] * alpha + p0 + p1;
-                acc[g].x = acc[g].x * alpha + p0 * v0.x + p1 * v1.x;
-                acc[g].y = acc[g].y * alpha + p0 * v0.y + p1 * v1.y;
-                acc[g].z = acc[g].z * alpha + p0 * v0.z + p1 * v1.z;
-                acc[g].w = acc[g].w * alpha + p0 * v0.w + p1 * v1.w;
+                float sc = 0.f;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) sc += q[g][e].x * kk[e].x + q[g][e].y * kk[e].y + q[g][e].z * kk[e].z + q[g][e].w * kk[e].w;
+                sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+                sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+                sc += __shfl_xor_sync(0xffffffffu, sc, 4);
+                sc = valid ? sc * a.scaling : -INFINITY;
+                const float mnew = fmaxf(m[g], sc);
+                const float muse = (mnew == -INFINITY) ? 0.f : mnew;
+                const float alpha = expf(m[g] - muse);
+                const float pp = expf(sc - muse);
+                l[g] = l[g] * alpha + pp;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    acc[g][e].x = acc[g][e].x * alpha + pp * vv[e].x;
+                    acc[g][e].y = acc[g][e].y * alpha + pp * vv[e].y;
+                    acc[g][e].z = acc[g][e].z * alpha + pp * vv[e].z;
+                    acc[g][e].w = acc[g][e].w * alpha + pp * vv[e].w;
+                }
                 m[g] = mnew;
             }
         }
         c.release(i);  // after the math: every shared-memory read of this stage has been consumed
     }
     c.it = i;
+    // merge the 4 token groups of the warp (lanes differing in bits 3,4), then publish the per-warp state
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-        if (lane == 0) { s.m[warp][g] = m[g]; s.l[warp][g] = l[g]; }
-        *reinterpret_cast<float4*>(&s.acc[warp][g][lane * 4]) = acc[g];
+        float M = fmaxf(m[g], __shfl_xor_sync(0xffffffffu, m[g], 8));
+        M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, 16));
+        const float sc = (m[g] == -INFINITY) ? 0.f : expf(m[g] - M);
+        float L = l[g] * sc;
+        L += __shfl_xor_sync(0xffffffffu, L, 8);
+        L += __shfl_xor_sync(0xffffffffu, L, 16);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float4 t = make_float4(acc[g][e].x * sc, acc[g][e].y * sc, acc[g][e].z * sc, acc[g][e].w * sc);
+            t.x += __shfl_xor_sync(0xffffffffu, t.x, 8); t.x += __shfl_xor_sync(0xffffffffu, t.x, 16);
+            t.y += __shfl_xor_sync(0xffffffffu, t.y, 8); t.y += __shfl_xor_sync(0xffffffffu, t.y, 16);
+            t.z += __shfl_xor_sync(0xffffffffu, t.z, 8); t.z += __shfl_xor_sync(0xffffffffu, t.z, 16);
+            t.w += __shfl_xor_sync(0xffffffffu, t.w, 8); t.w += __shfl_xor_sync(0xffffffffu, t.w, 16);
+            if (grp == 0) *reinterpret_cast<float4*>(&s.acc[warp][g][4 * sub + 32 * e]) = t;
+        }
+        if (lane == 0) { s.m[warp][g] = M; s.l[warp][g] = L; }
     }
     consumer_bar_sync();
     for (int idx = tid; idx < G * HD; idx += kFusedConsumers * 32) {
@@ -503,15 +578,17 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
         if (lane == 0) {
             Producer p;
             p.ring = ring;
+            int pe = 0;
+            AHA_STAMP(a, 1, pe);
             for (int l = 0; l < a.L; ++l) {
                 const FusedLayer& Ly = a.layers[l];
-                p.rows(Ly.qkv, a.qkv_dim, a.H, 1);
-                p.attn(a, l, ctx);
-                p.rows(Ly.o, a.H, a.nh * a.hd, 1);
-                p.rows(Ly.gu, 2 * a.I, a.H, 2);
-                p.rows(Ly.down, a.H, a.I, 1);
+                p.rows(Ly.qkv, a.qkv_dim, a.H, 1); AHA_STAMP(a, 1, pe);
+                p.attn(a, l, ctx); AHA_STAMP(a, 1, pe);
+                p.rows(Ly.o, a.H, a.nh * a.hd, 1); AHA_STAMP(a, 1, pe);
+                p.rows(Ly.gu, 2 * a.I, a.H, 2); AHA_STAMP(a, 1, pe);
+                p.rows(Ly.down, a.H, a.I, 1); AHA_STAMP(a, 1, pe);
             }
-            p.rows(a.lm_head, a.V, a.H, 1);
+            p.rows(a.lm_head, a.V, a.H, 1); AHA_STAMP(a, 1, pe);
         }
         return;
     }
@@ -522,33 +599,37 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
     float best = -INFINITY;
     int bi = 0x7fffffff;
     const __half* emb_row = a.embed + (size_t)token * a.H;
+    int ce = 0;
+#define CSTAMP() do { if (tid == 0) AHA_STAMP(a, 0, ce); } while (0)
+    CSTAMP();
     for (int l = 0; l < a.L; ++l) {
         const FusedLayer& Ly = a.layers[l];
         const bool first = (l == 0);
         // P1: qkv = Wqkv . rmsnorm(x)      (layer 0 reads the embedding row directly: Embedding::forward)
-        c.load_x(a.H, a.x, first ? emb_row : nullptr, Ly.ln1, a.eps);
-        c.template gemv<FE_QKV>(a, a.qkv_dim, a.H, Ly.qkv_b, nullptr, nullptr, a.qkv1, best, bi);
-        grid_barrier(&a.sync[0], seq, a.dbg);
+        c.load_x(a.H, a.x, first ? emb_row : nullptr, Ly.ln1, a.eps); CSTAMP();
+        c.template gemv<FE_QKV>(a, a.qkv_dim, a.H, Ly.qkv_b, nullptr, nullptr, a.qkv1, best, bi); CSTAMP();
+        grid_barrier(&a.sync[0], seq, a.dbg); CSTAMP();
         // P2: attention over the paged cache (+ q/k norm, RoPE, KV append)
-        fused_attention<G>(a, c, *as, l, Ly, t_new, rope_delta);
-        grid_barrier(&a.sync[0], seq, a.dbg);
+        CSTAMP();
+        fused_attention<G>(a, c, *as, l, Ly, t_new, rope_delta); CSTAMP();
+        grid_barrier(&a.sync[0], seq, a.dbg); CSTAMP();
         // P3: x = resid + Wo . attn
-        c.load_x(a.nh * a.hd, a.attn1, nullptr, nullptr, 0.f);
-        c.template gemv<FE_RESID>(a, a.H, a.nh * a.hd, Ly.o_b, a.x, first ? emb_row : nullptr, a.x, best, bi);
-        grid_barrier(&a.sync[0], seq, a.dbg);
+        c.load_x(a.nh * a.hd, a.attn1, nullptr, nullptr, 0.f); CSTAMP();
+        c.template gemv<FE_RESID>(a, a.H, a.nh * a.hd, Ly.o_b, a.x, first ? emb_row : nullptr, a.x, best, bi); CSTAMP();
+        grid_barrier(&a.sync[0], seq, a.dbg); CSTAMP();
         // P4: h = silu(gate) * up, gate/up rows interleaved, input rmsnorm(x)
-        c.load_x(a.H, a.x, nullptr, Ly.ln2, a.eps);
-        c.template gemv<FE_SWIGLU>(a, 2 * a.I, a.H, nullptr, nullptr, nullptr, a.h1, best, bi);
-        grid_barrier(&a.sync[0], seq, a.dbg);
+        c.load_x(a.H, a.x, nullptr, Ly.ln2, a.eps); CSTAMP();
+        c.template gemv<FE_SWIGLU>(a, 2 * a.I, a.H, nullptr, nullptr, nullptr, a.h1, best, bi); CSTAMP();
+        grid_barrier(&a.sync[0], seq, a.dbg); CSTAMP();
         // P5: x = x + Wdown . h
-        c.load_x(a.I, a.h1, nullptr, nullptr, 0.f);
-        c.template gemv<FE_RESID>(a, a.H, a.I, nullptr, a.x, nullptr, a.x, best, bi);
-        grid_barrier(&a.sync[0], seq, a.dbg);
+        c.load_x(a.I, a.h1, nullptr, nullptr, 0.f); CSTAMP();
+        c.template gemv<FE_RESID>(a, a.H, a.I, nullptr, a.x, nullptr, a.x, best, bi); CSTAMP();
+        grid_barrier(&a.sync[0], seq, a.dbg); CSTAMP();
     }
     // final: logits = lm_head . rmsnorm(x), per-CTA argmax candidate
     c.load_x(a.H, a.x, nullptr, a.final_norm, a.eps);
     best = -INFINITY; bi = 0x7fffffff;
-    c.template gemv<FE_LOGITS>(a, a.V, a.H, nullptr, nullptr, nullptr, a.logits, best, bi);
+    c.template gemv<FE_LOGITS>(a, a.V, a.H, nullptr, nullptr, nullptr, a.logits, best, bi); CSTAMP();
     // CTA-level argmax (first maximal index), then the last CTA to arrive reduces across CTAs
     for (int o = 16; o > 0; o >>= 1) {
         const float ov = __shfl_xor_sync(0xffffffffu, best, o);

@@ -241,6 +241,7 @@ struct TextModel {
     int decode_impl = 0;
     FusedLayer* d_fused_layers = nullptr;
     unsigned* d_sync = nullptr;   // [0] grid barrier, [1] final ticket, then kv tickets [nkv]
+    unsigned long long* d_ftrace = nullptr;
     int fused_grid = 0, fused_nsplit = 0;
     size_t fused_smem = 0;
 
@@ -348,6 +349,7 @@ struct TextModel {
         page_stride = (size_t)2 * nkv_l * kPage * cfg.hd;
         layer_stride = page_stride * num_pages;
         kv_pool = c.alloc<float>(layer_stride * cfg.L);
+        AHA_CUDA_CHECK(cudaMemset(kv_pool, 0, layer_stride * cfg.L * sizeof(float)));   // never feed uninitialised bits to the FMA pipes
         d_page_table = c.alloc<int>(num_pages);
         h_page_table.assign(num_pages, 0);
         reset_pages();
@@ -370,6 +372,8 @@ struct TextModel {
                 fl[l] = FusedLayer{T.qkv.w, T.o.w, T.gu.w, T.down.w, T.qkv.b, T.o.b, T.ln1, T.ln2, T.qn, T.kn};
             }
             d_fused_layers = upload(c, fl);
+            d_ftrace = c.alloc<unsigned long long>(2 * 4096);
+            AHA_CUDA_CHECK(cudaMemset(d_ftrace, 0, 2 * 4096 * sizeof(unsigned long long)));
             switch (nh_l / nkv_l) {
                 case 1: fused_prepare<1>(); break;
                 case 2: fused_prepare<2>(); break;
@@ -536,6 +540,7 @@ struct TextModel {
         fa.history = d_history; fa.hist_cap = hist_cap; fa.kv_pool = kv_pool; fa.layer_stride = layer_stride; fa.page_stride = page_stride;
         fa.page_table = d_page_table; fa.nsplit = fused_nsplit;
         { const char* e = getenv("AHA_FUSED_DBG"); fa.dbg = e ? atoi(e) : 0; }
+        fa.trace = d_ftrace;
         AHA_REQUIRE(fused_grid <= n_pcand || true, "");
         AHA_CUDA_CHECK(cudaMemsetAsync(d_sync, 0, (2 + nkv_l) * sizeof(unsigned), c.stream));
         switch (nh_l / nkv_l) {

@@ -17,3 +17,17 @@ m.forward_initial(synth.synth_text_ids(8, 1000, 1), 0, want_logits=False)
 toks, ms = m.decode_steps(5, ctx, steps, timed=True)
 toks, ms = m.decode_steps(5, ctx, steps, timed=True)
 print(f"impl={impl} dbg={os.environ.get('AHA_FUSED_DBG','0')} ctx={ctx} steps={steps} ms/step={ms/steps:.4f} tok/s={1e3*steps/ms:.1f}")
+if int(os.environ.get("AHA_FUSED_DBG", "0")) & 4:
+    m.decode_steps(5, ctx, 1)
+    c = m.debug_read("fused_trace", 0, 4096); p = m.debug_read("fused_trace", 1, 4096)
+    print("consumer stamps", len(c), "producer stamps", len(p), "total us", c[-1] / 1e3, p[-1] / 1e3)
+    # consumer: stamp0, then per layer: P1(load,gemv,bar) P2(start,attn,bar) P3(load,gemv,bar) P4(...) P5(...) => 15 per layer
+    import numpy as np
+    d = np.diff(c)[: 15 * 28].reshape(28, 15)
+    names = ["P1 load_x", "P1 gemv", "P1 bar", "P2 -", "P2 attn", "P2 bar", "P3 load_x", "P3 gemv", "P3 bar", "P4 load_x", "P4 gemv", "P4 bar", "P5 load_x", "P5 gemv", "P5 bar"]
+    for n, v in zip(names, d[2:].mean(0)):
+        print(f"  consumer {n:10s} {v/1e3:7.2f} us")
+    print("  consumer per layer", d[2:].sum(1).mean() / 1e3, "us; lm_head phase", (c[-1] - c[15 * 28]) / 1e3)
+    dp = np.diff(p)[: 5 * 28].reshape(28, 5)
+    for n, v in zip(["qkv", "attn", "o", "gate_up", "down"], dp[2:].mean(0)):
+        print(f"  producer {n:8s} {v/1e3:7.2f} us")
