@@ -37,6 +37,7 @@ constexpr int kFusedThreads = (kFusedConsumers + 1) * 32;
 constexpr int kFusedMaxRows = 8;                         // weight rows per stage (<= 16 KB)
 constexpr int kFusedMaxK = 8192;                         // activation vector staged in shared memory (32 KB)
 constexpr int kHalfPage = 16;                            // tokens per attention stage (K 8 KB + V 8 KB)
+constexpr int kFusedMaxPages = 512;                      // page-table entries staged in shared memory (16K tokens)
 
 struct FusedLayer {
     const __half *qkv, *o, *gu, *down;
@@ -60,7 +61,8 @@ struct FusedArgs {
     float* logits;     // [V]
     float* partial;    // [nh][nsplit][hd+2]
     int* kv_counters;  // [nkv]      (zeroed by the host before launch)
-    unsigned* sync;    // [0] grid-barrier counter, [1] final ticket   (zeroed by the host before launch)
+    unsigned* sync;    // [1] final ticket   (zeroed by the host before launch)
+    unsigned* flags;   // [grid * kFlagStride] grid-barrier flags (zeroed by the host before launch)
     float* pmax; int* pidx;  // [grid] per-CTA argmax candidates
     uint32_t* argmax_out;
     uint32_t* history; int hist_cap;
@@ -111,15 +113,16 @@ __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
     return v;
 }
 
-// Grid barrier joined by the consumer threads only.  `*seq` counts barriers passed by this CTA.
+// Grid barrier joined by the consumer threads only: one arrival counter in L2 (zeroed by the host before every
+// launch), polled by consumer thread 0 with relaxed loads; activations are always read with ld.global.cg.
 __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& seq, int dbg = 0) {
     if (dbg & 1) { consumer_bar_sync(); return; }
-    consumer_bar_sync();
+    consumer_bar_sync();                       // every consumer thread of this CTA has issued its writes
     if (threadIdx.x == 0) {
-        __threadfence();                       // publish this CTA's writes (ordered after them by the bar.sync above)
+        __threadfence();                       // publish them at gpu scope (cumulative through the bar.sync)
         atomicAdd(counter, 1u);
         const unsigned target = (seq + 1u) * gridDim.x;
-        while (ld_relaxed_u32(counter) < target) {}   // plain L2 polling; activations are read with ld.global.cg
+        while (ld_relaxed_u32(counter) < target) {}
         __threadfence();
     }
     seq += 1u;
@@ -180,6 +183,7 @@ struct Producer {
             ++it;
         }
     }
+    const int* pages = nullptr;   // page table staged in shared memory
     __device__ void attn(const FusedArgs& a, int layer, int ctx) {
         int kvh, split, hp0, hp1;
         if (!attn_item(a, ctx, kvh, split, hp0, hp1)) return;
@@ -188,7 +192,7 @@ struct Producer {
         for (int hp = hp0; hp < hp1; ++hp) {
             int slot;
             acquire(slot);
-            const int page = a.page_table[(hp * kHalfPage) >> kPageShift];
+            const int page = pages[(hp * kHalfPage) >> kPageShift];
             const size_t off = (size_t)page * a.page_stride + (size_t)kvh * kPage * a.hd + (size_t)((hp * kHalfPage) & (kPage - 1)) * a.hd;
             const uint32_t half_bytes = kHalfPage * a.hd * 4u;  // 8 KB for hd = 128
             uint8_t* dst = ring.buf + (size_t)slot * kFusedStageBytes;
@@ -557,6 +561,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
     uint64_t* empty = full + kFusedStages;
     float* red = reinterpret_cast<float*>(empty + kFusedStages);
     float* xs = red + 32;                                       // [kFusedMaxK] activations / attention scratch
+    int* spages = reinterpret_cast<int*>(xs + kFusedMaxK);      // [kFusedMaxPages] page table copy
     AttnSmem<G>* as = reinterpret_cast<AttnSmem<G>*>(xs);
     static_assert(sizeof(AttnSmem<G>) <= kFusedMaxK * sizeof(float), "attention scratch must fit in the xs region");
 
@@ -565,12 +570,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
         for (int i = 0; i < kFusedStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
-
     const int t_new = a.st->pos;
     const int rope_delta = a.st->rope_delta;
     const uint32_t token = a.st->token;
     const int ctx = t_new + 1;
+    for (int i = tid; i < (ctx + kPage - 1) / kPage && i < kFusedMaxPages; i += kFusedThreads) spages[i] = a.page_table[i];
+    __syncthreads();
     Ring ring{ringbuf, full, empty};
 
     if (warp == kFusedConsumers) {
@@ -578,10 +583,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
         if (lane == 0) {
             Producer p;
             p.ring = ring;
+            p.pages = spages;
             int pe = 0;
             AHA_STAMP(a, 1, pe);
+            FusedLayer nxt = a.layers[0];
             for (int l = 0; l < a.L; ++l) {
-                const FusedLayer& Ly = a.layers[l];
+                const FusedLayer Ly = nxt;
+                if (l + 1 < a.L) nxt = a.layers[l + 1];   // pointer table one layer ahead: off the issue path
                 p.rows(Ly.qkv, a.qkv_dim, a.H, 1); AHA_STAMP(a, 1, pe);
                 p.attn(a, l, ctx); AHA_STAMP(a, 1, pe);
                 p.rows(Ly.o, a.H, a.nh * a.hd, 1); AHA_STAMP(a, 1, pe);
@@ -602,8 +610,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
     int ce = 0;
 #define CSTAMP() do { if (tid == 0) AHA_STAMP(a, 0, ce); } while (0)
     CSTAMP();
+    FusedLayer nxtc = a.layers[0];
     for (int l = 0; l < a.L; ++l) {
-        const FusedLayer& Ly = a.layers[l];
+        const FusedLayer Ly = nxtc;
+        if (l + 1 < a.L) nxtc = a.layers[l + 1];
         const bool first = (l == 0);
         // P1: qkv = Wqkv . rmsnorm(x)      (layer 0 reads the embedding row directly: Embedding::forward)
         c.load_x(a.H, a.x, first ? emb_row : nullptr, Ly.ln1, a.eps); CSTAMP();
@@ -669,7 +679,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
 
 template <int G>
 inline size_t fused_smem_bytes() {
-    return (size_t)kFusedStages * kFusedStageBytes + 2 * kFusedStages * sizeof(uint64_t) + 32 * sizeof(float) + (size_t)kFusedMaxK * sizeof(float) + 64;
+    return (size_t)kFusedStages * kFusedStageBytes + 2 * kFusedStages * sizeof(uint64_t) + 32 * sizeof(float) + (size_t)kFusedMaxK * sizeof(float) +
+           (size_t)kFusedMaxPages * sizeof(int) + 64;
 }
 
 }  // namespace aha

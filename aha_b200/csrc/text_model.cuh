@@ -242,6 +242,7 @@ struct TextModel {
     FusedLayer* d_fused_layers = nullptr;
     unsigned* d_sync = nullptr;   // [0] grid barrier, [1] final ticket, then kv tickets [nkv]
     unsigned long long* d_ftrace = nullptr;
+    size_t sync_words = 0;
     int fused_grid = 0, fused_nsplit = 0;
     size_t fused_smem = 0;
 
@@ -316,6 +317,7 @@ struct TextModel {
         mrope_sel = upload(c, sel);
     }
 
+    int max_ctx_hint = 0;
     bool fused_supported(std::string* why) const {
         auto no = [&](const char* m) { if (why) *why = m; return false; };
         if (tp_world != 1) return no("tensor parallel");
@@ -325,6 +327,7 @@ struct TextModel {
         if (rows_per_stage_host(cfg.H) % 2) return no("a gate/up row pair does not fit one 16 KB stage");
         if (ctx->num_sms < nkv_l) return no("fewer SMs than kv heads");
         if (cfg.attn_bias) return no("attention bias");
+        if (max_ctx_hint > kFusedMaxPages * kPage) return no("max_ctx beyond the page table staged in shared memory");
         return true;
     }
     static int rows_per_stage_host(int K) { int r = kFusedStageBytes / (2 * K); r = r > kFusedMaxRows ? kFusedMaxRows : (r < 1 ? 1 : r); return r > 1 ? (r & ~1) : r; }
@@ -338,7 +341,7 @@ struct TextModel {
     }
     void alloc_runtime(int max_ctx_, int max_prefill_, bool graph, int decode_impl_ = 0) {
         Ctx& c = *ctx;
-        max_ctx = max_ctx_; max_prefill = max_prefill_; use_graph = graph; decode_impl = decode_impl_;
+        max_ctx = max_ctx_; max_prefill = max_prefill_; use_graph = graph; decode_impl = decode_impl_; max_ctx_hint = max_ctx_;
         {
             std::string why;
             const bool ok = fused_supported(&why);
@@ -362,8 +365,9 @@ struct TextModel {
         fused_grid = c.num_sms;
         fused_nsplit = std::max(1, std::min(32, fused_grid / std::max(1, nkv_l)));
         partial = c.alloc<float>((size_t)nh_l * std::max(kDecodeSplits, fused_nsplit) * (cfg.hd + 2));
-        d_sync = c.alloc<unsigned>(2 + nkv_l);
-        AHA_CUDA_CHECK(cudaMemset(d_sync, 0, (2 + nkv_l) * sizeof(unsigned)));
+        sync_words = 2 + nkv_l;
+        d_sync = c.alloc<unsigned>(sync_words);
+        AHA_CUDA_CHECK(cudaMemset(d_sync, 0, sync_words * sizeof(unsigned)));
         counters = reinterpret_cast<int*>(d_sync + 2);
         if (fused) {
             std::vector<FusedLayer> fl(cfg.L);
@@ -536,13 +540,13 @@ struct TextModel {
         fa.eps = cfg.eps; fa.scaling = (float)(1.0 / std::sqrt((double)cfg.hd));
         fa.embed = embed; fa.lm_head = lm_head; fa.final_norm = norm; fa.inv_freq = inv_freq; fa.st = d_state;
         fa.x = x1; fa.qkv1 = qkv1; fa.attn1 = attn1; fa.h1 = h1; fa.logits = logits; fa.partial = partial;
-        fa.kv_counters = counters; fa.sync = d_sync; fa.pmax = pmax; fa.pidx = pidx; fa.argmax_out = d_argmax;
+        fa.kv_counters = counters; fa.sync = d_sync; fa.flags = nullptr; fa.pmax = pmax; fa.pidx = pidx; fa.argmax_out = d_argmax;
         fa.history = d_history; fa.hist_cap = hist_cap; fa.kv_pool = kv_pool; fa.layer_stride = layer_stride; fa.page_stride = page_stride;
         fa.page_table = d_page_table; fa.nsplit = fused_nsplit;
         { const char* e = getenv("AHA_FUSED_DBG"); fa.dbg = e ? atoi(e) : 0; }
         fa.trace = d_ftrace;
         AHA_REQUIRE(fused_grid <= n_pcand || true, "");
-        AHA_CUDA_CHECK(cudaMemsetAsync(d_sync, 0, (2 + nkv_l) * sizeof(unsigned), c.stream));
+        AHA_CUDA_CHECK(cudaMemsetAsync(d_sync, 0, sync_words * sizeof(unsigned), c.stream));
         switch (nh_l / nkv_l) {
             case 1: launch_fused<1>(fa); break;
             case 2: launch_fused<2>(fa); break;
