@@ -54,15 +54,12 @@ struct FusedArgs {
     const float* final_norm;
     const float* inv_freq;
     DecodeState* st;
-    // Activations cross CTAs as LL pairs {fp32 bits, tag}: one 8-byte store is single-copy atomic, readers poll the
-    // tag (tag = epoch + 8*layer + phase), so no grid barrier, fence or flag is needed between phases.
-    uint2* x;          // [H]   residual stream
-    uint2* qkv1;       // [qkv_dim]
-    uint2* attn1;      // [nh*hd]
-    uint2* h1;         // [I]
+    float* x;          // [H]   residual stream
+    float* qkv1;       // [qkv_dim]
+    float* attn1;      // [nh*hd]
+    float* h1;         // [I]
     float* logits;     // [V]
-    uint2* partial;    // [nh][nsplit][hd+2]
-    unsigned epoch;    // base tag of this launch (monotonic across launches, never 0)
+    float* partial;    // [nh][nsplit][hd+2]
     int* kv_counters;  // [nkv]      (zeroed by the host before launch)
     unsigned* sync;    // [1] final ticket   (zeroed by the host before launch)
     unsigned* flags;   // [grid * kFlagStride] grid-barrier flags (zeroed by the host before launch)
@@ -110,24 +107,6 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define AHA_STAMP(a, who, idx) do { if (((a).dbg & 4) && blockIdx.x == 0 && (idx) < 4096) (a).trace[(who) * 4096 + (idx)++] = gtime(); } while (0)
 __device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kFusedConsumers * 32) : "memory"); }
-__device__ __forceinline__ void ll_store(uint2* p, float v, unsigned tag) {
-    asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
-}
-__device__ __forceinline__ uint2 ll_load(const uint2* p) {
-    uint2 r;
-    asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
-    return r;
-}
-__device__ __forceinline__ uint4 ll_load2(const uint2* p) {   // two consecutive pairs (16-byte aligned)
-    uint4 r;
-    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
-    return r;
-}
-__device__ __forceinline__ float ll_wait(const uint2* p, unsigned tag) {
-    uint2 r = ll_load(p);
-    while (r.y != tag) r = ll_load(p);
-    return __uint_as_float(r.x);
-}
 __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
     unsigned v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -251,58 +230,31 @@ struct Consumer {
     }
 
     // Stage the activation vector of a GEMV in shared memory (all consumer threads), optional RMSNorm.
-    // src is an LL vector produced by other CTAs under `tag` (polled until every element carries the tag)
-    // or an fp16 embedding row (static).  Rounds of 2048 elements: 2 float4 per thread per round.
-    __device__ void load_x(int K, const uint2* src, unsigned tag, const __half* src16, const float* norm_w, float eps) {
+    // src is fp32 global written by other CTAs (ld.global.cg) or an fp16 embedding row.
+    __device__ void load_x(int K, const float* src32, const __half* src16, const float* norm_w, float eps) {
         const int tid = threadIdx.x;
-        constexpr int kRound = kFusedConsumers * 32 * 4 * 2;
-        float4 w0[2];
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {   // norm gains of the first round: static data, in flight while we poll
-            const int e = (tid + j * kFusedConsumers * 32) * 4;
-            w0[j] = (norm_w && e < K) ? *reinterpret_cast<const float4*>(norm_w + e) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        constexpr int kPer = (kFusedMaxK + kFusedConsumers * 32 * 4 - 1) / (kFusedConsumers * 32 * 4);   // float4 per thread
+        float4 v[kPer], w[kPer];
         float ss = 0.f;
-        for (int base = 0; base < K; base += kRound) {
-            float4 v[2];
-            bool done[2];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int e = base + (tid + j * kFusedConsumers * 32) * 4;
-                v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                done[j] = e >= K;
-                if (src16 && !done[j]) {
+        for (int j = 0; j < kPer; ++j) {
+            const int e = (tid + j * kFusedConsumers * 32) * 4;
+            v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            w[j] = v[j];
+            if (e < K) {
+                if (norm_w) w[j] = *reinterpret_cast<const float4*>(norm_w + e);   // static data: in flight with x
+                if (src16) {
                     const uint2 u = *reinterpret_cast<const uint2*>(src16 + e);
                     const float2 a = h2_to_f2(u.x), b = h2_to_f2(u.y);
                     v[j] = make_float4(a.x, a.y, b.x, b.y);
-                    done[j] = true;
-                }
-            }
-            while (!(done[0] && done[1])) {   // poll: the loads of a round are in flight together
-                uint4 a[2], b[2];
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int e = base + (tid + j * kFusedConsumers * 32) * 4;
-                    if (!done[j]) { a[j] = ll_load2(src + e); b[j] = ll_load2(src + e + 2); }
-                }
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    if (!done[j] && a[j].y == tag && a[j].w == tag && b[j].y == tag && b[j].w == tag) {
-                        v[j] = make_float4(__uint_as_float(a[j].x), __uint_as_float(a[j].z), __uint_as_float(b[j].x), __uint_as_float(b[j].z));
-                        done[j] = true;
-                    }
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int e = base + (tid + j * kFusedConsumers * 32) * 4;
-                if (e < K) {
-                    ss += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
-                    *reinterpret_cast<float4*>(xs + e) = v[j];
+                } else {
+                    v[j] = __ldcg(reinterpret_cast<const float4*>(src32 + e));
                 }
             }
         }
         if (norm_w) {
+#pragma unroll
+            for (int j = 0; j < kPer; ++j) ss += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
             ss = warp_sum(ss);
             if (lane == 0) red[warp] = ss;
             consumer_bar_sync();
@@ -310,18 +262,13 @@ struct Consumer {
 #pragma unroll
             for (int q = 0; q < kFusedConsumers; ++q) tot += red[q];
             const float inv = 1.0f / sqrtf(tot / (float)K + eps);
-            for (int base = 0; base < K; base += kRound) {   // each thread rescales exactly the elements it wrote
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int e = base + (tid + j * kFusedConsumers * 32) * 4;
-                    if (e < K) {
-                        const float4 w = (base == 0) ? w0[j] : *reinterpret_cast<const float4*>(norm_w + e);
-                        float4 v = *reinterpret_cast<float4*>(xs + e);
-                        v.x *= inv * w.x; v.y *= inv * w.y; v.z *= inv * w.z; v.w *= inv * w.w;
-                        *reinterpret_cast<float4*>(xs + e) = v;
-                    }
-                }
-            }
+            for (int j = 0; j < kPer; ++j) { v[j].x *= inv * w[j].x; v[j].y *= inv * w[j].y; v[j].z *= inv * w[j].z; v[j].w *= inv * w[j].w; }
+        }
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) {
+            const int e = (tid + j * kFusedConsumers * 32) * 4;
+            if (e < K) *reinterpret_cast<float4*>(xs + e) = v[j];
         }
         consumer_bar_sync();
     }
@@ -362,11 +309,11 @@ struct Consumer {
         }
     }
 
-    // One GEMV phase: y[r0:r1) = W[r0:r1, :] . xs  with the fused epilogue; outputs are LL pairs tagged `tag`
-    // (FE_LOGITS writes plain floats).  Ends with a consumer barrier so that xs may be overwritten.
+    // One GEMV phase: y[r0:r1) = W[r0:r1, :] . xs  with the fused epilogue.  Ends with a consumer barrier so
+    // that xs may be overwritten by the next phase.
     template <int EPI>
-    __device__ void gemv(const FusedArgs& a, int N, int K, const float* bias, const uint2* resid, const __half* resid16, uint2* out, float* outf,
-                         unsigned tag, float& best, int& bi) {
+    __device__ void gemv(const FusedArgs& a, int N, int K, const float* bias, const float* resid32, const __half* resid16, float* out,
+                         float& best, int& bi) {
         int r0, r1;
         cta_rows(N, EPI == FE_SWIGLU ? 2 : 1, r0, r1);
         const int R = rows_per_stage(K);
@@ -374,9 +321,6 @@ struct Consumer {
         for (int r = r0; r < r1; r += R, ++i) {
             if (!owns(i)) continue;
             const int nr = min(R, r1 - r);
-            float res = 0.f;
-            if (EPI == FE_RESID && lane < nr)   // previous value of this CTA's own rows (written by this CTA): issue early
-                res = resid16 ? __half2float(resid16[r + lane]) : __uint_as_float(ll_load(resid + r + lane).x);
             const uint8_t* st = wait_full(i);
             float v[kFusedMaxRows];
 #pragma unroll
@@ -411,17 +355,13 @@ struct Consumer {
             if (lane < nr) {
                 const int row = r + lane;
                 if (EPI == FE_SWIGLU) {
-                    if ((lane & 1) == 0) ll_store(out + (row >> 1), silu_f(mine) * mate, tag);   // rows (2i, 2i+1) = (gate_i, up_i)
+                    if ((lane & 1) == 0) out[row >> 1] = silu_f(mine) * mate;   // rows (2i, 2i+1) = (gate_i, up_i)
                 } else {
                     float y = mine;
                     if (bias) y += bias[row];
-                    if (EPI == FE_RESID) y += res;
-                    if (EPI == FE_LOGITS) {
-                        outf[row] = y;
-                        if (y > best || (y == best && row < bi)) { best = y; bi = row; }
-                    } else {
-                        ll_store(out + row, y, tag);
-                    }
+                    if (EPI == FE_RESID) y += resid16 ? __half2float(resid16[row]) : __ldcg(resid32 + row);
+                    out[row] = y;
+                    if (EPI == FE_LOGITS && (y > best || (y == best && row < bi))) { best = y; bi = row; }
                 }
             }
         }
@@ -439,13 +379,11 @@ struct AttnSmem {
     float m[kFusedConsumers][G];
     float l[kFusedConsumers][G];
     float acc[kFusedConsumers][G][128];
+    int last;
 };
 
-// P2: split-KV attention of one (kv head, split) work item per CTA; split 0 of each kv head also merges the splits.
-// cs: [64] cos | [64] sin of the step's rotary angle (shared memory, computed once per kernel).
 template <int G>
-__device__ void fused_attention(const FusedArgs& a, Consumer& c, AttnSmem<G>& s, const float* cs, int layer, const FusedLayer& Ly, int t_new,
-                                const int* spages, unsigned tag_in, unsigned tag_part, unsigned tag_out) {
+__device__ void fused_attention(const FusedArgs& a, Consumer& c, AttnSmem<G>& s, const float* cs, const int* spages, int layer, const FusedLayer& Ly, int t_new) {
     constexpr int HD = 128;
     const int ctx = t_new + 1;
     const int lane = c.lane, warp = c.warp, tid = threadIdx.x;
@@ -453,31 +391,27 @@ __device__ void fused_attention(const FusedArgs& a, Consumer& c, AttnSmem<G>& s,
     const bool has_item = attn_item(a, ctx, kvh, split, hp0, hp1);
     if (!has_item) return;  // this CTA's producer issued nothing for the phase either
     // ---- prologue: q heads (warps 0..G-1) and the new k (warp G): RMSNorm over hd then RoPE; v copy (warp G+1)
-    if (warp <= G + 1) {
-        const bool is_q = warp < G, is_v = warp == G + 1;
-        const uint2* src = a.qkv1 + (size_t)(is_q ? (kvh * G + warp) : is_v ? (a.nh + a.nkv + kvh) : (a.nh + kvh)) * HD + lane * 4;
-        uint4 p0 = ll_load2(src), p1 = ll_load2(src + 2);
-        while (p0.y != tag_in || p0.w != tag_in || p1.y != tag_in || p1.w != tag_in) { p0 = ll_load2(src); p1 = ll_load2(src + 2); }
-        const float4 x = make_float4(__uint_as_float(p0.x), __uint_as_float(p0.z), __uint_as_float(p1.x), __uint_as_float(p1.z));
-        if (is_v) {
-            *reinterpret_cast<float4*>(s.vnew + lane * 4) = x;
-        } else {
-            float ss = x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
-            ss = warp_sum(ss);
-            const float inv = 1.0f / sqrtf(ss / (float)HD + a.eps);
-            const float4 w = *reinterpret_cast<const float4*>((is_q ? Ly.qn : Ly.kn) + lane * 4);
-            const float n[4] = {x.x * inv * w.x, x.y * inv * w.y, x.z * inv * w.z, x.w * inv * w.w};
-            float o[4];
+    if (warp <= G) {
+        const bool is_q = warp < G;
+        const float* src = a.qkv1 + (size_t)(is_q ? (kvh * G + warp) : (a.nh + kvh)) * HD;
+        const float4 x = __ldcg(reinterpret_cast<const float4*>(src + lane * 4));
+        float ss = x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+        ss = warp_sum(ss);
+        const float inv = 1.0f / sqrtf(ss / (float)HD + a.eps);
+        const float4 w = *reinterpret_cast<const float4*>((is_q ? Ly.qn : Ly.kn) + lane * 4);
+        const float n[4] = {x.x * inv * w.x, x.y * inv * w.y, x.z * inv * w.z, x.w * inv * w.w};
+        float o[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float partner = __shfl_xor_sync(0xffffffffu, n[e], 16);
-                const int d = lane * 4 + e, j = d & (HD / 2 - 1);
-                const float rot = (d < HD / 2) ? -partner : partner;
-                o[e] = n[e] * cs[j] + rot * cs[HD / 2 + j];
-            }
-            float* dst = is_q ? s.qs[warp] : s.knew;
-            *reinterpret_cast<float4*>(dst + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);
+        for (int e = 0; e < 4; ++e) {
+            const float partner = __shfl_xor_sync(0xffffffffu, n[e], 16);
+            const int d = lane * 4 + e, j = d & (HD / 2 - 1);
+            const float rot = (d < HD / 2) ? -partner : partner;
+            o[e] = n[e] * cs[j] + rot * cs[HD / 2 + j];
         }
+        float* dst = is_q ? s.qs[warp] : s.knew;
+        *reinterpret_cast<float4*>(dst + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);
+    } else if (warp == G + 1) {
+        *reinterpret_cast<float4*>(s.vnew + lane * 4) = __ldcg(reinterpret_cast<const float4*>(a.qkv1 + (size_t)(a.nh + a.nkv + kvh) * HD + lane * 4));
     }
     consumer_bar_sync();
     const int hp_new = t_new / kHalfPage;
@@ -573,7 +507,6 @@ __device__ void fused_attention(const FusedArgs& a, Consumer& c, AttnSmem<G>& s,
         if (lane == 0) { s.m[warp][g] = M; s.l[warp][g] = L; }
     }
     consumer_bar_sync();
-    // CTA-level merge over the 8 warps -> LL partial (O[hd], M, L) of this (head, split)
     for (int idx = tid; idx < G * HD; idx += kFusedConsumers * 32) {
         const int g = idx / HD, d = idx % HD;
         float M = -INFINITY;
@@ -588,28 +521,33 @@ __device__ void fused_attention(const FusedArgs& a, Consumer& c, AttnSmem<G>& s,
                 O += s.acc[w][g][d] * e;
             }
         }
-        uint2* p = a.partial + ((size_t)(kvh * G + g) * a.nsplit + split) * (HD + 2);
-        ll_store(p + d, O, tag_part);
-        if (d == 0) { ll_store(p + HD, M, tag_part); ll_store(p + HD + 1, L, tag_part); }
+        float* p = a.partial + ((size_t)(kvh * G + g) * a.nsplit + split) * (HD + 2);
+        p[d] = O;
+        if (d == 0) { p[HD] = M; p[HD + 1] = L; }
     }
-    if (split == 0) {  // the combiner of this kv head: wait for every split's partial (LL tags), merge, publish attn
+    __threadfence();
+    consumer_bar_sync();
+    if (tid == 0) s.last = (atomicAdd(&a.kv_counters[kvh], 1) == a.nsplit - 1) ? 1 : 0;
+    consumer_bar_sync();
+    if (s.last) {  // last CTA of this kv head merges the split partials
+        __threadfence();
         for (int idx = tid; idx < G * HD; idx += kFusedConsumers * 32) {
             const int g = idx / HD, d = idx % HD;
-            const uint2* pb = a.partial + (size_t)(kvh * G + g) * a.nsplit * (HD + 2);
+            const float* pb = a.partial + (size_t)(kvh * G + g) * a.nsplit * (HD + 2);
             float M = -INFINITY;
-            for (int sp = 0; sp < a.nsplit; ++sp) M = fmaxf(M, ll_wait(pb + (size_t)sp * (HD + 2) + HD, tag_part));
+            for (int sp = 0; sp < a.nsplit; ++sp) M = fmaxf(M, __ldcg(pb + (size_t)sp * (HD + 2) + HD));
             float L = 0.f, O = 0.f;
             for (int sp = 0; sp < a.nsplit; ++sp) {
-                const float ms = ll_wait(pb + (size_t)sp * (HD + 2) + HD, tag_part);
+                const float ms = __ldcg(pb + (size_t)sp * (HD + 2) + HD);
                 if (ms == -INFINITY) continue;
                 const float e = expf(ms - M);
-                L += ll_wait(pb + (size_t)sp * (HD + 2) + HD + 1, tag_part) * e;
-                O += ll_wait(pb + (size_t)sp * (HD + 2) + d, tag_part) * e;
+                L += __ldcg(pb + (size_t)sp * (HD + 2) + HD + 1) * e;
+                O += __ldcg(pb + (size_t)sp * (HD + 2) + d) * e;
             }
-            ll_store(a.attn1 + (size_t)(kvh * G + g) * HD + d, O / L, tag_out);
+            a.attn1[(size_t)(kvh * G + g) * HD + d] = O / L;
         }
+        if (tid == 0) a.kv_counters[kvh] = 0;
     }
-    consumer_bar_sync();   // the scratch aliases xs: finish before the next phase stages its activations
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
@@ -669,6 +607,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
     // ======================================================= CONSUMERS
     Consumer c;
     c.ring = ring; c.xs = xs; c.red = red; c.warp = warp; c.lane = lane;
+    unsigned seq = 0;
     float best = -INFINITY;
     int bi = 0x7fffffff;
     const __half* emb_row = a.embed + (size_t)token * a.H;
@@ -680,29 +619,31 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
         const FusedLayer Ly = nxtc;
         if (l + 1 < a.L) nxtc = a.layers[l + 1];
         const bool first = (l == 0);
-        // tags of the LL vectors produced in this layer (phase ids 1..6); the x of the previous layer carries id 5
-        const unsigned tg = a.epoch + 8u * (unsigned)l;
-        const unsigned tag_x_prev = tg - 8u + 5u, tag_qkv = tg + 1u, tag_part = tg + 2u, tag_attn = tg + 3u, tag_x_mid = tg + 4u, tag_x = tg + 5u,
-                       tag_h = tg + 6u;
         // P1: qkv = Wqkv . rmsnorm(x)      (layer 0 reads the embedding row directly: Embedding::forward)
-        c.load_x(a.H, a.x, tag_x_prev, first ? emb_row : nullptr, Ly.ln1, a.eps); CSTAMP();
-        c.template gemv<FE_QKV>(a, a.qkv_dim, a.H, Ly.qkv_b, nullptr, nullptr, a.qkv1, nullptr, tag_qkv, best, bi); CSTAMP();
+        c.load_x(a.H, a.x, first ? emb_row : nullptr, Ly.ln1, a.eps); CSTAMP();
+        c.template gemv<FE_QKV>(a, a.qkv_dim, a.H, Ly.qkv_b, nullptr, nullptr, a.qkv1, best, bi); CSTAMP();
+        grid_barrier(&a.sync[0], seq, a.dbg); CSTAMP();
         // P2: attention over the paged cache (+ q/k norm, RoPE, KV append)
-        fused_attention<G>(a, c, *as, cs, l, Ly, t_new, spages, tag_qkv, tag_part, tag_attn); CSTAMP();
+        CSTAMP();
+        fused_attention<G>(a, c, *as, cs, spages, l, Ly, t_new); CSTAMP();
+        grid_barrier(&a.sync[0], seq, a.dbg); CSTAMP();
         // P3: x = resid + Wo . attn
-        c.load_x(a.nh * a.hd, a.attn1, tag_attn, nullptr, nullptr, 0.f); CSTAMP();
-        c.template gemv<FE_RESID>(a, a.H, a.nh * a.hd, Ly.o_b, a.x, first ? emb_row : nullptr, a.x, nullptr, tag_x_mid, best, bi); CSTAMP();
+        c.load_x(a.nh * a.hd, a.attn1, nullptr, nullptr, 0.f); CSTAMP();
+        c.template gemv<FE_RESID>(a, a.H, a.nh * a.hd, Ly.o_b, a.x, first ? emb_row : nullptr, a.x, best, bi); CSTAMP();
+        grid_barrier(&a.sync[0], seq, a.dbg); CSTAMP();
         // P4: h = silu(gate) * up, gate/up rows interleaved, input rmsnorm(x)
-        c.load_x(a.H, a.x, tag_x_mid, nullptr, Ly.ln2, a.eps); CSTAMP();
-        c.template gemv<FE_SWIGLU>(a, 2 * a.I, a.H, nullptr, nullptr, nullptr, a.h1, nullptr, tag_h, best, bi); CSTAMP();
+        c.load_x(a.H, a.x, nullptr, Ly.ln2, a.eps); CSTAMP();
+        c.template gemv<FE_SWIGLU>(a, 2 * a.I, a.H, nullptr, nullptr, nullptr, a.h1, best, bi); CSTAMP();
+        grid_barrier(&a.sync[0], seq, a.dbg); CSTAMP();
         // P5: x = x + Wdown . h
-        c.load_x(a.I, a.h1, tag_h, nullptr, nullptr, 0.f); CSTAMP();
-        c.template gemv<FE_RESID>(a, a.H, a.I, nullptr, a.x, nullptr, a.x, nullptr, tag_x, best, bi); CSTAMP();
+        c.load_x(a.I, a.h1, nullptr, nullptr, 0.f); CSTAMP();
+        c.template gemv<FE_RESID>(a, a.H, a.I, nullptr, a.x, nullptr, a.x, best, bi); CSTAMP();
+        grid_barrier(&a.sync[0], seq, a.dbg); CSTAMP();
     }
     // final: logits = lm_head . rmsnorm(x), per-CTA argmax candidate
-    c.load_x(a.H, a.x, a.epoch + 8u * (unsigned)(a.L - 1) + 5u, nullptr, a.final_norm, a.eps);
+    c.load_x(a.H, a.x, nullptr, a.final_norm, a.eps);
     best = -INFINITY; bi = 0x7fffffff;
-    c.template gemv<FE_LOGITS>(a, a.V, a.H, nullptr, nullptr, nullptr, nullptr, a.logits, 0u, best, bi); CSTAMP();
+    c.template gemv<FE_LOGITS>(a, a.V, a.H, nullptr, nullptr, nullptr, a.logits, best, bi); CSTAMP();
     // CTA-level argmax (first maximal index), then the last CTA to arrive reduces across CTAs
     for (int o = 16; o > 0; o >>= 1) {
         const float ov = __shfl_xor_sync(0xffffffffu, best, o);

@@ -243,8 +243,6 @@ struct TextModel {
     unsigned* d_sync = nullptr;   // [0] grid barrier, [1] final ticket, then kv tickets [nkv]
     unsigned long long* d_ftrace = nullptr;
     size_t sync_words = 0;
-    uint2 *ll_x = nullptr, *ll_qkv = nullptr, *ll_attn = nullptr, *ll_h = nullptr, *ll_partial = nullptr;
-    unsigned fused_epoch = 16;
     int fused_grid = 0, fused_nsplit = 0;
     size_t fused_smem = 0;
 
@@ -380,11 +378,6 @@ struct TextModel {
             }
             d_fused_layers = upload(c, fl);
             d_ftrace = c.alloc<unsigned long long>(2 * 4096);
-            ll_x = c.alloc<uint2>(cfg.H); ll_qkv = c.alloc<uint2>(qkv_dim); ll_attn = c.alloc<uint2>((size_t)nh_l * cfg.hd); ll_h = c.alloc<uint2>(I_l);
-            ll_partial = c.alloc<uint2>((size_t)nh_l * fused_nsplit * (cfg.hd + 2));
-            AHA_CUDA_CHECK(cudaMemset(ll_x, 0, cfg.H * sizeof(uint2))); AHA_CUDA_CHECK(cudaMemset(ll_qkv, 0, qkv_dim * sizeof(uint2)));
-            AHA_CUDA_CHECK(cudaMemset(ll_attn, 0, (size_t)nh_l * cfg.hd * sizeof(uint2))); AHA_CUDA_CHECK(cudaMemset(ll_h, 0, I_l * sizeof(uint2)));
-            AHA_CUDA_CHECK(cudaMemset(ll_partial, 0, (size_t)nh_l * fused_nsplit * (cfg.hd + 2) * sizeof(uint2)));
             AHA_CUDA_CHECK(cudaMemset(d_ftrace, 0, 2 * 4096 * sizeof(unsigned long long)));
             switch (nh_l / nkv_l) {
                 case 1: fused_prepare<1>(); break;
@@ -546,10 +539,7 @@ struct TextModel {
         fa.layers = d_fused_layers; fa.L = cfg.L; fa.H = cfg.H; fa.I = I_l; fa.nh = nh_l; fa.nkv = nkv_l; fa.hd = cfg.hd; fa.V = cfg.V; fa.qkv_dim = qkv_dim;
         fa.eps = cfg.eps; fa.scaling = (float)(1.0 / std::sqrt((double)cfg.hd));
         fa.embed = embed; fa.lm_head = lm_head; fa.final_norm = norm; fa.inv_freq = inv_freq; fa.st = d_state;
-        fa.x = ll_x; fa.qkv1 = ll_qkv; fa.attn1 = ll_attn; fa.h1 = ll_h; fa.logits = logits; fa.partial = ll_partial;
-        fa.epoch = fused_epoch;
-        fused_epoch += 8u * (unsigned)cfg.L + 8u;           // tags are unique per (launch, layer, phase)
-        if (fused_epoch > 0xf0000000u) fused_epoch = 16;   // wrap far away from any live tag
+        fa.x = x1; fa.qkv1 = qkv1; fa.attn1 = attn1; fa.h1 = h1; fa.logits = logits; fa.partial = partial;
         fa.kv_counters = counters; fa.sync = d_sync; fa.flags = nullptr; fa.pmax = pmax; fa.pidx = pidx; fa.argmax_out = d_argmax;
         fa.history = d_history; fa.hist_cap = hist_cap; fa.kv_pool = kv_pool; fa.layer_stride = layer_stride; fa.page_stride = page_stride;
         fa.page_table = d_page_table; fa.nsplit = fused_nsplit;

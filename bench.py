@@ -252,14 +252,11 @@ def main():
         kernels[name] = {"avg_us": kms * 1e3, "bytes": kb, "gbps": kb / (kms * 1e-3) / 1e9}
     fused = st["kernels_per_decode_step"] == 1
 
-    ms_t = torch.tensor([best_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
-    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
-    if dist is not None:
-        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    step_ms = ms_t.item() / K
-    value = world * K / (ms_t.item() * 1e-3)
-    e2e_val = world * K / e2e_t.item()
+    from aha_b200 import dist_util
+    dev = f"cuda:{local_rank}"
+    value, max_ms = dist_util.aggregate_throughput(K, best_ms, world, dist, dev)       # units of all ranks / slowest rank
+    e2e_val, _ = dist_util.aggregate_throughput(K, e2e_s * 1e3, world, dist, dev)
+    step_ms = max_ms / K
     avg_ctx = S + W + (K - 1) / 2.0 + 1
     step_bytes = st["decode_bytes_per_step_fixed"] + st["kv_bytes_per_token"] * (avg_ctx + 1)
     kv_read = st["kv_bytes_per_token"] * avg_ctx
