@@ -69,6 +69,7 @@ struct FusedArgs {
     float* kv_pool; size_t layer_stride, page_stride;
     const int* page_table;
     int nsplit;
+    int stages;        // ring slots in use (<= kFusedStages)
     int dbg;           // timing experiments only: bit0 = skip grid barriers, bit1 = skip the GEMV math, bit2 = timestamps
     unsigned long long* trace;  // [2][4096] globaltimer stamps of CTA 0 (consumer thread 0 / producer), dbg bit2
 };
@@ -165,9 +166,10 @@ struct Ring {
 struct Producer {
     Ring ring;
     unsigned it = 0;
+    unsigned ns = kFusedStages;
     __device__ __forceinline__ void acquire(int& slot) {
-        slot = it % kFusedStages;
-        mbar_wait(&ring.empty[slot], ((it / kFusedStages) & 1u) ^ 1u);
+        slot = it % ns;
+        mbar_wait(&ring.empty[slot], ((it / ns) & 1u) ^ 1u);
     }
     __device__ void rows(const __half* W, int N, int K, int unit) {
         int r0, r1;
@@ -218,15 +220,16 @@ struct Consumer {
     float* red;         // [32] scratch
     int warp, lane;
 
-    __device__ __forceinline__ bool owns(unsigned i) const { return (int)((i % kFusedStages) % kFusedConsumers) == warp; }
+    unsigned ns = kFusedStages;
+    __device__ __forceinline__ bool owns(unsigned i) const { return (int)((i % ns) % kFusedConsumers) == warp; }
     __device__ __forceinline__ const uint8_t* wait_full(unsigned i) {
-        const int slot = i % kFusedStages;
-        mbar_wait(&ring.full[slot], (i / kFusedStages) & 1u);
+        const int slot = i % ns;
+        mbar_wait(&ring.full[slot], (i / ns) & 1u);
         return ring.buf + (size_t)slot * kFusedStageBytes;
     }
     __device__ __forceinline__ void release(unsigned i) {
         __syncwarp();
-        if (lane == 0) mbar_arrive(&ring.empty[i % kFusedStages]);
+        if (lane == 0) mbar_arrive(&ring.empty[i % ns]);
     }
 
     // Stage the activation vector of a GEMV in shared memory (all consumer threads), optional RMSNorm.
@@ -587,6 +590,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
         if (lane == 0) {
             Producer p;
             p.ring = ring;
+            p.ns = (unsigned)a.stages;
             p.pages = spages;
             int pe = 0;
             AHA_STAMP(a, 1, pe);
@@ -606,7 +610,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
     }
     // ======================================================= CONSUMERS
     Consumer c;
-    c.ring = ring; c.xs = xs; c.red = red; c.warp = warp; c.lane = lane;
+    c.ring = ring; c.ns = (unsigned)a.stages; c.xs = xs; c.red = red; c.warp = warp; c.lane = lane;
     unsigned seq = 0;
     float best = -INFINITY;
     int bi = 0x7fffffff;

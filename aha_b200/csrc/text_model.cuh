@@ -243,6 +243,7 @@ struct TextModel {
     unsigned* d_sync = nullptr;   // [0] grid barrier, [1] final ticket, then kv tickets [nkv]
     unsigned long long* d_ftrace = nullptr;
     size_t sync_words = 0;
+    int fused_stages = 8;   // measured best on B200 (profiles/README.md): deeper prefetch queues urgent stages behind other CTAs' prefetches
     int fused_grid = 0, fused_nsplit = 0;
     size_t fused_smem = 0;
 
@@ -545,6 +546,7 @@ struct TextModel {
         fa.page_table = d_page_table; fa.nsplit = fused_nsplit;
         { const char* e = getenv("AHA_FUSED_DBG"); fa.dbg = e ? atoi(e) : 0; }
         fa.trace = d_ftrace;
+        { const char* e = getenv("AHA_FUSED_STAGES"); fa.stages = e ? std::max(2, std::min(kFusedStages, atoi(e))) : fused_stages; }
         AHA_REQUIRE(fused_grid <= n_pcand || true, "");
         AHA_CUDA_CHECK(cudaMemsetAsync(d_sync, 0, sync_words * sizeof(unsigned), c.stream));
         switch (nh_l / nkv_l) {

@@ -31,3 +31,10 @@ if int(os.environ.get("AHA_FUSED_DBG", "0")) & 4:
     dp = np.diff(p)[: 5 * 28].reshape(28, 5)
     for n, v in zip(["qkv", "attn", "o", "gate_up", "down"], dp[2:].mean(0)):
         print(f"  producer {n:8s} {v/1e3:7.2f} us")
+    # one layer on a common time axis (us since kernel start)
+    Lx = 10
+    cb = c[1 + 15 * Lx: 1 + 15 * (Lx + 1)] / 1e3
+    pb = p[1 + 5 * Lx: 1 + 5 * (Lx + 1)] / 1e3
+    t0 = c[15 * Lx] / 1e3
+    print(f"  layer {Lx} starts at {t0:.1f} us; consumer events (rel):", " ".join(f"{n.replace(' ', '')}@{v - t0:.1f}" for n, v in zip(names, cb)))
+    print(f"  producer finished issuing (rel): ", " ".join(f"{n}@{v - t0:.1f}" for n, v in zip(["qkv", "attn", "o", "gate_up", "down"], pb)))
