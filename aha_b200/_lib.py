@@ -68,6 +68,8 @@ SYMBOLS = {
     "aha_b200_set_trace": (C.c_int, [_P, C.c_int]),
     "aha_b200_debug_read": (C.c_int, [_P, C.c_char_p, C.c_int, _F32P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "aha_b200_decode_steps": (C.c_int, [_P, C.c_uint32, C.c_size_t, C.c_size_t, _U32P, C.POINTER(C.c_double)]),
+    "aha_b200_debug_gemm": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _F32P, C.POINTER(C.c_uint16), _F32P, _F32P, _F32P,
+                                      C.c_int, C.POINTER(C.c_double)]),
     "aha_b200_bench_kernel": (C.c_int, [_P, C.c_char_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
 }
 

@@ -308,6 +308,7 @@ int aha_b200_create(const char* kind, const char* config_json, const aha_tensor_
         m = new aha_model();
         m->ctx.device = o.device;
         m->ctx.num_sms = prop.multiProcessorCount;
+        m->ctx.gemm_impl = o.gemm_impl;
         AHA_CUDA_CHECK(cudaSetDevice(o.device));
         AHA_CUDA_CHECK(cudaStreamCreateWithFlags(&m->ctx.stream, cudaStreamNonBlocking));
         AHA_CUDA_CHECK(cudaEventCreate(&m->ev0));
@@ -551,6 +552,42 @@ int aha_b200_image_patchify(aha_model* m, const uint8_t* img_hwc, size_t h, size
         } catch (...) { cudaFree(d_img); throw; }
         cudaFree(d_img);
         grid_thw_out[0] = 1; grid_thw_out[1] = (uint32_t)gh; grid_thw_out[2] = (uint32_t)gw;
+    });
+}
+
+int aha_b200_debug_gemm(aha_model* m, int impl, int epi, int act, int M, int N, int K, const float* x, const uint16_t* w, const float* bias,
+                        const float* resid, float* out, int iters, double* device_ms) {
+    return guarded(m, [&] {
+        AHA_REQUIRE(x && w && out && M > 0 && N > 0 && K > 0, "x, w, out and positive sizes are required");
+        Ctx& c = m->ctx;
+        float *dx = nullptr, *db = nullptr, *dr = nullptr, *dy = nullptr;
+        __half* dw = nullptr;
+        const int Nout = epi == EPI_SWIGLU ? N / 2 : N;
+        auto cleanup = [&] { cudaFree(dx); cudaFree(db); cudaFree(dr); cudaFree(dy); cudaFree(dw); };
+        try {
+            AHA_CUDA_CHECK(cudaMalloc(&dx, (size_t)M * K * 4)); AHA_CUDA_CHECK(cudaMalloc(&dw, (size_t)N * K * 2)); AHA_CUDA_CHECK(cudaMalloc(&dy, (size_t)M * Nout * 4));
+            AHA_CUDA_CHECK(cudaMemcpy(dx, x, (size_t)M * K * 4, cudaMemcpyHostToDevice));
+            AHA_CUDA_CHECK(cudaMemcpy(dw, w, (size_t)N * K * 2, cudaMemcpyHostToDevice));
+            if (bias) { AHA_CUDA_CHECK(cudaMalloc(&db, (size_t)N * 4)); AHA_CUDA_CHECK(cudaMemcpy(db, bias, (size_t)N * 4, cudaMemcpyHostToDevice)); }
+            if (epi == EPI_RESID) {
+                AHA_REQUIRE(resid, "resid is required for the residual epilogue");
+                AHA_CUDA_CHECK(cudaMalloc(&dr, (size_t)M * N * 4)); AHA_CUDA_CHECK(cudaMemcpy(dr, resid, (size_t)M * N * 4, cudaMemcpyHostToDevice));
+            }
+            LinearW W; W.w = dw; W.b = db; W.N = N; W.K = K;
+            const int saved = c.gemm_impl;
+            c.gemm_impl = impl;
+            try {
+                linear_gemm(c, epi, dx, K, W, dr, N, dy, Nout, M, act);   // warm-up + correctness run
+                AHA_CUDA_CHECK(cudaEventRecord(m->ev0, c.stream));
+                for (int i = 0; i < std::max(iters, 0); ++i) linear_gemm(c, epi, dx, K, W, dr, N, dy, Nout, M, act);
+                AHA_CUDA_CHECK(cudaEventRecord(m->ev1, c.stream));
+                AHA_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+            } catch (...) { c.gemm_impl = saved; throw; }
+            c.gemm_impl = saved;
+            if (device_ms) { float ms = 0.f; AHA_CUDA_CHECK(cudaEventElapsedTime(&ms, m->ev0, m->ev1)); *device_ms = ms; }
+            AHA_CUDA_CHECK(cudaMemcpy(out, dy, (size_t)M * Nout * 4, cudaMemcpyDeviceToHost));
+        } catch (...) { cleanup(); throw; }
+        cleanup();
     });
 }
 

@@ -274,11 +274,8 @@ struct AudioModel {
         return frames;
     }
 
-    void gemm(int epi, const float* A, int lda, const LinearW& W, const float* resid, int ldr, float* C, int ldc, int M, int act = ACT_NONE) {
-        GemmArgs g;
-        g.A = A; g.lda = lda; g.W = W.w; g.bias = W.b; g.resid = resid; g.ldr = ldr; g.C = C; g.ldc = ldc; g.M = M; g.N = W.N; g.K = W.K; g.act = act;
-        gemm_simt(ctx->stream, epi, g);
-        ctx->cnt.kernels++;
+    void gemm(int epi, const float* A, int lda, LinearW& W, const float* resid, int ldr, float* C, int ldc, int M, int act = ACT_NONE) {
+        linear_gemm(*ctx, epi, A, lda, W, resid, ldr, C, ldc, M, act);
     }
 
     // mel: device (n_mels, T).  Returns token count; result in audio_embeds.

@@ -14,6 +14,7 @@
 #include "decode_fused.cuh"
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 #include "gemv.cuh"
 #include "json.hpp"
 #include "kernels_common.cuh"
@@ -33,6 +34,17 @@ struct Ctx {  // per-handle launch context
     bool capturing = false;
     std::vector<void*> allocs;
     size_t alloc_bytes = 0;
+    int gemm_impl = 0;            // 0 = auto (tcgen05 where the shape tiles), 1 = SIMT fp32, 2 = tcgen05 required
+    __half* split_ws = nullptr;   // [2][rows*K] hi | lo halves of the activation operand
+    size_t split_cap = 0;         // halfs per half-buffer
+    __half* split_buf(size_t halfs) {
+        if (halfs > split_cap) {
+            if (split_ws) { AHA_CUDA_CHECK(cudaStreamSynchronize(stream)); cudaFree(split_ws); }
+            AHA_CUDA_CHECK(cudaMalloc(&split_ws, 2 * halfs * sizeof(__half)));
+            split_cap = halfs;
+        }
+        return split_ws;
+    }
 
     template <typename T>
     T* alloc(size_t n) {
@@ -45,6 +57,7 @@ struct Ctx {  // per-handle launch context
     void free_all() {
         for (void* p : allocs) cudaFree(p);
         allocs.clear();
+        if (split_ws) { cudaFree(split_ws); split_ws = nullptr; split_cap = 0; }
     }
 };
 
@@ -126,7 +139,34 @@ struct LinearW {
     __half* w = nullptr;  // [N, K]
     float* b = nullptr;   // [N] or nullptr
     int N = 0, K = 0;
+    CUtensorMap tmap;     // TMA descriptor of w (128 x 64 boxes, SWIZZLE_128B) when has_tmap
+    bool has_tmap = false;
 };
+
+// y = x W^T with the fused epilogues of gemm_simt.cuh.  Dispatch: tcgen05 split-fp16 kernel (gemm_tc.cuh) when the
+// shape tiles (K % 64 == 0, N % 32 == 0) and there are enough rows to fill a tile, else the exact SIMT kernel.
+inline void linear_gemm(Ctx& c, int epi, const float* A, int lda, LinearW& W, const float* resid, int ldr, float* C, int ldc, int M, int act = ACT_NONE) {
+    if (M == 0) return;
+    const bool tc_ok = gemm_tc_supported(M, W.N, W.K) && lda % 4 == 0;
+    AHA_REQUIRE(c.gemm_impl != 2 || tc_ok, "gemm_impl=2 (tcgen05) requested but the shape does not tile (K % 64, N % 32)");
+    if (c.gemm_impl == 1 || !tc_ok || (c.gemm_impl == 0 && M < 32)) {
+        GemmArgs g;
+        g.A = A; g.lda = lda; g.W = W.w; g.bias = W.b; g.resid = resid; g.ldr = ldr; g.C = C; g.ldc = ldc; g.M = M; g.N = W.N; g.K = W.K; g.act = act;
+        gemm_simt(c.stream, epi, g);
+        c.cnt.kernels++;
+        return;
+    }
+    if (!W.has_tmap) { W.tmap = make_tmap_f16(W.w, (uint64_t)W.N, (uint64_t)W.K); W.has_tmap = true; }
+    const size_t halfs = (size_t)M * W.K;
+    __half* hi = c.split_buf(halfs);
+    __half* lo = hi + c.split_cap;
+    const size_t n4 = halfs / 4;
+    split_f32_to_f16x2_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, c.stream>>>(A, lda, hi, lo, M, W.K);
+    GemmTcArgs g;
+    g.bias = W.b; g.resid = resid; g.ldr = ldr; g.C = C; g.ldc = ldc; g.M = M; g.N = W.N; g.K = W.K; g.act = act;
+    gemm_tc_launch(c.stream, epi, hi, lo, W.tmap, g);
+    c.cnt.kernels += 2;
+}
 
 // Upload `names` stacked along the output dimension ([sum N_i, K]); optional row interleave of two
 // equally-sized matrices (gate/up -> rows g0,u0,g1,u1,...).  Row/col slices implement tensor parallelism.
@@ -429,11 +469,8 @@ struct TextModel {
     }
 
     // ---- GEMM dispatch (SIMT exact path; the tcgen05 path plugs in here)
-    void gemm(int epi, const float* A, int lda, const LinearW& W, const float* resid, int ldr, float* C, int ldc, int M, int act = ACT_NONE) {
-        GemmArgs g;
-        g.A = A; g.lda = lda; g.W = W.w; g.bias = W.b; g.resid = resid; g.ldr = ldr; g.C = C; g.ldc = ldc; g.M = M; g.N = W.N; g.K = W.K; g.act = act;
-        gemm_simt(ctx->stream, epi, g);
-        ctx->cnt.kernels++;
+    void gemm(int epi, const float* A, int lda, LinearW& W, const float* resid, int ldr, float* C, int ldc, int M, int act = ACT_NONE) {
+        linear_gemm(*ctx, epi, A, lda, W, resid, ldr, C, ldc, M, act);
     }
 
     // ---- prefill: ids already on device in d_ids (or embeddings already in x when embeds_ready), pos3 in d_pos3.

@@ -165,13 +165,10 @@ struct VisionModel {
         if (on && !trace_buf) trace_buf = ctx->alloc<float>((size_t)(cfg.depth + 1) * max_patches * cfg.H);
         trace = on;
     }
-    void gemm(int epi, const float* A, int lda, const LinearW& W, const float* resid, int ldr, float* C, int ldc, int M, int act = ACT_NONE) {
-        GemmArgs g;
-        g.A = A; g.lda = lda; g.W = W.w; g.bias = W.b; g.resid = resid; g.ldr = ldr; g.C = C; g.ldc = ldc; g.M = M; g.N = W.N; g.K = W.K; g.act = act;
-        gemm_simt(ctx->stream, epi, g);
-        ctx->cnt.kernels++;
+    void gemm(int epi, const float* A, int lda, LinearW& W, const float* resid, int ldr, float* C, int ldc, int M, int act = ACT_NONE) {
+        linear_gemm(*ctx, epi, A, lda, W, resid, ldr, C, ldc, M, act);
     }
-    void run_merger(const Merger& m, const float* in, int N, float* out) {
+    void run_merger(Merger& m, const float* in, int N, float* out) {
         cudaStream_t st = ctx->stream;
         const int m2 = cfg.merge * cfg.merge, Hm = cfg.H * m2;
         if (m.post) layernorm_kernel<<<N / m2, 256, 0, st>>>(in, m.nw, m.nb, 1e-6f, xn, Hm);

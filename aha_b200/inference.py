@@ -167,6 +167,21 @@ class B200Model:
         self._check(self._lib.aha_b200_bench_kernel(self._h, which.encode(), int(iters), C.byref(ms), C.byref(nb)))
         return ms.value, int(nb.value)
 
+    def debug_gemm(self, x, w16, bias=None, resid=None, impl=2, epi=0, act=0, iters=0):
+        """y = epilogue(x @ w16.T + bias) through the library's GEMM (impl 1 = SIMT, 2 = tcgen05). -> (y, ms)"""
+        x = np.ascontiguousarray(x, np.float32)
+        w16 = np.ascontiguousarray(w16, np.float16)
+        M, K = x.shape
+        N = w16.shape[0]
+        out = np.empty((M, N // 2 if epi == 3 else N), np.float32)
+        fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float)) if a is not None else None
+        b = np.ascontiguousarray(bias, np.float32) if bias is not None else None
+        r = np.ascontiguousarray(resid, np.float32) if resid is not None else None
+        ms = C.c_double(0.0)
+        self._check(self._lib.aha_b200_debug_gemm(self._h, impl, epi, act, M, N, K, fp(x), w16.ctypes.data_as(C.POINTER(C.c_uint16)),
+                                                  fp(b), fp(r), fp(out), iters, C.byref(ms)))
+        return out, ms.value
+
     def stream_ptr(self):
         return int(self._lib.aha_b200_stream(self._h) or 0)
 

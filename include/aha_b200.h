@@ -166,6 +166,12 @@ int aha_b200_decode_steps(aha_model* m, uint32_t first_token, size_t seqlen_offs
  * layers' weights so that consecutive launches never hit L2.  which = "gemv_gate_up" | "gemv_qkv" |
  * "gemv_down" | "gemv_o" | "gemv_lm_head" | "decode_attn".  bytes_per_launch = algorithmic bytes. */
 int aha_b200_bench_kernel(aha_model* m, const char* which, int iters, double* avg_ms, uint64_t* bytes_per_launch);
+/* Run ONE Linear layer y = epilogue(x W^T + b) through the library's GEMM dispatch on host data (unit tests of the
+ * tcgen05 and SIMT kernels against numpy): impl 1 = SIMT fp32, 2 = tcgen05 split-fp16; epi 0 = store, 1 = residual
+ * add (resid [M,N]), 2 = activation (act: 1 silu, 2 gelu-erf, 3 gelu-tanh), 3 = SwiGLU on interleaved columns
+ * (out [M,N/2]).  x [M,K] f32, w [N,K] f16 bits, bias [N] f32 or NULL.  device_ms: CUDA-event time of `iters` runs. */
+int aha_b200_debug_gemm(aha_model* m, int impl, int epi, int act, int M, int N, int K, const float* x, const uint16_t* w,
+                        const float* bias, const float* resid, float* out, int iters, double* device_ms);
 
 #ifdef __cplusplus
 }
