@@ -28,7 +28,7 @@ def build_lib(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + SOURCES
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + SOURCES + ["-ldl"]
     if verbose:
         print(" ".join(cmd), file=sys.stderr)
     r = subprocess.run(cmd, capture_output=True, text=True)

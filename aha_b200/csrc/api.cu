@@ -351,6 +351,7 @@ int aha_b200_create(const char* kind, const char* config_json, const aha_tensor_
             throw std::runtime_error("unknown model kind '" + k + "' (expected qwen3 | qwen3vl | qwen3_asr)");
         }
         m->text.alloc_runtime(max_ctx, max_prefill, o.use_graph != 0, o.decode_impl);
+        m->text.init_tp(o.tp_comm);
         m->max_scatter = max_prefill;
         m->d_scatter_idx = m->ctx.alloc<int>(max_prefill);
         for (size_t i = 0; i < n_eos; ++i) m->stop_ids.push_back(eos_ids[i]);
@@ -589,6 +590,21 @@ int aha_b200_debug_gemm(aha_model* m, int impl, int epi, int act, int M, int N, 
         } catch (...) { cleanup(); throw; }
         cleanup();
     });
+}
+
+int aha_b200_nccl_unique_id(uint8_t out[128]) {
+    try {
+        AHA_REQUIRE(out != nullptr, "out is required");
+        NcclApi& n = NcclApi::get();
+        NcclApi::unique_id id;
+        n.check(n.GetUniqueId(&id), "ncclGetUniqueId");
+        std::memcpy(out, &id, 128);
+        return 0;
+    } catch (const std::exception& e) {
+        std::lock_guard<std::mutex> lk(g_err_mu);
+        g_create_error = e.what();
+        return 1;
+    }
 }
 
 void aha_b200_destroy(aha_model* m) {

@@ -18,6 +18,7 @@
 #include "gemv.cuh"
 #include "json.hpp"
 #include "kernels_common.cuh"
+#include "nccl_shim.h"
 
 namespace aha {
 
@@ -244,6 +245,8 @@ struct TextModel {
     TextCfg cfg;
     Ctx* ctx = nullptr;
     int tp_rank = 0, tp_world = 1;
+    NcclApi::comm_t comm = nullptr;   // tensor-parallel communicator (tp_world > 1)
+    float *tp_tmp = nullptr, *tp_tmp1 = nullptr;  // partial o_proj / down_proj outputs awaiting the all-reduce
     int nh_l = 0, nkv_l = 0, I_l = 0, qkv_dim = 0;  // per-rank (tensor-parallel) sizes
     __half* embed = nullptr;
     __half* lm_head = nullptr;
@@ -402,6 +405,7 @@ struct TextModel {
         x = c.alloc<float>(S * cfg.H); xn = c.alloc<float>(S * cfg.H);
         qkv = c.alloc<float>(S * qkv_dim); attn = c.alloc<float>(S * nh_l * cfg.hd); hbuf = c.alloc<float>(S * I_l);
         d_ids = c.alloc<uint32_t>(S); d_pos3 = c.alloc<int>(3 * S);
+        if (tp_world > 1) { tp_tmp = c.alloc<float>(S * cfg.H); tp_tmp1 = c.alloc<float>(cfg.H); }
         x1 = c.alloc<float>(cfg.H); qkv1 = c.alloc<float>(qkv_dim); attn1 = c.alloc<float>((size_t)nh_l * cfg.hd); h1 = c.alloc<float>(I_l);
         logits = c.alloc<float>(cfg.V);
         fused_grid = c.num_sms;
@@ -473,6 +477,22 @@ struct TextModel {
         linear_gemm(*ctx, epi, A, lda, W, resid, ldr, C, ldc, M, act);
     }
 
+    void init_tp(const void* unique_id) {
+        if (tp_world <= 1) return;
+        AHA_REQUIRE(unique_id != nullptr, "tp_world > 1 needs aha_options.tp_comm (128-byte ncclUniqueId)");
+        NcclApi& n = NcclApi::get();
+        NcclApi::unique_id id;
+        std::memcpy(&id, unique_id, sizeof(id));
+        n.check(n.CommInitRank(&comm, tp_world, id, tp_rank), "ncclCommInitRank");
+    }
+    // all-reduce(sum) of a partial projection over the tensor-parallel ranks, then x += sum (the residual add)
+    void tp_reduce_add(float* partial, float* xdst, size_t n) {
+        NcclApi& api = NcclApi::get();
+        api.check(api.AllReduce(partial, partial, n, NcclApi::kFloat32, NcclApi::kSum, comm, ctx->stream), "ncclAllReduce");
+        add_inplace_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(xdst, partial, n);
+        ctx->cnt.kernels++;
+    }
+
     // ---- prefill: ids already on device in d_ids (or embeddings already in x when embeds_ready), pos3 in d_pos3.
     // visual_idx/deepstack: Qwen3-VL deepstack injection (qwen3vl/model.rs:815-824).
     void prefill(int S, int pos0, bool embeds_ready, const int* d_visual_idx, int n_visual, const std::vector<const float*>& deepstack) {
@@ -480,7 +500,6 @@ struct TextModel {
         cudaStream_t st = c.stream;
         const int H = cfg.H, hd = cfg.hd;
         AHA_REQUIRE(S <= max_prefill, "prompt of " + std::to_string(S) + " tokens exceeds max_prefill " + std::to_string(max_prefill));
-        AHA_REQUIRE(tp_world == 1, "tensor-parallel prefill is not implemented in this build");
         ensure_tokens(pos0 + S);
         if (!embeds_ready) { embed_gather_kernel<<<S, 256, 0, st>>>(d_ids, embed, x, S, H, cfg.V); c.cnt.kernels++; }
         RopeArgs rp{inv_freq, mrope_sel, d_pos3, S};
@@ -497,10 +516,12 @@ struct TextModel {
             fa.out = attn; fa.o_tok_stride = (size_t)nh_l * hd; fa.o_head_stride = hd;
             fa.Sq = S; fa.Skv = pos0 + S; fa.q0 = 0; fa.kv0 = 0; fa.groups = nh_l / nkv_l; fa.scaling = scaling;
             flash_attn<128>(st, fa, nh_l, true); c.cnt.kernels++;
-            gemm(EPI_RESID, attn, nh_l * hd, T.o, x, H, x, H, S);
+            if (tp_world > 1) { gemm(EPI_STORE, attn, nh_l * hd, T.o, nullptr, 0, tp_tmp, H, S); tp_reduce_add(tp_tmp, x, (size_t)S * H); }
+            else gemm(EPI_RESID, attn, nh_l * hd, T.o, x, H, x, H, S);
             rmsnorm_kernel<<<S, 256, 0, st>>>(x, T.ln2, cfg.eps, xn, H); c.cnt.kernels++;
             gemm(EPI_SWIGLU, xn, H, T.gu, nullptr, 0, hbuf, I_l, S);
-            gemm(EPI_RESID, hbuf, I_l, T.down, x, H, x, H, S);
+            if (tp_world > 1) { gemm(EPI_STORE, hbuf, I_l, T.down, nullptr, 0, tp_tmp, H, S); tp_reduce_add(tp_tmp, x, (size_t)S * H); }
+            else gemm(EPI_RESID, hbuf, I_l, T.down, x, H, x, H, S);
             if (l < (int)deepstack.size() && n_visual > 0) {
                 scatter_rows_kernel<<<n_visual, 256, 0, st>>>(d_visual_idx, deepstack[l], x, H, 1); c.cnt.kernels++;
             }
@@ -532,7 +553,6 @@ struct TextModel {
         Ctx& c = *ctx;
         cudaStream_t st = c.stream;
         const int H = cfg.H, hd = cfg.hd;
-        AHA_REQUIRE(tp_world == 1, "tensor-parallel decode is not implemented in this build");
         embed_gather_kernel<<<1, 256, 0, st>>>(&d_state->token, embed, x1, 1, H, cfg.V); c.cnt.kernels++;
         const float scaling = (float)(1.0 / std::sqrt((double)hd));
         for (int l = 0; l < cfg.L; ++l) {
@@ -554,13 +574,15 @@ struct TextModel {
             c.cnt.kernels++;
             GemvArgs o{};
             o.W = T.o.w; o.bias = T.o.b; o.x = attn1; o.resid = x1; o.out = x1; o.N = T.o.N; o.K = T.o.K;
-            gemv(st, PRO_NONE, GEPI_RESID, o); c.cnt.kernels++;
+            if (tp_world > 1) { o.resid = nullptr; o.out = tp_tmp1; gemv(st, PRO_NONE, GEPI_STORE, o); c.cnt.kernels++; tp_reduce_add(tp_tmp1, x1, H); }
+            else { gemv(st, PRO_NONE, GEPI_RESID, o); c.cnt.kernels++; }
             GemvArgs g{};
             g.W = T.gu.w; g.x = x1; g.norm_w = T.ln2; g.eps = cfg.eps; g.out = h1; g.N = T.gu.N; g.K = T.gu.K;
             gemv(st, PRO_RMSNORM, GEPI_SWIGLU, g); c.cnt.kernels++;
             GemvArgs dn{};
             dn.W = T.down.w; dn.x = h1; dn.resid = x1; dn.out = x1; dn.N = T.down.N; dn.K = T.down.K;
-            gemv(st, PRO_NONE, GEPI_RESID, dn); c.cnt.kernels++;
+            if (tp_world > 1) { dn.resid = nullptr; dn.out = tp_tmp1; gemv(st, PRO_NONE, GEPI_STORE, dn); c.cnt.kernels++; tp_reduce_add(tp_tmp1, x1, H); }
+            else { gemv(st, PRO_NONE, GEPI_RESID, dn); c.cnt.kernels++; }
         }
         head(x1);
         finish_argmax(1);
@@ -620,6 +642,7 @@ struct TextModel {
     }
     void destroy() {
         if (step_graph) { cudaGraphExecDestroy(step_graph); step_graph = nullptr; }
+        if (comm) { NcclApi::get().CommDestroy(comm); comm = nullptr; }
     }
 };
 

@@ -24,9 +24,18 @@ class MultiModalData:
         self.data_vec = list(data_vec)
 
 
+def nccl_unique_id():
+    """128-byte ncclUniqueId created by the calling rank (rank 0); broadcast it to the other ranks."""
+    lib = L.load()
+    buf = (C.c_uint8 * 128)()
+    if lib.aha_b200_nccl_unique_id(buf) != 0:
+        raise B200Error(lib.aha_b200_last_error(None).decode())
+    return bytes(buf)
+
+
 class B200Model:
     def __init__(self, kind, config, weights, eos_ids=(), device=0, max_ctx=8192, max_prefill=0, max_patches=0,
-                 max_frames=0, use_graph=True, decode_impl=0, gemm_impl=0, tp_rank=0, tp_world=1):
+                 max_frames=0, use_graph=True, decode_impl=0, gemm_impl=0, tp_rank=0, tp_world=1, tp_unique_id=None):
         self._lib = L.load()
         self.kind = kind
         self.config = config
@@ -38,6 +47,11 @@ class B200Model:
         opts = L.Options(device=device, tp_rank=tp_rank, tp_world=tp_world, max_ctx=max_ctx, max_prefill=max_prefill,
                          max_patches=max_patches, max_frames=max_frames, use_graph=1 if use_graph else 0,
                          decode_impl=decode_impl, gemm_impl=gemm_impl)
+        if tp_world > 1:
+            if tp_unique_id is None or len(tp_unique_id) != 128:
+                raise ValueError("tp_world > 1 needs the 128-byte NCCL unique id (nccl_unique_id() on rank 0, then broadcast)")
+            self._tp_id = (C.c_uint8 * 128)(*bytes(tp_unique_id))
+            opts.tp_comm = C.cast(self._tp_id, C.c_void_p)
         h = C.c_void_p()
         rc = self._lib.aha_b200_create(kind.encode(), cfg_json, descs, len(names),
                                        eos.ctypes.data_as(C.POINTER(C.c_uint32)), len(eos), C.byref(opts), C.byref(h))

@@ -126,6 +126,8 @@ def main():
     ap.add_argument("--preset", default=os.environ.get("AHA_BENCH_PRESET", "vl2"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--decode-impl", type=int, default=int(os.environ.get("AHA_DECODE_IMPL", "0")))
+    ap.add_argument("--parallelism", default=os.environ.get("AHA_PARALLELISM", "replicas"), choices=["replicas", "tp"],
+                    help="N > 1: independent replicas (one request per GPU, default) or tensor parallelism of ONE request")
     args = ap.parse_args()
     K, W = args.steps, max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -144,7 +146,9 @@ def main():
                           f"({n_img_tok} image tokens) + {wl['n_text']} text ids, greedy decode at ctx {S}+",
               "prompt_tokens": S, "kv_dtype": "f32", "weight_dtype": "f16", "accumulate": "f32", "batch": 1,
               "l2_policy": "inputs larger than L2 (3.4 GB of weights streamed per step, 126 MB L2)",
-              "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one request per GPU)"}
+              "parallelism": "single GPU" if world == 1 else (
+                  f"tp{world}: one request, heads/MLP rows sharded, NCCL all-reduce after o_proj and down_proj" if args.parallelism == "tp"
+                  else f"{world} independent replicas (one request per GPU, no data-path collective)")}
 
     # --------------------------------------------------------------------------------- reference arm (CPU)
     if args.impl == "reference":
@@ -191,8 +195,15 @@ def main():
     wts = synth.make_weights(wl["kind"], cfg, 0)
     log(f"[rank {rank}] weights generated in {time.time() - t0:.1f}s")
     t0 = time.time()
+    tp = world > 1 and args.parallelism == "tp"
+    tp_kw = {}
+    if tp:
+        from aha_b200 import nccl_unique_id
+        uid = [nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        tp_kw = dict(tp_rank=rank, tp_world=world, tp_unique_id=uid[0])
     m = B200Model(wl["kind"], cfg, wts, eos_ids=[], device=local_rank, max_ctx=wl["max_ctx"], max_prefill=wl["max_ctx"],
-                  max_patches=wl["max_patches"], decode_impl=args.decode_impl)
+                  max_patches=wl["max_patches"], decode_impl=args.decode_impl, **tp_kw)
     log(f"[rank {rank}] model created in {time.time() - t0:.1f}s")
     img = synth.synth_image(h, w_, 1)
     pv, grid = m.image_patchify(img)
@@ -254,8 +265,9 @@ def main():
 
     from aha_b200 import dist_util
     dev = f"cuda:{local_rank}"
-    value, max_ms = dist_util.aggregate_throughput(K, best_ms, world, dist, dev)       # units of all ranks / slowest rank
-    e2e_val, _ = dist_util.aggregate_throughput(K, e2e_s * 1e3, world, dist, dev)
+    jobs = 1 if tp else world                                                           # TP decodes ONE request on all ranks
+    value, max_ms = dist_util.aggregate_throughput(K, best_ms, jobs, dist, dev)        # units of all ranks / slowest rank
+    e2e_val, _ = dist_util.aggregate_throughput(K, e2e_s * 1e3, jobs, dist, dev)
     step_ms = max_ms / K
     avg_ctx = S + W + (K - 1) / 2.0 + 1
     step_bytes = st["decode_bytes_per_step_fixed"] + st["kv_bytes_per_token"] * (avg_ctx + 1)
@@ -276,7 +288,8 @@ def main():
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": step_ms,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (fp16 weights, fp32 activations/accumulate/KV)",
+                "higher_is_better": True, "scaling": "strong" if tp else "weak", "vs_baseline": None,
+                "dtype": "f32 (fp16 weights, fp32 activations/accumulate/KV)",
                 "data": "synthetic", "config": dict(config, prefill_secs=usage["prompt_secs"], vision_secs=usage["vision_secs"],
                                                     kernels_per_step=st["kernels_per_decode_step"], reps=reps,
                                                     value_wall_check_s=wall_value),

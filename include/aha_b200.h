@@ -141,6 +141,12 @@ int aha_b200_mel_spectrogram(aha_model* m, const float* wave, size_t n_samples,
 int aha_b200_image_patchify(aha_model* m, const uint8_t* img_hwc, size_t h, size_t w,
                             float* pixel_values_out, size_t cap, uint32_t grid_thw_out[3]);
 
+/* Tensor parallelism (new design; the reference has none): rank 0 creates a 128-byte ncclUniqueId, the host side
+ * distributes it (bench.py broadcasts it between the per-GPU processes) and every rank passes it in aha_options.tp_comm together
+ * with tp_rank / tp_world.  Heads and MLP rows are sharded; the only exchange steps are all-reduce(sum) after
+ * o_proj and down_proj. */
+int aha_b200_nccl_unique_id(uint8_t out[128]);
+
 void aha_b200_destroy(aha_model* m);
 
 /* Last error message of the handle (or of the failed create when m == NULL). */

@@ -1,0 +1,55 @@
+"""Tensor-parallel check, one process per GPU (launched by tests/test_tp_gpu.py through torch.distributed.run):
+every rank builds its shard of the tiny Qwen3 model, prefill + teacher-forced decode logits must match the
+single-GPU oracle within 1e-3 on every rank, and all ranks must agree bit-for-bit with each other."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("gloo")
+    from aha_b200 import B200Model, nccl_unique_id, synth
+    from oracle.qwen3 import Qwen3Model
+    uid = [nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    cfg = synth.get_config("qwen3", "tiny")
+    w = synth.make_weights("qwen3", cfg, 0)
+    m = B200Model("qwen3", cfg, w, device=local, max_ctx=256, tp_rank=rank, tp_world=world, tp_unique_id=uid[0])
+    o = Qwen3Model(cfg, w)
+    ids = synth.synth_text_ids(70, cfg["vocab_size"] - 8, 3)
+    S = 64
+    got = m.forward_initial(ids[:S], 0)[0, 0]
+    want = o.forward_initial(ids[:S].reshape(1, -1), 0)[0, 0]
+    errs = [float(np.abs(got - want).max())]
+    outs = [got]
+    for i in range(6):
+        got = m.forward_step(ids[S + i:S + i + 1], S + i)[0, 0]
+        want = o.forward_step(ids[S + i:S + i + 1].reshape(1, 1), S + i)[0, 0]
+        errs.append(float(np.abs(got - want).max()))
+        outs.append(got)
+    assert max(errs) <= 1e-3, errs
+    mine = torch.from_numpy(np.stack(outs))
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    for g in gathered:
+        assert torch.equal(g, gathered[0]), "ranks disagree"
+    toks = m.decode_steps(5, S + 6, 8)
+    tl = [None] * world
+    dist.all_gather_object(tl, toks)
+    assert all(t == tl[0] for t in tl)
+    if rank == 0:
+        print(f"TP{world} ok: max abs logit err {max(errs):.2e}, kernels/step {m.stats()['kernels_per_decode_step']}")
+    m.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
