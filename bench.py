@@ -117,7 +117,24 @@ def cpu_decode_steps(m, ctx, n, tok=5):
     return time.perf_counter() - t0
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line of this run, written to the real stdout (fd 1 is pointed at stderr for everything else so that
+    library chatter such as NCCL's version banner can never pollute it)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=128)
@@ -173,7 +190,7 @@ def main():
                                            f"reference's Qwen3-VL text stack at ctx {S}+ with a synthetic KV cache; ViT+prefill not in the sample; "
                                            "the reference itself (Rust/Candle) cannot be built here (no cargo/rustc)"},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
 
     # --------------------------------------------------------------------------------- B200 arm
@@ -312,7 +329,7 @@ def main():
                                       "roofline_kv_tok_s": peak * 1e9 / kv_read}},
                 "decode_impl": "fused persistent kernel" if fused else "per-op kernels (CUDA graph)",
                 "cpu_baseline": cpu_base}
-        print(json.dumps(line), flush=True)
+        emit(line)
     m.close()
     if dist is not None:
         dist.destroy_process_group()
