@@ -20,6 +20,10 @@ _MROPE = dict(rope_type="default", mrope_section=[24, 20, 20], mrope_interleaved
 
 QWEN3 = {
     "tiny": dict(_TEXT_TINY),
+    # Qwen3-VL-2B text-stack row shapes (H=2048, I=6144, 16/8 heads) with 2 layers and a small vocabulary: exercises the
+    # production code paths of the decode kernels (4-row K=2048 stages, 1-row K=6144 stages) at test cost
+    "mid": dict(_TEXT_06, hidden_size=2048, intermediate_size=6144, num_hidden_layers=2, vocab_size=4096, rope_theta=5000000.0,
+                eos_token_id=4095),
     "tiny-untied": dict(_TEXT_TINY, tie_word_embeddings=False),
     "q0.6": dict(_TEXT_06),
 }

@@ -130,6 +130,21 @@ def emit(line):
         os.write(_REAL_STDOUT, data)
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one decode_step_fused_kernel launch, from the committed
+    `ncu --set full` summary (profiles/r01_fused_decode_ncu_summary.csv)."""
+    p = os.path.join(ROOT, "profiles", "r01_fused_decode_ncu_summary.csv")
+    try:
+        tot = 0.0
+        for row in open(p).read().splitlines()[1:]:
+            name, unit, val = row.split(",")
+            if name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(val) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit]
+        return tot or None
+    except Exception:
+        return None
+
+
 def main():
     global _REAL_STDOUT
     sys.stdout.flush()
@@ -315,7 +330,7 @@ def main():
                         "with_logits_d2h_tokens_per_s": 1.0 / e2e_logits_s, "logits_bytes": 4 * tc["vocab_size"]},
                 "roofline": ({"bound": "hbm", "kernel": "decode_step_fused_kernel (the whole decode step: one launch per token)",
                               "achieved": step_bytes / (step_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                              "frac": step_bytes / (step_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src, "traffic": None,
+                              "frac": step_bytes / (step_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src, "traffic": ncu_traffic_bytes(),
                               "bytes_per_launch": step_bytes, "avg_launch_us": step_ms * 1e3, "per_op_kernels": kernels}
                              if fused else
                              {"bound": "hbm", "kernel": "gemv_kernel<rmsnorm, swiglu> (gate/up projection)",

@@ -123,6 +123,32 @@ def test_qwen3_long_context_decode(impl):
         m.close()
 
 
+@pytest.mark.parametrize("impl", [1, 2])
+def test_qwen3_production_row_shapes(impl):
+    """Qwen3-VL-2B text-stack row shapes (H=2048, I=6144; 2 layers): the 4-row / 1-row tensor-core stage paths of the
+    fused kernel (impl 2) and the per-op kernels (impl 1) against the oracle, teacher-forced over page boundaries."""
+    cfg, w, m = make_model("qwen3", "mid", max_ctx=512, decode_impl=impl)
+    try:
+        o = make_oracle("qwen3", cfg, w)
+        S, n = 90, 40
+        ids = _ids(S + n, cfg["vocab_size"], 13)
+        got = m.forward_initial(ids[:S], 0)[0, 0]
+        want = o.forward_initial(ids[:S].reshape(1, -1), 0)[0, 0]
+        assert np.abs(got - want).max() <= TOL
+        worst = 0.0
+        for i in range(n):
+            got = m.forward_step(ids[S + i:S + i + 1], S + i)[0, 0]
+            want = o.forward_step(ids[S + i:S + i + 1].reshape(1, 1), S + i)[0, 0]
+            err = np.abs(got - want).max()
+            worst = max(worst, err)
+            assert err <= TOL, (i, err)
+            if top2_gap(want) > 10 * max(err, 1e-6):
+                assert m.last_argmax == int(np.argmax(want)), i
+        print(f"impl {impl}: worst abs logit err over {n} decode steps {worst:.2e}")
+    finally:
+        m.close()
+
+
 def test_qwen3_untied_lm_head():
     cfg, w, m = make_model("qwen3", "tiny-untied", max_ctx=128)
     try:
