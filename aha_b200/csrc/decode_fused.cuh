@@ -70,7 +70,7 @@ struct FusedArgs {
     const int* page_table;
     int nsplit;
     int stages;        // ring slots in use (<= kFusedStages)
-    int dbg;           // timing experiments only: bit0 = skip grid barriers, bit1 = skip the GEMV math, bit2 = timestamps, bit3 = FFMA dot products instead of mma
+    int dbg;           // timing experiments only: bit0 = skip grid barriers, bit1 = skip the GEMV math, bit2 = timestamps
     unsigned long long* trace;  // [2][4096] globaltimer stamps of CTA 0 (consumer thread 0 / producer), dbg bit2
 };
 
@@ -128,19 +128,6 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& seq, i
     }
     seq += 1u;
     consumer_bar_sync();
-}
-
-// mma.sync m16n8k16 (fp16 x fp16 -> fp32): D += A (16x16, row) * B (16x8, col).  a1/a3 (rows 8..15) are zero here.
-__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
-}
-// The tensor-core dot-product path is used for the two production stage shapes: 4 rows (K % 64 == 0) and 1 row
-// (K % 128 == 0); everything else keeps the convert + FFMA path.
-__device__ __forceinline__ bool fused_use_mma(int K, int R, int dbg) {
-    if (dbg & 8) return false;
-    return (R == 4 && (K & 63) == 0) || (R == 1 && (K & 127) == 0);
 }
 
 // ------------------------------------------------------------------------------------------------ schedule
@@ -247,8 +234,7 @@ struct Consumer {
 
     // Stage the activation vector of a GEMV in shared memory (all consumer threads), optional RMSNorm.
     // src is fp32 global written by other CTAs (ld.global.cg) or an fp16 embedding row.
-    // split = true: store the vector as fp16 hi[K] | lo[K] (x = hi + lo to ~2^-22) for the mma path instead of fp32.
-    __device__ void load_x(int K, const float* src32, const __half* src16, const float* norm_w, float eps, bool split) {
+    __device__ void load_x(int K, const float* src32, const __half* src16, const float* norm_w, float eps) {
         const int tid = threadIdx.x;
         constexpr int kPer = (kFusedMaxK + kFusedConsumers * 32 * 4 - 1) / (kFusedConsumers * 32 * 4);   // float4 per thread
         float4 v[kPer], w[kPer];
@@ -285,81 +271,9 @@ struct Consumer {
 #pragma unroll
         for (int j = 0; j < kPer; ++j) {
             const int e = (tid + j * kFusedConsumers * 32) * 4;
-            if (e < K) {
-                if (split) {
-                    __half* xh = reinterpret_cast<__half*>(xs);
-                    __half* xl = xh + K;
-                    const float x[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-                    __half hh[4], ll[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) { hh[q] = __float2half_rn(x[q]); ll[q] = __float2half_rn(x[q] - __half2float(hh[q])); }
-                    *reinterpret_cast<uint2*>(xh + e) = make_uint2(*reinterpret_cast<uint32_t*>(&hh[0]), *reinterpret_cast<uint32_t*>(&hh[2]));
-                    *reinterpret_cast<uint2*>(xl + e) = make_uint2(*reinterpret_cast<uint32_t*>(&ll[0]), *reinterpret_cast<uint32_t*>(&ll[2]));
-                } else {
-                    *reinterpret_cast<float4*>(xs + e) = v[j];
-                }
-            }
+            if (e < K) *reinterpret_cast<float4*>(xs + e) = v[j];
         }
         consumer_bar_sync();
-    }
-
-    // Tensor-core dot products of a full 4-row stage (K % 64 == 0).  Per 64-wide k block each lane loads 16 bytes of
-    // weights (virtual row v = lane/4 = 2*row + k-half, quad t = lane%4) and 16 bytes of the activation column
-    // n = lane/4 (k-half n/2, hi/lo n%2) and issues two m16n8k16 MMAs; D[v][n] is wanted where n/2 == v%2.
-    __device__ __forceinline__ void stage_dots_mma4(const uint8_t* st, int K, float (&v)[kFusedMaxRows]) const {
-        const int g = lane >> 2, t = lane & 3;
-        const uint8_t* ap = st + (size_t)(g >> 1) * K * 2 + (g & 1) * 64 + t * 16;
-        const uint8_t* bp = reinterpret_cast<const uint8_t*>(xs) + (size_t)(g & 1) * K * 2 + (g >> 1) * 64 + t * 16;   // hi | lo halves
-        const bool bvalid = g < 4;
-        float c[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) c[i][j] = 0.f;
-        const int nkb = K >> 6;
-#pragma unroll 1
-        for (int kb = 0; kb < nkb; kb += 4) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (kb + u < nkb) {
-                    const uint4 a = *reinterpret_cast<const uint4*>(ap + (size_t)(kb + u) * 128);
-                    uint4 b = make_uint4(0u, 0u, 0u, 0u);
-                    if (bvalid) b = *reinterpret_cast<const uint4*>(bp + (size_t)(kb + u) * 128);
-                    mma16816(c[u], a.x, a.y, b.x, b.y);
-                    mma16816(c[u], a.z, a.w, b.z, b.w);
-                }
-            }
-        }
-        const float pl = (t == (g & 1)) ? (c[0][0] + c[1][0] + c[2][0] + c[3][0]) + (c[0][1] + c[1][1] + c[2][1] + c[3][1]) : 0.f;
-        const int r = g >> 1;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) v[q] = (q == r) ? pl : 0.f;
-    }
-    // One-row stage (K % 128 == 0): virtual row v = lane/4 covers k part v%4 of a 128-wide block (rows 4..7 mirror 0..3
-    // and are ignored); column n = lane/4 is (part n/2, hi/lo n%2).
-    __device__ __forceinline__ void stage_dots_mma1(const uint8_t* st, int K, float (&v)[kFusedMaxRows]) const {
-        const int g = lane >> 2, t = lane & 3;
-        const uint8_t* ap = st + (g & 3) * 64 + t * 16;
-        const uint8_t* bp = reinterpret_cast<const uint8_t*>(xs) + (size_t)(g & 1) * K * 2 + (g >> 1) * 64 + t * 16;
-        float c[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) c[i][j] = 0.f;
-        const int nkb = K >> 7;
-#pragma unroll 1
-        for (int kb = 0; kb < nkb; kb += 4) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (kb + u < nkb) {
-                    const uint4 a = *reinterpret_cast<const uint4*>(ap + (size_t)(kb + u) * 256);
-                    const uint4 b = *reinterpret_cast<const uint4*>(bp + (size_t)(kb + u) * 256);
-                    mma16816(c[u], a.x, a.y, b.x, b.y);
-                    mma16816(c[u], a.z, a.w, b.z, b.w);
-                }
-            }
-        }
-        v[0] = (g < 4 && t == g) ? (c[0][0] + c[1][0] + c[2][0] + c[3][0]) + (c[0][1] + c[1][1] + c[2][1] + c[3][1]) : 0.f;
     }
 
     // dot products of a FULL stage of R rows against xs; NA independent accumulators per row break the FMA chain
@@ -406,7 +320,6 @@ struct Consumer {
         int r0, r1;
         cta_rows(N, EPI == FE_SWIGLU ? 2 : 1, r0, r1);
         const int R = rows_per_stage(K);
-        const bool use_mma = fused_use_mma(K, R, a.dbg);
         unsigned i = it;
         for (int r = r0; r < r1; r += R, ++i) {
             if (!owns(i)) continue;
@@ -416,10 +329,7 @@ struct Consumer {
 #pragma unroll
             for (int q = 0; q < kFusedMaxRows; ++q) v[q] = 0.f;
             if (!(a.dbg & 2)) {
-                if (use_mma) {   // rows beyond nr of a tail stage produce values nobody reads
-                    if (R == 4) stage_dots_mma4(st, K, v);
-                    else stage_dots_mma1(st, K, v);
-                } else if (nr == R) {
+                if (nr == R) {
                     switch (R) {
                         case 8: stage_dots<8, 1>(st, K, v); break;
                         case 4: stage_dots<4, 2>(st, K, v); break;
@@ -714,7 +624,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
         if (l + 1 < a.L) nxtc = a.layers[l + 1];
         const bool first = (l == 0);
         // P1: qkv = Wqkv . rmsnorm(x)      (layer 0 reads the embedding row directly: Embedding::forward)
-        c.load_x(a.H, a.x, first ? emb_row : nullptr, Ly.ln1, a.eps, fused_use_mma(a.H, rows_per_stage(a.H), a.dbg)); CSTAMP();
+        c.load_x(a.H, a.x, first ? emb_row : nullptr, Ly.ln1, a.eps); CSTAMP();
         c.template gemv<FE_QKV>(a, a.qkv_dim, a.H, Ly.qkv_b, nullptr, nullptr, a.qkv1, best, bi); CSTAMP();
         grid_barrier(&a.sync[0], seq, a.dbg); CSTAMP();
         // P2: attention over the paged cache (+ q/k norm, RoPE, KV append)
@@ -722,20 +632,20 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
         fused_attention<G>(a, c, *as, cs, spages, l, Ly, t_new); CSTAMP();
         grid_barrier(&a.sync[0], seq, a.dbg); CSTAMP();
         // P3: x = resid + Wo . attn
-        c.load_x(a.nh * a.hd, a.attn1, nullptr, nullptr, 0.f, fused_use_mma(a.nh * a.hd, rows_per_stage(a.nh * a.hd), a.dbg)); CSTAMP();
+        c.load_x(a.nh * a.hd, a.attn1, nullptr, nullptr, 0.f); CSTAMP();
         c.template gemv<FE_RESID>(a, a.H, a.nh * a.hd, Ly.o_b, a.x, first ? emb_row : nullptr, a.x, best, bi); CSTAMP();
         grid_barrier(&a.sync[0], seq, a.dbg); CSTAMP();
         // P4: h = silu(gate) * up, gate/up rows interleaved, input rmsnorm(x)
-        c.load_x(a.H, a.x, nullptr, Ly.ln2, a.eps, fused_use_mma(a.H, rows_per_stage(a.H), a.dbg)); CSTAMP();
+        c.load_x(a.H, a.x, nullptr, Ly.ln2, a.eps); CSTAMP();
         c.template gemv<FE_SWIGLU>(a, 2 * a.I, a.H, nullptr, nullptr, nullptr, a.h1, best, bi); CSTAMP();
         grid_barrier(&a.sync[0], seq, a.dbg); CSTAMP();
         // P5: x = x + Wdown . h
-        c.load_x(a.I, a.h1, nullptr, nullptr, 0.f, fused_use_mma(a.I, rows_per_stage(a.I), a.dbg)); CSTAMP();
+        c.load_x(a.I, a.h1, nullptr, nullptr, 0.f); CSTAMP();
         c.template gemv<FE_RESID>(a, a.H, a.I, nullptr, a.x, nullptr, a.x, best, bi); CSTAMP();
         grid_barrier(&a.sync[0], seq, a.dbg); CSTAMP();
     }
     // final: logits = lm_head . rmsnorm(x), per-CTA argmax candidate
-    c.load_x(a.H, a.x, nullptr, a.final_norm, a.eps, fused_use_mma(a.H, rows_per_stage(a.H), a.dbg));
+    c.load_x(a.H, a.x, nullptr, a.final_norm, a.eps);
     best = -INFINITY; bi = 0x7fffffff;
     c.template gemv<FE_LOGITS>(a, a.V, a.H, nullptr, nullptr, nullptr, a.logits, best, bi); CSTAMP();
     // CTA-level argmax (first maximal index), then the last CTA to arrive reduces across CTAs
