@@ -309,6 +309,7 @@ int aha_b200_create(const char* kind, const char* config_json, const aha_tensor_
         m->ctx.device = o.device;
         m->ctx.num_sms = prop.multiProcessorCount;
         m->ctx.gemm_impl = o.gemm_impl;
+        m->ctx.attn_impl = o.reserved[0];   // 0 = tensor-core flash attention, 1 = fp32 SIMT twin
         AHA_CUDA_CHECK(cudaSetDevice(o.device));
         AHA_CUDA_CHECK(cudaStreamCreateWithFlags(&m->ctx.stream, cudaStreamNonBlocking));
         AHA_CUDA_CHECK(cudaEventCreate(&m->ev0));

@@ -320,7 +320,7 @@ struct AudioModel {
             fa.kv.tok_stride = 3 * D; fa.kv.head_stride = 64;
             fa.out = attn; fa.o_tok_stride = D; fa.o_head_stride = 64;
             fa.Sq = N; fa.Skv = N; fa.q0 = 0; fa.kv0 = 0; fa.groups = 1; fa.scaling = scaling;
-            flash_attn<64>(st, fa, cfg.heads, false); c.cnt.kernels++;
+            flash_dispatch<64>(c, fa, cfg.heads, false);
             gemm(EPI_RESID, attn, D, A.out, x, D, x, D, N);
             layernorm_kernel<<<N, 256, 0, st>>>(x, A.ln2w, A.ln2b, 1e-5f, xn, D); c.cnt.kernels++;
             gemm(EPI_ACT, xn, D, A.fc1, nullptr, 0, h, cfg.ffn, N, cfg.act);

@@ -11,6 +11,7 @@
 
 #include "../../include/aha_b200.h"
 #include "attention.cuh"
+#include "attention_mma.cuh"
 #include "decode_fused.cuh"
 #include "common.cuh"
 #include "gemm_simt.cuh"
@@ -35,6 +36,7 @@ struct Ctx {  // per-handle launch context
     bool capturing = false;
     std::vector<void*> allocs;
     size_t alloc_bytes = 0;
+    int attn_impl = 0;            // 0 = auto (tensor-core flash attention), 1 = fp32 SIMT flash attention
     int gemm_impl = 0;            // 0 = auto (tcgen05 where the shape tiles), 1 = SIMT fp32, 2 = tcgen05 required
     __half* split_ws = nullptr;   // [2][rows*K] hi | lo halves of the activation operand
     size_t split_cap = 0;         // halfs per half-buffer
@@ -143,6 +145,14 @@ struct LinearW {
     CUtensorMap tmap;     // TMA descriptor of w (128 x 64 boxes, SWIZZLE_128B) when has_tmap
     bool has_tmap = false;
 };
+
+// Prefill attention dispatch: tensor-core kernel (attention_mma.cuh) unless the exact SIMT twin is requested.
+template <int HD>
+inline void flash_dispatch(Ctx& c, const FlashArgs& a, int nheads, bool causal) {
+    if (c.attn_impl == 1) flash_attn<HD>(c.stream, a, nheads, causal);
+    else flash_attn_mma<HD>(c.stream, a, nheads, causal);
+    c.cnt.kernels++;
+}
 
 // y = x W^T with the fused epilogues of gemm_simt.cuh.  Dispatch: tcgen05 split-fp16 kernel (gemm_tc.cuh) when the
 // shape tiles (K % 64 == 0, N % 32 == 0) and there are enough rows to fill a tile, else the exact SIMT kernel.
@@ -515,7 +525,7 @@ struct TextModel {
             fa.q = qkv; fa.q_tok_stride = qkv_dim; fa.q_head_stride = hd; fa.kv = kv;
             fa.out = attn; fa.o_tok_stride = (size_t)nh_l * hd; fa.o_head_stride = hd;
             fa.Sq = S; fa.Skv = pos0 + S; fa.q0 = 0; fa.kv0 = 0; fa.groups = nh_l / nkv_l; fa.scaling = scaling;
-            flash_attn<128>(st, fa, nh_l, true); c.cnt.kernels++;
+            flash_dispatch<128>(c, fa, nh_l, true);
             if (tp_world > 1) { gemm(EPI_STORE, attn, nh_l * hd, T.o, nullptr, 0, tp_tmp, H, S); tp_reduce_add(tp_tmp, x, (size_t)S * H); }
             else gemm(EPI_RESID, attn, nh_l * hd, T.o, x, H, x, H, S);
             rmsnorm_kernel<<<S, 256, 0, st>>>(x, T.ln2, cfg.eps, xn, H); c.cnt.kernels++;

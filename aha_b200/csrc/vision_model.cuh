@@ -211,7 +211,7 @@ struct VisionModel {
                 fa.kv.tok_stride = 3 * Hv; fa.kv.head_stride = 64;
                 fa.out = attn; fa.o_tok_stride = Hv; fa.o_head_stride = 64;
                 fa.Sq = sg.second; fa.Skv = sg.second; fa.q0 = sg.first; fa.kv0 = sg.first; fa.groups = 1; fa.scaling = scaling;
-                flash_attn<64>(st, fa, cfg.heads, false); c.cnt.kernels++;
+                flash_dispatch<64>(c, fa, cfg.heads, false);
             }
             gemm(EPI_RESID, attn, Hv, b.proj, x, Hv, x, Hv, N);
             layernorm_kernel<<<N, 256, 0, st>>>(x, b.n2w, b.n2b, 1e-6f, xn, Hv); c.cnt.kernels++;

@@ -35,7 +35,7 @@ def nccl_unique_id():
 
 class B200Model:
     def __init__(self, kind, config, weights, eos_ids=(), device=0, max_ctx=8192, max_prefill=0, max_patches=0,
-                 max_frames=0, use_graph=True, decode_impl=0, gemm_impl=0, tp_rank=0, tp_world=1, tp_unique_id=None):
+                 max_frames=0, use_graph=True, decode_impl=0, gemm_impl=0, attn_impl=0, tp_rank=0, tp_world=1, tp_unique_id=None):
         self._lib = L.load()
         self.kind = kind
         self.config = config
@@ -47,6 +47,7 @@ class B200Model:
         opts = L.Options(device=device, tp_rank=tp_rank, tp_world=tp_world, max_ctx=max_ctx, max_prefill=max_prefill,
                          max_patches=max_patches, max_frames=max_frames, use_graph=1 if use_graph else 0,
                          decode_impl=decode_impl, gemm_impl=gemm_impl)
+        opts.reserved[0] = attn_impl
         if tp_world > 1:
             if tp_unique_id is None or len(tp_unique_id) != 128:
                 raise ValueError("tp_world > 1 needs the 128-byte NCCL unique id (nccl_unique_id() on rank 0, then broadcast)")

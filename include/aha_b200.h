@@ -69,7 +69,7 @@ typedef struct aha_options {
     int32_t decode_impl;   /* 0 = auto, 1 = per-op kernels, 2 = persistent fused step kernel */
     int32_t gemm_impl;     /* 0 = auto, 1 = SIMT fp32, 2 = tcgen05 (split-fp16, fp32-exact) */
     const void* tp_comm;   /* opaque: ncclUniqueId bytes (128) when tp_world > 1, else NULL */
-    int32_t reserved[8];
+    int32_t reserved[8];   /* reserved[0]: prefill attention, 0 = tensor-core (mma, split-fp16) kernel, 1 = fp32 SIMT twin */
 } aha_options;
 
 typedef struct aha_gen_params {      /* ChatCompletionParameters subset used by generate_generic */
