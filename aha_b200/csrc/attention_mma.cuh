@@ -36,52 +36,104 @@ __device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t&
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+// ---- pre-pass: split fp32 q / k / v rows into packed fp16 hi | lo buffers, layout [head][token][HD] ------------------
+// (one pass per layer instead of one conversion per CTA per KV tile)
+struct SplitQKVArgs {
+    FlashArgs f;
+    __half *q_hi, *q_lo, *k_hi, *k_lo, *v_hi, *v_lo;
+    int nheads, nkv;
+};
+template <int HD>
+__global__ void split_qkv_kernel(SplitQKVArgs s) {
+    // blockIdx.y: 0 = q, 1 = k, 2 = v; blockIdx.x: row index (head * S + token)
+    const int which = blockIdx.y;
+    const int S = which == 0 ? s.f.Sq : s.f.Skv, H = which == 0 ? s.nheads : s.nkv;
+    const size_t row = blockIdx.x;
+    if (row >= (size_t)S * H) return;
+    const int head = (int)(row / S), tok = (int)(row % S);
+    const float* src = which == 0 ? s.f.q + (size_t)(s.f.q0 + tok) * s.f.q_tok_stride + (size_t)head * s.f.q_head_stride
+                                  : (which == 1 ? s.f.kv.k : s.f.kv.v) + s.f.kv.off(s.f.kv0 + tok, head);
+    __half* hi = (which == 0 ? s.q_hi : which == 1 ? s.k_hi : s.v_hi) + row * HD;
+    __half* lo = (which == 0 ? s.q_lo : which == 1 ? s.k_lo : s.v_lo) + row * HD;
+    for (int c4 = threadIdx.x * 4; c4 < HD; c4 += blockDim.x * 4) {
+        const float4 v = *reinterpret_cast<const float4*>(src + c4);
+        uint32_t h0, l0, h1, l1;
+        split2(v.x, v.y, h0, l0);
+        split2(v.z, v.w, h1, l1);
+        *reinterpret_cast<uint2*>(hi + c4) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(lo + c4) = make_uint2(l0, l1);
+    }
+}
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(fa_smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct FlashMmaArgs {
+    const __half *q_hi, *q_lo, *k_hi, *k_lo, *v_hi, *v_lo;   // packed [head][token][HD]
+    float* out; size_t o_tok_stride, o_head_stride;
+    int Sq, Skv, q0, groups;
+    float scaling;
+};
+
+// One CTA = 128 queries of one head (8 warps x 16 rows); K/V tiles of 64 tokens, cp.async double buffered.
 template <int HD, bool CAUSAL>
-__global__ void __launch_bounds__(128) flash_attn_mma_kernel(FlashArgs a) {
-    constexpr int BQ = 64, BKV = 64, LD = HD + 8;   // row stride in halfs: +16 bytes keeps ldmatrix conflict-free
+__global__ void __launch_bounds__(256) flash_attn_mma_kernel(FlashMmaArgs a) {
+    constexpr int BQ = 128, BKV = 64, LD = HD + 8;   // row stride in halfs: +16 bytes keeps ldmatrix conflict-free
+    constexpr int CH = HD / 8;                       // 16-byte chunks per row
     extern __shared__ __align__(16) __half fa_smem[];
     __half* Qh = fa_smem;            __half* Ql = Qh + BQ * LD;
-    __half* Kh = Ql + BQ * LD;       __half* Kl = Kh + BKV * LD;
-    __half* Vh = Kl + BKV * LD;      __half* Vl = Vh + BKV * LD;
+    __half* KV = Ql + BQ * LD;       // [2 buffers][Kh | Kl | Vh | Vl][BKV * LD]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int head = blockIdx.y, kvh = head / a.groups;
     const int qt0 = blockIdx.x * BQ;
+    const size_t qbase = (size_t)head * a.Sq, kbase = (size_t)kvh * a.Skv;
 
-    // stage one [64 x HD] fp32 tile as hi/lo fp16 (rows past `valid` are zero)
-    auto stage = [&](const float* base, size_t row_off_fn_dummy, __half* hi, __half* lo, int valid, auto row_ptr) {
-        (void)base; (void)row_off_fn_dummy;
-        for (int idx = tid; idx < 64 * (HD / 4); idx += 128) {
-            const int r = idx / (HD / 4), c4 = (idx % (HD / 4)) * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < valid) v = *reinterpret_cast<const float4*>(row_ptr(r) + c4);
-            uint32_t h0, l0, h1, l1;
-            split2(v.x, v.y, h0, l0);
-            split2(v.z, v.w, h1, l1);
-            *reinterpret_cast<uint2*>(hi + r * LD + c4) = make_uint2(h0, h1);
-            *reinterpret_cast<uint2*>(lo + r * LD + c4) = make_uint2(l0, l1);
+    auto load_kv = [&](int tile, int buf) {
+        __half* dst = KV + (size_t)buf * 4 * BKV * LD;
+        const int kt0 = tile * BKV;
+        for (int idx = tid; idx < 4 * BKV * CH; idx += 256) {
+            const int arr = idx / (BKV * CH), rem = idx % (BKV * CH), r = rem / CH, c = rem % CH;
+            const int tok = min(kt0 + r, a.Skv - 1);   // rows past Skv are masked; clamp keeps the data finite
+            const __half* src = (arr == 0 ? a.k_hi : arr == 1 ? a.k_lo : arr == 2 ? a.v_hi : a.v_lo) + (kbase + tok) * HD + c * 8;
+            cp_async16(dst + (size_t)arr * BKV * LD + r * LD + c * 8, src);
         }
     };
-    stage(nullptr, 0, Qh, Ql, min(BQ, a.Sq - qt0),
-          [&](int r) { return a.q + (size_t)(a.q0 + qt0 + r) * a.q_tok_stride + (size_t)head * a.q_head_stride; });
+    // Q tile (once) + first K/V tile
+    for (int idx = tid; idx < 2 * BQ * CH; idx += 256) {
+        const int arr = idx / (BQ * CH), rem = idx % (BQ * CH), r = rem / CH, c = rem % CH;
+        const int tok = min(qt0 + r, a.Sq - 1);
+        cp_async16((arr == 0 ? Qh : Ql) + r * LD + c * 8, (arr == 0 ? a.q_hi : a.q_lo) + (qbase + tok) * HD + c * 8);
+    }
+    const int causal_shift = a.Skv - a.Sq;
+    int kv_end = a.Skv;
+    if (CAUSAL) kv_end = min(a.Skv, qt0 + BQ + causal_shift);
+    const int ntiles = (kv_end + BKV - 1) / BKV;
+    load_kv(0, 0);
+    cp_async_commit();
 
     float o[HD / 8][4];
 #pragma unroll
     for (int i = 0; i < HD / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;   // rows g and g+8 of this warp's 16
-    const int causal_shift = a.Skv - a.Sq;
-    int kv_end = a.Skv;
-    if (CAUSAL) kv_end = min(a.Skv, qt0 + BQ + causal_shift);
-    const int ntiles = (kv_end + BKV - 1) / BKV;
     const int qrow0 = qt0 + warp * 16 + g, qrow1 = qrow0 + 8;
 
     for (int tile = 0; tile < ntiles; ++tile) {
-        const int kt0 = tile * BKV;
-        __syncthreads();   // previous tile consumed (and the Q tile staged, first iteration)
-        const int valid = min(BKV, a.Skv - kt0);
-        stage(nullptr, 0, Kh, Kl, valid, [&](int r) { return a.kv.k + a.kv.off(a.kv0 + kt0 + r, kvh); });
-        stage(nullptr, 0, Vh, Vl, valid, [&](int r) { return a.kv.v + a.kv.off(a.kv0 + kt0 + r, kvh); });
-        __syncthreads();
-
+        const int kt0 = tile * BKV, buf = tile & 1;
+        cp_async_wait<0>();
+        __syncthreads();                       // tile `tile` landed for everyone; buffer buf^1 is free again
+        if (tile + 1 < ntiles) load_kv(tile + 1, buf ^ 1);
+        cp_async_commit();
+        const __half* Kh = KV + (size_t)buf * 4 * BKV * LD;
+        const __half* Kl = Kh + BKV * LD;
+        const __half* Vh = Kl + BKV * LD;
+        const __half* Vl = Vh + BKV * LD;
+        // a warp whose 16 rows are entirely above the causal frontier of this tile has nothing to add
+        const bool warp_active = !CAUSAL || (kt0 <= qt0 + warp * 16 + 15 + causal_shift);
+        if (warp_active) {
         // ---- S = Q K^T (16 x 64 per warp)
         float s[8][4];
 #pragma unroll
@@ -161,6 +213,7 @@ __global__ void __launch_bounds__(128) flash_attn_mma_kernel(FlashArgs a) {
                 mma_f16(o[2 * dp + 1], pl, vh[2], vh[3]);
             }
         }
+        }   // warp_active
     }
     const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
 #pragma unroll
@@ -173,17 +226,34 @@ __global__ void __launch_bounds__(128) flash_attn_mma_kernel(FlashArgs a) {
     }
 }
 
+// `ws`: workspace of at least flash_mma_ws_halfs() halfs (hi/lo copies of q, k, v).
 template <int HD>
-inline void flash_attn_mma(cudaStream_t st, const FlashArgs& a, int nheads, bool causal) {
+inline size_t flash_mma_ws_halfs(const FlashArgs& a, int nheads) {
+    const int nkv = nheads / a.groups;
+    return 2 * ((size_t)nheads * a.Sq + 2 * (size_t)nkv * a.Skv) * HD;
+}
+template <int HD>
+inline void flash_attn_mma(cudaStream_t st, const FlashArgs& a, int nheads, bool causal, __half* ws) {
     if (a.Sq == 0) return;
-    const size_t smem = (size_t)6 * 64 * (HD + 8) * sizeof(__half);
-    dim3 grid(ceil_div(a.Sq, 64), nheads);
+    const int nkv = nheads / a.groups;
+    SplitQKVArgs sp;
+    sp.f = a; sp.nheads = nheads; sp.nkv = nkv;
+    const size_t nq = (size_t)nheads * a.Sq * HD, nk = (size_t)nkv * a.Skv * HD;
+    sp.q_hi = ws; sp.q_lo = ws + nq; sp.k_hi = ws + 2 * nq; sp.k_lo = sp.k_hi + nk; sp.v_hi = sp.k_lo + nk; sp.v_lo = sp.v_hi + nk;
+    const unsigned rows = (unsigned)std::max((size_t)nheads * a.Sq, (size_t)nkv * a.Skv);
+    split_qkv_kernel<HD><<<dim3(rows, 3), HD / 4, 0, st>>>(sp);
+    FlashMmaArgs m;
+    m.q_hi = sp.q_hi; m.q_lo = sp.q_lo; m.k_hi = sp.k_hi; m.k_lo = sp.k_lo; m.v_hi = sp.v_hi; m.v_lo = sp.v_lo;
+    m.out = a.out; m.o_tok_stride = a.o_tok_stride; m.o_head_stride = a.o_head_stride;
+    m.Sq = a.Sq; m.Skv = a.Skv; m.q0 = a.q0; m.groups = a.groups; m.scaling = a.scaling;
+    const size_t smem = (size_t)(2 * 128 + 8 * 64) * (HD + 8) * sizeof(__half);
+    dim3 grid(ceil_div(a.Sq, 128), nheads);
     if (causal) {
         AHA_CUDA_CHECK(cudaFuncSetAttribute(flash_attn_mma_kernel<HD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        flash_attn_mma_kernel<HD, true><<<grid, 128, smem, st>>>(a);
+        flash_attn_mma_kernel<HD, true><<<grid, 256, smem, st>>>(m);
     } else {
         AHA_CUDA_CHECK(cudaFuncSetAttribute(flash_attn_mma_kernel<HD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        flash_attn_mma_kernel<HD, false><<<grid, 128, smem, st>>>(a);
+        flash_attn_mma_kernel<HD, false><<<grid, 256, smem, st>>>(m);
     }
     AHA_CUDA_CHECK(cudaGetLastError());
 }
