@@ -60,6 +60,8 @@ SYMBOLS = {
                                     C.POINTER(C.c_size_t), C.POINTER(Usage)]),
     "aha_b200_mel_spectrogram": (C.c_int, [_P, _F32P, C.c_size_t, _F32P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "aha_b200_image_patchify": (C.c_int, [_P, C.POINTER(C.c_uint8), C.c_size_t, C.c_size_t, _F32P, C.c_size_t, _U32P]),
+    "aha_b200_embed": (C.c_int, [_P, _U32P, C.c_size_t, _F32P]),
+    "aha_b200_rerank": (C.c_int, [_P, _U32P, C.c_size_t, _U32P, C.POINTER(C.c_size_t), C.c_size_t, _F32P]),
     "aha_b200_nccl_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
     "aha_b200_destroy": (None, [_P]),
     "aha_b200_last_error": (C.c_char_p, [_P]),

@@ -593,6 +593,50 @@ int aha_b200_debug_gemm(aha_model* m, int impl, int epi, int act, int M, int N, 
     });
 }
 
+namespace {
+// Qwen3Model::forward_hidden + l2_normalize for one text; result left in T.xn[0:H] and copied to `out`
+void embed_one(aha_model* m, const uint32_t* ids, size_t S, float* out) {
+    AHA_REQUIRE(m->kind == aha_model::QWEN3, "embeddings need a qwen3 handle (Qwen3-Embedding shares Qwen3Model)");
+    AHA_REQUIRE(ids && S >= 1 && out, "ids, seq_len and out are required");
+    TextModel& T = m->text;
+    m->text.reset_pages();
+    upload_ids(m, ids, S);
+    std::vector<int> pos3((size_t)3 * S);
+    for (int r = 0; r < 3; ++r) for (size_t i = 0; i < S; ++i) pos3[(size_t)r * S + i] = (int)i;
+    upload_pos(m, pos3);
+    T.prefill((int)S, 0, false, nullptr, 0, {});
+    const int H = T.cfg.H;
+    rmsnorm_kernel<<<1, 256, 0, m->ctx.stream>>>(T.x + (size_t)(S - 1) * H, T.norm, T.cfg.eps, T.xn, H);
+    l2_normalize_kernel<<<1, 256, 0, m->ctx.stream>>>(T.xn, T.xn + H, H);
+    m->ctx.cnt.kernels += 2;
+    AHA_CUDA_CHECK(cudaMemcpyAsync(out, T.xn + H, (size_t)H * sizeof(float), cudaMemcpyDeviceToHost, m->ctx.stream));
+    AHA_CUDA_CHECK(cudaStreamSynchronize(m->ctx.stream));
+    m->text.reset_pages();   // clear_kv_cache()
+}
+}  // namespace
+
+int aha_b200_embed(aha_model* m, const uint32_t* ids, size_t seq_len, float* out) {
+    return guarded(m, [&] { embed_one(m, ids, seq_len, out); });
+}
+
+int aha_b200_rerank(aha_model* m, const uint32_t* query_ids, size_t query_len, const uint32_t* doc_ids, const size_t* doc_lens, size_t n_docs,
+                    float* scores_out) {
+    return guarded(m, [&] {
+        AHA_REQUIRE(doc_ids && doc_lens && scores_out && n_docs >= 1, "documents are required (embedding input cannot be empty)");
+        const int H = m->text.cfg.H;
+        std::vector<float> q(H), d(H);
+        embed_one(m, query_ids, query_len, q.data());
+        size_t off = 0;
+        for (size_t i = 0; i < n_docs; ++i) {
+            embed_one(m, doc_ids + off, doc_lens[i], d.data());
+            off += doc_lens[i];
+            float acc = 0.f;   // (1,H) x (H,1) in fp32, like the reference's matmul of two host-side f32 tensors
+            for (int k = 0; k < H; ++k) acc += q[k] * d[k];
+            scores_out[i] = acc;
+        }
+    });
+}
+
 int aha_b200_nccl_unique_id(uint8_t out[128]) {
     try {
         AHA_REQUIRE(out != nullptr, "out is required");

@@ -56,6 +56,17 @@ __global__ void scatter_rows_kernel(const int* __restrict__ idx, const float* __
     for (int i = threadIdx.x; i < H; i += blockDim.x) o[i] = add ? (o[i] + s[i]) : s[i];
 }
 
+// l2_normalize (/root/reference/src/models/common/modules.rs:1287-1294): x / sqrt(sum(x^2) + 1e-6), one row per block.
+__global__ void l2_normalize_kernel(const float* __restrict__ x, float* __restrict__ out, int H) {
+    __shared__ float red[32];
+    const float* xr = x + (size_t)blockIdx.x * H;
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < H; i += blockDim.x) ss = fmaf(xr[i], xr[i], ss);
+    ss = block_sum(ss, red);
+    const float inv = 1.0f / sqrtf(ss + 1e-6f);
+    for (int i = threadIdx.x; i < H; i += blockDim.x) out[(size_t)blockIdx.x * H + i] = xr[i] * inv;
+}
+
 __global__ void add_inplace_kernel(float* __restrict__ x, const float* __restrict__ y, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) x[i] += y[i];

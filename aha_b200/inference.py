@@ -143,6 +143,27 @@ class B200Model:
                      completion_secs=u.completion_secs, vision_secs=u.vision_secs)
         return [int(out[i]) for i in range(n.value)], usage
 
+    # ------------------------------------------------------------------ Qwen3-Embedding / Qwen3-Reranker
+    def embed(self, input_ids):
+        """Qwen3Embedding::embed_one on token ids -> unit vector (hidden_size,) float32."""
+        ids = self._ids(input_ids)
+        out = np.empty(self.hidden_size, np.float32)
+        self._check(self._lib.aha_b200_embed(self._h, ids.ctypes.data_as(C.POINTER(C.c_uint32)), ids.size,
+                                             out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
+    def rerank(self, query_ids, documents_ids):
+        """Qwen3Reranker::rerank on token ids -> cosine scores (n_docs,) float32."""
+        q = self._ids(query_ids)
+        docs = [self._ids(d) for d in documents_ids]
+        cat = np.ascontiguousarray(np.concatenate(docs)) if docs else np.zeros(0, np.uint32)
+        lens = (C.c_size_t * max(len(docs), 1))(*[d.size for d in docs])
+        out = np.empty(len(docs), np.float32)
+        self._check(self._lib.aha_b200_rerank(self._h, q.ctypes.data_as(C.POINTER(C.c_uint32)), q.size,
+                                              cat.ctypes.data_as(C.POINTER(C.c_uint32)), lens, len(docs),
+                                              out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
     # ------------------------------------------------------------------ frontends
     def mel_spectrogram(self, wave):
         wave = np.ascontiguousarray(wave, dtype=np.float32).reshape(-1)

@@ -141,6 +141,16 @@ int aha_b200_mel_spectrogram(aha_model* m, const float* wave, size_t n_samples,
 int aha_b200_image_patchify(aha_model* m, const uint8_t* img_hwc, size_t h, size_t w,
                             float* pixel_values_out, size_t cap, uint32_t grid_thw_out[3]);
 
+/* Qwen3Embedding::embed_one (/root/reference/src/models/qwen3_embedding/mod.rs:50-64): forward_hidden over the ids
+ * (offset 0), last-token hidden state after the final RMSNorm, L2-normalised (x / sqrt(sum x^2 + 1e-6),
+ * src/models/common/modules.rs:1287-1294); the cache is cleared afterwards.  out: hidden_size floats.  "qwen3" handles. */
+int aha_b200_embed(aha_model* m, const uint32_t* ids, size_t seq_len, float* out);
+/* Qwen3Reranker::rerank (/root/reference/src/models/qwen3_reranker/mod.rs:23-31): cosine score of the query embedding
+ * against each document embedding (cosine_similarity_no_l2 on unit vectors).  doc_ids holds the documents back to back,
+ * doc_lens[n_docs] their lengths; scores_out: n_docs floats. */
+int aha_b200_rerank(aha_model* m, const uint32_t* query_ids, size_t query_len, const uint32_t* doc_ids, const size_t* doc_lens,
+                    size_t n_docs, float* scores_out);
+
 /* Tensor parallelism (new design; the reference has none): rank 0 creates a 128-byte ncclUniqueId, the host side
  * distributes it (bench.py broadcasts it between the per-GPU processes) and every rank passes it in aha_options.tp_comm together
  * with tp_rank / tp_world.  Heads and MLP rows are sharded; the only exchange steps are all-reduce(sum) after

@@ -161,6 +161,23 @@ def test_qwen3_untied_lm_head():
         m.close()
 
 
+def test_qwen3_embedding_and_reranker(q3):
+    from oracle.qwen3_embedding import Qwen3Embedding, Qwen3Reranker
+    cfg, w, m, o = q3
+    oe = Qwen3Embedding(cfg, w)
+    for n in (1, 17, 80):
+        ids = _ids(n, cfg["vocab_size"], 40 + n)
+        got, want = m.embed(ids), oe.embed_one(ids)
+        assert abs(float(np.linalg.norm(got)) - 1.0) < 1e-4
+        assert np.abs(got - want).max() <= 1e-5
+    q = _ids(9, cfg["vocab_size"], 1)
+    docs = [_ids(n, cfg["vocab_size"], 50 + n) for n in (5, 33, 12)]
+    got = m.rerank(q, docs)
+    want = Qwen3Reranker(cfg, w).rerank(q, docs)
+    assert np.abs(got - want).max() <= 1e-5
+    assert m.forward_initial(_ids(4, cfg["vocab_size"], 1), 0).shape == (1, 1, cfg["vocab_size"])   # handle still serves decoding
+
+
 def test_error_behaviour(q3):
     from aha_b200 import B200Error
     cfg, w, m, o = q3
