@@ -70,7 +70,7 @@ struct FusedArgs {
     const int* page_table;
     int nsplit;
     int stages;        // ring slots in use (<= kFusedStages)
-    int dbg;           // timing experiments only: bit0 = skip grid barriers, bit1 = skip the GEMV math, bit2 = timestamps
+    int dbg;           // timing experiments only: bit0 = skip grid barriers, bit1 = skip the GEMV math, bit2 = timestamps, bit4 / bit5 = drop the L2 evict-first hint on weight / KV copies
     unsigned long long* trace;  // [2][4096] globaltimer stamps of CTA 0 (consumer thread 0 / producer), dbg bit2
 };
 
@@ -107,6 +107,18 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
 }
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define AHA_STAMP(a, who, idx) do { if (((a).dbg & 4) && blockIdx.x == 0 && (idx) < 4096) (a).trace[(who) * 4096 + (idx)++] = gtime(); } while (0)
+// Same copy with an L2 evict-first policy: weights are read exactly once per step, so they should not displace the
+// activations / partials / barrier words that every CTA re-reads from L2.
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
 __device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kFusedConsumers * 32) : "memory"); }
 __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
     unsigned v;
@@ -167,6 +179,8 @@ struct Producer {
     Ring ring;
     unsigned it = 0;
     unsigned ns = kFusedStages;
+    bool use_hint = false, hint_kv = false;
+    uint64_t policy = 0;
     __device__ __forceinline__ void acquire(int& slot) {
         slot = it % ns;
         mbar_wait(&ring.empty[slot], ((it / ns) & 1u) ^ 1u);
@@ -181,7 +195,8 @@ struct Producer {
             acquire(slot);
             const uint32_t bytes = (uint32_t)nr * K * 2u;
             mbar_expect_tx(&ring.full[slot], bytes);
-            tma_bulk_g2s(ring.buf + (size_t)slot * kFusedStageBytes, W + (size_t)r * K, bytes, &ring.full[slot]);
+            if (use_hint) tma_bulk_g2s_hint(ring.buf + (size_t)slot * kFusedStageBytes, W + (size_t)r * K, bytes, &ring.full[slot], policy);
+            else tma_bulk_g2s(ring.buf + (size_t)slot * kFusedStageBytes, W + (size_t)r * K, bytes, &ring.full[slot]);
             ++it;
         }
     }
@@ -199,8 +214,13 @@ struct Producer {
             const uint32_t half_bytes = kHalfPage * a.hd * 4u;  // 8 KB for hd = 128
             uint8_t* dst = ring.buf + (size_t)slot * kFusedStageBytes;
             mbar_expect_tx(&ring.full[slot], 2u * half_bytes);
-            tma_bulk_g2s(dst, kbase + off, half_bytes, &ring.full[slot]);
-            tma_bulk_g2s(dst + half_bytes, kbase + vofs + off, half_bytes, &ring.full[slot]);
+            if (hint_kv) {
+                tma_bulk_g2s_hint(dst, kbase + off, half_bytes, &ring.full[slot], policy);
+                tma_bulk_g2s_hint(dst + half_bytes, kbase + vofs + off, half_bytes, &ring.full[slot], policy);
+            } else {
+                tma_bulk_g2s(dst, kbase + off, half_bytes, &ring.full[slot]);
+                tma_bulk_g2s(dst + half_bytes, kbase + vofs + off, half_bytes, &ring.full[slot]);
+            }
             ++it;
         }
     }
@@ -591,6 +611,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
             Producer p;
             p.ring = ring;
             p.ns = (unsigned)a.stages;
+            p.use_hint = (a.dbg & 16) == 0;      // dbg bit4 switches the L2 evict-first hint off (A/B runs)
+            p.hint_kv = (a.dbg & 32) == 0;       // bit5: same switch for the KV half-page copies
+            p.policy = l2_evict_first_policy();
             p.pages = spages;
             int pe = 0;
             AHA_STAMP(a, 1, pe);
