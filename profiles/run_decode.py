@@ -16,7 +16,7 @@ m.forward_initial(synth.synth_text_ids(8, 1000, 1), 0, want_logits=False)
 # decode at offset ctx: KV pages below ctx hold whatever is in the pool (timing only)
 toks, ms = m.decode_steps(5, ctx, steps, timed=True)
 toks, ms = m.decode_steps(5, ctx, steps, timed=True)
-print(f"impl={impl} dbg={os.environ.get('AHA_FUSED_DBG','0')} ctx={ctx} steps={steps} ms/step={ms/steps:.4f} tok/s={1e3*steps/ms:.1f}")
+print(f"impl={impl} pf={os.environ.get('AHA_FUSED_PF','-')} dbg={os.environ.get('AHA_FUSED_DBG','0')} ctx={ctx} steps={steps} ms/step={ms/steps:.4f} tok/s={1e3*steps/ms:.1f}")
 if int(os.environ.get("AHA_FUSED_DBG", "0")) & 4:
     m.decode_steps(5, ctx, 1)
     c = m.debug_read("fused_trace", 0, 4096); p = m.debug_read("fused_trace", 1, 4096)
