@@ -726,6 +726,15 @@ int aha_b200_debug_read(aha_model* m, const char* what, int index, float* out, s
             size_t k = 0;
             for (; k < 4096 && h[k]; ++k) out[k] = (float)(double)(h[k] - h[0]);
             *n = k; return;
+        } else if (w == "fused_cta_trace") {  // barrier arrival stamps of CTA `index` (ns relative to CTA 0's first), [255] = %smid
+            AHA_REQUIRE(T.d_ftrace && index >= 0 && index < 256 && cap >= 256, "fused trace not available");
+            std::vector<unsigned long long> h(256);
+            unsigned long long base = 0;
+            AHA_CUDA_CHECK(cudaMemcpy(&base, T.d_ftrace + 8192, sizeof(base), cudaMemcpyDeviceToHost));
+            AHA_CUDA_CHECK(cudaMemcpy(h.data(), T.d_ftrace + 8192 + (size_t)index * 256, 256 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            for (size_t k = 0; k < 255; ++k) out[k] = h[k] ? (float)((double)h[k] - (double)base) : -1e30f;
+            out[255] = (float)h[255];
+            *n = 256; return;
         } else if (w == "rope_delta") {
             AHA_REQUIRE(cap >= 1, "out too small");
             out[0] = (float)m->rope_delta; *n = 1; return;

@@ -37,6 +37,7 @@ constexpr int kFusedThreads = (kFusedConsumers + 1) * 32;
 constexpr int kFusedMaxRows = 8;                         // weight rows per stage (<= 16 KB)
 constexpr int kFusedMaxK = 8192;                         // activation vector staged in shared memory (32 KB)
 constexpr int kHalfPage = 16;                            // tokens per attention stage (K 8 KB + V 8 KB)
+constexpr int kFusedTraceWords = 2 * 4096 + 256 * 256;     // timing traces: CTA 0 consumer/producer stamps + [cta][256] barrier arrivals
 constexpr int kFusedMaxPages = 512;                      // page-table entries staged in shared memory (16K tokens)
 
 struct FusedLayer {
@@ -70,7 +71,7 @@ struct FusedArgs {
     const int* page_table;
     int nsplit;
     int stages;        // ring slots in use (<= kFusedStages)
-    int dbg;           // timing experiments only: bit0 = skip grid barriers, bit1 = skip the GEMV math, bit2 = timestamps, bit4 / bit5 = drop the L2 evict-first hint on weight / KV copies
+    int dbg;           // timing experiments only: bit0 = skip grid barriers, bit1 = skip the GEMV math, bit2 = timestamps, bit3 = old full-fence grid barrier, bit6 = per-CTA barrier arrival stamps, bit4 / bit5 = drop the L2 evict-first hint on weight / KV copies
     unsigned long long* trace;  // [2][4096] globaltimer stamps of CTA 0 (consumer thread 0 / producer), dbg bit2
 };
 
@@ -126,17 +127,39 @@ __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
     return v;
 }
 
+// Lighter synchronisation primitives than __threadfence() (= MEMBAR.SC.GPU + CCTL.IVALL per call on sm_100): a release
+// reduction / acq_rel atomic issued by ONE thread after a CTA barrier publishes the whole CTA's writes (release is
+// cumulative over the bar.sync), and a relaxed poll + fence.acq_rel is the matching acquire.  Cross-CTA data is always
+// read with ld.global.cg, so no L1 line can be stale.
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned atom_acq_rel_add(unsigned* p, unsigned v) {
+    unsigned old;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
 // Grid barrier joined by the consumer threads only: one arrival counter in L2 (zeroed by the host before every
 // launch), polled by consumer thread 0 with relaxed loads; activations are always read with ld.global.cg.
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& seq, int dbg = 0) {
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& seq, int dbg = 0, unsigned long long* trace = nullptr) {
     if (dbg & 1) { consumer_bar_sync(); return; }
     consumer_bar_sync();                       // every consumer thread of this CTA has issued its writes
     if (threadIdx.x == 0) {
-        __threadfence();                       // publish them at gpu scope (cumulative through the bar.sync)
-        atomicAdd(counter, 1u);
-        const unsigned target = (seq + 1u) * gridDim.x;
-        while (ld_relaxed_u32(counter) < target) {}
-        __threadfence();
+        if ((dbg & 64) && seq < 255) trace[8192 + blockIdx.x * 256 + seq] = gtime();   // per-CTA arrival times (skew analysis)
+        if (dbg & 8) {                         // A/B: the old full-fence barrier
+            __threadfence();
+            atomicAdd(counter, 1u);
+            const unsigned target = (seq + 1u) * gridDim.x;
+            while (ld_relaxed_u32(counter) < target) {}
+            __threadfence();
+        } else {
+            red_release_add(counter, 1u);      // publish the CTA's writes at gpu scope (cumulative through the bar.sync)
+            const unsigned target = (seq + 1u) * gridDim.x;
+            while (ld_relaxed_u32(counter) < target) {}
+            fence_acq_rel_gpu();
+        }
     }
     seq += 1u;
     consumer_bar_sync();
@@ -252,6 +275,10 @@ struct Consumer {
         if (lane == 0) mbar_arrive(&ring.empty[i % ns]);
     }
 
+    // Shared-memory layout of the activation vector: element e = 8c + j sits at 4c + j (j < 4) or K/2 + 4c + (j - 4), so
+    // the two float4 halves of chunk c are read by lane c at a 16-byte lane stride -- conflict-free LDS.128 (a plain
+    // [K] layout puts the lanes 32 bytes apart and every x read pays a 2-way bank conflict).
+    static __device__ __forceinline__ int xs_pos(int e, int K) { return ((e >> 2) & 1) * (K >> 1) + (e >> 3) * 4; }
     // Stage the activation vector of a GEMV in shared memory (all consumer threads), optional RMSNorm.
     // src is fp32 global written by other CTAs (ld.global.cg) or an fp16 embedding row.
     __device__ void load_x(int K, const float* src32, const __half* src16, const float* norm_w, float eps) {
@@ -291,7 +318,7 @@ struct Consumer {
 #pragma unroll
         for (int j = 0; j < kPer; ++j) {
             const int e = (tid + j * kFusedConsumers * 32) * 4;
-            if (e < K) *reinterpret_cast<float4*>(xs + e) = v[j];
+            if (e < K) *reinterpret_cast<float4*>(xs + xs_pos(e, K)) = v[j];
         }
         consumer_bar_sync();
     }
@@ -310,16 +337,16 @@ struct Consumer {
 #pragma unroll
             for (int n = 0; n < NA; ++n) {
                 const int cc = c + 32 * n;
-                const float4 x0 = *reinterpret_cast<const float4*>(xs + cc * 8);
-                const float4 x1 = *reinterpret_cast<const float4*>(xs + cc * 8 + 4);
+                const float4 x0 = *reinterpret_cast<const float4*>(xs + cc * 4);
+                const float4 x1 = *reinterpret_cast<const float4*>(xs + (K >> 1) + cc * 4);
 #pragma unroll
                 for (int q = 0; q < R; ++q)
                     acc[q][n] = dot8(*reinterpret_cast<const uint4*>(st + (size_t)cc * 16 + (size_t)q * K * 2), x0, x1, acc[q][n]);
             }
         }
         for (; c < nchunk; c += 32) {
-            const float4 x0 = *reinterpret_cast<const float4*>(xs + c * 8);
-            const float4 x1 = *reinterpret_cast<const float4*>(xs + c * 8 + 4);
+            const float4 x0 = *reinterpret_cast<const float4*>(xs + c * 4);
+            const float4 x1 = *reinterpret_cast<const float4*>(xs + (K >> 1) + c * 4);
 #pragma unroll
             for (int q = 0; q < R; ++q) acc[q][0] = dot8(*reinterpret_cast<const uint4*>(st + (size_t)c * 16 + (size_t)q * K * 2), x0, x1, acc[q][0]);
         }
@@ -402,6 +429,8 @@ struct AttnSmem {
     float m[kFusedConsumers][G];
     float l[kFusedConsumers][G];
     float acc[kFusedConsumers][G][128];
+    float e[G][160];      // softmax weight of every split in the final merge (nsplit <= 148)
+    float L[G];
     int last;
 };
 
@@ -548,26 +577,41 @@ __device__ void fused_attention(const FusedArgs& a, Consumer& c, AttnSmem<G>& s,
         p[d] = O;
         if (d == 0) { p[HD] = M; p[HD + 1] = L; }
     }
-    __threadfence();
     consumer_bar_sync();
-    if (tid == 0) s.last = (atomicAdd(&a.kv_counters[kvh], 1) == a.nsplit - 1) ? 1 : 0;
+    if (tid == 0) s.last = (atom_acq_rel_add(reinterpret_cast<unsigned*>(&a.kv_counters[kvh]), 1u) == (unsigned)(a.nsplit - 1)) ? 1 : 0;
     consumer_bar_sync();
     if (s.last) {  // last CTA of this kv head merges the split partials
-        __threadfence();
+        // (1) warp g: softmax weights of head g's splits -- every L2 load of a pass is in flight at once
+        if (warp < G) {
+            const float* pb = a.partial + (size_t)(kvh * G + warp) * a.nsplit * (HD + 2);
+            float M = -INFINITY;
+            for (int sp = lane; sp < a.nsplit; sp += 32) M = fmaxf(M, __ldcg(pb + (size_t)sp * (HD + 2) + HD));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
+            float L = 0.f;
+            for (int sp = lane; sp < a.nsplit; sp += 32) {
+                const float ms = __ldcg(pb + (size_t)sp * (HD + 2) + HD);
+                const float e = (ms == -INFINITY) ? 0.f : expf(ms - M);
+                L += __ldcg(pb + (size_t)sp * (HD + 2) + HD + 1) * e;
+                s.e[warp][sp] = e;
+            }
+            L = warp_sum(L);
+            if (lane == 0) s.L[warp] = L;
+        }
+        consumer_bar_sync();
+        // (2) thread (g, d): weighted sum over the splits, 16 independent loads per batch
         for (int idx = tid; idx < G * HD; idx += kFusedConsumers * 32) {
             const int g = idx / HD, d = idx % HD;
-            const float* pb = a.partial + (size_t)(kvh * G + g) * a.nsplit * (HD + 2);
-            float M = -INFINITY;
-            for (int sp = 0; sp < a.nsplit; ++sp) M = fmaxf(M, __ldcg(pb + (size_t)sp * (HD + 2) + HD));
-            float L = 0.f, O = 0.f;
-            for (int sp = 0; sp < a.nsplit; ++sp) {
-                const float ms = __ldcg(pb + (size_t)sp * (HD + 2) + HD);
-                if (ms == -INFINITY) continue;
-                const float e = expf(ms - M);
-                L += __ldcg(pb + (size_t)sp * (HD + 2) + HD + 1) * e;
-                O += __ldcg(pb + (size_t)sp * (HD + 2) + d) * e;
+            const float* pb = a.partial + (size_t)(kvh * G + g) * a.nsplit * (HD + 2) + d;
+            float O = 0.f;
+            for (int sp0 = 0; sp0 < a.nsplit; sp0 += 16) {
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = (sp0 + j < a.nsplit) ? __ldcg(pb + (size_t)(sp0 + j) * (HD + 2)) : 0.f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) if (sp0 + j < a.nsplit) O += v[j] * s.e[g][sp0 + j];
             }
-            a.attn1[(size_t)(kvh * G + g) * HD + d] = O / L;
+            a.attn1[(size_t)(kvh * G + g) * HD + d] = O / s.L[g];
         }
         if (tid == 0) a.kv_counters[kvh] = 0;
     }
@@ -592,6 +636,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
         for (int i = 0; i < kFusedStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if ((a.dbg & 64) && tid == 0) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); a.trace[8192 + blockIdx.x * 256 + 255] = smid; }
     const int t_new = a.st->pos;
     const int rope_delta = a.st->rope_delta;
     const uint32_t token = a.st->token;
@@ -649,23 +694,23 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
         // P1: qkv = Wqkv . rmsnorm(x)      (layer 0 reads the embedding row directly: Embedding::forward)
         c.load_x(a.H, a.x, first ? emb_row : nullptr, Ly.ln1, a.eps); CSTAMP();
         c.template gemv<FE_QKV>(a, a.qkv_dim, a.H, Ly.qkv_b, nullptr, nullptr, a.qkv1, best, bi); CSTAMP();
-        grid_barrier(&a.sync[0], seq, a.dbg); CSTAMP();
+        grid_barrier(&a.sync[0], seq, a.dbg, a.trace); CSTAMP();
         // P2: attention over the paged cache (+ q/k norm, RoPE, KV append)
         CSTAMP();
         fused_attention<G>(a, c, *as, cs, spages, l, Ly, t_new); CSTAMP();
-        grid_barrier(&a.sync[0], seq, a.dbg); CSTAMP();
+        grid_barrier(&a.sync[0], seq, a.dbg, a.trace); CSTAMP();
         // P3: x = resid + Wo . attn
         c.load_x(a.nh * a.hd, a.attn1, nullptr, nullptr, 0.f); CSTAMP();
         c.template gemv<FE_RESID>(a, a.H, a.nh * a.hd, Ly.o_b, a.x, first ? emb_row : nullptr, a.x, best, bi); CSTAMP();
-        grid_barrier(&a.sync[0], seq, a.dbg); CSTAMP();
+        grid_barrier(&a.sync[0], seq, a.dbg, a.trace); CSTAMP();
         // P4: h = silu(gate) * up, gate/up rows interleaved, input rmsnorm(x)
         c.load_x(a.H, a.x, nullptr, Ly.ln2, a.eps); CSTAMP();
         c.template gemv<FE_SWIGLU>(a, 2 * a.I, a.H, nullptr, nullptr, nullptr, a.h1, best, bi); CSTAMP();
-        grid_barrier(&a.sync[0], seq, a.dbg); CSTAMP();
+        grid_barrier(&a.sync[0], seq, a.dbg, a.trace); CSTAMP();
         // P5: x = x + Wdown . h
         c.load_x(a.I, a.h1, nullptr, nullptr, 0.f); CSTAMP();
         c.template gemv<FE_RESID>(a, a.H, a.I, nullptr, a.x, nullptr, a.x, best, bi); CSTAMP();
-        grid_barrier(&a.sync[0], seq, a.dbg); CSTAMP();
+        grid_barrier(&a.sync[0], seq, a.dbg, a.trace); CSTAMP();
     }
     // final: logits = lm_head . rmsnorm(x), per-CTA argmax candidate
     c.load_x(a.H, a.x, nullptr, a.final_norm, a.eps);
@@ -687,17 +732,24 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
         }
         a.pmax[blockIdx.x] = best;
         a.pidx[blockIdx.x] = bi;
-        __threadfence();
-        const unsigned ticket = atomicAdd(&a.sync[1], 1u);
-        if (ticket == gridDim.x - 1) {
-            __threadfence();
-            float gb = -INFINITY;
-            int gi = 0x7fffffff;
-            for (unsigned i = 0; i < gridDim.x; ++i) {
-                const float v = __ldcg(a.pmax + i);
-                const int id = __ldcg(a.pidx + i);
-                if (v > gb || (v == gb && id < gi)) { gb = v; gi = id; }
-            }
+        const unsigned ticket = atom_acq_rel_add(&a.sync[1], 1u);
+        reinterpret_cast<int*>(red)[31] = (ticket == gridDim.x - 1) ? 1 : 0;
+    }
+    consumer_bar_sync();
+    if (warp == 0 && reinterpret_cast<int*>(red)[31]) {   // last CTA to arrive: warp 0 reduces the per-CTA candidates
+        float gb = -INFINITY;
+        int gi = 0x7fffffff;
+        for (unsigned i = lane; i < gridDim.x; i += 32) {
+            const float v = __ldcg(a.pmax + i);
+            const int id = __ldcg(a.pidx + i);
+            if (v > gb || (v == gb && id < gi)) { gb = v; gi = id; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, gb, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, gi, o);
+            if (ov > gb || (ov == gb && oi < gi)) { gb = ov; gi = oi; }
+        }
+        if (lane == 0) {
             *a.argmax_out = (uint32_t)gi;
             DecodeState* st = a.st;
             st->token = (uint32_t)gi;

@@ -432,8 +432,8 @@ struct TextModel {
                 fl[l] = FusedLayer{T.qkv.w, T.o.w, T.gu.w, T.down.w, T.qkv.b, T.o.b, T.ln1, T.ln2, T.qn, T.kn};
             }
             d_fused_layers = upload(c, fl);
-            d_ftrace = c.alloc<unsigned long long>(2 * 4096);
-            AHA_CUDA_CHECK(cudaMemset(d_ftrace, 0, 2 * 4096 * sizeof(unsigned long long)));
+            d_ftrace = c.alloc<unsigned long long>(kFusedTraceWords);
+            AHA_CUDA_CHECK(cudaMemset(d_ftrace, 0, kFusedTraceWords * sizeof(unsigned long long)));
             switch (nh_l / nkv_l) {
                 case 1: fused_prepare<1>(); break;
                 case 2: fused_prepare<2>(); break;

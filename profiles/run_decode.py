@@ -38,3 +38,10 @@ if int(os.environ.get("AHA_FUSED_DBG", "0")) & 4:
     t0 = c[15 * Lx] / 1e3
     print(f"  layer {Lx} starts at {t0:.1f} us; consumer events (rel):", " ".join(f"{n.replace(' ', '')}@{v - t0:.1f}" for n, v in zip(names, cb)))
     print(f"  producer finished issuing (rel): ", " ".join(f"{n}@{v - t0:.1f}" for n, v in zip(["qkv", "attn", "o", "gate_up", "down"], pb)))
+
+if int(os.environ.get("AHA_FUSED_DBG", "0")) & 64:
+    m.decode_steps(5, ctx, 1)
+    arr = np.stack([m.debug_read("fused_cta_trace", i, 256) for i in range(148)])
+    os.makedirs("gpurun_out", exist_ok=True)
+    np.save("gpurun_out/cta_trace.npy", arr)
+    print("saved gpurun_out/cta_trace.npy", arr.shape)
