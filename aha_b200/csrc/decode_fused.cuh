@@ -30,7 +30,7 @@
 
 namespace aha {
 
-constexpr int kFusedStages = 12;
+constexpr int kFusedStages = 11;                         // ring slots allocated (8 in use by default, see text_model.cuh)
 constexpr int kFusedStageBytes = 16384;
 constexpr int kFusedConsumers = 11;                      // consumer warps (+1 producer = 12 warps: register allocation granularity)
 constexpr int kFusedThreads = (kFusedConsumers + 1) * 32;
@@ -38,6 +38,9 @@ constexpr int kFusedMaxRows = 8;                         // weight rows per stag
 constexpr int kFusedMaxK = 8192;                         // activation vector staged in shared memory (32 KB)
 constexpr int kHalfPage = 16;                            // tokens per attention stage (K 8 KB + V 8 KB)
 constexpr int kFusedTraceWords = 2 * 4096 + 256 * 256;     // timing traces: CTA 0 consumer/producer stamps + [cta][256] barrier arrivals
+constexpr int kFusedMaxOwnRows = 64;                     // residual-stream rows owned by one CTA (H / grid, rounded up)
+constexpr int kFusedPartialStride = 128 + 4;             // floats per (head, split) attention partial: acc[128], m, l, pad (16-byte rows)
+constexpr int kFusedMergeChunk = 20;                     // splits merged per pass when the o_proj input is assembled
 constexpr int kFusedMaxPages = 512;                      // page-table entries staged in shared memory (16K tokens)
 
 struct FusedLayer {
@@ -60,7 +63,7 @@ struct FusedArgs {
     float* attn1;      // [nh*hd]
     float* h1;         // [I]
     float* logits;     // [V]
-    float* partial;    // [nh][nsplit][hd+2]
+    float* partial;    // [nh][nsplit][kFusedPartialStride]
     int* kv_counters;  // [nkv]      (zeroed by the host before launch)
     unsigned* sync;    // [1] final ticket   (zeroed by the host before launch)
     unsigned* flags;   // [grid * kFlagStride] grid-barrier flags (zeroed by the host before launch)
@@ -172,10 +175,15 @@ __device__ __forceinline__ void cta_rows(int N, int unit, int& r0, int& r1) {
     r0 = (int)((units * blockIdx.x) / gridDim.x) * unit;
     r1 = (int)((units * (blockIdx.x + 1)) / gridDim.x) * unit;
 }
-__device__ __forceinline__ int rows_per_stage(int K) {
+// Rows per ring stage.  Short phases (few rows per CTA) use smaller stages so that the slab spreads over more consumer
+// warps -- the per-stage latency of one warp is on the critical path of every phase.
+__host__ __device__ __forceinline__ int rows_per_stage(int K, int N, int grid) {
     int r = kFusedStageBytes / (2 * K);
     r = r > kFusedMaxRows ? kFusedMaxRows : (r < 1 ? 1 : r);
-    return r > 1 ? (r & ~1) : r;   // even, so interleaved gate/up pairs never straddle a stage
+    if (r > 1) r &= ~1;            // even, so interleaved gate/up pairs never straddle a stage
+    const int per_cta = N / grid;
+    while (r > 2 && per_cta < r * 5) r >>= 1;
+    return r;
 }
 // attention work item of this CTA: (kv head, [hp0, hp1) half pages); empty when the CTA has no item
 __device__ __forceinline__ bool attn_item(const FusedArgs& a, int ctx, int& kvh, int& split, int& hp0, int& hp1) {
@@ -211,7 +219,7 @@ struct Producer {
     __device__ void rows(const __half* W, int N, int K, int unit) {
         int r0, r1;
         cta_rows(N, unit, r0, r1);
-        const int R = rows_per_stage(K);
+        const int R = rows_per_stage(K, N, gridDim.x);
         for (int r = r0; r < r1; r += R) {
             const int nr = min(R, r1 - r);
             int slot;
@@ -261,6 +269,7 @@ struct Consumer {
     unsigned it = 0;    // global stage counter (same sequence as the producer's)
     float* xs;          // [K] activation vector (shared), also aliased by the attention scratch
     float* red;         // [32] scratch
+    float* xown;        // [kFusedMaxOwnRows] this CTA's rows of the residual stream (never re-read from global memory)
     int warp, lane;
 
     unsigned ns = kFusedStages;
@@ -323,6 +332,46 @@ struct Consumer {
         consumer_bar_sync();
     }
 
+    // Input of o_proj: merge the split-KV attention partials of every head straight into xs -- each CTA does the (tiny)
+    // merge redundantly from L2 instead of one "last" CTA per kv head publishing it behind a fence + atomic + two more
+    // dependent L2 round trips.  One warp per head; all loads of a pass are in flight at once.
+    __device__ void load_attn(const FusedArgs& a) {
+        constexpr int HD = 128, PS = kFusedPartialStride, CH = kFusedMergeChunk;
+        const int K = a.nh * HD;
+        for (int h = warp; h < a.nh; h += kFusedConsumers) {
+            const float* pb = a.partial + (size_t)h * a.nsplit * PS;
+            float M = -INFINITY, L = 0.f;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int s0 = 0; s0 < a.nsplit; s0 += CH) {
+                float4 v[CH];
+#pragma unroll
+                for (int j = 0; j < CH; ++j)
+                    v[j] = (s0 + j < a.nsplit) ? __ldcg(reinterpret_cast<const float4*>(pb + (size_t)(s0 + j) * PS) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float m = -INFINITY, l = 0.f;
+                if (lane < CH && s0 + lane < a.nsplit) {
+                    const float2 ml = __ldcg(reinterpret_cast<const float2*>(pb + (size_t)(s0 + lane) * PS + HD));
+                    m = ml.x; l = ml.y;
+                }
+                float cm = m;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+                const float Mn = fmaxf(M, cm);
+                const float so = (M == -INFINITY) ? 0.f : expf(M - Mn);
+                const float e = (m == -INFINITY) ? 0.f : expf(m - Mn);
+                L = L * so + warp_sum(l * e);
+                acc.x *= so; acc.y *= so; acc.z *= so; acc.w *= so;
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    const float ej = __shfl_sync(0xffffffffu, e, j);
+                    acc.x += v[j].x * ej; acc.y += v[j].y * ej; acc.z += v[j].z * ej; acc.w += v[j].w * ej;
+                }
+                M = Mn;
+            }
+            *reinterpret_cast<float4*>(xs + xs_pos(h * HD + 4 * lane, K)) = make_float4(acc.x / L, acc.y / L, acc.z / L, acc.w / L);
+        }
+        consumer_bar_sync();
+    }
+
     // dot products of a FULL stage of R rows against xs; NA independent accumulators per row break the FMA chain
     template <int R, int NA>
     __device__ __forceinline__ void stage_dots(const uint8_t* st, int K, float (&v)[kFusedMaxRows]) const {
@@ -362,11 +411,10 @@ struct Consumer {
     // One GEMV phase: y[r0:r1) = W[r0:r1, :] . xs  with the fused epilogue.  Ends with a consumer barrier so
     // that xs may be overwritten by the next phase.
     template <int EPI>
-    __device__ void gemv(const FusedArgs& a, int N, int K, const float* bias, const float* resid32, const __half* resid16, float* out,
-                         float& best, int& bi) {
+    __device__ void gemv(const FusedArgs& a, int N, int K, const float* bias, float* out, float& best, int& bi) {
         int r0, r1;
         cta_rows(N, EPI == FE_SWIGLU ? 2 : 1, r0, r1);
-        const int R = rows_per_stage(K);
+        const int R = rows_per_stage(K, N, gridDim.x);
         unsigned i = it;
         for (int r = r0; r < r1; r += R, ++i) {
             if (!owns(i)) continue;
@@ -409,7 +457,7 @@ struct Consumer {
                 } else {
                     float y = mine;
                     if (bias) y += bias[row];
-                    if (EPI == FE_RESID) y += resid16 ? __half2float(resid16[row]) : __ldcg(resid32 + row);
+                    if (EPI == FE_RESID) { y += xown[row - r0]; xown[row - r0] = y; }   // o_proj and down own the same rows of x
                     out[row] = y;
                     if (EPI == FE_LOGITS && (y > best || (y == best && row < bi))) { best = y; bi = row; }
                 }
@@ -429,9 +477,7 @@ struct AttnSmem {
     float m[kFusedConsumers][G];
     float l[kFusedConsumers][G];
     float acc[kFusedConsumers][G][128];
-    float e[G][160];      // softmax weight of every split in the final merge (nsplit <= 148)
-    float L[G];
-    int last;
+
 };
 
 template <int G>
@@ -573,48 +619,11 @@ __device__ void fused_attention(const FusedArgs& a, Consumer& c, AttnSmem<G>& s,
                 O += s.acc[w][g][d] * e;
             }
         }
-        float* p = a.partial + ((size_t)(kvh * G + g) * a.nsplit + split) * (HD + 2);
+        float* p = a.partial + ((size_t)(kvh * G + g) * a.nsplit + split) * kFusedPartialStride;
         p[d] = O;
         if (d == 0) { p[HD] = M; p[HD + 1] = L; }
     }
-    consumer_bar_sync();
-    if (tid == 0) s.last = (atom_acq_rel_add(reinterpret_cast<unsigned*>(&a.kv_counters[kvh]), 1u) == (unsigned)(a.nsplit - 1)) ? 1 : 0;
-    consumer_bar_sync();
-    if (s.last) {  // last CTA of this kv head merges the split partials
-        // (1) warp g: softmax weights of head g's splits -- every L2 load of a pass is in flight at once
-        if (warp < G) {
-            const float* pb = a.partial + (size_t)(kvh * G + warp) * a.nsplit * (HD + 2);
-            float M = -INFINITY;
-            for (int sp = lane; sp < a.nsplit; sp += 32) M = fmaxf(M, __ldcg(pb + (size_t)sp * (HD + 2) + HD));
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
-            float L = 0.f;
-            for (int sp = lane; sp < a.nsplit; sp += 32) {
-                const float ms = __ldcg(pb + (size_t)sp * (HD + 2) + HD);
-                const float e = (ms == -INFINITY) ? 0.f : expf(ms - M);
-                L += __ldcg(pb + (size_t)sp * (HD + 2) + HD + 1) * e;
-                s.e[warp][sp] = e;
-            }
-            L = warp_sum(L);
-            if (lane == 0) s.L[warp] = L;
-        }
-        consumer_bar_sync();
-        // (2) thread (g, d): weighted sum over the splits, 16 independent loads per batch
-        for (int idx = tid; idx < G * HD; idx += kFusedConsumers * 32) {
-            const int g = idx / HD, d = idx % HD;
-            const float* pb = a.partial + (size_t)(kvh * G + g) * a.nsplit * (HD + 2) + d;
-            float O = 0.f;
-            for (int sp0 = 0; sp0 < a.nsplit; sp0 += 16) {
-                float v[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = (sp0 + j < a.nsplit) ? __ldcg(pb + (size_t)(sp0 + j) * (HD + 2)) : 0.f;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) if (sp0 + j < a.nsplit) O += v[j] * s.e[g][sp0 + j];
-            }
-            a.attn1[(size_t)(kvh * G + g) * HD + d] = O / s.L[g];
-        }
-        if (tid == 0) a.kv_counters[kvh] = 0;
-    }
+    // the split partials are merged by the consumers of the next phase (Consumer::load_attn), after the grid barrier
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
@@ -625,7 +634,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
     uint64_t* full = reinterpret_cast<uint64_t*>(fused_smem_raw + (size_t)kFusedStages * kFusedStageBytes);
     uint64_t* empty = full + kFusedStages;
     float* red = reinterpret_cast<float*>(empty + kFusedStages);
-    float* cs = red + 32;                                       // [128] cos | sin of the step's rotary angles
+    float* xown = red + 32;                                     // [kFusedMaxOwnRows]
+    float* cs = xown + kFusedMaxOwnRows;                        // [128] cos | sin of the step's rotary angles
     float* xs = cs + 128;                                       // [kFusedMaxK] activations / attention scratch
     int* spages = reinterpret_cast<int*>(xs + kFusedMaxK);      // [kFusedMaxPages] page table copy
     AttnSmem<G>* as = reinterpret_cast<AttnSmem<G>*>(xs);
@@ -678,11 +688,16 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
     }
     // ======================================================= CONSUMERS
     Consumer c;
-    c.ring = ring; c.ns = (unsigned)a.stages; c.xs = xs; c.red = red; c.warp = warp; c.lane = lane;
+    c.ring = ring; c.ns = (unsigned)a.stages; c.xs = xs; c.red = red; c.xown = xown; c.warp = warp; c.lane = lane;
     unsigned seq = 0;
     float best = -INFINITY;
     int bi = 0x7fffffff;
     const __half* emb_row = a.embed + (size_t)token * a.H;
+    {   // the rows of the residual stream this CTA owns start as the embedding row (Embedding::forward)
+        int r0, r1;
+        cta_rows(a.H, 1, r0, r1);
+        if (tid < r1 - r0) xown[tid] = __half2float(emb_row[r0 + tid]);
+    }
     int ce = 0;
 #define CSTAMP() do { if (tid == 0) AHA_STAMP(a, 0, ce); } while (0)
     CSTAMP();
@@ -693,29 +708,29 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
         const bool first = (l == 0);
         // P1: qkv = Wqkv . rmsnorm(x)      (layer 0 reads the embedding row directly: Embedding::forward)
         c.load_x(a.H, a.x, first ? emb_row : nullptr, Ly.ln1, a.eps); CSTAMP();
-        c.template gemv<FE_QKV>(a, a.qkv_dim, a.H, Ly.qkv_b, nullptr, nullptr, a.qkv1, best, bi); CSTAMP();
+        c.template gemv<FE_QKV>(a, a.qkv_dim, a.H, Ly.qkv_b, a.qkv1, best, bi); CSTAMP();
         grid_barrier(&a.sync[0], seq, a.dbg, a.trace); CSTAMP();
         // P2: attention over the paged cache (+ q/k norm, RoPE, KV append)
         CSTAMP();
         fused_attention<G>(a, c, *as, cs, spages, l, Ly, t_new); CSTAMP();
         grid_barrier(&a.sync[0], seq, a.dbg, a.trace); CSTAMP();
         // P3: x = resid + Wo . attn
-        c.load_x(a.nh * a.hd, a.attn1, nullptr, nullptr, 0.f); CSTAMP();
-        c.template gemv<FE_RESID>(a, a.H, a.nh * a.hd, Ly.o_b, a.x, first ? emb_row : nullptr, a.x, best, bi); CSTAMP();
+        c.load_attn(a); CSTAMP();
+        c.template gemv<FE_RESID>(a, a.H, a.nh * a.hd, Ly.o_b, a.x, best, bi); CSTAMP();
         grid_barrier(&a.sync[0], seq, a.dbg, a.trace); CSTAMP();
         // P4: h = silu(gate) * up, gate/up rows interleaved, input rmsnorm(x)
         c.load_x(a.H, a.x, nullptr, Ly.ln2, a.eps); CSTAMP();
-        c.template gemv<FE_SWIGLU>(a, 2 * a.I, a.H, nullptr, nullptr, nullptr, a.h1, best, bi); CSTAMP();
+        c.template gemv<FE_SWIGLU>(a, 2 * a.I, a.H, nullptr, a.h1, best, bi); CSTAMP();
         grid_barrier(&a.sync[0], seq, a.dbg, a.trace); CSTAMP();
         // P5: x = x + Wdown . h
         c.load_x(a.I, a.h1, nullptr, nullptr, 0.f); CSTAMP();
-        c.template gemv<FE_RESID>(a, a.H, a.I, nullptr, a.x, nullptr, a.x, best, bi); CSTAMP();
+        c.template gemv<FE_RESID>(a, a.H, a.I, nullptr, a.x, best, bi); CSTAMP();
         grid_barrier(&a.sync[0], seq, a.dbg, a.trace); CSTAMP();
     }
     // final: logits = lm_head . rmsnorm(x), per-CTA argmax candidate
     c.load_x(a.H, a.x, nullptr, a.final_norm, a.eps);
     best = -INFINITY; bi = 0x7fffffff;
-    c.template gemv<FE_LOGITS>(a, a.V, a.H, nullptr, nullptr, nullptr, a.logits, best, bi); CSTAMP();
+    c.template gemv<FE_LOGITS>(a, a.V, a.H, nullptr, a.logits, best, bi); CSTAMP();
     // CTA-level argmax (first maximal index), then the last CTA to arrive reduces across CTAs
     for (int o = 16; o > 0; o >>= 1) {
         const float ov = __shfl_xor_sync(0xffffffffu, best, o);
@@ -762,7 +777,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
 
 template <int G>
 inline size_t fused_smem_bytes() {
-    return (size_t)kFusedStages * kFusedStageBytes + 2 * kFusedStages * sizeof(uint64_t) + (32 + 128) * sizeof(float) + (size_t)kFusedMaxK * sizeof(float) +
+    return (size_t)kFusedStages * kFusedStageBytes + 2 * kFusedStages * sizeof(uint64_t) + (32 + kFusedMaxOwnRows + 128) * sizeof(float) + (size_t)kFusedMaxK * sizeof(float) +
            (size_t)kFusedMaxPages * sizeof(int) + 64;
 }
 

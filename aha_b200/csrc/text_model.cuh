@@ -378,14 +378,14 @@ struct TextModel {
         if (cfg.hd != 128) return no("head_dim != 128");
         if (cfg.H % 8 || I_l % 8) return no("K not a multiple of 8");
         if (cfg.H > kFusedMaxK || I_l > kFusedMaxK || nh_l * cfg.hd > kFusedMaxK) return no("K > 8192");
-        if (rows_per_stage_host(cfg.H) % 2) return no("a gate/up row pair does not fit one 16 KB stage");
+        if (rows_per_stage(cfg.H, 2 * I_l, ctx->num_sms) % 2) return no("a gate/up row pair does not fit one 16 KB stage");
+        if ((cfg.H + ctx->num_sms - 1) / ctx->num_sms > kFusedMaxOwnRows) return no("more residual rows per SM than the fused kernel keeps on chip");
         if (ctx->num_sms < nkv_l) return no("fewer SMs than kv heads");
         if (cfg.attn_bias) return no("attention bias");
         if (nh_l / nkv_l > 4) return no("GQA group > 4");
         if (max_ctx_hint > kFusedMaxPages * kPage) return no("max_ctx beyond the page table staged in shared memory");
         return true;
     }
-    static int rows_per_stage_host(int K) { int r = kFusedStageBytes / (2 * K); r = r > kFusedMaxRows ? kFusedMaxRows : (r < 1 ? 1 : r); return r > 1 ? (r & ~1) : r; }
     template <int G>
     void fused_prepare() {
         fused_smem = fused_smem_bytes<G>();
@@ -420,7 +420,7 @@ struct TextModel {
         logits = c.alloc<float>(cfg.V);
         fused_grid = c.num_sms;
         fused_nsplit = std::max(1, std::min(32, fused_grid / std::max(1, nkv_l)));
-        partial = c.alloc<float>((size_t)nh_l * std::max(kDecodeSplits, fused_nsplit) * (cfg.hd + 2));
+        partial = c.alloc<float>((size_t)nh_l * std::max(kDecodeSplits, fused_nsplit) * (cfg.hd + 4));   // fused kernel: 16-byte aligned rows
         sync_words = 2 + nkv_l;
         d_sync = c.alloc<unsigned>(sync_words);
         AHA_CUDA_CHECK(cudaMemset(d_sync, 0, sync_words * sizeof(unsigned)));
