@@ -338,7 +338,8 @@ struct Consumer {
     __device__ void load_attn(const FusedArgs& a) {
         constexpr int HD = 128, PS = kFusedPartialStride, CH = kFusedMergeChunk;
         const int K = a.nh * HD;
-        for (int h = warp; h < a.nh; h += kFusedConsumers) {
+        for (int h0 = warp; h0 < a.nh; h0 += kFusedConsumers) {
+            const int h = (h0 + (int)blockIdx.x) % a.nh;   // all CTAs read the same lines: rotate the head order so they spread over the L2 slices
             const float* pb = a.partial + (size_t)h * a.nsplit * PS;
             float M = -INFINITY, L = 0.f;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
