@@ -53,6 +53,7 @@ class Qwen3ASRAudioEncoder:
         self.p1, self.p1b, self.p2, self.p2b = g("proj1.weight"), g("proj1.bias"), g("proj2.weight"), g("proj2.bias")
         self.act = nn.activation(ac.get("activation_function", "gelu"))
         self.conv_chunksize = ac.get("conv_chunksize", 500)
+        self.conv_act = nn.gelu_tanh  # Tensor::gelu() == tanh approx (model.rs:200-202); HF uses erf here (tests swap it to cross-check the rest)
         self.trace = None
 
     def forward(self, xs):
@@ -77,7 +78,7 @@ class Qwen3ASRAudioEncoder:
         for s in range(0, feat.shape[0], self.conv_chunksize):
             e = feat[s:s + self.conv_chunksize]
             for cwt, cb in self.convs:
-                e = nn.gelu_tanh(nn.conv2d(e, cwt, cb, 2, 1))  # Tensor::gelu() == tanh approx (model.rs:200-202)
+                e = self.conv_act(nn.conv2d(e, cwt, cb, 2, 1))
             outs.append(e)
         e = np.concatenate(outs, 0)
         b, c, f, t = e.shape

@@ -1,5 +1,6 @@
 """Cross-check of the oracle against HF transformers where the reference has no quirk (text decoder, ViT,
-pos-embed interpolation, 2-D RoPE, deepstack, M-RoPE, get_rope_index, slaney mel bank).  CPU only."""
+pos-embed interpolation, 2-D RoPE, deepstack, M-RoPE, get_rope_index, slaney mel bank, the audio tower with the
+reference's two deviations from HF -- tanh-GELU in the conv stem, no attention windows -- neutralised).  CPU only."""
 import numpy as np
 import pytest
 
@@ -69,3 +70,80 @@ def test_mel_filter_bank_matches_hf():
     from oracle.audio import mel_filter_bank
     h = hfmel(201, 128, 0.0, 8000.0, 16000, norm="slaney", mel_scale="slaney")
     assert np.abs(h - mel_filter_bank(201, 128, 0.0, 8000.0, 16000)).max() < 1e-6
+
+
+def test_audio_tower_matches_hf_omni_encoder():
+    """The ASR audio tower against HF's Qwen3-Omni audio encoder (the architecture it was derived from).  The two places
+    where the reference differs are neutralised: the conv-stem GELU is switched to erf in the oracle
+    (qwen3_asr/model.rs:200-202 uses the tanh form; covered by test_activations_match_definitions), HF's attention
+    window is made larger than the sequence (the reference attends over all chunks, model.rs:218-220), and the oracle's
+    sinusoid table gets HF's timescales: the reference builds it from the RoPE helper, 10000^(-i/(d/2))
+    (sinusoidal_pe.rs:13, rope.rs:7-13), where HF/Whisper use 10000^(-i/(d/2-1)) -- a third deviation this test found;
+    the oracle and the CUDA path keep the reference's form."""
+    try:
+        from transformers.models.qwen3_omni_moe.configuration_qwen3_omni_moe import Qwen3OmniMoeAudioEncoderConfig
+        from transformers.models.qwen3_omni_moe.modeling_qwen3_omni_moe import Qwen3OmniMoeAudioEncoder
+    except ImportError:
+        pytest.skip("transformers build without qwen3_omni_moe")
+    from oracle import nn as onn
+    from oracle.audio import get_feat_extract_output_lengths
+    from oracle.qwen3_asr import Qwen3ASRAudioEncoder
+    cfg = synth.get_config("qwen3_asr", "tiny")
+    ac = cfg["thinker_config"]["audio_config"]
+    w = synth.make_weights("qwen3_asr", cfg, 0)
+    hc = Qwen3OmniMoeAudioEncoderConfig(**dict(ac, n_window_infer=100 * 1000))
+    hc._attn_implementation = "eager"
+    hf = Qwen3OmniMoeAudioEncoder(hc).float().eval()
+    pre = "thinker.audio_tower."
+    sd = {k[len(pre):]: torch.from_numpy(v.astype(np.float32)) for k, v in w.items() if k.startswith(pre)}
+    missing, unexpected = hf.load_state_dict(sd, strict=False)
+    assert not unexpected and all("positional_embedding" in k for k in missing), (missing, unexpected)
+    T = 250                                                   # chunks of 100, 100, 50 frames -> 13 + 13 + 7 tokens
+    rng = np.random.default_rng(3)
+    mel = rng.standard_normal((ac["num_mel_bins"], T)).astype(np.float32)
+    enc = Qwen3ASRAudioEncoder(ac, w)
+    enc.conv_act = onn.gelu_erf
+    half = ac["d_model"] // 2
+    ref_form = enc.pe.inv_freq.copy()
+    enc.pe.inv_freq = np.exp(-np.log(10000.0) / (half - 1) * np.arange(half, dtype=np.float32))[None].astype(np.float32)
+    assert np.abs(ref_form - np.float32(10000.0) ** (-np.arange(half, dtype=np.float32) / np.float32(half))).max() < 1e-6   # sinusoidal_pe.rs:13
+    got = enc.forward(mel)
+    with torch.no_grad():
+        want = hf(torch.from_numpy(mel), feature_lens=torch.tensor([T]),
+                  aftercnn_lens=torch.tensor([get_feat_extract_output_lengths(T)])).last_hidden_state.numpy()
+    assert got.shape == want.shape == (33, ac["output_dim"])
+    assert np.abs(got - want).max() < 2e-5
+
+
+def test_log_mel_matches_hf_whisper_frontend():
+    """The whole log-mel frontend (framing, power spectrum, slaney bank, log10, -8 dB clamp, (x+4)/4) against HF's
+    WhisperFeatureExtractor on 30 s of audio.  Neutralised: the Hann window (the reference's is symmetric,
+    audio_utils.rs:1071-1082; HF's periodic).  Excluded: the last frame, the only one that reaches into the right
+    reflect pad, which the reference cuts from the already left-padded tensor (tensor_utils.rs:525-549)."""
+    from transformers import WhisperFeatureExtractor as HFExtractor
+    from oracle.audio import WhisperFeatureExtractor
+    wav = synth.synth_audio(30.0, 16000, 2)
+    want = HFExtractor(feature_size=128)(wav, sampling_rate=16000, return_tensors="np", padding="max_length")["input_features"][0]
+    fe = WhisperFeatureExtractor()
+    symmetric = fe.extract_fbank_features(wav[None])[0]
+    fe.window = (0.5 - 0.5 * np.cos(2 * np.pi * np.arange(400) / 400)).astype(np.float32)
+    got = fe.extract_fbank_features(wav[None])[0]
+    assert got.shape == want.shape == (128, 3000)
+    assert np.abs(got[:, :-1] - want[:, :-1]).max() < 5e-4        # f32 power spectrum vs HF's f64, in the log domain
+    assert np.abs(got[:, -1] - want[:, -1]).max() > 1e-2          # the reflect-pad quirk is real ...
+    assert np.abs(symmetric[:, :-1] - want[:, :-1]).max() > 1e-2  # ... and so is the window's
+
+
+def test_image_patchify_matches_hf_processor():
+    """img_transform + the 9-D patchify permute (qwen3vl/processor.rs:151-251) against HF's Qwen2VLImageProcessor for an
+    image that needs no resize (the CatmullRom resize itself is out of scope)."""
+    from transformers import Qwen2VLImageProcessor
+    from oracle.qwen3vl import process_image
+    for h, w in ((256, 320), (64, 1024)):
+        img = synth.synth_image(h, w, 1)
+        pv, grid = process_image(img)
+        ip = Qwen2VLImageProcessor(patch_size=16, temporal_patch_size=2, merge_size=2, image_mean=[0.5] * 3, image_std=[0.5] * 3,
+                                   min_pixels=65536, max_pixels=16777216)
+        out = ip(images=[img], return_tensors="np")
+        assert (np.asarray(out["image_grid_thw"]) == grid).all()
+        assert np.abs(out["pixel_values"] - pv).max() < 1e-6
