@@ -12,8 +12,9 @@ un-vendored crates candle-core / candle-nn / candle-transformers 0.9.2 (Cargo.to
 gemm 0.18, realfft 3.5.  The restatement is therefore anchored on
   (1) the reference's call sites, line by line (each function cites file:line),
   (2) closed-form known answers derivable from the source (tests/test_oracle_kat.py),
-  (3) a cross-check against HF transformers 5.5 where the reference has no quirk
-      (tests/golden/make_hf_crosscheck.py, run in the build container).
+  (3) cross-checks against HF transformers 5.5 (tests/test_oracle_hf.py): Qwen3, Qwen3-VL, the
+      image patchify, the ASR audio tower and the log-mel frontend, the reference's deliberate
+      deviations from HF switched off for the comparison and covered by known-answer tests.
 Candle op semantics assumed (published behaviour of candle 0.9.x):
   Linear = x @ W^T (+ b); RmsNorm = x / sqrt(mean(x^2) + eps) * w with f32 statistics;
   LayerNorm = (x - mean) / sqrt(var + eps) * w + b; softmax_last_dim is max-subtracted;
