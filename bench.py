@@ -132,8 +132,10 @@ def emit(line):
 
 def ncu_traffic_bytes():
     """dram__bytes_read.sum + dram__bytes_write.sum of one decode_step_fused_kernel launch, from the committed
-    `ncu --set full` summary (profiles/r01_fused_decode_ncu_summary.csv)."""
-    p = os.path.join(ROOT, "profiles", "r01_fused_decode_ncu_summary.csv")
+    `ncu --set full` summary (profiles/r01_fused_decode_final_ncu_summary.csv)."""
+    p = os.path.join(ROOT, "profiles", "r01_fused_decode_final_ncu_summary.csv")   # capture of the final tree of round 1
+    if not os.path.exists(p):
+        p = os.path.join(ROOT, "profiles", "r01_fused_decode_ncu_summary.csv")
     try:
         tot = 0.0
         for row in open(p).read().splitlines()[1:]:

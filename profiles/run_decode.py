@@ -8,7 +8,9 @@ steps = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 impl = int(os.environ.get("AHA_DECODE_IMPL", "0"))
 ctx = int(os.environ.get("AHA_CTX", "2554"))
 cfg = synth.get_config("qwen3", "q0.6")
-cfg.update(hidden_size=2048, intermediate_size=6144, rope_theta=5e6)   # Qwen3-VL-2B text stack shape
+shape = os.environ.get("AHA_SHAPE", "vl2")
+if shape == "vl2":
+    cfg.update(hidden_size=2048, intermediate_size=6144, rope_theta=5e6)   # Qwen3-VL-2B text stack shape (else: Qwen3-0.6B / ASR-0.6B)
 w = synth.make_weights("qwen3", cfg, 0)
 m = B200Model("qwen3", cfg, w, max_ctx=4096, max_prefill=64, decode_impl=impl)
 del w
@@ -16,7 +18,7 @@ m.forward_initial(synth.synth_text_ids(8, 1000, 1), 0, want_logits=False)
 # decode at offset ctx: KV pages below ctx hold whatever is in the pool (timing only)
 toks, ms = m.decode_steps(5, ctx, steps, timed=True)
 toks, ms = m.decode_steps(5, ctx, steps, timed=True)
-print(f"impl={impl} pf={os.environ.get('AHA_FUSED_PF','-')} dbg={os.environ.get('AHA_FUSED_DBG','0')} ctx={ctx} steps={steps} ms/step={ms/steps:.4f} tok/s={1e3*steps/ms:.1f}")
+print(f"shape={shape} impl={impl} pf={os.environ.get('AHA_FUSED_PF','-')} dbg={os.environ.get('AHA_FUSED_DBG','0')} ctx={ctx} steps={steps} ms/step={ms/steps:.4f} tok/s={1e3*steps/ms:.1f}")
 if int(os.environ.get("AHA_FUSED_DBG", "0")) & 4:
     m.decode_steps(5, ctx, 1)
     c = m.debug_read("fused_trace", 0, 4096); p = m.debug_read("fused_trace", 1, 4096)
