@@ -4,17 +4,18 @@
 // Qwen3-VL-2B, ~1 FLOP/byte) cut into ~140 dependent pieces of 8-50 MB; as separate launches every piece pays
 // launch + pipeline ramp and the memory system idles between them.  Here one CTA per SM stays resident for
 // the whole step:
-//   * warp 8 (one elected lane) is the PRODUCER: it walks this CTA's static schedule of transfers for all
+//   * the last warp (one elected lane) is the PRODUCER: it walks this CTA's static schedule of transfers for all
 //     layers -- weight row slabs and paged-KV half pages -- and issues TMA bulk copies
-//     (cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes, SASS UBLKCP) into a 12 x 16 KB
-//     shared-memory ring guarded by full/empty mbarriers.  It never waits for activations, so weights for
-//     the next phases keep streaming while the consumers sit in a grid barrier;
-//   * warps 0-7 are CONSUMERS: per phase they stage the activation vector in shared memory (RMSNorm fused),
-//     and each warp consumes the ring slots it owns (slot % 8): a whole stage of weight rows is reduced by one
-//     warp with fp32 dot products (fp16 weights converted exactly) and the fused epilogue (residual add,
-//     SwiGLU, argmax) is applied by its lanes; attention is split-KV with per-warp online softmax over the
-//     half pages the warp owns, q/k RMSNorm + RoPE + KV append fused in;
-//   * phases are separated by a grid-wide barrier (atomic counter in L2) that only the consumers join.
+//     (cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes, SASS UBLKCP, L2 evict-first policy) into
+//     a ring of 16 KB shared-memory stages guarded by full/empty mbarriers.  It never waits for activations, so
+//     weights for the next phases keep streaming while the consumers sit in a grid barrier;
+//   * the other 11 warps are CONSUMERS: per phase they stage the activation vector in shared memory (RMSNorm
+//     fused), and each warp consumes the ring slots it owns: a whole stage of weight rows is reduced by one warp
+//     with fp32 dot products (fp16 weights converted exactly) and the fused epilogue (residual add from the rows
+//     of the residual stream the CTA keeps on chip, SwiGLU, argmax) is applied by its lanes; attention is split-KV
+//     with per-warp online softmax over the half pages the warp owns, q/k RMSNorm + RoPE + KV append fused in, and
+//     the merge of the splits folded into the o_proj input load;
+//   * phases are separated by a grid-wide barrier (one counter in L2, release/acquire) that only the consumers join.
 // Phases per layer: [rmsnorm+qkv] -> [attention] -> [o_proj+residual] -> [rmsnorm+gate/up+SwiGLU] ->
 // [down+residual]; then [final norm + lm_head + argmax] and the on-device token feedback.
 //
@@ -60,13 +61,10 @@ struct FusedArgs {
     DecodeState* st;
     float* x;          // [H]   residual stream
     float* qkv1;       // [qkv_dim]
-    float* attn1;      // [nh*hd]
     float* h1;         // [I]
     float* logits;     // [V]
     float* partial;    // [nh][nsplit][kFusedPartialStride]
-    int* kv_counters;  // [nkv]      (zeroed by the host before launch)
-    unsigned* sync;    // [1] final ticket   (zeroed by the host before launch)
-    unsigned* flags;   // [grid * kFlagStride] grid-barrier flags (zeroed by the host before launch)
+    unsigned* sync;    // [2] grid-barrier counter, final ticket   (zeroed by the host before launch)
     float* pmax; int* pidx;  // [grid] per-CTA argmax candidates
     uint32_t* argmax_out;
     uint32_t* history; int hist_cap;

@@ -609,14 +609,13 @@ struct TextModel {
         fa.layers = d_fused_layers; fa.L = cfg.L; fa.H = cfg.H; fa.I = I_l; fa.nh = nh_l; fa.nkv = nkv_l; fa.hd = cfg.hd; fa.V = cfg.V; fa.qkv_dim = qkv_dim;
         fa.eps = cfg.eps; fa.scaling = (float)(1.0 / std::sqrt((double)cfg.hd));
         fa.embed = embed; fa.lm_head = lm_head; fa.final_norm = norm; fa.inv_freq = inv_freq; fa.st = d_state;
-        fa.x = x1; fa.qkv1 = qkv1; fa.attn1 = attn1; fa.h1 = h1; fa.logits = logits; fa.partial = partial;
-        fa.kv_counters = counters; fa.sync = d_sync; fa.flags = nullptr; fa.pmax = pmax; fa.pidx = pidx; fa.argmax_out = d_argmax;
+        fa.x = x1; fa.qkv1 = qkv1; fa.h1 = h1; fa.logits = logits; fa.partial = partial;
+        fa.sync = d_sync; fa.pmax = pmax; fa.pidx = pidx; fa.argmax_out = d_argmax;
         fa.history = d_history; fa.hist_cap = hist_cap; fa.kv_pool = kv_pool; fa.layer_stride = layer_stride; fa.page_stride = page_stride;
         fa.page_table = d_page_table; fa.nsplit = fused_nsplit;
         { const char* e = getenv("AHA_FUSED_DBG"); fa.dbg = e ? atoi(e) : 0; }
         fa.trace = d_ftrace;
         { const char* e = getenv("AHA_FUSED_STAGES"); fa.stages = e ? std::max(2, std::min(kFusedStages, atoi(e))) : fused_stages; }
-        AHA_REQUIRE(fused_grid <= n_pcand || true, "");
         AHA_CUDA_CHECK(cudaMemsetAsync(d_sync, 0, sync_words * sizeof(unsigned), c.stream));
         switch (nh_l / nkv_l) {
             case 1: launch_fused<1>(fa); break;
