@@ -31,7 +31,7 @@
 
 namespace aha {
 
-constexpr int kFusedStages = 11;                         // ring slots allocated (8 in use by default, see text_model.cuh)
+constexpr int kFusedStages = 11;                         // ring slots (all in use by default: one per consumer warp)
 constexpr int kFusedStageBytes = 16384;
 constexpr int kFusedConsumers = 11;                      // consumer warps (+1 producer = 12 warps: register allocation granularity)
 constexpr int kFusedThreads = (kFusedConsumers + 1) * 32;

@@ -296,7 +296,7 @@ struct TextModel {
     unsigned* d_sync = nullptr;   // [0] grid barrier, [1] final ticket, then kv tickets [nkv]
     unsigned long long* d_ftrace = nullptr;
     size_t sync_words = 0;
-    int fused_stages = 8;   // measured best on B200 (profiles/README.md): deeper prefetch queues urgent stages behind other CTAs' prefetches
+    int fused_stages = kFusedStages;   // ring depth: re-measured on the final kernel of round 1, 11 slots 773 tok/s vs 8 slots 762 (profiles/README.md)
     int fused_grid = 0, fused_nsplit = 0;
     size_t fused_smem = 0;
 
