@@ -652,6 +652,27 @@ int aha_b200_nccl_unique_id(uint8_t out[128]) {
     }
 }
 
+int aha_b200_rope_index(const uint32_t* ids, size_t seq_len, const uint32_t* grid_thw, size_t n_images, uint32_t spatial_merge_size,
+                        uint32_t image_token_id, uint32_t vision_start_token_id, int32_t* pos3_out, int32_t* rope_delta_out) {
+    try {
+        AHA_REQUIRE(ids != nullptr && seq_len > 0 && pos3_out != nullptr && rope_delta_out != nullptr, "ids, pos3_out and rope_delta_out are required");
+        AHA_REQUIRE(n_images == 0 || grid_thw != nullptr, "grid_thw is required when n_images > 0");
+        AHA_REQUIRE(spatial_merge_size > 0 && seq_len < (size_t)1 << 30, "bad spatial_merge_size / seq_len");
+        std::vector<std::array<int, 3>> grid(n_images);
+        for (size_t i = 0; i < n_images; ++i) grid[i] = {(int)grid_thw[3 * i], (int)grid_thw[3 * i + 1], (int)grid_thw[3 * i + 2]};
+        std::vector<int> pos3;
+        int delta = 0;
+        get_rope_index(ids, (int)seq_len, grid, (int)spatial_merge_size, (int)image_token_id, (int)vision_start_token_id, pos3, delta);
+        for (size_t i = 0; i < pos3.size(); ++i) pos3_out[i] = pos3[i];
+        *rope_delta_out = delta;
+        return 0;
+    } catch (const std::exception& e) {
+        std::lock_guard<std::mutex> lk(g_err_mu);
+        g_create_error = e.what();
+        return 1;
+    }
+}
+
 void aha_b200_destroy(aha_model* m) {
     if (!m) return;
     cudaSetDevice(m->ctx.device);

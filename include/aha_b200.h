@@ -159,7 +159,14 @@ int aha_b200_nccl_unique_id(uint8_t out[128]);
 
 void aha_b200_destroy(aha_model* m);
 
-/* Last error message of the handle (or of the failed create when m == NULL). */
+/* Host-only helper (no device work, usable without a GPU): Qwen3VLModel::get_rope_index, image branch
+ * (/root/reference/src/models/qwen3vl/model.rs:901-1133) -- the M-RoPE position ids of a prompt whose image
+ * placeholders follow <|vision_start|>.  grid_thw: n_images x 3 (t, h, w in patches).  pos3_out: [3][seq_len] (t, h, w rows),
+ * rope_delta_out: max position + 1 - seq_len.  This is the routine aha_b200_forward_initial runs on the first call. */
+int aha_b200_rope_index(const uint32_t* ids, size_t seq_len, const uint32_t* grid_thw, size_t n_images, uint32_t spatial_merge_size,
+                        uint32_t image_token_id, uint32_t vision_start_token_id, int32_t* pos3_out, int32_t* rope_delta_out);
+
+/* Last error message of the handle (or of the failed create / handle-less call when m == NULL). */
 const char* aha_b200_last_error(aha_model* m);
 
 /* --- introspection used by tests / bench (not part of the reference seam) --- */

@@ -1,0 +1,71 @@
+"""Host-side logic of the library that needs no GPU: the C++ M-RoPE index builder behind aha_b200_forward_initial
+(aha_b200_rope_index) against the oracle restatement of Qwen3VLModel::get_rope_index
+(/root/reference/src/models/qwen3vl/model.rs:901-1133), which tests/test_oracle_hf.py in turn pins against HF."""
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+from aha_b200 import B200Error, rope_index, synth
+from oracle.qwen3vl import get_rope_index
+
+CFG = synth.get_config("qwen3vl", "tiny")
+
+
+def build_prompt(grids, texts, seed=30):
+    ids = []
+    for k, n in enumerate(texts):
+        ids += synth.synth_text_ids(n, 1000, seed + k).tolist()
+        if k < len(grids):
+            ids += synth.vl_prompt_ids(CFG, [grids[k]], 0).tolist()
+    return np.asarray(ids, dtype=np.uint32)
+
+
+@pytest.mark.parametrize("grids,texts", [
+    ([[1, 4, 6]], [5, 7]),
+    ([[1, 4, 6], [1, 8, 2]], [3, 4, 9]),
+    ([[1, 2, 2], [1, 6, 10], [1, 4, 4]], [0, 1, 0, 6]),
+    ([[1, 68, 120]], [0, 512]),
+])
+def test_rope_index_matches_oracle(grids, texts):
+    ids = build_prompt(grids, texts)
+    pos, delta = rope_index(ids, grids, CFG)
+    want, want_delta = get_rope_index(ids.astype(np.int64), np.asarray(grids), CFG)
+    assert pos.shape == (3, ids.size)
+    assert (pos == want[:, 0]).all()
+    assert delta == want_delta
+
+
+def test_rope_index_1080p_known_answer():  # rope_deltas = max(34, 60) - 2040, whatever text surrounds the image
+    for texts in ([0, 512], [7, 100], [1, 0]):
+        _, delta = rope_index(build_prompt([[1, 68, 120]], texts), [[1, 68, 120]], CFG)
+        assert delta == -1980
+
+
+def test_rope_index_text_only_is_arange():
+    ids = synth.synth_text_ids(17, 1000, 3)
+    pos, delta = rope_index(ids, None, CFG)
+    assert delta == 0 and (pos == np.arange(17)[None]).all()
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.lists(st.tuples(st.integers(1, 6), st.integers(1, 6)), min_size=1, max_size=4), st.data())
+def test_rope_index_random_prompts(shapes, data):
+    grids = [[1, 2 * h, 2 * w] for h, w in shapes]
+    texts = [data.draw(st.integers(0, 9)) for _ in range(len(grids) + 1)]
+    ids = build_prompt(grids, texts, seed=data.draw(st.integers(0, 1000)))
+    pos, delta = rope_index(ids, grids, CFG)
+    want, want_delta = get_rope_index(ids.astype(np.int64), np.asarray(grids), CFG)
+    assert (pos == want[:, 0]).all() and delta == want_delta
+    assert (pos[:, 1:].max(0) >= pos[:, :-1].min(0)).all()          # positions never jump backwards past a whole chunk
+    assert delta == int(pos.max()) + 1 - ids.size
+
+
+def test_rope_index_errors_are_reported_not_thrown():
+    ids = build_prompt([[1, 4, 6], [1, 4, 6]], [2, 2, 2])
+    with pytest.raises(B200Error, match="more image placeholders"):
+        rope_index(ids, [[1, 4, 6]], CFG)                           # two placeholders, one grid row
+    with pytest.raises(B200Error, match="does not cover|exceed"):
+        rope_index(ids, [[1, 4, 6], [1, 8, 8]], CFG)                # grid larger than the placeholder run
+    tail = np.append(synth.synth_text_ids(4, 1000, 1), np.uint32(CFG["vision_start_token_id"]))
+    with pytest.raises(B200Error, match="vision_start"):
+        rope_index(tail, [[1, 4, 6]], CFG)

@@ -147,3 +147,37 @@ def test_image_patchify_matches_hf_processor():
         out = ip(images=[img], return_tensors="np")
         assert (np.asarray(out["image_grid_thw"]) == grid).all()
         assert np.abs(out["pixel_values"] - pv).max() < 1e-6
+
+
+def test_get_rope_index_matches_hf_on_interleaved_images():
+    """M-RoPE position ids (qwen3vl/model.rs:901-1133) for prompts with several images of different grids separated by
+    text, against HF's Qwen3VLModel.get_rope_index -- every position of all three rows, and rope_deltas."""
+    from transformers import Qwen3VLConfig, Qwen3VLForConditionalGeneration
+    from oracle.qwen3vl import get_rope_index
+    cfg = synth.get_config("qwen3vl", "tiny")
+    hc = Qwen3VLConfig(text_config=dict(cfg["text_config"], max_position_embeddings=4096), vision_config=cfg["vision_config"],
+                       image_token_id=cfg["image_token_id"], video_token_id=cfg["video_token_id"],
+                       vision_start_token_id=cfg["vision_start_token_id"], vision_end_token_id=cfg["vision_end_token_id"],
+                       tie_word_embeddings=True)
+    hf = Qwen3VLForConditionalGeneration(hc).eval()
+    cases = [
+        ([[1, 4, 6]], [5, 7]),                          # text, image, text
+        ([[1, 4, 6], [1, 8, 2]], [3, 4, 9]),            # two images, text on every side
+        ([[1, 2, 2], [1, 6, 10], [1, 4, 4]], [0, 1, 0, 6]),   # leading image, adjacent images, trailing text
+        ([[1, 68, 120]], [0, 512]),                     # the north-star prompt shape: 2040 image tokens + 512 ids
+    ]
+    for grids, texts in cases:
+        ids = []
+        for k, n in enumerate(texts):
+            ids += synth.synth_text_ids(n, 1000, 20 + k).tolist()
+            if k < len(grids):
+                ids += synth.vl_prompt_ids(cfg, [grids[k]], 0).tolist()
+        ids = np.asarray(ids, dtype=np.int64)
+        grid = np.asarray(grids, dtype=np.int64)
+        pos, delta = get_rope_index(ids, grid, cfg)
+        mm = torch.from_numpy((ids == cfg["image_token_id"]).astype(np.int32))[None]
+        want_pos, want_delta = hf.model.get_rope_index(torch.from_numpy(ids)[None], mm, image_grid_thw=torch.from_numpy(grid))
+        assert (pos == want_pos.numpy()).all(), (grids, texts)
+        assert delta == int(want_delta.reshape(-1)[0])
+    pos, delta = get_rope_index(ids, grid, cfg)
+    assert delta == -1980                               # SURVEY 8c: max(34, 60) - 2040
