@@ -19,6 +19,13 @@
 // Phases per layer: [rmsnorm+qkv] -> [attention] -> [o_proj+residual] -> [rmsnorm+gate/up+SwiGLU] ->
 // [down+residual]; then [final norm + lm_head + argmax] and the on-device token feedback.
 //
+// Variant KS (template flag, opt-in through aha_options.decode_impl = 3; NOT the default): the down projection is
+// computed K-split right behind gate/up -- CTA c multiplies the k-rows of Wdown^T that match its own slice of
+// silu(gate)*up (still in shared memory) into all H outputs and adds them into a global fp32 accumulator with
+// red.global.add.f32 -- so the grid barrier and the h round trip between the two disappear (4 barriers per layer).
+// The next consumer of the residual stream adds the accumulator while it loads x.  Summation order across CTAs is
+// then run-dependent (fp32 atomics).
+//
 // Reference semantics are those of Qwen3DecoderLayer::forward / QKNormAttention::forward / GateUpDownMLP
 // (/root/reference/src/models/qwen3/model.rs:71-87, src/models/common/modules.rs:81-87,530-579,757-813)
 // with seq_len = 1; arithmetic is fp32 throughout, identical to the per-op kernels in gemv.cuh/attention.cuh.
@@ -42,12 +49,14 @@ constexpr int kFusedTraceWords = 2 * 4096 + 256 * 256;     // timing traces: CTA
 constexpr int kFusedMaxOwnRows = 64;                     // residual-stream rows owned by one CTA (H / grid, rounded up)
 constexpr int kFusedPartialStride = 128 + 4;             // floats per (head, split) attention partial: acc[128], m, l, pad (16-byte rows)
 constexpr int kFusedMergeChunk = 20;                     // splits merged per pass when the o_proj input is assembled
+constexpr int kFusedMaxHs = 128;                         // SwiGLU outputs one CTA keeps in shared memory (K-split variant): I / grid, rounded up
 constexpr int kFusedMaxPages = 512;                      // page-table entries staged in shared memory (16K tokens)
 
 struct FusedLayer {
     const __half *qkv, *o, *gu, *down;
     const float *qkv_b, *o_b;
     const float *ln1, *ln2, *qn, *kn;
+    const __half* down_t;   // [I][H] transposed copy of `down` (K-split variant only, else nullptr)
 };
 
 struct FusedArgs {
@@ -64,6 +73,7 @@ struct FusedArgs {
     float* h1;         // [I]
     float* logits;     // [V]
     float* partial;    // [nh][nsplit][kFusedPartialStride]
+    float* acc2;       // [2][H] fp32 accumulators of the K-split down projection (variant KS), zeroed by the host before launch
     unsigned* sync;    // [2] grid-barrier counter, final ticket   (zeroed by the host before launch)
     float* pmax; int* pidx;  // [grid] per-CTA argmax candidates
     uint32_t* argmax_out;
@@ -229,6 +239,23 @@ struct Producer {
             ++it;
         }
     }
+    // K-split down projection: k-rows [r0/2, r1/2) of Wdown^T [I][H] -- the rows that match this CTA's slice of h.
+    __device__ void rows_t(const __half* Wt, int I2, int H) {
+        int r0, r1;
+        cta_rows(I2, 2, r0, r1);
+        const int k0 = r0 >> 1, k1 = r1 >> 1;
+        const int R = max(1, kFusedStageBytes / (2 * H));
+        for (int k = k0; k < k1; k += R) {
+            const int nr = min(R, k1 - k);
+            int slot;
+            acquire(slot);
+            const uint32_t bytes = (uint32_t)nr * H * 2u;
+            mbar_expect_tx(&ring.full[slot], bytes);
+            if (use_hint) tma_bulk_g2s_hint(ring.buf + (size_t)slot * kFusedStageBytes, Wt + (size_t)k * H, bytes, &ring.full[slot], policy);
+            else tma_bulk_g2s(ring.buf + (size_t)slot * kFusedStageBytes, Wt + (size_t)k * H, bytes, &ring.full[slot]);
+            ++it;
+        }
+    }
     const int* pages = nullptr;   // page table staged in shared memory
     __device__ void attn(const FusedArgs& a, int layer, int ctx) {
         int kvh, split, hp0, hp1;
@@ -288,7 +315,11 @@ struct Consumer {
     static __device__ __forceinline__ int xs_pos(int e, int K) { return ((e >> 2) & 1) * (K >> 1) + (e >> 3) * 4; }
     // Stage the activation vector of a GEMV in shared memory (all consumer threads), optional RMSNorm.
     // src is fp32 global written by other CTAs (ld.global.cg) or an fp16 embedding row.
-    __device__ void load_x(int K, const float* src32, const __half* src16, const float* norm_w, float eps) {
+    // ADD2 (K-split variant): x = src32 + src32b (the residual stream plus the accumulated down projection); the rows
+    // [own_r0, own_r1) this CTA owns are captured into xown on the way.
+    template <bool ADD2 = false>
+    __device__ void load_x(int K, const float* src32, const __half* src16, const float* norm_w, float eps, const float* src32b = nullptr,
+                           int own_r0 = 0, int own_r1 = 0) {
         const int tid = threadIdx.x;
         constexpr int kPer = (kFusedMaxK + kFusedConsumers * 32 * 4 - 1) / (kFusedConsumers * 32 * 4);   // float4 per thread
         float4 v[kPer], w[kPer];
@@ -306,6 +337,15 @@ struct Consumer {
                     v[j] = make_float4(a.x, a.y, b.x, b.y);
                 } else {
                     v[j] = __ldcg(reinterpret_cast<const float4*>(src32 + e));
+                    if (ADD2) {
+                        const float4 b = __ldcg(reinterpret_cast<const float4*>(src32b + e));
+                        v[j].x += b.x; v[j].y += b.y; v[j].z += b.z; v[j].w += b.w;
+                        if (e + 3 >= own_r0 && e < own_r1) {
+                            const float t[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) if (e + q >= own_r0 && e + q < own_r1) xown[e + q - own_r0] = t[q];
+                        }
+                    }
                 }
             }
         }
@@ -405,6 +445,61 @@ struct Consumer {
             for (int n = 0; n < NA; ++n) t += acc[q][n];
             v[q] = t;
         }
+    }
+
+    // K-split down projection (variant KS): acc[n] += sum_{k in this CTA's slice} Wdown^T[k][n] * h[k].  Every consumer
+    // warp reads every stage (thread t owns the 8-column output chunks t, t + 352, ...); the warp that finishes a stage
+    // last hands the slot back to the producer.  NCH = output chunks per thread.
+    template <int NCH>
+    __device__ void down_ksplit(const FusedArgs& a, const float* hs, int* slot_done, float* acc) {
+        int r0, r1;
+        cta_rows(2 * a.I, 2, r0, r1);
+        const int k0 = r0 >> 1, k1 = r1 >> 1;
+        const int H = a.H, R = max(1, kFusedStageBytes / (2 * H));
+        const int nchunk = H >> 3;
+        float av[NCH][8];
+#pragma unroll
+        for (int j = 0; j < NCH; ++j)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) av[j][e] = 0.f;
+        unsigned i = it;
+        for (int k = k0; k < k1; k += R, ++i) {
+            const int nr = min(R, k1 - k);
+            const uint8_t* st = wait_full(i);
+            for (int q = 0; q < nr; ++q) {
+                const float hv = hs[k - k0 + q];
+#pragma unroll
+                for (int j = 0; j < NCH; ++j) {
+                    const int ch = (int)threadIdx.x + j * kFusedConsumers * 32;
+                    if (ch < nchunk) {
+                        const uint4 w = *reinterpret_cast<const uint4*>(st + (size_t)q * H * 2 + (size_t)ch * 16);
+                        const float2 w0 = h2_to_f2(w.x), w1 = h2_to_f2(w.y), w2 = h2_to_f2(w.z), w3 = h2_to_f2(w.w);
+                        av[j][0] = fmaf(w0.x, hv, av[j][0]); av[j][1] = fmaf(w0.y, hv, av[j][1]);
+                        av[j][2] = fmaf(w1.x, hv, av[j][2]); av[j][3] = fmaf(w1.y, hv, av[j][3]);
+                        av[j][4] = fmaf(w2.x, hv, av[j][4]); av[j][5] = fmaf(w2.y, hv, av[j][5]);
+                        av[j][6] = fmaf(w3.x, hv, av[j][6]); av[j][7] = fmaf(w3.y, hv, av[j][7]);
+                    }
+                }
+            }
+            __syncwarp();   // every lane's shared-memory reads of the stage have fed its FMAs
+            if (lane == 0) {
+                const int slot = i % ns;
+                if (atomicAdd(&slot_done[slot], 1) == kFusedConsumers - 1) {
+                    slot_done[slot] = 0;   // ordered before the slot's next use by the mbarrier release / acquire chain
+                    mbar_arrive(&ring.empty[slot]);
+                }
+            }
+        }
+        it = i;
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+            const int ch = (int)threadIdx.x + j * kFusedConsumers * 32;
+            if (ch < nchunk) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) atomicAdd(acc + ch * 8 + e, av[j][e]);   // result unused: RED.E.ADD.F32
+            }
+        }
+        consumer_bar_sync();
     }
 
     // One GEMV phase: y[r0:r1) = W[r0:r1, :] . xs  with the fused epilogue.  Ends with a consumer barrier so
@@ -626,7 +721,7 @@ __device__ void fused_attention(const FusedArgs& a, Consumer& c, AttnSmem<G>& s,
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
-template <int G>
+template <int G, bool KS = false>
 __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(FusedArgs a) {
     extern __shared__ __align__(1024) uint8_t fused_smem_raw[];
     uint8_t* ringbuf = fused_smem_raw;
@@ -637,6 +732,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
     float* cs = xown + kFusedMaxOwnRows;                        // [128] cos | sin of the step's rotary angles
     float* xs = cs + 128;                                       // [kFusedMaxK] activations / attention scratch
     int* spages = reinterpret_cast<int*>(xs + kFusedMaxK);      // [kFusedMaxPages] page table copy
+    float* hs = reinterpret_cast<float*>(spages + kFusedMaxPages);   // [kFusedMaxHs] this CTA's slice of silu(gate)*up (variant KS)
+    int* slot_done = reinterpret_cast<int*>(hs + kFusedMaxHs);       // [kFusedStages] warps done with a shared stage (variant KS)
     AttnSmem<G>* as = reinterpret_cast<AttnSmem<G>*>(xs);
     static_assert(sizeof(AttnSmem<G>) <= kFusedMaxK * sizeof(float), "attention scratch must fit in the xs region");
 
@@ -645,6 +742,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
         for (int i = 0; i < kFusedStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (KS && tid < kFusedStages) slot_done[tid] = 0;
     if ((a.dbg & 64) && tid == 0) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); a.trace[8192 + blockIdx.x * 256 + 255] = smid; }
     const int t_new = a.st->pos;
     const int rope_delta = a.st->rope_delta;
@@ -679,7 +777,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
                 p.attn(a, l, ctx); AHA_STAMP(a, 1, pe);
                 p.rows(Ly.o, a.H, a.nh * a.hd, 1); AHA_STAMP(a, 1, pe);
                 p.rows(Ly.gu, 2 * a.I, a.H, 2); AHA_STAMP(a, 1, pe);
-                p.rows(Ly.down, a.H, a.I, 1); AHA_STAMP(a, 1, pe);
+                if (KS) p.rows_t(Ly.down_t, 2 * a.I, a.H); else p.rows(Ly.down, a.H, a.I, 1);
+                AHA_STAMP(a, 1, pe);
             }
             p.rows(a.lm_head, a.V, a.H, 1); AHA_STAMP(a, 1, pe);
         }
@@ -692,11 +791,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
     float best = -INFINITY;
     int bi = 0x7fffffff;
     const __half* emb_row = a.embed + (size_t)token * a.H;
-    {   // the rows of the residual stream this CTA owns start as the embedding row (Embedding::forward)
-        int r0, r1;
-        cta_rows(a.H, 1, r0, r1);
-        if (tid < r1 - r0) xown[tid] = __half2float(emb_row[r0 + tid]);
-    }
+    int own_r0, own_r1, hs_k0 = 0;
+    cta_rows(a.H, 1, own_r0, own_r1);
+    if (tid < own_r1 - own_r0) xown[tid] = __half2float(emb_row[own_r0 + tid]);   // the rows of the residual stream this CTA owns start as the embedding row
+    if (KS) { int g0, g1; cta_rows(2 * a.I, 2, g0, g1); hs_k0 = g0 >> 1; }
     int ce = 0;
 #define CSTAMP() do { if (tid == 0) AHA_STAMP(a, 0, ce); } while (0)
     CSTAMP();
@@ -705,8 +803,14 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
         const FusedLayer Ly = nxtc;
         if (l + 1 < a.L) nxtc = a.layers[l + 1];
         const bool first = (l == 0);
+        // variant KS: layer l accumulates its down projection into acc2[l & 1]; layer l + 1 adds it while loading x and
+        // re-zeroes its own rows of it one barrier later, two barriers before layer l + 2 accumulates into it again
+        float* const acc_prev = a.acc2 + (size_t)((l + 1) & 1) * a.H;
+        float* const acc_cur = a.acc2 + (size_t)(l & 1) * a.H;
         // P1: qkv = Wqkv . rmsnorm(x)      (layer 0 reads the embedding row directly: Embedding::forward)
-        c.load_x(a.H, a.x, first ? emb_row : nullptr, Ly.ln1, a.eps); CSTAMP();
+        if (KS && !first) c.template load_x<true>(a.H, a.x, nullptr, Ly.ln1, a.eps, acc_prev, own_r0, own_r1);
+        else c.load_x(a.H, a.x, first ? emb_row : nullptr, Ly.ln1, a.eps);
+        CSTAMP();
         c.template gemv<FE_QKV>(a, a.qkv_dim, a.H, Ly.qkv_b, a.qkv1, best, bi); CSTAMP();
         grid_barrier(&a.sync[0], seq, a.dbg, a.trace); CSTAMP();
         // P2: attention over the paged cache (+ q/k norm, RoPE, KV append)
@@ -715,19 +819,34 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
         grid_barrier(&a.sync[0], seq, a.dbg, a.trace); CSTAMP();
         // P3: x = resid + Wo . attn
         c.load_attn(a); CSTAMP();
+        if (KS && !first && tid < own_r1 - own_r0) acc_prev[own_r0 + tid] = 0.f;   // read last in P1 (before its barrier), accumulated next by layer l + 1
         c.template gemv<FE_RESID>(a, a.H, a.nh * a.hd, Ly.o_b, a.x, best, bi); CSTAMP();
         grid_barrier(&a.sync[0], seq, a.dbg, a.trace); CSTAMP();
         // P4: h = silu(gate) * up, gate/up rows interleaved, input rmsnorm(x)
         c.load_x(a.H, a.x, nullptr, Ly.ln2, a.eps); CSTAMP();
-        c.template gemv<FE_SWIGLU>(a, 2 * a.I, a.H, nullptr, a.h1, best, bi); CSTAMP();
-        grid_barrier(&a.sync[0], seq, a.dbg, a.trace); CSTAMP();
-        // P5: x = x + Wdown . h
-        c.load_x(a.I, a.h1, nullptr, nullptr, 0.f); CSTAMP();
-        c.template gemv<FE_RESID>(a, a.H, a.I, nullptr, a.x, best, bi); CSTAMP();
-        grid_barrier(&a.sync[0], seq, a.dbg, a.trace); CSTAMP();
+        if (KS) {
+            // h stays in shared memory; P5 follows without a barrier: acc_cur += Wdown[:, slice] . h[slice]
+            c.template gemv<FE_SWIGLU>(a, 2 * a.I, a.H, nullptr, hs - hs_k0, best, bi); CSTAMP();
+            CSTAMP(); CSTAMP();
+            switch ((a.H / 8 + kFusedConsumers * 32 - 1) / (kFusedConsumers * 32)) {
+                case 1: c.template down_ksplit<1>(a, hs, slot_done, acc_cur); break;
+                case 2: c.template down_ksplit<2>(a, hs, slot_done, acc_cur); break;
+                default: c.template down_ksplit<3>(a, hs, slot_done, acc_cur); break;
+            }
+            CSTAMP();
+            grid_barrier(&a.sync[0], seq, a.dbg, a.trace); CSTAMP();
+        } else {
+            c.template gemv<FE_SWIGLU>(a, 2 * a.I, a.H, nullptr, a.h1, best, bi); CSTAMP();
+            grid_barrier(&a.sync[0], seq, a.dbg, a.trace); CSTAMP();
+            // P5: x = x + Wdown . h
+            c.load_x(a.I, a.h1, nullptr, nullptr, 0.f); CSTAMP();
+            c.template gemv<FE_RESID>(a, a.H, a.I, nullptr, a.x, best, bi); CSTAMP();
+            grid_barrier(&a.sync[0], seq, a.dbg, a.trace); CSTAMP();
+        }
     }
     // final: logits = lm_head . rmsnorm(x), per-CTA argmax candidate
-    c.load_x(a.H, a.x, nullptr, a.final_norm, a.eps);
+    if (KS) c.template load_x<true>(a.H, a.x, nullptr, a.final_norm, a.eps, a.acc2 + (size_t)((a.L - 1) & 1) * a.H, own_r0, own_r1);
+    else c.load_x(a.H, a.x, nullptr, a.final_norm, a.eps);
     best = -INFINITY; bi = 0x7fffffff;
     c.template gemv<FE_LOGITS>(a, a.V, a.H, nullptr, a.logits, best, bi); CSTAMP();
     // CTA-level argmax (first maximal index), then the last CTA to arrive reduces across CTAs
@@ -777,7 +896,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
 template <int G>
 inline size_t fused_smem_bytes() {
     return (size_t)kFusedStages * kFusedStageBytes + 2 * kFusedStages * sizeof(uint64_t) + (32 + kFusedMaxOwnRows + 128) * sizeof(float) + (size_t)kFusedMaxK * sizeof(float) +
-           (size_t)kFusedMaxPages * sizeof(int) + 64;
+           (size_t)kFusedMaxPages * sizeof(int) + (size_t)kFusedMaxHs * sizeof(float) + (size_t)kFusedStages * sizeof(int) + 64;
 }
 
 }  // namespace aha

@@ -291,6 +291,8 @@ struct TextModel {
     bool use_graph = true;
     // fused persistent decode kernel (decode_fused.cuh)
     bool fused = false;
+    bool ksplit = false;                 // fused variant KS (decode_impl = 3): K-split down projection, see decode_fused.cuh
+    float* acc2 = nullptr;               // [2][H] accumulators of that variant
     int decode_impl = 0;
     FusedLayer* d_fused_layers = nullptr;
     unsigned* d_sync = nullptr;   // [0] grid barrier, [1] final ticket, then kv tickets [nkv]
@@ -389,10 +391,14 @@ struct TextModel {
     template <int G>
     void fused_prepare() {
         fused_smem = fused_smem_bytes<G>();
-        AHA_CUDA_CHECK(cudaFuncSetAttribute(decode_step_fused_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem));
-        int nb = 0;
-        AHA_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, decode_step_fused_kernel<G>, kFusedThreads, fused_smem));
-        AHA_REQUIRE(nb >= 1, "fused decode kernel does not fit on an SM");
+        auto prep = [&](auto kernel) {
+            AHA_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem));
+            int nb = 0;
+            AHA_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kFusedThreads, fused_smem));
+            AHA_REQUIRE(nb >= 1, "fused decode kernel does not fit on an SM");
+        };
+        if (ksplit) prep(decode_step_fused_kernel<G, true>);
+        else prep(decode_step_fused_kernel<G, false>);
     }
     void alloc_runtime(int max_ctx_, int max_prefill_, bool graph, int decode_impl_ = 0) {
         Ctx& c = *ctx;
@@ -400,8 +406,10 @@ struct TextModel {
         {
             std::string why;
             const bool ok = fused_supported(&why);
-            AHA_REQUIRE(decode_impl != 2 || ok, "fused decode kernel unsupported for this model: " + why);
+            AHA_REQUIRE((decode_impl != 2 && decode_impl != 3) || ok, "fused decode kernel unsupported for this model: " + why);
             fused = ok && decode_impl != 1;
+            ksplit = fused && decode_impl == 3;
+            AHA_REQUIRE(!ksplit || (I_l + ctx->num_sms - 1) / ctx->num_sms + 2 <= kFusedMaxHs, "K-split variant: more SwiGLU outputs per SM than it keeps in shared memory");
         }
         num_pages = ceil_div(max_ctx, kPage);
         page_stride = (size_t)2 * nkv_l * kPage * cfg.hd;
@@ -429,7 +437,18 @@ struct TextModel {
             std::vector<FusedLayer> fl(cfg.L);
             for (int l = 0; l < cfg.L; ++l) {
                 TextLayer& T = layers[l];
-                fl[l] = FusedLayer{T.qkv.w, T.o.w, T.gu.w, T.down.w, T.qkv.b, T.o.b, T.ln1, T.ln2, T.qn, T.kn};
+                fl[l] = FusedLayer{T.qkv.w, T.o.w, T.gu.w, T.down.w, T.qkv.b, T.o.b, T.ln1, T.ln2, T.qn, T.kn, nullptr};
+                if (ksplit) {   // Wdown^T [I][H]: the k-rows a CTA needs become contiguous 2*H-byte rows
+                    __half* wt = c.alloc<__half>((size_t)I_l * cfg.H);
+                    transpose_f16_kernel<<<dim3((unsigned)ceil_div(I_l, 32), (unsigned)ceil_div(cfg.H, 32)), dim3(32, 8), 0, c.stream>>>(T.down.w, wt, cfg.H, I_l);
+                    AHA_CUDA_CHECK(cudaGetLastError());
+                    fl[l].down_t = wt;
+                }
+            }
+            if (ksplit) {
+                acc2 = c.alloc<float>((size_t)2 * cfg.H);
+                AHA_CUDA_CHECK(cudaMemsetAsync(acc2, 0, (size_t)2 * cfg.H * sizeof(float), c.stream));
+                AHA_CUDA_CHECK(cudaStreamSynchronize(c.stream));
             }
             d_fused_layers = upload(c, fl);
             d_ftrace = c.alloc<unsigned long long>(kFusedTraceWords);
@@ -601,7 +620,8 @@ struct TextModel {
     template <int G>
     void launch_fused(FusedArgs& fa) {
         void* args[] = {&fa};
-        AHA_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)decode_step_fused_kernel<G>, dim3(fused_grid), dim3(kFusedThreads), args, fused_smem, ctx->stream));
+        void* kernel = ksplit ? (void*)decode_step_fused_kernel<G, true> : (void*)decode_step_fused_kernel<G, false>;
+        AHA_CUDA_CHECK(cudaLaunchCooperativeKernel(kernel, dim3(fused_grid), dim3(kFusedThreads), args, fused_smem, ctx->stream));
     }
     void decode_step_fused() {
         Ctx& c = *ctx;
@@ -617,6 +637,8 @@ struct TextModel {
         fa.trace = d_ftrace;
         { const char* e = getenv("AHA_FUSED_STAGES"); fa.stages = e ? std::max(2, std::min(kFusedStages, atoi(e))) : fused_stages; }
         AHA_CUDA_CHECK(cudaMemsetAsync(d_sync, 0, sync_words * sizeof(unsigned), c.stream));
+        fa.acc2 = acc2;
+        if (ksplit) AHA_CUDA_CHECK(cudaMemsetAsync(acc2, 0, (size_t)2 * cfg.H * sizeof(float), c.stream));
         switch (nh_l / nkv_l) {
             case 1: launch_fused<1>(fa); break;
             case 2: launch_fused<2>(fa); break;
