@@ -25,6 +25,9 @@ QWEN3 = {
     "mid": dict(_TEXT_06, hidden_size=2048, intermediate_size=6144, num_hidden_layers=2, vocab_size=4096, rope_theta=5000000.0,
                 eos_token_id=4095),
     "tiny-untied": dict(_TEXT_TINY, tie_word_embeddings=False),
+    # GQA groups other than 2 (every shipped Qwen3 size the fused kernel accepts has nh / nkv = 2): MHA and a group of 4
+    "tiny-g1": dict(_TEXT_TINY, num_attention_heads=2, num_key_value_heads=2),
+    "tiny-g4": dict(_TEXT_TINY, num_attention_heads=4, num_key_value_heads=1),
     "q0.6": dict(_TEXT_06),
 }
 

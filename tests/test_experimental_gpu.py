@@ -1,6 +1,8 @@
 """Opt-in variants that have not been validated on hardware yet.  They are NOT on any default path; these tests only run
 when AHA_TEST_EXPERIMENTAL=1 so that an unfinished experiment can never turn the GPU suite red.
 
+GQA groups 1 and 4: instantiations of the decode attention (fused and per-op) that no shipped model shape reaches.
+
 decode_impl = 3: the fused decode kernel with the K-split down projection (decode_fused.cuh, variant KS): gate/up and
 down in one phase, fp32 reductions into a global accumulator, 4 grid barriers per layer instead of 5."""
 import os
@@ -44,3 +46,23 @@ def test_ksplit_decode_matches_the_default_fused_kernel_and_the_oracle(preset):
         assert list(a) == list(b)                    # greedy ids agree (ties aside, fp32 reduction order differs)
     finally:
         m.close(); k.close()
+
+
+@pytest.mark.parametrize("preset", ["tiny-g1", "tiny-g4"])
+@pytest.mark.parametrize("impl", [1, 2])
+def test_decode_with_other_gqa_groups(preset, impl):
+    cfg, w, m = make_model("qwen3", preset, max_ctx=512, decode_impl=impl)
+    o = make_oracle("qwen3", cfg, w)
+    try:
+        ids = _ids(70, cfg["vocab_size"], 11)
+        got = m.forward_initial(ids, 0)[0, 0]
+        want = o.forward_initial(ids.reshape(1, -1), 0)[0, 0]
+        assert np.abs(got - want).max() <= TOL
+        tok = int(np.argmax(want))
+        for step in range(16):
+            lg = m.forward_step(np.array([tok], np.uint32), 70 + step)[0, 0]
+            lo = o.forward_step(np.array([[tok]]), 70 + step)[0, 0]
+            assert np.abs(lg - lo).max() <= TOL, (step, np.abs(lg - lo).max())
+            tok = int(np.argmax(lo))
+    finally:
+        m.close()
