@@ -10,10 +10,11 @@ torch = pytest.importorskip("torch")
 transformers = pytest.importorskip("transformers")
 
 
-def test_qwen3_matches_hf():
+@pytest.mark.parametrize("preset", ["tiny", "tiny-g1", "tiny-g4"])   # GQA groups 2, 1 (MHA) and 4
+def test_qwen3_matches_hf(preset):
     from transformers import Qwen3Config, Qwen3ForCausalLM
     from oracle.qwen3 import Qwen3Model
-    cfg = synth.get_config("qwen3", "tiny")
+    cfg = synth.get_config("qwen3", preset)
     w = synth.make_weights("qwen3", cfg, 0)
     hc = Qwen3Config(**cfg, max_position_embeddings=4096)
     hc._attn_implementation = "eager"
