@@ -26,6 +26,11 @@
 // The next consumer of the residual stream adds the accumulator while it loads x.  Summation order across CTAs is
 // then run-dependent (fp32 atomics).
 //
+// Variant KO (template flag, decode_impl = 4, or 5 together with KS; NOT the default): o_proj is computed K-split per
+// kv group right behind the attention.  The grid barrier between the two becomes a barrier over the nsplit CTAs of
+// the group, each CTA merges only its own group's partials (G heads instead of all of them) and multiplies its slice
+// of the rows of that group's column block of Wo, adding the result into the residual stream with fp32 reductions.
+//
 // Reference semantics are those of Qwen3DecoderLayer::forward / QKNormAttention::forward / GateUpDownMLP
 // (/root/reference/src/models/qwen3/model.rs:71-87, src/models/common/modules.rs:81-87,530-579,757-813)
 // with seq_len = 1; arithmetic is fp32 throughout, identical to the per-op kernels in gemv.cuh/attention.cuh.
@@ -56,7 +61,8 @@ struct FusedLayer {
     const __half *qkv, *o, *gu, *down;
     const float *qkv_b, *o_b;
     const float *ln1, *ln2, *qn, *kn;
-    const __half* down_t;   // [I][H] transposed copy of `down` (K-split variant only, else nullptr)
+    const __half* down_t;   // [I][H] transposed copy of `down` (variant KS only, else nullptr)
+    const __half* o_g;      // [nkv][H][G*hd] column blocks of `o`, one per kv group (variant KO only, else nullptr)
 };
 
 struct FusedArgs {
@@ -73,6 +79,8 @@ struct FusedArgs {
     float* h1;         // [I]
     float* logits;     // [V]
     float* partial;    // [nh][nsplit][kFusedPartialStride]
+    float* xo;         // [2][H] variant KO: residual stream the K-split o_proj accumulates into, by layer parity (owners write x, CTAs add)
+    unsigned* gsync;   // [nkv] variant KO: arrival counters of the per-kv-group barriers (zeroed by the host before launch)
     float* acc2;       // [2][H] fp32 accumulators of the K-split down projection (variant KS), zeroed by the host before launch
     unsigned* sync;    // [2] grid-barrier counter, final ticket   (zeroed by the host before launch)
     float* pmax; int* pidx;  // [grid] per-CTA argmax candidates
@@ -176,6 +184,18 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& seq, i
     consumer_bar_sync();
 }
 
+// Barrier over the CTAs that share one arrival counter (variant KO: the nsplit CTAs of a kv group), same protocol as
+// grid_barrier: release reduction, relaxed poll, acquire fence; consumer threads only.
+__device__ __forceinline__ void group_barrier(unsigned* counter, unsigned target) {
+    consumer_bar_sync();
+    if (threadIdx.x == 0) {
+        red_release_add(counter, 1u);
+        while (ld_relaxed_u32(counter) < target) {}
+        fence_acq_rel_gpu();
+    }
+    consumer_bar_sync();
+}
+
 // ------------------------------------------------------------------------------------------------ schedule
 // Row slab of a [N,K] fp16 matrix owned by this CTA: contiguous rows [r0, r1); `unit` = 2 keeps SwiGLU pairs together.
 __device__ __forceinline__ void cta_rows(int N, int unit, int& r0, int& r1) {
@@ -192,6 +212,15 @@ __host__ __device__ __forceinline__ int rows_per_stage(int K, int N, int grid) {
     const int per_cta = N / grid;
     while (r > 2 && per_cta < r * 5) r >>= 1;
     return r;
+}
+// variant KO: rows of o_proj computed by split `split` of a kv group, and rows per stage for its K' = G*hd columns
+__device__ __forceinline__ void ko_rows(int H, int nsplit, int split, int& r0, int& r1) {
+    r0 = (int)(((long long)H * split) / nsplit);
+    r1 = (int)(((long long)H * (split + 1)) / nsplit);
+}
+__device__ __forceinline__ int ko_rows_per_stage(int Kp) {
+    const int r = kFusedStageBytes / (2 * Kp);
+    return r > kFusedMaxRows ? kFusedMaxRows : (r < 1 ? 1 : r);
 }
 // attention work item of this CTA: (kv head, [hp0, hp1) half pages); empty when the CTA has no item
 __device__ __forceinline__ bool attn_item(const FusedArgs& a, int ctx, int& kvh, int& split, int& hp0, int& hp1) {
@@ -253,6 +282,26 @@ struct Producer {
             mbar_expect_tx(&ring.full[slot], bytes);
             if (use_hint) tma_bulk_g2s_hint(ring.buf + (size_t)slot * kFusedStageBytes, Wt + (size_t)k * H, bytes, &ring.full[slot], policy);
             else tma_bulk_g2s(ring.buf + (size_t)slot * kFusedStageBytes, Wt + (size_t)k * H, bytes, &ring.full[slot]);
+            ++it;
+        }
+    }
+    // variant KO: this CTA's row slice of its kv group's column block of Wo
+    __device__ void rows_o_group(const FusedArgs& a, const __half* o_g, int ctx) {
+        int kvh, split, hp0, hp1;
+        if (!attn_item(a, ctx, kvh, split, hp0, hp1)) return;
+        const int Kp = (a.nh / a.nkv) * a.hd;
+        int r0, r1;
+        ko_rows(a.H, a.nsplit, split, r0, r1);
+        const int R = ko_rows_per_stage(Kp);
+        const __half* W = o_g + (size_t)kvh * a.H * Kp;
+        for (int r = r0; r < r1; r += R) {
+            const int nr = min(R, r1 - r);
+            int slot;
+            acquire(slot);
+            const uint32_t bytes = (uint32_t)nr * Kp * 2u;
+            mbar_expect_tx(&ring.full[slot], bytes);
+            if (use_hint) tma_bulk_g2s_hint(ring.buf + (size_t)slot * kFusedStageBytes, W + (size_t)r * Kp, bytes, &ring.full[slot], policy);
+            else tma_bulk_g2s(ring.buf + (size_t)slot * kFusedStageBytes, W + (size_t)r * Kp, bytes, &ring.full[slot]);
             ++it;
         }
     }
@@ -445,6 +494,85 @@ struct Consumer {
             for (int n = 0; n < NA; ++n) t += acc[q][n];
             v[q] = t;
         }
+    }
+
+    // variant KO, input of the K-split o_proj: merge the split partials of the G heads of THIS CTA's kv group into
+    // xs[0 .. G*hd) (same arithmetic as load_attn, a G-th of the heads).
+    __device__ void load_attn_group(const FusedArgs& a, int kvh, int G) {
+        constexpr int HD = 128, PS = kFusedPartialStride, CH = kFusedMergeChunk;
+        const int Kp = G * HD;
+        if (warp < G) {
+            const float* pb = a.partial + (size_t)(kvh * G + warp) * a.nsplit * PS;
+            float M = -INFINITY, L = 0.f;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int s0 = 0; s0 < a.nsplit; s0 += CH) {
+                float4 v[CH];
+#pragma unroll
+                for (int j = 0; j < CH; ++j)
+                    v[j] = (s0 + j < a.nsplit) ? __ldcg(reinterpret_cast<const float4*>(pb + (size_t)(s0 + j) * PS) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float m = -INFINITY, l = 0.f;
+                if (lane < CH && s0 + lane < a.nsplit) {
+                    const float2 ml = __ldcg(reinterpret_cast<const float2*>(pb + (size_t)(s0 + lane) * PS + HD));
+                    m = ml.x; l = ml.y;
+                }
+                float cm = m;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+                const float Mn = fmaxf(M, cm);
+                const float so = (M == -INFINITY) ? 0.f : expf(M - Mn);
+                const float e = (m == -INFINITY) ? 0.f : expf(m - Mn);
+                L = L * so + warp_sum(l * e);
+                acc.x *= so; acc.y *= so; acc.z *= so; acc.w *= so;
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    const float ej = __shfl_sync(0xffffffffu, e, j);
+                    acc.x += v[j].x * ej; acc.y += v[j].y * ej; acc.z += v[j].z * ej; acc.w += v[j].w * ej;
+                }
+                M = Mn;
+            }
+            *reinterpret_cast<float4*>(xs + xs_pos(warp * HD + 4 * lane, Kp)) = make_float4(acc.x / L, acc.y / L, acc.z / L, acc.w / L);
+        }
+        consumer_bar_sync();
+    }
+
+    // variant KO: xo[r] += Wo_g[kvh][r, :] . xs for this CTA's rows of the group's column block (fp32 reductions into the
+    // residual stream; the 8 kv groups add into the same element).
+    __device__ void o_ksplit(const FusedArgs& a, int split, int G, float* xo) {
+        const int Kp = G * a.hd;
+        int r0, r1;
+        ko_rows(a.H, a.nsplit, split, r0, r1);
+        const int R = ko_rows_per_stage(Kp);
+        unsigned i = it;
+        for (int r = r0; r < r1; r += R, ++i) {
+            if (!owns(i)) continue;
+            const int nr = min(R, r1 - r);
+            const uint8_t* st = wait_full(i);
+            float v[kFusedMaxRows];
+#pragma unroll
+            for (int q = 0; q < kFusedMaxRows; ++q) v[q] = 0.f;
+            if (nr == R && R == 8) stage_dots<8, 1>(st, Kp, v);
+            else if (nr == R && R == 4) stage_dots<4, 2>(st, Kp, v);
+            else {
+                for (int q = 0; q < nr; ++q) {
+                    float t[kFusedMaxRows];
+                    stage_dots<1, 4>(st + (size_t)q * Kp * 2, Kp, t);
+#pragma unroll
+                    for (int z = 0; z < kFusedMaxRows; ++z) if (z == q) v[z] = t[0];
+                }
+            }
+            release(i);
+            float mine = 0.f;
+#pragma unroll
+            for (int q = 0; q < kFusedMaxRows; ++q) {
+                if (q < nr) {
+                    const float t = warp_sum(v[q]);
+                    if (lane == q) mine = t;
+                }
+            }
+            if (lane < nr) atomicAdd(xo + r + lane, mine);   // result unused: RED.E.ADD.F32
+        }
+        it = i;
+        consumer_bar_sync();
     }
 
     // K-split down projection (variant KS): acc[n] += sum_{k in this CTA's slice} Wdown^T[k][n] * h[k].  Every consumer
@@ -721,7 +849,7 @@ __device__ void fused_attention(const FusedArgs& a, Consumer& c, AttnSmem<G>& s,
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
-template <int G, bool KS = false>
+template <int G, bool KS = false, bool KO = false>
 __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(FusedArgs a) {
     extern __shared__ __align__(1024) uint8_t fused_smem_raw[];
     uint8_t* ringbuf = fused_smem_raw;
@@ -775,7 +903,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
                 if (l + 1 < a.L) nxt = a.layers[l + 1];   // pointer table one layer ahead: off the issue path
                 p.rows(Ly.qkv, a.qkv_dim, a.H, 1); AHA_STAMP(a, 1, pe);
                 p.attn(a, l, ctx); AHA_STAMP(a, 1, pe);
-                p.rows(Ly.o, a.H, a.nh * a.hd, 1); AHA_STAMP(a, 1, pe);
+                if (KO) p.rows_o_group(a, Ly.o_g, ctx); else p.rows(Ly.o, a.H, a.nh * a.hd, 1);
+                AHA_STAMP(a, 1, pe);
                 p.rows(Ly.gu, 2 * a.I, a.H, 2); AHA_STAMP(a, 1, pe);
                 if (KS) p.rows_t(Ly.down_t, 2 * a.I, a.H); else p.rows(Ly.down, a.H, a.I, 1);
                 AHA_STAMP(a, 1, pe);
@@ -807,23 +936,47 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
         // re-zeroes its own rows of it one barrier later, two barriers before layer l + 2 accumulates into it again
         float* const acc_prev = a.acc2 + (size_t)((l + 1) & 1) * a.H;
         float* const acc_cur = a.acc2 + (size_t)(l & 1) * a.H;
+        // variant KO: x after o_proj lives in xo[l & 1] (double-buffered so that the owners' writes for layer l never meet a
+        // reader of layer l - 1)
+        float* const xo_cur = KO ? a.xo + (size_t)(l & 1) * a.H : nullptr;
+        const float* const xo_prev = KO ? a.xo + (size_t)((l + 1) & 1) * a.H : nullptr;
         // P1: qkv = Wqkv . rmsnorm(x)      (layer 0 reads the embedding row directly: Embedding::forward)
-        if (KS && !first) c.template load_x<true>(a.H, a.x, nullptr, Ly.ln1, a.eps, acc_prev, own_r0, own_r1);
+        if (KS && !first) c.template load_x<true>(a.H, KO ? xo_prev : a.x, nullptr, Ly.ln1, a.eps, acc_prev, own_r0, own_r1);
         else c.load_x(a.H, a.x, first ? emb_row : nullptr, Ly.ln1, a.eps);
+        if (KO && tid < own_r1 - own_r0) xo_cur[own_r0 + tid] = xown[tid];   // x entering the layer; the o_proj partial sums are added to it after the next barrier
         CSTAMP();
         c.template gemv<FE_QKV>(a, a.qkv_dim, a.H, Ly.qkv_b, a.qkv1, best, bi); CSTAMP();
         grid_barrier(&a.sync[0], seq, a.dbg, a.trace); CSTAMP();
         // P2: attention over the paged cache (+ q/k norm, RoPE, KV append)
         CSTAMP();
         fused_attention<G>(a, c, *as, cs, spages, l, Ly, t_new); CSTAMP();
-        grid_barrier(&a.sync[0], seq, a.dbg, a.trace); CSTAMP();
-        // P3: x = resid + Wo . attn
-        c.load_attn(a); CSTAMP();
-        if (KS && !first && tid < own_r1 - own_r0) acc_prev[own_r0 + tid] = 0.f;   // read last in P1 (before its barrier), accumulated next by layer l + 1
-        c.template gemv<FE_RESID>(a, a.H, a.nh * a.hd, Ly.o_b, a.x, best, bi); CSTAMP();
-        grid_barrier(&a.sync[0], seq, a.dbg, a.trace); CSTAMP();
+        if (KO) {
+            // P3 (variant KO): only the CTAs of this kv group synchronise; each merges its group's heads and adds its rows
+            // of Wo[:, group columns] . attn_group into xo
+            int kvh, split, hp0, hp1;
+            const bool has_item = attn_item(a, ctx, kvh, split, hp0, hp1);
+            if (has_item) {
+                group_barrier(&a.gsync[kvh], (unsigned)(l + 1) * (unsigned)a.nsplit); CSTAMP();
+                c.load_attn_group(a, kvh, G); CSTAMP();
+            } else { CSTAMP(); CSTAMP(); }
+            if (KS && !first && tid < own_r1 - own_r0) acc_prev[own_r0 + tid] = 0.f;
+            if (has_item) c.o_ksplit(a, split, G, xo_cur);
+            CSTAMP();
+            grid_barrier(&a.sync[0], seq, a.dbg, a.trace); CSTAMP();
+        } else {
+            grid_barrier(&a.sync[0], seq, a.dbg, a.trace); CSTAMP();
+            // P3: x = resid + Wo . attn
+            c.load_attn(a); CSTAMP();
+            if (KS && !first && tid < own_r1 - own_r0) acc_prev[own_r0 + tid] = 0.f;   // read last in P1 (before its barrier), accumulated next by layer l + 1
+            c.template gemv<FE_RESID>(a, a.H, a.nh * a.hd, Ly.o_b, a.x, best, bi); CSTAMP();
+            grid_barrier(&a.sync[0], seq, a.dbg, a.trace); CSTAMP();
+        }
         // P4: h = silu(gate) * up, gate/up rows interleaved, input rmsnorm(x)
-        c.load_x(a.H, a.x, nullptr, Ly.ln2, a.eps); CSTAMP();
+        float own_mid = 0.f;
+        if (KO && tid < own_r1 - own_r0) own_mid = __ldcg(xo_cur + own_r0 + tid);   // this CTA's rows of x after o_proj, in flight with the load below
+        c.load_x(a.H, KO ? xo_cur : a.x, nullptr, Ly.ln2, a.eps);
+        if (KO && tid < own_r1 - own_r0) xown[tid] = own_mid;   // residual of the down projection (read in its epilogue, CTA barriers away)
+        CSTAMP();
         if (KS) {
             // h stays in shared memory; P5 follows without a barrier: acc_cur += Wdown[:, slice] . h[slice]
             c.template gemv<FE_SWIGLU>(a, 2 * a.I, a.H, nullptr, hs - hs_k0, best, bi); CSTAMP();
@@ -845,7 +998,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
         }
     }
     // final: logits = lm_head . rmsnorm(x), per-CTA argmax candidate
-    if (KS) c.template load_x<true>(a.H, a.x, nullptr, a.final_norm, a.eps, a.acc2 + (size_t)((a.L - 1) & 1) * a.H, own_r0, own_r1);
+    if (KS) c.template load_x<true>(a.H, KO ? a.xo + (size_t)((a.L - 1) & 1) * a.H : a.x, nullptr, a.final_norm, a.eps, a.acc2 + (size_t)((a.L - 1) & 1) * a.H, own_r0, own_r1);
     else c.load_x(a.H, a.x, nullptr, a.final_norm, a.eps);
     best = -INFINITY; bi = 0x7fffffff;
     c.template gemv<FE_LOGITS>(a, a.V, a.H, nullptr, a.logits, best, bi); CSTAMP();

@@ -82,6 +82,15 @@ __global__ void transpose_f16_kernel(const __half* __restrict__ in, __half* __re
     }
 }
 
+// out[g][r][c] = in[r][g * Kp + c] for an fp16 matrix [R][K]: K / Kp column blocks, each stored as its own [R][Kp] matrix.
+__global__ void split_columns_f16_kernel(const __half* __restrict__ in, __half* __restrict__ out, int R, int K, int Kp) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)R * K) return;
+    const int r = (int)(i / K), k = (int)(i % K);
+    const int g = k / Kp, c = k % Kp;
+    out[((size_t)g * R + r) * Kp + c] = in[i];
+}
+
 __global__ void add_inplace_kernel(float* __restrict__ x, const float* __restrict__ y, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) x[i] += y[i];

@@ -293,6 +293,8 @@ struct TextModel {
     bool fused = false;
     bool ksplit = false;                 // fused variant KS (decode_impl = 3): K-split down projection, see decode_fused.cuh
     float* acc2 = nullptr;               // [2][H] accumulators of that variant
+    bool kosplit = false;                // fused variant KO (decode_impl = 4, or 5 with KS): K-split o_proj behind a kv-group barrier
+    float* xo = nullptr;                 // [2][H] residual stream of that variant
     int decode_impl = 0;
     FusedLayer* d_fused_layers = nullptr;
     unsigned* d_sync = nullptr;   // [0] grid barrier, [1] final ticket, then kv tickets [nkv]
@@ -389,6 +391,13 @@ struct TextModel {
         return true;
     }
     template <int G>
+    void (*fused_kernel() const)(FusedArgs) {
+        if (ksplit && kosplit) return decode_step_fused_kernel<G, true, true>;
+        if (kosplit) return decode_step_fused_kernel<G, false, true>;
+        if (ksplit) return decode_step_fused_kernel<G, true, false>;
+        return decode_step_fused_kernel<G, false, false>;
+    }
+    template <int G>
     void fused_prepare() {
         fused_smem = fused_smem_bytes<G>();
         auto prep = [&](auto kernel) {
@@ -397,8 +406,7 @@ struct TextModel {
             AHA_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kFusedThreads, fused_smem));
             AHA_REQUIRE(nb >= 1, "fused decode kernel does not fit on an SM");
         };
-        if (ksplit) prep(decode_step_fused_kernel<G, true>);
-        else prep(decode_step_fused_kernel<G, false>);
+        prep(fused_kernel<G>());
     }
     void alloc_runtime(int max_ctx_, int max_prefill_, bool graph, int decode_impl_ = 0) {
         Ctx& c = *ctx;
@@ -406,9 +414,12 @@ struct TextModel {
         {
             std::string why;
             const bool ok = fused_supported(&why);
-            AHA_REQUIRE((decode_impl != 2 && decode_impl != 3) || ok, "fused decode kernel unsupported for this model: " + why);
+            AHA_REQUIRE(decode_impl < 2 || decode_impl > 5 || ok, "fused decode kernel unsupported for this model: " + why);
+            AHA_REQUIRE(decode_impl >= 0 && decode_impl <= 5, "decode_impl must be 0..5");
             fused = ok && decode_impl != 1;
-            ksplit = fused && decode_impl == 3;
+            ksplit = fused && (decode_impl == 3 || decode_impl == 5);
+            kosplit = fused && (decode_impl == 4 || decode_impl == 5);
+            AHA_REQUIRE(!kosplit || !layers[0].o.b, "K-split o_proj variant: o_proj bias is not supported");
             AHA_REQUIRE(!ksplit || (I_l + ctx->num_sms - 1) / ctx->num_sms + 2 <= kFusedMaxHs, "K-split variant: more SwiGLU outputs per SM than it keeps in shared memory");
         }
         num_pages = ceil_div(max_ctx, kPage);
@@ -437,7 +448,15 @@ struct TextModel {
             std::vector<FusedLayer> fl(cfg.L);
             for (int l = 0; l < cfg.L; ++l) {
                 TextLayer& T = layers[l];
-                fl[l] = FusedLayer{T.qkv.w, T.o.w, T.gu.w, T.down.w, T.qkv.b, T.o.b, T.ln1, T.ln2, T.qn, T.kn, nullptr};
+                fl[l] = FusedLayer{T.qkv.w, T.o.w, T.gu.w, T.down.w, T.qkv.b, T.o.b, T.ln1, T.ln2, T.qn, T.kn, nullptr, nullptr};
+                if (kosplit) {   // Wo as nkv column blocks [H][G*hd]: the slice a CTA of kv group g multiplies becomes contiguous rows
+                    const int Kp = (nh_l / nkv_l) * cfg.hd, Kt = nh_l * cfg.hd;
+                    __half* og = c.alloc<__half>((size_t)cfg.H * Kt);
+                    const size_t n = (size_t)cfg.H * Kt;
+                    split_columns_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(T.o.w, og, cfg.H, Kt, Kp);
+                    AHA_CUDA_CHECK(cudaGetLastError());
+                    fl[l].o_g = og;
+                }
                 if (ksplit) {   // Wdown^T [I][H]: the k-rows a CTA needs become contiguous 2*H-byte rows
                     __half* wt = c.alloc<__half>((size_t)I_l * cfg.H);
                     transpose_f16_kernel<<<dim3((unsigned)ceil_div(I_l, 32), (unsigned)ceil_div(cfg.H, 32)), dim3(32, 8), 0, c.stream>>>(T.down.w, wt, cfg.H, I_l);
@@ -445,6 +464,7 @@ struct TextModel {
                     fl[l].down_t = wt;
                 }
             }
+            if (kosplit) xo = c.alloc<float>((size_t)2 * cfg.H);
             if (ksplit) {
                 acc2 = c.alloc<float>((size_t)2 * cfg.H);
                 AHA_CUDA_CHECK(cudaMemsetAsync(acc2, 0, (size_t)2 * cfg.H * sizeof(float), c.stream));
@@ -620,8 +640,7 @@ struct TextModel {
     template <int G>
     void launch_fused(FusedArgs& fa) {
         void* args[] = {&fa};
-        void* kernel = ksplit ? (void*)decode_step_fused_kernel<G, true> : (void*)decode_step_fused_kernel<G, false>;
-        AHA_CUDA_CHECK(cudaLaunchCooperativeKernel(kernel, dim3(fused_grid), dim3(kFusedThreads), args, fused_smem, ctx->stream));
+        AHA_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)fused_kernel<G>(), dim3(fused_grid), dim3(kFusedThreads), args, fused_smem, ctx->stream));
     }
     void decode_step_fused() {
         Ctx& c = *ctx;
@@ -637,7 +656,7 @@ struct TextModel {
         fa.trace = d_ftrace;
         { const char* e = getenv("AHA_FUSED_STAGES"); fa.stages = e ? std::max(2, std::min(kFusedStages, atoi(e))) : fused_stages; }
         AHA_CUDA_CHECK(cudaMemsetAsync(d_sync, 0, sync_words * sizeof(unsigned), c.stream));
-        fa.acc2 = acc2;
+        fa.acc2 = acc2; fa.xo = xo; fa.gsync = reinterpret_cast<unsigned*>(counters);
         if (ksplit) AHA_CUDA_CHECK(cudaMemsetAsync(acc2, 0, (size_t)2 * cfg.H * sizeof(float), c.stream));
         switch (nh_l / nkv_l) {
             case 1: launch_fused<1>(fa); break;

@@ -4,7 +4,9 @@ when AHA_TEST_EXPERIMENTAL=1 so that an unfinished experiment can never turn the
 GQA groups 1 and 4: instantiations of the decode attention (fused and per-op) that no shipped model shape reaches.
 
 decode_impl = 3: the fused decode kernel with the K-split down projection (decode_fused.cuh, variant KS): gate/up and
-down in one phase, fp32 reductions into a global accumulator, 4 grid barriers per layer instead of 5."""
+down in one phase, fp32 reductions into a global accumulator, 4 grid barriers per layer instead of 5.
+decode_impl = 4: variant KO, K-split o_proj behind a kv-group barrier (each CTA merges only its own group's partials).
+decode_impl = 5: both."""
 import os
 
 import numpy as np
@@ -20,10 +22,11 @@ def _ids(n, vocab, seed):
     return np.random.default_rng(seed).integers(0, min(vocab, 1000), n).astype(np.uint32)
 
 
+@pytest.mark.parametrize("impl", [3, 4, 5])
 @pytest.mark.parametrize("preset", ["tiny", "mid"])
-def test_ksplit_decode_matches_the_default_fused_kernel_and_the_oracle(preset):
+def test_ksplit_decode_matches_the_default_fused_kernel_and_the_oracle(preset, impl):
     cfg, w, m = make_model("qwen3", preset, max_ctx=512)
-    _, _, k = make_model("qwen3", preset, max_ctx=512, decode_impl=3)
+    _, _, k = make_model("qwen3", preset, max_ctx=512, decode_impl=impl)
     o = make_oracle("qwen3", cfg, w)
     try:
         ids = _ids(50, cfg["vocab_size"], 8)
