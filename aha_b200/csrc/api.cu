@@ -172,6 +172,7 @@ void fetch_outputs(aha_model* m, float* logits_out, uint32_t* argmax_out) {
     if (logits_out) AHA_CUDA_CHECK(cudaMemcpyAsync(logits_out, T.logits, (size_t)T.cfg.V * sizeof(float), cudaMemcpyDeviceToHost, m->ctx.stream));
     if (argmax_out) AHA_CUDA_CHECK(cudaMemcpyAsync(m->h_pin, T.d_argmax, sizeof(uint32_t), cudaMemcpyDeviceToHost, m->ctx.stream));
     AHA_CUDA_CHECK(cudaStreamSynchronize(m->ctx.stream));
+    T.check_ll_abort();
     if (argmax_out) *argmax_out = m->h_pin[0];
 }
 
@@ -267,7 +268,7 @@ void forward_any(aha_model* m, const uint32_t* ids, size_t S, size_t offset, con
         AHA_REQUIRE(ids[0] < (uint32_t)T.cfg.V, "token id out of range");
         T.ensure_tokens((int)offset + 1);
         T.set_state(ids[0], (int)offset, m->kind == aha_model::QWEN3VL ? m->rope_delta : 0, 0);
-        T.decode_step();
+        T.decode_step(logits_out != nullptr);
     } else {
         // The reference builds an (S,S) causal mask with offset 0 for every multi-token call
         // (qwen3/model.rs:164-175); with a non-empty cache its broadcast_add against (S, off+S) scores fails.
@@ -316,6 +317,7 @@ int aha_b200_create(const char* kind, const char* config_json, const aha_tensor_
         AHA_CUDA_CHECK(cudaEventCreate(&m->ev1));
         AHA_CUDA_CHECK(cudaMallocHost(&m->h_pin, 64));
         gemv_init();
+        gemm_tc_init();
         const std::string k = kind;
         const std::string cfg_text = config_json;
         Json root = JsonParser(cfg_text).parse();
@@ -427,6 +429,7 @@ int aha_b200_generate(aha_model* m, const uint32_t* ids, size_t seq_len, const a
                 burst.resize(n);
                 AHA_CUDA_CHECK(cudaMemcpyAsync(burst.data(), T.d_history + (done - 1), n * sizeof(uint32_t), cudaMemcpyDeviceToHost, m->ctx.stream));
                 AHA_CUDA_CHECK(cudaStreamSynchronize(m->ctx.stream));
+                T.check_ll_abort();
                 for (size_t i = 0; i < n; ++i) {
                     generated.push_back(burst[i]);
                     ++done;
@@ -469,6 +472,7 @@ int aha_b200_decode_steps(aha_model* m, uint32_t first_token, size_t seqlen_offs
         AHA_CUDA_CHECK(cudaEventRecord(m->ev1, m->ctx.stream));
         if (out_tokens) AHA_CUDA_CHECK(cudaMemcpyAsync(out_tokens, T.d_history, n_steps * sizeof(uint32_t), cudaMemcpyDeviceToHost, m->ctx.stream));
         AHA_CUDA_CHECK(cudaStreamSynchronize(m->ctx.stream));
+        T.check_ll_abort();
         if (device_ms) { float ms = 0.f; AHA_CUDA_CHECK(cudaEventElapsedTime(&ms, m->ev0, m->ev1)); *device_ms = ms; }
     });
 }
@@ -756,6 +760,24 @@ int aha_b200_debug_read(aha_model* m, const char* what, int index, float* out, s
             for (size_t k = 0; k < 255; ++k) out[k] = h[k] ? (float)((double)h[k] - (double)base) : -1e30f;
             out[255] = (float)h[255];
             *n = 256; return;
+        } else if (w == "fused_stage_trace") {  // AHA_STAGE_TRACE builds: 4 stamps per ring stage of the traced CTA, ns relative to the earliest stamp (0 = missing)
+            AHA_REQUIRE(T.d_ftrace && cap >= 4 * 8192, "fused trace not available");
+            std::vector<unsigned long long> h(4 * 8192);
+            AHA_CUDA_CHECK(cudaMemcpy(h.data(), T.d_ftrace + 8192, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            unsigned long long base = ~0ull;
+            for (auto v : h) if (v && v < base) base = v;
+            for (size_t k = 0; k < h.size(); ++k) out[k] = h[k] ? (float)((double)(h[k] - base) + 1.0) : 0.f;
+            AHA_CUDA_CHECK(cudaMemset(T.d_ftrace + 8192, 0, h.size() * sizeof(unsigned long long)));
+            *n = h.size(); return;
+        } else if (w == "fused_sync_trace") {  // AHA_STAGE_TRACE builds, dbg bit10: [0, 4096) = 8 words per grid barrier, [4096, 8192) = 4 per activation load
+            AHA_REQUIRE(T.d_ftrace && cap >= 8192, "fused trace not available");
+            std::vector<unsigned long long> h(8192);
+            AHA_CUDA_CHECK(cudaMemcpy(h.data(), T.d_ftrace + 8192 + 32768, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            unsigned long long base = ~0ull;
+            for (auto v : h) if (v > 1000000000000ull && v < base) base = v;
+            for (size_t k = 0; k < h.size(); ++k) out[k] = h[k] > 1000000000000ull ? (float)((double)(h[k] - base) + 1.0) : (float)h[k];   // small values are counts
+            AHA_CUDA_CHECK(cudaMemset(T.d_ftrace + 8192 + 32768, 0, h.size() * sizeof(unsigned long long)));
+            *n = h.size(); return;
         } else if (w == "rope_delta") {
             AHA_REQUIRE(cap >= 1, "out too small");
             out[0] = (float)m->rope_delta; *n = 1; return;

@@ -15,21 +15,18 @@
 //     of the residual stream the CTA keeps on chip, SwiGLU, argmax) is applied by its lanes; attention is split-KV
 //     with per-warp online softmax over the half pages the warp owns, q/k RMSNorm + RoPE + KV append fused in, and
 //     the merge of the splits folded into the o_proj input load;
-//   * phases are separated by a grid-wide barrier (one counter in L2, release/acquire) that only the consumers join.
+//   * phases exchange their (tiny) outputs through L2 as TAGGED PACKETS {value, tag} (template flag LL, the default): the
+//     producer of a value stores 8 bytes -- single-copy atomic, so the tag validates the value -- and the consumer of a
+//     vector polls the packets it needs until their tags carry this step's layer tag.  No fence, no counter, no separate
+//     load after a barrier: one store -> one (re)load per dependency instead of the four dependent L2 round trips of
+//     store-ack / release / poll / load that a grid barrier costs (measured: red.release 1.0 us + poll 0.7 us +
+//     fence.acq_rel 0.4 us + activation load 1.1 us per phase boundary, 5 boundaries per layer; profiles/README.md).
+//     The same protocol carries the tensor-parallel exchange: o_proj / down partial sums are stored straight into
+//     every peer GPU's packet buffer over NVLink (8-byte stores are atomic there too) and summed in rank order by the
+//     reader -- a one-shot all-reduce with no collective call and no cross-GPU barrier.
+//     LL = false keeps the grid-barrier version (one counter in L2, release/acquire) as the A/B twin (decode_impl = 3).
 // Phases per layer: [rmsnorm+qkv] -> [attention] -> [o_proj+residual] -> [rmsnorm+gate/up+SwiGLU] ->
 // [down+residual]; then [final norm + lm_head + argmax] and the on-device token feedback.
-//
-// Variant KS (template flag, opt-in through aha_options.decode_impl = 3; NOT the default): the down projection is
-// computed K-split right behind gate/up -- CTA c multiplies the k-rows of Wdown^T that match its own slice of
-// silu(gate)*up (still in shared memory) into all H outputs and adds them into a global fp32 accumulator with
-// red.global.add.f32 -- so the grid barrier and the h round trip between the two disappear (4 barriers per layer).
-// The next consumer of the residual stream adds the accumulator while it loads x.  Summation order across CTAs is
-// then run-dependent (fp32 atomics).
-//
-// Variant KO (template flag, decode_impl = 4, or 5 together with KS; NOT the default): o_proj is computed K-split per
-// kv group right behind the attention.  The grid barrier between the two becomes a barrier over the nsplit CTAs of
-// the group, each CTA merges only its own group's partials (G heads instead of all of them) and multiplies its slice
-// of the rows of that group's column block of Wo, adding the result into the residual stream with fp32 reductions.
 //
 // Reference semantics are those of Qwen3DecoderLayer::forward / QKNormAttention::forward / GateUpDownMLP
 // (/root/reference/src/models/qwen3/model.rs:71-87, src/models/common/modules.rs:81-87,530-579,757-813)
@@ -54,15 +51,16 @@ constexpr int kFusedTraceWords = 2 * 4096 + 256 * 256;     // timing traces: CTA
 constexpr int kFusedMaxOwnRows = 64;                     // residual-stream rows owned by one CTA (H / grid, rounded up)
 constexpr int kFusedPartialStride = 128 + 4;             // floats per (head, split) attention partial: acc[128], m, l, pad (16-byte rows)
 constexpr int kFusedMergeChunk = 20;                     // splits merged per pass when the o_proj input is assembled
-constexpr int kFusedMaxHs = 128;                         // SwiGLU outputs one CTA keeps in shared memory (K-split variant): I / grid, rounded up
 constexpr int kFusedMaxPages = 512;                      // page-table entries staged in shared memory (16K tokens)
+constexpr int kFusedMaxH = 4096;                         // residual stream kept per CTA in shared memory (LL mode)
+constexpr int kFusedMaxTp = 8;                           // tensor-parallel ranks on one NVSwitch domain
+
+struct __align__(8) LLPk { float v; uint32_t tag; };     // one tagged packet: 8-byte stores / loads are single-copy atomic
 
 struct FusedLayer {
     const __half *qkv, *o, *gu, *down;
     const float *qkv_b, *o_b;
     const float *ln1, *ln2, *qn, *kn;
-    const __half* down_t;   // [I][H] transposed copy of `down` (variant KS only, else nullptr)
-    const __half* o_g;      // [nkv][H][G*hd] column blocks of `o`, one per kv group (variant KO only, else nullptr)
 };
 
 struct FusedArgs {
@@ -79,9 +77,6 @@ struct FusedArgs {
     float* h1;         // [I]
     float* logits;     // [V]
     float* partial;    // [nh][nsplit][kFusedPartialStride]
-    float* xo;         // [2][H] variant KO: residual stream the K-split o_proj accumulates into, by layer parity (owners write x, CTAs add)
-    unsigned* gsync;   // [nkv] variant KO: arrival counters of the per-kv-group barriers (zeroed by the host before launch)
-    float* acc2;       // [2][H] fp32 accumulators of the K-split down projection (variant KS), zeroed by the host before launch
     unsigned* sync;    // [2] grid-barrier counter, final ticket   (zeroed by the host before launch)
     float* pmax; int* pidx;  // [grid] per-CTA argmax candidates
     uint32_t* argmax_out;
@@ -90,8 +85,19 @@ struct FusedArgs {
     const int* page_table;
     int nsplit;
     int stages;        // ring slots in use (<= kFusedStages)
-    int dbg;           // timing experiments only: bit0 = skip grid barriers, bit1 = skip the GEMV math, bit2 = timestamps, bit3 = old full-fence grid barrier, bit6 = per-CTA barrier arrival stamps, bit4 / bit5 = drop the L2 evict-first hint on weight / KV copies
+    int dbg;           // timing experiments only: bit0 = skip grid barriers, bit1 = skip the GEMV math, bit2 = timestamps, bit3 = old full-fence grid barrier, bit6 = per-CTA barrier arrival stamps, bit4 / bit5 = drop the L2 evict-first hint on weight / KV copies, bit7 = per-stage trace of CTA (dbg >> 16) & 0xff (AHA_STAGE_TRACE builds), bit8 = skip the activation / partial loads (streaming-rate experiments; results are garbage), bit9 = sync only (no weight stream, no math), bit10 = sync anatomy stamps of the traced CTA (AHA_STAGE_TRACE builds)
     unsigned long long* trace;  // [2][4096] globaltimer stamps of CTA 0 (consumer thread 0 / producer), dbg bit2
+    // ---- LL mode: packet buffers (device memory, zero-initialised once; tags make every step's data self-validating)
+    LLPk* ll_qkv;      // [qkv_dim]
+    LLPk* ll_pb;       // [nh][nsplit][kFusedPartialStride] split-KV attention partials (acc[128], m, l)
+    LLPk* ll_att;      // [nh * hd] merged attention output
+    LLPk* ll_h;        // [I]
+    LLPk* ll_xp[2][kFusedMaxTp];   // [o_proj | down][destination rank] -> that rank's [tp_world][H] block of partial sums (own rank = local memory)
+    LLPk* ll_cand[kFusedMaxTp];    // [destination rank] -> that rank's [tp_world][2] argmax candidates (value, index) of the vocabulary shards
+    uint32_t ll_tag;   // tag of layer 0 of this launch; layer l uses ll_tag + l, the final phase ll_tag + L (never 0, never reused)
+    int tp_rank, tp_world;
+    int v0, V_l;       // vocabulary shard [v0, v0 + V_l) of the lm_head this rank multiplies (tp_world == 1: the whole of it)
+    int* ll_abort;     // set by any thread whose wait timed out (a peer died): every later wait returns at once
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -127,6 +133,18 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
 }
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define AHA_STAMP(a, who, idx) do { if (((a).dbg & 4) && blockIdx.x == 0 && (idx) < 4096) (a).trace[(who) * 4096 + (idx)++] = gtime(); } while (0)
+// Per-stage trace (compiled only with -DAHA_STAGE_TRACE, a profiling build: variants/trace.so): for ring stage i of the
+// traced CTA, word 4i+0 = producer acquired the slot and issued the copy, 4i+1 = the owner warp started waiting for it,
+// 4i+2 = the data had landed, 4i+3 = the warp released the slot.  Lives in the [cta][256] arrival region of the trace buffer.
+#ifdef AHA_STAGE_TRACE
+#define AHA_STAGE_STAMP(tr, i, k) do { if ((tr) && (i) < 8192u) (tr)[(size_t)(i) * 4 + (k)] = gtime(); } while (0)
+// sync anatomy (dbg bit10, traced CTA, thread 0): 8 stamps per grid barrier at trace[8192 + 32768 + 8 * seq + k] and 4 per
+// activation load at trace[8192 + 32768 + 2048 + 4 * n + k]
+#define AHA_SYNC_STAMP(tr, idx, k, per) do { if ((tr) && (idx) < 400u) (tr)[(size_t)(idx) * (per) + (k)] = gtime(); } while (0)
+#else
+#define AHA_STAGE_STAMP(tr, i, k) do { } while (0)
+#define AHA_SYNC_STAMP(tr, idx, k, per) do { } while (0)
+#endif
 // Same copy with an L2 evict-first policy: weights are read exactly once per step, so they should not displace the
 // activations / partials / barrier words that every CTA re-reads from L2.
 __device__ __forceinline__ uint64_t l2_evict_first_policy() {
@@ -146,6 +164,76 @@ __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
     return v;
 }
 
+// ---- tagged packets.  Stores and loads are relaxed (strong) accesses, so polling them is race-free without fences; the
+// .sys forms are used for buffers that a peer GPU writes or reads over NVLink.
+template <bool SYS>
+__device__ __forceinline__ void ll_store(LLPk* p, float v, uint32_t tag) {
+    if (SYS) asm volatile("st.relaxed.sys.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+    else asm volatile("st.relaxed.gpu.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+template <bool SYS>
+__device__ __forceinline__ uint4 ll_load2(const LLPk* p) {   // two packets (16-byte aligned): {v0, tag0, v1, tag1}
+    uint4 r;
+    if (SYS) asm volatile("ld.relaxed.sys.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    else asm volatile("ld.relaxed.gpu.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+template <bool SYS>
+__device__ __forceinline__ uint2 ll_load1(const LLPk* p) {
+    uint2 r;
+    if (SYS) asm volatile("ld.relaxed.sys.global.v2.b32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
+    else asm volatile("ld.relaxed.gpu.global.v2.b32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
+    return r;
+}
+// Bounded wait: a missing packet means a peer CTA / GPU died.  After ~2 s of polling the waiter raises the abort flag
+// and every wait in the grid (and, through the host, the request) ends instead of hanging the GPU.
+struct LLWait {
+    int* abort_flag;
+    long long t0 = 0;
+    unsigned n = 0;
+    bool dead = false;
+    __device__ __forceinline__ bool giveup() {
+        if ((++n & 1023u) != 0) return dead;
+        if (t0 == 0) t0 = clock64();
+        if (*reinterpret_cast<volatile int*>(abort_flag) != 0) dead = true;
+        else if (clock64() - t0 > 4000000000ll) { *reinterpret_cast<volatile int*>(abort_flag) = 1; dead = true; }
+        return dead;
+    }
+};
+// The polling loops live out of line: the fast path (packet already there) is a load and four compares in the caller, and
+// the rare slow path must not cost the callers any registers.
+template <bool SYS>
+__device__ __noinline__ float ll_spin1(const LLPk* p, uint32_t tag, int* abort_flag) {
+    LLWait w{abort_flag};
+    uint2 r;
+    do { r = ll_load1<SYS>(p); } while (r.y != tag && !w.giveup());
+    return __uint_as_float(r.x);
+}
+template <bool SYS>
+__device__ __forceinline__ float ll_wait1(const LLPk* p, uint32_t tag, int* abort_flag) {
+    const uint2 r = ll_load1<SYS>(p);
+    return r.y == tag ? __uint_as_float(r.x) : ll_spin1<SYS>(p, tag, abort_flag);
+}
+// four consecutive packets (32-byte aligned) -> float4
+template <bool SYS>
+__device__ __noinline__ float4 ll_spin4(const LLPk* p, uint32_t tag, int* abort_flag) {
+    LLWait w{abort_flag};
+    uint4 a, b;
+    bool ok;
+    do {
+        a = ll_load2<SYS>(p); b = ll_load2<SYS>(p + 2);
+        ok = a.y == tag && a.w == tag && b.y == tag && b.w == tag;
+    } while (!ok && !w.giveup());
+    return make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(b.x), __uint_as_float(b.z));
+}
+template <bool SYS>
+__device__ __forceinline__ float4 ll_wait4(const LLPk* p, uint32_t tag, int* abort_flag) {
+    const uint4 a = ll_load2<SYS>(p), b = ll_load2<SYS>(p + 2);
+    if (a.y == tag && a.w == tag && b.y == tag && b.w == tag)
+        return make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(b.x), __uint_as_float(b.z));
+    return ll_spin4<SYS>(p, tag, abort_flag);
+}
+
 // Lighter synchronisation primitives than __threadfence() (= MEMBAR.SC.GPU + CCTL.IVALL per call on sm_100): a release
 // reduction / acq_rel atomic issued by ONE thread after a CTA barrier publishes the whole CTA's writes (release is
 // cumulative over the bar.sync), and a relaxed poll + fence.acq_rel is the matching acquire.  Cross-CTA data is always
@@ -162,10 +250,12 @@ __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_re
 
 // Grid barrier joined by the consumer threads only: one arrival counter in L2 (zeroed by the host before every
 // launch), polled by consumer thread 0 with relaxed loads; activations are always read with ld.global.cg.
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& seq, int dbg = 0, unsigned long long* trace = nullptr) {
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& seq, int dbg = 0, unsigned long long* trace = nullptr, unsigned long long* sy = nullptr) {
     if (dbg & 1) { consumer_bar_sync(); return; }
+    if (threadIdx.x == 0) AHA_SYNC_STAMP(sy, seq, 0, 8);
     consumer_bar_sync();                       // every consumer thread of this CTA has issued its writes
     if (threadIdx.x == 0) {
+        AHA_SYNC_STAMP(sy, seq, 1, 8);
         if ((dbg & 64) && seq < 255) trace[8192 + blockIdx.x * 256 + seq] = gtime();   // per-CTA arrival times (skew analysis)
         if (dbg & 8) {                         // A/B: the old full-fence barrier
             __threadfence();
@@ -175,25 +265,21 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& seq, i
             __threadfence();
         } else {
             red_release_add(counter, 1u);      // publish the CTA's writes at gpu scope (cumulative through the bar.sync)
+            AHA_SYNC_STAMP(sy, seq, 2, 8);
             const unsigned target = (seq + 1u) * gridDim.x;
-            while (ld_relaxed_u32(counter) < target) {}
+            unsigned polls = 0;
+            while (ld_relaxed_u32(counter) < target) { ++polls; }
+            AHA_SYNC_STAMP(sy, seq, 3, 8);
             fence_acq_rel_gpu();
+            AHA_SYNC_STAMP(sy, seq, 4, 8);
+#ifdef AHA_STAGE_TRACE
+            if (sy && seq < 400u) sy[(size_t)seq * 8 + 6] = polls;
+#endif
         }
     }
+    consumer_bar_sync();
+    if (threadIdx.x == 0) AHA_SYNC_STAMP(sy, seq, 5, 8);
     seq += 1u;
-    consumer_bar_sync();
-}
-
-// Barrier over the CTAs that share one arrival counter (variant KO: the nsplit CTAs of a kv group), same protocol as
-// grid_barrier: release reduction, relaxed poll, acquire fence; consumer threads only.
-__device__ __forceinline__ void group_barrier(unsigned* counter, unsigned target) {
-    consumer_bar_sync();
-    if (threadIdx.x == 0) {
-        red_release_add(counter, 1u);
-        while (ld_relaxed_u32(counter) < target) {}
-        fence_acq_rel_gpu();
-    }
-    consumer_bar_sync();
 }
 
 // ------------------------------------------------------------------------------------------------ schedule
@@ -212,15 +298,6 @@ __host__ __device__ __forceinline__ int rows_per_stage(int K, int N, int grid) {
     const int per_cta = N / grid;
     while (r > 2 && per_cta < r * 5) r >>= 1;
     return r;
-}
-// variant KO: rows of o_proj computed by split `split` of a kv group, and rows per stage for its K' = G*hd columns
-__device__ __forceinline__ void ko_rows(int H, int nsplit, int split, int& r0, int& r1) {
-    r0 = (int)(((long long)H * split) / nsplit);
-    r1 = (int)(((long long)H * (split + 1)) / nsplit);
-}
-__device__ __forceinline__ int ko_rows_per_stage(int Kp) {
-    const int r = kFusedStageBytes / (2 * Kp);
-    return r > kFusedMaxRows ? kFusedMaxRows : (r < 1 ? 1 : r);
 }
 // attention work item of this CTA: (kv head, [hp0, hp1) half pages); empty when the CTA has no item
 __device__ __forceinline__ bool attn_item(const FusedArgs& a, int ctx, int& kvh, int& split, int& hp0, int& hp1) {
@@ -249,9 +326,11 @@ struct Producer {
     unsigned ns = kFusedStages;
     bool use_hint = false, hint_kv = false;
     uint64_t policy = 0;
+    unsigned long long* st_trace = nullptr;
     __device__ __forceinline__ void acquire(int& slot) {
         slot = it % ns;
         mbar_wait(&ring.empty[slot], ((it / ns) & 1u) ^ 1u);
+        AHA_STAGE_STAMP(st_trace, it, 0);
     }
     __device__ void rows(const __half* W, int N, int K, int unit) {
         int r0, r1;
@@ -265,43 +344,6 @@ struct Producer {
             mbar_expect_tx(&ring.full[slot], bytes);
             if (use_hint) tma_bulk_g2s_hint(ring.buf + (size_t)slot * kFusedStageBytes, W + (size_t)r * K, bytes, &ring.full[slot], policy);
             else tma_bulk_g2s(ring.buf + (size_t)slot * kFusedStageBytes, W + (size_t)r * K, bytes, &ring.full[slot]);
-            ++it;
-        }
-    }
-    // K-split down projection: k-rows [r0/2, r1/2) of Wdown^T [I][H] -- the rows that match this CTA's slice of h.
-    __device__ void rows_t(const __half* Wt, int I2, int H) {
-        int r0, r1;
-        cta_rows(I2, 2, r0, r1);
-        const int k0 = r0 >> 1, k1 = r1 >> 1;
-        const int R = max(1, kFusedStageBytes / (2 * H));
-        for (int k = k0; k < k1; k += R) {
-            const int nr = min(R, k1 - k);
-            int slot;
-            acquire(slot);
-            const uint32_t bytes = (uint32_t)nr * H * 2u;
-            mbar_expect_tx(&ring.full[slot], bytes);
-            if (use_hint) tma_bulk_g2s_hint(ring.buf + (size_t)slot * kFusedStageBytes, Wt + (size_t)k * H, bytes, &ring.full[slot], policy);
-            else tma_bulk_g2s(ring.buf + (size_t)slot * kFusedStageBytes, Wt + (size_t)k * H, bytes, &ring.full[slot]);
-            ++it;
-        }
-    }
-    // variant KO: this CTA's row slice of its kv group's column block of Wo
-    __device__ void rows_o_group(const FusedArgs& a, const __half* o_g, int ctx) {
-        int kvh, split, hp0, hp1;
-        if (!attn_item(a, ctx, kvh, split, hp0, hp1)) return;
-        const int Kp = (a.nh / a.nkv) * a.hd;
-        int r0, r1;
-        ko_rows(a.H, a.nsplit, split, r0, r1);
-        const int R = ko_rows_per_stage(Kp);
-        const __half* W = o_g + (size_t)kvh * a.H * Kp;
-        for (int r = r0; r < r1; r += R) {
-            const int nr = min(R, r1 - r);
-            int slot;
-            acquire(slot);
-            const uint32_t bytes = (uint32_t)nr * Kp * 2u;
-            mbar_expect_tx(&ring.full[slot], bytes);
-            if (use_hint) tma_bulk_g2s_hint(ring.buf + (size_t)slot * kFusedStageBytes, W + (size_t)r * Kp, bytes, &ring.full[slot], policy);
-            else tma_bulk_g2s(ring.buf + (size_t)slot * kFusedStageBytes, W + (size_t)r * Kp, bytes, &ring.full[slot]);
             ++it;
         }
     }
@@ -343,19 +385,28 @@ struct Consumer {
     unsigned it = 0;    // global stage counter (same sequence as the producer's)
     float* xs;          // [K] activation vector (shared), also aliased by the attention scratch
     float* red;         // [32] scratch
-    float* xown;        // [kFusedMaxOwnRows] this CTA's rows of the residual stream (never re-read from global memory)
+    float* xown;        // [kFusedMaxOwnRows] this CTA's rows of the residual stream (never re-read from global memory; barrier mode)
+    float* xres = nullptr;   // [H] LL mode: the whole residual stream, kept by every CTA (thread t always touches the same elements)
+    int* ll_abort = nullptr;
     int warp, lane;
 
     unsigned ns = kFusedStages;
+    unsigned long long* st_trace = nullptr;
+    bool skip_loads = false;   // dbg bit8: timing experiments only
+    bool sync_only = false;    // dbg bit9: no weight stream and no math, only the barriers and activation loads
+    unsigned long long* sy_trace = nullptr;   // sync anatomy stamps (AHA_STAGE_TRACE builds, dbg bit10)
+    unsigned n_loads = 0;
     __device__ __forceinline__ bool owns(unsigned i) const { return (int)((i % ns) % kFusedConsumers) == warp; }
     __device__ __forceinline__ const uint8_t* wait_full(unsigned i) {
         const int slot = i % ns;
+        if (lane == 0) AHA_STAGE_STAMP(st_trace, i, 1);
         mbar_wait(&ring.full[slot], (i / ns) & 1u);
+        if (lane == 0) AHA_STAGE_STAMP(st_trace, i, 2);
         return ring.buf + (size_t)slot * kFusedStageBytes;
     }
     __device__ __forceinline__ void release(unsigned i) {
         __syncwarp();
-        if (lane == 0) mbar_arrive(&ring.empty[i % ns]);
+        if (lane == 0) { AHA_STAGE_STAMP(st_trace, i, 3); mbar_arrive(&ring.empty[i % ns]); }
     }
 
     // Shared-memory layout of the activation vector: element e = 8c + j sits at 4c + j (j < 4) or K/2 + 4c + (j - 4), so
@@ -364,21 +415,18 @@ struct Consumer {
     static __device__ __forceinline__ int xs_pos(int e, int K) { return ((e >> 2) & 1) * (K >> 1) + (e >> 3) * 4; }
     // Stage the activation vector of a GEMV in shared memory (all consumer threads), optional RMSNorm.
     // src is fp32 global written by other CTAs (ld.global.cg) or an fp16 embedding row.
-    // ADD2 (K-split variant): x = src32 + src32b (the residual stream plus the accumulated down projection); the rows
-    // [own_r0, own_r1) this CTA owns are captured into xown on the way.
-    template <bool ADD2 = false>
-    __device__ void load_x(int K, const float* src32, const __half* src16, const float* norm_w, float eps, const float* src32b = nullptr,
-                           int own_r0 = 0, int own_r1 = 0) {
+    __device__ void load_x(int K, const float* src32, const __half* src16, const float* norm_w, float eps, bool capture = false) {
         const int tid = threadIdx.x;
         constexpr int kPer = (kFusedMaxK + kFusedConsumers * 32 * 4 - 1) / (kFusedConsumers * 32 * 4);   // float4 per thread
         float4 v[kPer], w[kPer];
         float ss = 0.f;
+        if (tid == 0) AHA_SYNC_STAMP(sy_trace ? sy_trace + 4096 : nullptr, n_loads, 0, 4);
 #pragma unroll
         for (int j = 0; j < kPer; ++j) {
             const int e = (tid + j * kFusedConsumers * 32) * 4;
             v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             w[j] = v[j];
-            if (e < K) {
+            if (e < K && !skip_loads) {
                 if (norm_w) w[j] = *reinterpret_cast<const float4*>(norm_w + e);   // static data: in flight with x
                 if (src16) {
                     const uint2 u = *reinterpret_cast<const uint2*>(src16 + e);
@@ -386,19 +434,95 @@ struct Consumer {
                     v[j] = make_float4(a.x, a.y, b.x, b.y);
                 } else {
                     v[j] = __ldcg(reinterpret_cast<const float4*>(src32 + e));
-                    if (ADD2) {
-                        const float4 b = __ldcg(reinterpret_cast<const float4*>(src32b + e));
-                        v[j].x += b.x; v[j].y += b.y; v[j].z += b.z; v[j].w += b.w;
-                        if (e + 3 >= own_r0 && e < own_r1) {
-                            const float t[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) if (e + q >= own_r0 && e + q < own_r1) xown[e + q - own_r0] = t[q];
-                        }
-                    }
                 }
             }
         }
+        if (capture) {
+#pragma unroll
+            for (int j = 0; j < kPer; ++j) {
+                const int e = (tid + j * kFusedConsumers * 32) * 4;
+                if (e < K) *reinterpret_cast<float4*>(xres + e) = v[j];
+            }
+        }
         if (norm_w) {
+#pragma unroll
+            for (int j = 0; j < kPer; ++j) ss += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+            ss = warp_sum(ss);
+            if (lane == 0) red[warp] = ss;
+            if (tid == 0) AHA_SYNC_STAMP(sy_trace ? sy_trace + 4096 : nullptr, n_loads, 1, 4);
+            consumer_bar_sync();
+            if (tid == 0) AHA_SYNC_STAMP(sy_trace ? sy_trace + 4096 : nullptr, n_loads, 2, 4);
+            float tot = 0.f;
+#pragma unroll
+            for (int q = 0; q < kFusedConsumers; ++q) tot += red[q];
+            const float inv = 1.0f / sqrtf(tot / (float)K + eps);
+#pragma unroll
+            for (int j = 0; j < kPer; ++j) { v[j].x *= inv * w[j].x; v[j].y *= inv * w[j].y; v[j].z *= inv * w[j].z; v[j].w *= inv * w[j].w; }
+        }
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) {
+            const int e = (tid + j * kFusedConsumers * 32) * 4;
+            if (e < K) *reinterpret_cast<float4*>(xs + xs_pos(e, K)) = v[j];
+        }
+        consumer_bar_sync();
+        if (tid == 0) AHA_SYNC_STAMP(sy_trace ? sy_trace + 4096 : nullptr, n_loads, 3, 4);
+        ++n_loads;
+    }
+
+    // LL mode: stage x = [residual +] sum_r packets[r * vstride + e] in xs (optional RMSNorm).  The packets are polled until
+    // they carry `tag`; all loads of a vector are issued before the first tag is looked at, and the common case (data already
+    // there) costs one L2 round trip.  RESID: the sum is added into the residual stream this CTA keeps in shared memory
+    // (fixed rank order r = 0, 1, ... -> every CTA of every GPU forms bit-identical sums).
+    template <bool SYS, bool RESID>
+    __device__ __forceinline__ void load_ll(int K, const LLPk* pk, int nvec, size_t vstride, uint32_t tag, const float* norm_w, float eps) {
+        constexpr int kChunk = kFusedConsumers * 32 * 4;   // elements one pass of the consumer threads covers
+        if (K <= 2 * kChunk) load_ll_n<SYS, RESID, 2>(K, pk, nvec, vstride, tag, norm_w, eps);
+        else if (K <= 3 * kChunk) load_ll_n<SYS, RESID, 3>(K, pk, nvec, vstride, tag, norm_w, eps);
+        else load_ll_n<SYS, RESID, (kFusedMaxK + kChunk - 1) / kChunk>(K, pk, nvec, vstride, tag, norm_w, eps);
+    }
+    template <bool SYS, bool RESID, int kPer>
+    __device__ void load_ll_n(int K, const LLPk* pk, int nvec, size_t vstride, uint32_t tag, const float* norm_w, float eps) {
+        const int tid = threadIdx.x;
+        float4 v[kPer], w[kPer];
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) {
+            const int e = (tid + j * kFusedConsumers * 32) * 4;
+            v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            w[j] = v[j];
+            if (e < K) {
+                if (norm_w) w[j] = *reinterpret_cast<const float4*>(norm_w + e);
+                if (RESID) v[j] = *reinterpret_cast<const float4*>(xres + e);
+            }
+        }
+        for (int r = 0; r < nvec; ++r) {
+            const LLPk* base = pk + (size_t)r * vstride;
+            uint4 pa[kPer], pb[kPer];
+#pragma unroll
+            for (int j = 0; j < kPer; ++j) {
+                const int e = (tid + j * kFusedConsumers * 32) * 4;
+                if (e < K) { pa[j] = ll_load2<SYS>(base + e); pb[j] = ll_load2<SYS>(base + e + 2); }
+            }
+#pragma unroll
+            for (int j = 0; j < kPer; ++j) {
+                const int e = (tid + j * kFusedConsumers * 32) * 4;
+                if (e < K) {
+                    float4 t;
+                    if (pa[j].y == tag && pa[j].w == tag && pb[j].y == tag && pb[j].w == tag)
+                        t = make_float4(__uint_as_float(pa[j].x), __uint_as_float(pa[j].z), __uint_as_float(pb[j].x), __uint_as_float(pb[j].z));
+                    else t = ll_spin4<SYS>(base + e, tag, ll_abort);
+                    v[j].x += t.x; v[j].y += t.y; v[j].z += t.z; v[j].w += t.w;
+                }
+            }
+        }
+        if (RESID) {
+#pragma unroll
+            for (int j = 0; j < kPer; ++j) {
+                const int e = (tid + j * kFusedConsumers * 32) * 4;
+                if (e < K) *reinterpret_cast<float4*>(xres + e) = v[j];
+            }
+        }
+        if (norm_w) {
+            float ss = 0.f;
 #pragma unroll
             for (int j = 0; j < kPer; ++j) ss += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
             ss = warp_sum(ss);
@@ -425,7 +549,7 @@ struct Consumer {
     __device__ void load_attn(const FusedArgs& a) {
         constexpr int HD = 128, PS = kFusedPartialStride, CH = kFusedMergeChunk;
         const int K = a.nh * HD;
-        for (int h0 = warp; h0 < a.nh; h0 += kFusedConsumers) {
+        for (int h0 = warp; h0 < a.nh && !skip_loads; h0 += kFusedConsumers) {
             const int h = (h0 + (int)blockIdx.x) % a.nh;   // all CTAs read the same lines: rotate the head order so they spread over the L2 slices
             const float* pb = a.partial + (size_t)h * a.nsplit * PS;
             float M = -INFINITY, L = 0.f;
@@ -496,147 +620,16 @@ struct Consumer {
         }
     }
 
-    // variant KO, input of the K-split o_proj: merge the split partials of the G heads of THIS CTA's kv group into
-    // xs[0 .. G*hd) (same arithmetic as load_attn, a G-th of the heads).
-    __device__ void load_attn_group(const FusedArgs& a, int kvh, int G) {
-        constexpr int HD = 128, PS = kFusedPartialStride, CH = kFusedMergeChunk;
-        const int Kp = G * HD;
-        if (warp < G) {
-            const float* pb = a.partial + (size_t)(kvh * G + warp) * a.nsplit * PS;
-            float M = -INFINITY, L = 0.f;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int s0 = 0; s0 < a.nsplit; s0 += CH) {
-                float4 v[CH];
-#pragma unroll
-                for (int j = 0; j < CH; ++j)
-                    v[j] = (s0 + j < a.nsplit) ? __ldcg(reinterpret_cast<const float4*>(pb + (size_t)(s0 + j) * PS) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-                float m = -INFINITY, l = 0.f;
-                if (lane < CH && s0 + lane < a.nsplit) {
-                    const float2 ml = __ldcg(reinterpret_cast<const float2*>(pb + (size_t)(s0 + lane) * PS + HD));
-                    m = ml.x; l = ml.y;
-                }
-                float cm = m;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, o));
-                const float Mn = fmaxf(M, cm);
-                const float so = (M == -INFINITY) ? 0.f : expf(M - Mn);
-                const float e = (m == -INFINITY) ? 0.f : expf(m - Mn);
-                L = L * so + warp_sum(l * e);
-                acc.x *= so; acc.y *= so; acc.z *= so; acc.w *= so;
-#pragma unroll
-                for (int j = 0; j < CH; ++j) {
-                    const float ej = __shfl_sync(0xffffffffu, e, j);
-                    acc.x += v[j].x * ej; acc.y += v[j].y * ej; acc.z += v[j].z * ej; acc.w += v[j].w * ej;
-                }
-                M = Mn;
-            }
-            *reinterpret_cast<float4*>(xs + xs_pos(warp * HD + 4 * lane, Kp)) = make_float4(acc.x / L, acc.y / L, acc.z / L, acc.w / L);
-        }
-        consumer_bar_sync();
-    }
-
-    // variant KO: xo[r] += Wo_g[kvh][r, :] . xs for this CTA's rows of the group's column block (fp32 reductions into the
-    // residual stream; the 8 kv groups add into the same element).
-    __device__ void o_ksplit(const FusedArgs& a, int split, int G, float* xo) {
-        const int Kp = G * a.hd;
-        int r0, r1;
-        ko_rows(a.H, a.nsplit, split, r0, r1);
-        const int R = ko_rows_per_stage(Kp);
-        unsigned i = it;
-        for (int r = r0; r < r1; r += R, ++i) {
-            if (!owns(i)) continue;
-            const int nr = min(R, r1 - r);
-            const uint8_t* st = wait_full(i);
-            float v[kFusedMaxRows];
-#pragma unroll
-            for (int q = 0; q < kFusedMaxRows; ++q) v[q] = 0.f;
-            if (nr == R && R == 8) stage_dots<8, 1>(st, Kp, v);
-            else if (nr == R && R == 4) stage_dots<4, 2>(st, Kp, v);
-            else {
-                for (int q = 0; q < nr; ++q) {
-                    float t[kFusedMaxRows];
-                    stage_dots<1, 4>(st + (size_t)q * Kp * 2, Kp, t);
-#pragma unroll
-                    for (int z = 0; z < kFusedMaxRows; ++z) if (z == q) v[z] = t[0];
-                }
-            }
-            release(i);
-            float mine = 0.f;
-#pragma unroll
-            for (int q = 0; q < kFusedMaxRows; ++q) {
-                if (q < nr) {
-                    const float t = warp_sum(v[q]);
-                    if (lane == q) mine = t;
-                }
-            }
-            if (lane < nr) atomicAdd(xo + r + lane, mine);   // result unused: RED.E.ADD.F32
-        }
-        it = i;
-        consumer_bar_sync();
-    }
-
-    // K-split down projection (variant KS): acc[n] += sum_{k in this CTA's slice} Wdown^T[k][n] * h[k].  Every consumer
-    // warp reads every stage (thread t owns the 8-column output chunks t, t + 352, ...); the warp that finishes a stage
-    // last hands the slot back to the producer.  NCH = output chunks per thread.
-    template <int NCH>
-    __device__ void down_ksplit(const FusedArgs& a, const float* hs, int* slot_done, float* acc) {
-        int r0, r1;
-        cta_rows(2 * a.I, 2, r0, r1);
-        const int k0 = r0 >> 1, k1 = r1 >> 1;
-        const int H = a.H, R = max(1, kFusedStageBytes / (2 * H));
-        const int nchunk = H >> 3;
-        float av[NCH][8];
-#pragma unroll
-        for (int j = 0; j < NCH; ++j)
-#pragma unroll
-            for (int e = 0; e < 8; ++e) av[j][e] = 0.f;
-        unsigned i = it;
-        for (int k = k0; k < k1; k += R, ++i) {
-            const int nr = min(R, k1 - k);
-            const uint8_t* st = wait_full(i);
-            for (int q = 0; q < nr; ++q) {
-                const float hv = hs[k - k0 + q];
-#pragma unroll
-                for (int j = 0; j < NCH; ++j) {
-                    const int ch = (int)threadIdx.x + j * kFusedConsumers * 32;
-                    if (ch < nchunk) {
-                        const uint4 w = *reinterpret_cast<const uint4*>(st + (size_t)q * H * 2 + (size_t)ch * 16);
-                        const float2 w0 = h2_to_f2(w.x), w1 = h2_to_f2(w.y), w2 = h2_to_f2(w.z), w3 = h2_to_f2(w.w);
-                        av[j][0] = fmaf(w0.x, hv, av[j][0]); av[j][1] = fmaf(w0.y, hv, av[j][1]);
-                        av[j][2] = fmaf(w1.x, hv, av[j][2]); av[j][3] = fmaf(w1.y, hv, av[j][3]);
-                        av[j][4] = fmaf(w2.x, hv, av[j][4]); av[j][5] = fmaf(w2.y, hv, av[j][5]);
-                        av[j][6] = fmaf(w3.x, hv, av[j][6]); av[j][7] = fmaf(w3.y, hv, av[j][7]);
-                    }
-                }
-            }
-            __syncwarp();   // every lane's shared-memory reads of the stage have fed its FMAs
-            if (lane == 0) {
-                const int slot = i % ns;
-                if (atomicAdd(&slot_done[slot], 1) == kFusedConsumers - 1) {
-                    slot_done[slot] = 0;   // ordered before the slot's next use by the mbarrier release / acquire chain
-                    mbar_arrive(&ring.empty[slot]);
-                }
-            }
-        }
-        it = i;
-#pragma unroll
-        for (int j = 0; j < NCH; ++j) {
-            const int ch = (int)threadIdx.x + j * kFusedConsumers * 32;
-            if (ch < nchunk) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) atomicAdd(acc + ch * 8 + e, av[j][e]);   // result unused: RED.E.ADD.F32
-            }
-        }
-        consumer_bar_sync();
-    }
-
     // One GEMV phase: y[r0:r1) = W[r0:r1, :] . xs  with the fused epilogue.  Ends with a consumer barrier so
     // that xs may be overwritten by the next phase.
-    template <int EPI>
-    __device__ void gemv(const FusedArgs& a, int N, int K, const float* bias, float* out, float& best, int& bi) {
+    // LL: the outputs leave as tagged packets (qkv -> ll_qkv, SwiGLU -> ll_h, o_proj / down partial sums -> the [rank][H]
+    // block `par` of every tensor-parallel peer, WITHOUT the residual: readers add it from their own copy of the stream).
+    template <int EPI, bool LL = false>
+    __device__ void gemv(const FusedArgs& a, int N, int K, const float* bias, float* out, float& best, int& bi, uint32_t tag = 0, int par = 0, int row_off = 0) {
         int r0, r1;
         cta_rows(N, EPI == FE_SWIGLU ? 2 : 1, r0, r1);
         const int R = rows_per_stage(K, N, gridDim.x);
+        if (sync_only) { consumer_bar_sync(); return; }
         unsigned i = it;
         for (int r = r0; r < r1; r += R, ++i) {
             if (!owns(i)) continue;
@@ -675,13 +668,23 @@ struct Consumer {
             if (lane < nr) {
                 const int row = r + lane;
                 if (EPI == FE_SWIGLU) {
-                    if ((lane & 1) == 0) out[row >> 1] = silu_f(mine) * mate;   // rows (2i, 2i+1) = (gate_i, up_i)
+                    if ((lane & 1) == 0) {   // rows (2i, 2i+1) = (gate_i, up_i)
+                        const float hval = silu_f(mine) * mate;
+                        if (LL) ll_store<false>(a.ll_h + (row >> 1), hval, tag);
+                        else out[row >> 1] = hval;
+                    }
                 } else {
                     float y = mine;
                     if (bias) y += bias[row];
-                    if (EPI == FE_RESID) { y += xown[row - r0]; xown[row - r0] = y; }   // o_proj and down own the same rows of x
-                    out[row] = y;
-                    if (EPI == FE_LOGITS && (y > best || (y == best && row < bi))) { best = y; bi = row; }
+                    if (LL && EPI == FE_RESID) {
+                        for (int w = 0; w < a.tp_world; ++w) ll_store<true>(a.ll_xp[par][w] + (size_t)a.tp_rank * a.H + row, y, tag);
+                    } else if (LL && EPI == FE_QKV) {
+                        ll_store<false>(a.ll_qkv + row, y, tag);
+                    } else {
+                        if (EPI == FE_RESID) { y += xown[row - r0]; xown[row - r0] = y; }   // o_proj and down own the same rows of x
+                        out[row] = y;
+                        if (EPI == FE_LOGITS && (y > best || (y == best && row + row_off < bi))) { best = y; bi = row + row_off; }
+                    }
                 }
             }
         }
@@ -693,28 +696,28 @@ struct Consumer {
 // Attention scratch in shared memory (consumer side; aliases the xs region, unused during this phase)
 template <int G>
 struct AttnSmem {
-    float qs[G][128];
-    float knew[128];
-    float vnew[128];
+    alignas(16) float qs[G][128];
+    alignas(16) float knew[128];
+    alignas(16) float vnew[128];
     float m[kFusedConsumers][G];
     float l[kFusedConsumers][G];
-    float acc[kFusedConsumers][G][128];
+    alignas(16) float acc[kFusedConsumers][G][128];   // float4 stores: for G = 1 the two arrays above end on an 8-byte boundary
 
 };
 
-template <int G>
-__device__ void fused_attention(const FusedArgs& a, Consumer& c, AttnSmem<G>& s, const float* cs, const int* spages, int layer, const FusedLayer& Ly, int t_new) {
+template <int G, bool LL = false>
+__device__ void fused_attention(const FusedArgs& a, Consumer& c, AttnSmem<G>& s, const float* cs, const int* spages, int layer, const FusedLayer& Ly, int t_new, uint32_t tag = 0) {
     constexpr int HD = 128;
     const int ctx = t_new + 1;
     const int lane = c.lane, warp = c.warp, tid = threadIdx.x;
     int kvh, split, hp0, hp1;
     const bool has_item = attn_item(a, ctx, kvh, split, hp0, hp1);
-    if (!has_item) return;  // this CTA's producer issued nothing for the phase either
+    if (!has_item || c.sync_only) return;  // this CTA's producer issued nothing for the phase either
     // ---- prologue: q heads (warps 0..G-1) and the new k (warp G): RMSNorm over hd then RoPE; v copy (warp G+1)
     if (warp <= G) {
         const bool is_q = warp < G;
-        const float* src = a.qkv1 + (size_t)(is_q ? (kvh * G + warp) : (a.nh + kvh)) * HD;
-        const float4 x = __ldcg(reinterpret_cast<const float4*>(src + lane * 4));
+        const size_t src_off = (size_t)(is_q ? (kvh * G + warp) : (a.nh + kvh)) * HD + lane * 4;
+        const float4 x = LL ? ll_wait4<false>(a.ll_qkv + src_off, tag, c.ll_abort) : __ldcg(reinterpret_cast<const float4*>(a.qkv1 + src_off));
         float ss = x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
         ss = warp_sum(ss);
         const float inv = 1.0f / sqrtf(ss / (float)HD + a.eps);
@@ -731,7 +734,8 @@ __device__ void fused_attention(const FusedArgs& a, Consumer& c, AttnSmem<G>& s,
         float* dst = is_q ? s.qs[warp] : s.knew;
         *reinterpret_cast<float4*>(dst + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);
     } else if (warp == G + 1) {
-        *reinterpret_cast<float4*>(s.vnew + lane * 4) = __ldcg(reinterpret_cast<const float4*>(a.qkv1 + (size_t)(a.nh + a.nkv + kvh) * HD + lane * 4));
+        const size_t src_off = (size_t)(a.nh + a.nkv + kvh) * HD + lane * 4;
+        *reinterpret_cast<float4*>(s.vnew + lane * 4) = LL ? ll_wait4<false>(a.ll_qkv + src_off, tag, c.ll_abort) : __ldcg(reinterpret_cast<const float4*>(a.qkv1 + src_off));
     }
     consumer_bar_sync();
     const int hp_new = t_new / kHalfPage;
@@ -841,27 +845,60 @@ __device__ void fused_attention(const FusedArgs& a, Consumer& c, AttnSmem<G>& s,
                 O += s.acc[w][g][d] * e;
             }
         }
-        float* p = a.partial + ((size_t)(kvh * G + g) * a.nsplit + split) * kFusedPartialStride;
-        p[d] = O;
-        if (d == 0) { p[HD] = M; p[HD + 1] = L; }
+        const size_t po = ((size_t)(kvh * G + g) * a.nsplit + split) * kFusedPartialStride;
+        if (LL) {
+            ll_store<false>(a.ll_pb + po + d, O, tag);
+            if (d == 0) { ll_store<false>(a.ll_pb + po + HD, M, tag); ll_store<false>(a.ll_pb + po + HD + 1, L, tag); }
+        } else {
+            float* p = a.partial + po;
+            p[d] = O;
+            if (d == 0) { p[HD] = M; p[HD + 1] = L; }
+        }
     }
-    // the split partials are merged by the consumers of the next phase (Consumer::load_attn), after the grid barrier
+    // barrier mode: the split partials are merged by the consumers of the next phase (Consumer::load_attn), after the grid barrier
+    if (!LL) return;
+    // LL mode: the nsplit CTAs of this kv head merge the partials among themselves -- CTA `split` owns the dims
+    // [d0, d1) of the group's G heads: warp g takes head g, lane s takes split s (all (m, l) pairs and value packets of a
+    // pass are in flight together), and the merged values leave as packets of the attention vector that o_proj reads.
+    // 150 KB of partials per reader (every CTA merging every head) becomes 2-3 KB here plus the 16 KB vector.
+    if (warp < G) {
+        const int per = (HD + a.nsplit - 1) / a.nsplit;
+        const int d0 = split * per, d1 = min(HD, d0 + per);
+        const int h = kvh * G + warp;
+        const LLPk* pbase = a.ll_pb + ((size_t)h * a.nsplit + lane) * kFusedPartialStride;   // lane = split index
+        const bool on = lane < a.nsplit;
+        float m = -INFINITY, l = 0.f;
+        if (on) {
+            m = ll_wait1<false>(pbase + HD, tag, c.ll_abort);
+            l = ll_wait1<false>(pbase + HD + 1, tag, c.ll_abort);
+        }
+        float M = m;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
+        const float e = (m == -INFINITY) ? 0.f : expf(m - M);
+        const float Ls = warp_sum(l * e);
+        for (int d = d0; d < d1; ++d) {
+            // the packets of a partial were stored by different threads: each one is validated on its own
+            const float val = on ? ll_wait1<false>(pbase + d, tag, c.ll_abort) : 0.f;
+            const float O = warp_sum(val * e) / Ls;
+            if (lane == 0) ll_store<false>(a.ll_att + (size_t)h * HD + d, O, tag);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
-template <int G, bool KS = false, bool KO = false>
+template <int G, bool LL>
 __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(FusedArgs a) {
     extern __shared__ __align__(1024) uint8_t fused_smem_raw[];
     uint8_t* ringbuf = fused_smem_raw;
     uint64_t* full = reinterpret_cast<uint64_t*>(fused_smem_raw + (size_t)kFusedStages * kFusedStageBytes);
     uint64_t* empty = full + kFusedStages;
     float* red = reinterpret_cast<float*>(empty + kFusedStages);
-    float* xown = red + 32;                                     // [kFusedMaxOwnRows]
-    float* cs = xown + kFusedMaxOwnRows;                        // [128] cos | sin of the step's rotary angles
+    float* xown = red + 32;                                     // [kFusedMaxOwnRows] (barrier mode only: LL mode keeps the whole stream in xres)
+    float* cs = xown + (LL ? 0 : kFusedMaxOwnRows);             // [128] cos | sin of the step's rotary angles
     float* xs = cs + 128;                                       // [kFusedMaxK] activations / attention scratch
     int* spages = reinterpret_cast<int*>(xs + kFusedMaxK);      // [kFusedMaxPages] page table copy
-    float* hs = reinterpret_cast<float*>(spages + kFusedMaxPages);   // [kFusedMaxHs] this CTA's slice of silu(gate)*up (variant KS)
-    int* slot_done = reinterpret_cast<int*>(hs + kFusedMaxHs);       // [kFusedStages] warps done with a shared stage (variant KS)
+    float* xres = reinterpret_cast<float*>(spages + kFusedMaxPages);   // [kFusedMaxH] LL mode: the residual stream (not carved in barrier mode)
     AttnSmem<G>* as = reinterpret_cast<AttnSmem<G>*>(xs);
     static_assert(sizeof(AttnSmem<G>) <= kFusedMaxK * sizeof(float), "attention scratch must fit in the xs region");
 
@@ -870,11 +907,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
         for (int i = 0; i < kFusedStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (KS && tid < kFusedStages) slot_done[tid] = 0;
     if ((a.dbg & 64) && tid == 0) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); a.trace[8192 + blockIdx.x * 256 + 255] = smid; }
     const int t_new = a.st->pos;
     const int rope_delta = a.st->rope_delta;
-    const uint32_t token = a.st->token;
+    const uint32_t token = min(a.st->token, (uint32_t)(a.V - 1));   // a NaN logit row publishes 0x7fffffff: never index the embedding table with it
     const int ctx = t_new + 1;
     for (int i = tid; i < (ctx + kPage - 1) / kPage && i < kFusedMaxPages; i += kFusedThreads) spages[i] = a.page_table[i];
     if (tid < 64) {   // RoPE angle of this step (same for every layer): cos/sin once per kernel
@@ -895,35 +931,48 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
             p.hint_kv = (a.dbg & 32) == 0;       // bit5: same switch for the KV half-page copies
             p.policy = l2_evict_first_policy();
             p.pages = spages;
+#ifdef AHA_STAGE_TRACE
+            if ((a.dbg & 128) && (int)blockIdx.x == ((a.dbg >> 16) & 0xff)) p.st_trace = a.trace + 8192;
+#endif
             int pe = 0;
             AHA_STAMP(a, 1, pe);
+            if (a.dbg & 512) return;   // sync-only experiment: no weight stream
             FusedLayer nxt = a.layers[0];
             for (int l = 0; l < a.L; ++l) {
                 const FusedLayer Ly = nxt;
                 if (l + 1 < a.L) nxt = a.layers[l + 1];   // pointer table one layer ahead: off the issue path
                 p.rows(Ly.qkv, a.qkv_dim, a.H, 1); AHA_STAMP(a, 1, pe);
                 p.attn(a, l, ctx); AHA_STAMP(a, 1, pe);
-                if (KO) p.rows_o_group(a, Ly.o_g, ctx); else p.rows(Ly.o, a.H, a.nh * a.hd, 1);
+                p.rows(Ly.o, a.H, a.nh * a.hd, 1);
                 AHA_STAMP(a, 1, pe);
                 p.rows(Ly.gu, 2 * a.I, a.H, 2); AHA_STAMP(a, 1, pe);
-                if (KS) p.rows_t(Ly.down_t, 2 * a.I, a.H); else p.rows(Ly.down, a.H, a.I, 1);
+                p.rows(Ly.down, a.H, a.I, 1);
                 AHA_STAMP(a, 1, pe);
             }
-            p.rows(a.lm_head, a.V, a.H, 1); AHA_STAMP(a, 1, pe);
+            p.rows(a.lm_head + (size_t)a.v0 * a.H, a.V_l, a.H, 1); AHA_STAMP(a, 1, pe);
         }
         return;
     }
     // ======================================================= CONSUMERS
     Consumer c;
     c.ring = ring; c.ns = (unsigned)a.stages; c.xs = xs; c.red = red; c.xown = xown; c.warp = warp; c.lane = lane;
+#ifdef AHA_STAGE_TRACE
+    if ((a.dbg & 128) && (int)blockIdx.x == ((a.dbg >> 16) & 0xff)) c.st_trace = a.trace + 8192;
+#endif
+    c.xres = xres; c.ll_abort = a.ll_abort;
+    c.skip_loads = (a.dbg & 256) != 0;
+    c.sync_only = (a.dbg & 512) != 0;
+    unsigned long long* sy = nullptr;
+#ifdef AHA_STAGE_TRACE
+    if ((a.dbg & 1024) && (int)blockIdx.x == ((a.dbg >> 16) & 0xff)) { sy = a.trace + 8192 + 32768; c.sy_trace = sy; }
+#endif
     unsigned seq = 0;
     float best = -INFINITY;
     int bi = 0x7fffffff;
     const __half* emb_row = a.embed + (size_t)token * a.H;
-    int own_r0, own_r1, hs_k0 = 0;
+    int own_r0, own_r1;
     cta_rows(a.H, 1, own_r0, own_r1);
-    if (tid < own_r1 - own_r0) xown[tid] = __half2float(emb_row[own_r0 + tid]);   // the rows of the residual stream this CTA owns start as the embedding row
-    if (KS) { int g0, g1; cta_rows(2 * a.I, 2, g0, g1); hs_k0 = g0 >> 1; }
+    if (!LL && tid < own_r1 - own_r0) xown[tid] = __half2float(emb_row[own_r0 + tid]);   // the rows of the residual stream this CTA owns start as the embedding row
     int ce = 0;
 #define CSTAMP() do { if (tid == 0) AHA_STAMP(a, 0, ce); } while (0)
     CSTAMP();
@@ -932,76 +981,64 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
         const FusedLayer Ly = nxtc;
         if (l + 1 < a.L) nxtc = a.layers[l + 1];
         const bool first = (l == 0);
-        // variant KS: layer l accumulates its down projection into acc2[l & 1]; layer l + 1 adds it while loading x and
-        // re-zeroes its own rows of it one barrier later, two barriers before layer l + 2 accumulates into it again
-        float* const acc_prev = a.acc2 + (size_t)((l + 1) & 1) * a.H;
-        float* const acc_cur = a.acc2 + (size_t)(l & 1) * a.H;
-        // variant KO: x after o_proj lives in xo[l & 1] (double-buffered so that the owners' writes for layer l never meet a
-        // reader of layer l - 1)
-        float* const xo_cur = KO ? a.xo + (size_t)(l & 1) * a.H : nullptr;
-        const float* const xo_prev = KO ? a.xo + (size_t)((l + 1) & 1) * a.H : nullptr;
+        if constexpr (LL) {
+            // Data-flow version: every phase polls the packets it needs (tag of this layer), no grid barrier anywhere.
+            const uint32_t tag = a.ll_tag + (uint32_t)l;
+            const LLPk* xp_o = a.ll_xp[0][a.tp_rank];     // this rank's [tp_world][H] blocks of o_proj / down partial sums
+            const LLPk* xp_d = a.ll_xp[1][a.tp_rank];
+            // P1: qkv = Wqkv . rmsnorm(x); x = residual + the down partial sums of layer l - 1 (layer 0: the embedding row)
+            if (first) c.load_x(a.H, nullptr, emb_row, Ly.ln1, a.eps, true);
+            else c.template load_ll<true, true>(a.H, xp_d, a.tp_world, (size_t)a.H, tag - 1u, Ly.ln1, a.eps);
+            CSTAMP();
+            c.template gemv<FE_QKV, true>(a, a.qkv_dim, a.H, Ly.qkv_b, nullptr, best, bi, tag); CSTAMP();
+            CSTAMP();
+            // P2: attention over the paged cache (+ q/k norm, RoPE, KV append), then the merge of the splits inside the kv group
+            CSTAMP();
+            fused_attention<G, true>(a, c, *as, cs, spages, l, Ly, t_new, tag); CSTAMP();
+            CSTAMP();
+            // P3: o_proj partial sums (this rank's heads) -> every rank
+            c.template load_ll<false, false>(a.nh * a.hd, a.ll_att, 1, 0, tag, nullptr, 0.f); CSTAMP();
+            c.template gemv<FE_RESID, true>(a, a.H, a.nh * a.hd, Ly.o_b, nullptr, best, bi, tag, 0); CSTAMP();
+            CSTAMP();
+            // P4: h = silu(gate) * up on rmsnorm(x), x = residual + sum over ranks of the o_proj partial sums
+            c.template load_ll<true, true>(a.H, xp_o, a.tp_world, (size_t)a.H, tag, Ly.ln2, a.eps);
+            CSTAMP();
+            c.template gemv<FE_SWIGLU, true>(a, 2 * a.I, a.H, nullptr, nullptr, best, bi, tag); CSTAMP();
+            CSTAMP();
+            // P5: down partial sums (this rank's slice of the intermediate dimension) -> every rank
+            c.template load_ll<false, false>(a.I, a.ll_h, 1, 0, tag, nullptr, 0.f); CSTAMP();
+            c.template gemv<FE_RESID, true>(a, a.H, a.I, nullptr, nullptr, best, bi, tag, 1); CSTAMP();
+            CSTAMP();
+        } else {
         // P1: qkv = Wqkv . rmsnorm(x)      (layer 0 reads the embedding row directly: Embedding::forward)
-        if (KS && !first) c.template load_x<true>(a.H, KO ? xo_prev : a.x, nullptr, Ly.ln1, a.eps, acc_prev, own_r0, own_r1);
-        else c.load_x(a.H, a.x, first ? emb_row : nullptr, Ly.ln1, a.eps);
-        if (KO && tid < own_r1 - own_r0) xo_cur[own_r0 + tid] = xown[tid];   // x entering the layer; the o_proj partial sums are added to it after the next barrier
+        c.load_x(a.H, a.x, first ? emb_row : nullptr, Ly.ln1, a.eps);
         CSTAMP();
         c.template gemv<FE_QKV>(a, a.qkv_dim, a.H, Ly.qkv_b, a.qkv1, best, bi); CSTAMP();
-        grid_barrier(&a.sync[0], seq, a.dbg, a.trace); CSTAMP();
+        grid_barrier(&a.sync[0], seq, a.dbg, a.trace, sy); CSTAMP();
         // P2: attention over the paged cache (+ q/k norm, RoPE, KV append)
         CSTAMP();
         fused_attention<G>(a, c, *as, cs, spages, l, Ly, t_new); CSTAMP();
-        if (KO) {
-            // P3 (variant KO): only the CTAs of this kv group synchronise; each merges its group's heads and adds its rows
-            // of Wo[:, group columns] . attn_group into xo
-            int kvh, split, hp0, hp1;
-            const bool has_item = attn_item(a, ctx, kvh, split, hp0, hp1);
-            if (has_item) {
-                group_barrier(&a.gsync[kvh], (unsigned)(l + 1) * (unsigned)a.nsplit); CSTAMP();
-                c.load_attn_group(a, kvh, G); CSTAMP();
-            } else { CSTAMP(); CSTAMP(); }
-            if (KS && !first && tid < own_r1 - own_r0) acc_prev[own_r0 + tid] = 0.f;
-            if (has_item) c.o_ksplit(a, split, G, xo_cur);
-            CSTAMP();
-            grid_barrier(&a.sync[0], seq, a.dbg, a.trace); CSTAMP();
-        } else {
-            grid_barrier(&a.sync[0], seq, a.dbg, a.trace); CSTAMP();
-            // P3: x = resid + Wo . attn
-            c.load_attn(a); CSTAMP();
-            if (KS && !first && tid < own_r1 - own_r0) acc_prev[own_r0 + tid] = 0.f;   // read last in P1 (before its barrier), accumulated next by layer l + 1
-            c.template gemv<FE_RESID>(a, a.H, a.nh * a.hd, Ly.o_b, a.x, best, bi); CSTAMP();
-            grid_barrier(&a.sync[0], seq, a.dbg, a.trace); CSTAMP();
-        }
+        grid_barrier(&a.sync[0], seq, a.dbg, a.trace, sy); CSTAMP();
+        // P3: x = resid + Wo . attn
+        c.load_attn(a); CSTAMP();
+        c.template gemv<FE_RESID>(a, a.H, a.nh * a.hd, Ly.o_b, a.x, best, bi); CSTAMP();
+        grid_barrier(&a.sync[0], seq, a.dbg, a.trace, sy); CSTAMP();
         // P4: h = silu(gate) * up, gate/up rows interleaved, input rmsnorm(x)
-        float own_mid = 0.f;
-        if (KO && tid < own_r1 - own_r0) own_mid = __ldcg(xo_cur + own_r0 + tid);   // this CTA's rows of x after o_proj, in flight with the load below
-        c.load_x(a.H, KO ? xo_cur : a.x, nullptr, Ly.ln2, a.eps);
-        if (KO && tid < own_r1 - own_r0) xown[tid] = own_mid;   // residual of the down projection (read in its epilogue, CTA barriers away)
+        c.load_x(a.H, a.x, nullptr, Ly.ln2, a.eps);
         CSTAMP();
-        if (KS) {
-            // h stays in shared memory; P5 follows without a barrier: acc_cur += Wdown[:, slice] . h[slice]
-            c.template gemv<FE_SWIGLU>(a, 2 * a.I, a.H, nullptr, hs - hs_k0, best, bi); CSTAMP();
-            CSTAMP(); CSTAMP();
-            switch ((a.H / 8 + kFusedConsumers * 32 - 1) / (kFusedConsumers * 32)) {
-                case 1: c.template down_ksplit<1>(a, hs, slot_done, acc_cur); break;
-                case 2: c.template down_ksplit<2>(a, hs, slot_done, acc_cur); break;
-                default: c.template down_ksplit<3>(a, hs, slot_done, acc_cur); break;
-            }
-            CSTAMP();
-            grid_barrier(&a.sync[0], seq, a.dbg, a.trace); CSTAMP();
-        } else {
-            c.template gemv<FE_SWIGLU>(a, 2 * a.I, a.H, nullptr, a.h1, best, bi); CSTAMP();
-            grid_barrier(&a.sync[0], seq, a.dbg, a.trace); CSTAMP();
-            // P5: x = x + Wdown . h
-            c.load_x(a.I, a.h1, nullptr, nullptr, 0.f); CSTAMP();
-            c.template gemv<FE_RESID>(a, a.H, a.I, nullptr, a.x, best, bi); CSTAMP();
-            grid_barrier(&a.sync[0], seq, a.dbg, a.trace); CSTAMP();
+        c.template gemv<FE_SWIGLU>(a, 2 * a.I, a.H, nullptr, a.h1, best, bi); CSTAMP();
+        grid_barrier(&a.sync[0], seq, a.dbg, a.trace, sy); CSTAMP();
+        // P5: x = x + Wdown . h
+        c.load_x(a.I, a.h1, nullptr, nullptr, 0.f); CSTAMP();
+        c.template gemv<FE_RESID>(a, a.H, a.I, nullptr, a.x, best, bi); CSTAMP();
+        grid_barrier(&a.sync[0], seq, a.dbg, a.trace, sy); CSTAMP();
         }
     }
-    // final: logits = lm_head . rmsnorm(x), per-CTA argmax candidate
-    if (KS) c.template load_x<true>(a.H, KO ? a.xo + (size_t)((a.L - 1) & 1) * a.H : a.x, nullptr, a.final_norm, a.eps, a.acc2 + (size_t)((a.L - 1) & 1) * a.H, own_r0, own_r1);
+    // final: logits = lm_head . rmsnorm(x) over this rank's vocabulary shard, per-CTA argmax candidate
+    if constexpr (LL) c.template load_ll<true, true>(a.H, a.ll_xp[1][a.tp_rank], a.tp_world, (size_t)a.H, a.ll_tag + (uint32_t)a.L - 1u, a.final_norm, a.eps);
     else c.load_x(a.H, a.x, nullptr, a.final_norm, a.eps);
     best = -INFINITY; bi = 0x7fffffff;
-    c.template gemv<FE_LOGITS>(a, a.V, a.H, nullptr, a.logits, best, bi); CSTAMP();
+    c.template gemv<FE_LOGITS>(a, a.V_l, a.H, nullptr, a.logits + a.v0, best, bi, 0, 0, a.v0); CSTAMP();
     // CTA-level argmax (first maximal index), then the last CTA to arrive reduces across CTAs
     for (int o = 16; o > 0; o >>= 1) {
         const float ov = __shfl_xor_sync(0xffffffffu, best, o);
@@ -1035,6 +1072,28 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
             const int oi = __shfl_xor_sync(0xffffffffu, gi, o);
             if (ov > gb || (ov == gb && oi < gi)) { gb = ov; gi = oi; }
         }
+        if (LL && a.tp_world > 1) {
+            // vocabulary shards: every rank publishes its (value, index) candidate to every rank and picks the same winner
+            // (largest value, lowest index on ties)
+            const uint32_t ftag = a.ll_tag + (uint32_t)a.L;
+            if (lane < a.tp_world) {
+                ll_store<true>(a.ll_cand[lane] + a.tp_rank * 2, gb, ftag);
+                ll_store<true>(a.ll_cand[lane] + a.tp_rank * 2 + 1, __int_as_float(gi), ftag);
+            }
+            float cb = -INFINITY;
+            int ci = 0x7fffffff;
+            if (lane < a.tp_world) {
+                cb = ll_wait1<true>(a.ll_cand[a.tp_rank] + lane * 2, ftag, a.ll_abort);
+                ci = __float_as_int(ll_wait1<true>(a.ll_cand[a.tp_rank] + lane * 2 + 1, ftag, a.ll_abort));
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, cb, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, ci, o);
+                if (ov > cb || (ov == cb && oi < ci)) { cb = ov; ci = oi; }
+            }
+            gb = cb; gi = ci;
+        }
+        if (gi < 0 || gi >= a.V) gi = 0;   // all-NaN logits: publish a valid id (the reference would pick some index too)
         if (lane == 0) {
             *a.argmax_out = (uint32_t)gi;
             DecodeState* st = a.st;
@@ -1047,9 +1106,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
 }
 
 template <int G>
-inline size_t fused_smem_bytes() {
-    return (size_t)kFusedStages * kFusedStageBytes + 2 * kFusedStages * sizeof(uint64_t) + (32 + kFusedMaxOwnRows + 128) * sizeof(float) + (size_t)kFusedMaxK * sizeof(float) +
-           (size_t)kFusedMaxPages * sizeof(int) + (size_t)kFusedMaxHs * sizeof(float) + (size_t)kFusedStages * sizeof(int) + 64;
+inline size_t fused_smem_bytes(bool ll) {
+    return (ll ? (size_t)kFusedMaxH * sizeof(float) : (size_t)kFusedMaxOwnRows * sizeof(float)) + (size_t)kFusedStages * kFusedStageBytes + 2 * kFusedStages * sizeof(uint64_t) + (32 + 128) * sizeof(float) + (size_t)kFusedMaxK * sizeof(float) +
+           (size_t)kFusedMaxPages * sizeof(int) + 64;
 }
 
 }  // namespace aha

@@ -250,6 +250,16 @@ inline size_t gemm_tc_smem_bytes() { return (size_t)kTcStages * kTcStageBytes + 
 
 inline bool gemm_tc_supported(int M, int N, int K) { return K % kTcBK == 0 && N % 32 == 0 && M >= 1; }
 
+// The > 48 KB dynamic shared memory opt-in is a per-device function attribute: aha_b200_create calls this after
+// cudaSetDevice for every handle (a process-wide once-flag would leave a second device without it).
+inline void gemm_tc_init() {
+    const int smem = (int)gemm_tc_smem_bytes();
+    AHA_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    AHA_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<EPI_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    AHA_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<EPI_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    AHA_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<EPI_SWIGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+}
+
 // A already split: hi/lo fp16 [M, K] row-major.  tm_w describes W [N, K].
 inline void gemm_tc_launch(cudaStream_t st, int epi, const __half* a_hi, const __half* a_lo, const CUtensorMap& tm_w, const GemmTcArgs& g) {
     const CUtensorMap tm_hi = make_tmap_f16(a_hi, (uint64_t)g.M, (uint64_t)g.K);
@@ -257,11 +267,7 @@ inline void gemm_tc_launch(cudaStream_t st, int epi, const __half* a_hi, const _
     const size_t smem = gemm_tc_smem_bytes();
     dim3 grid(ceil_div(g.N, kTcBN), ceil_div(g.M, kTcBM));
 #define AHA_TC_CASE(E)                                                                                                             \
-    case E: {                                                                                                                      \
-        static bool once = false;                                                                                                  \
-        if (!once) { AHA_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); once = true; } \
-        gemm_tc_kernel<E><<<grid, kTcThreads, smem, st>>>(tm_hi, tm_lo, tm_w, g);                                                 \
-    } break;
+    case E: gemm_tc_kernel<E><<<grid, kTcThreads, smem, st>>>(tm_hi, tm_lo, tm_w, g); break;
     switch (epi) {
         AHA_TC_CASE(EPI_STORE)
         AHA_TC_CASE(EPI_RESID)

@@ -67,30 +67,6 @@ __global__ void l2_normalize_kernel(const float* __restrict__ x, float* __restri
     for (int i = threadIdx.x; i < H; i += blockDim.x) out[(size_t)blockIdx.x * H + i] = xr[i] * inv;
 }
 
-// out[c][r] = in[r][c] for an fp16 matrix [R][C] (load-time weight repacking), 32 x 32 tiles, block (32, 8).
-__global__ void transpose_f16_kernel(const __half* __restrict__ in, __half* __restrict__ out, int R, int C) {
-    __shared__ __half tile[32][33];
-    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-    for (int j = threadIdx.y; j < 32; j += 8) {
-        const int r = r0 + j, c = c0 + threadIdx.x;
-        if (r < R && c < C) tile[j][threadIdx.x] = in[(size_t)r * C + c];
-    }
-    __syncthreads();
-    for (int j = threadIdx.y; j < 32; j += 8) {
-        const int c = c0 + j, r = r0 + threadIdx.x;
-        if (r < R && c < C) out[(size_t)c * R + r] = tile[threadIdx.x][j];
-    }
-}
-
-// out[g][r][c] = in[r][g * Kp + c] for an fp16 matrix [R][K]: K / Kp column blocks, each stored as its own [R][Kp] matrix.
-__global__ void split_columns_f16_kernel(const __half* __restrict__ in, __half* __restrict__ out, int R, int K, int Kp) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)R * K) return;
-    const int r = (int)(i / K), k = (int)(i % K);
-    const int g = k / Kp, c = k % Kp;
-    out[((size_t)g * R + r) * Kp + c] = in[i];
-}
-
 __global__ void add_inplace_kernel(float* __restrict__ x, const float* __restrict__ y, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) x[i] += y[i];

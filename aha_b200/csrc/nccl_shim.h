@@ -20,9 +20,10 @@ struct NcclApi {
     int (*CommInitRank)(comm_t*, int, unique_id, int) = nullptr;
     int (*CommDestroy)(comm_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int /*dtype*/, int /*op*/, comm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t /*sendcount*/, int /*dtype*/, comm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
     void* handle = nullptr;
-    static constexpr int kFloat32 = 7, kSum = 0;
+    static constexpr int kFloat32 = 7, kInt8 = 0, kSum = 0;
 
     static NcclApi& get() {
         static NcclApi api;
@@ -38,6 +39,7 @@ struct NcclApi {
             api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
             api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
             api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+            api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
             api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
         }
         return api;

@@ -291,11 +291,16 @@ struct TextModel {
     bool use_graph = true;
     // fused persistent decode kernel (decode_fused.cuh)
     bool fused = false;
-    bool ksplit = false;                 // fused variant KS (decode_impl = 3): K-split down projection, see decode_fused.cuh
-    float* acc2 = nullptr;               // [2][H] accumulators of that variant
-    bool kosplit = false;                // fused variant KO (decode_impl = 4, or 5 with KS): K-split o_proj behind a kv-group barrier
-    float* xo = nullptr;                 // [2][H] residual stream of that variant
+    bool fused_ll = false;               // packet (data-flow) version of the fused kernel; false = the grid-barrier twin (decode_impl = 3)
     int decode_impl = 0;
+    // LL packet buffers.  The blocks a tensor-parallel peer writes (partial sums, argmax candidates) live in ONE separate
+    // allocation per rank so that a single CUDA IPC handle maps them into the peers.
+    LLPk *ll_qkv = nullptr, *ll_pb = nullptr, *ll_att = nullptr, *ll_h = nullptr;
+    LLPk* ll_sym = nullptr;                         // [2][W][H] partial sums | [W][2] candidates   (this rank's copy)
+    LLPk* ll_peer_sym[kFusedMaxTp] = {};            // the same block of every rank (own entry = ll_sym)
+    int* d_ll_abort = nullptr;
+    uint32_t ll_launches = 0;
+    size_t ll_sym_packets() const { return (size_t)2 * tp_world * cfg.H + (size_t)tp_world * 2; }
     FusedLayer* d_fused_layers = nullptr;
     unsigned* d_sync = nullptr;   // [0] grid barrier, [1] final ticket, then kv tickets [nkv]
     unsigned long long* d_ftrace = nullptr;
@@ -378,8 +383,9 @@ struct TextModel {
     int max_ctx_hint = 0;
     bool fused_supported(std::string* why) const {
         auto no = [&](const char* m) { if (why) *why = m; return false; };
-        if (tp_world != 1) return no("tensor parallel");
+        if (tp_world > kFusedMaxTp) return no("more than 8 tensor-parallel ranks");
         if (cfg.hd != 128) return no("head_dim != 128");
+        if (cfg.H > kFusedMaxH) return no("hidden_size > 4096 (residual stream kept in shared memory)");
         if (cfg.H % 8 || I_l % 8) return no("K not a multiple of 8");
         if (cfg.H > kFusedMaxK || I_l > kFusedMaxK || nh_l * cfg.hd > kFusedMaxK) return no("K > 8192");
         if (rows_per_stage(cfg.H, 2 * I_l, ctx->num_sms) % 2) return no("a gate/up row pair does not fit one 16 KB stage");
@@ -391,15 +397,10 @@ struct TextModel {
         return true;
     }
     template <int G>
-    void (*fused_kernel() const)(FusedArgs) {
-        if (ksplit && kosplit) return decode_step_fused_kernel<G, true, true>;
-        if (kosplit) return decode_step_fused_kernel<G, false, true>;
-        if (ksplit) return decode_step_fused_kernel<G, true, false>;
-        return decode_step_fused_kernel<G, false, false>;
-    }
+    void (*fused_kernel() const)(FusedArgs) { return fused_ll ? decode_step_fused_kernel<G, true> : decode_step_fused_kernel<G, false>; }
     template <int G>
     void fused_prepare() {
-        fused_smem = fused_smem_bytes<G>();
+        fused_smem = fused_smem_bytes<G>(fused_ll);
         auto prep = [&](auto kernel) {
             AHA_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem));
             int nb = 0;
@@ -414,13 +415,11 @@ struct TextModel {
         {
             std::string why;
             const bool ok = fused_supported(&why);
-            AHA_REQUIRE(decode_impl < 2 || decode_impl > 5 || ok, "fused decode kernel unsupported for this model: " + why);
-            AHA_REQUIRE(decode_impl >= 0 && decode_impl <= 5, "decode_impl must be 0..5");
+            AHA_REQUIRE(decode_impl >= 0 && decode_impl <= 3, "decode_impl must be 0 (auto), 1 (per-op kernels), 2 (fused persistent kernel) or 3 (fused, grid-barrier twin)");
+            AHA_REQUIRE(decode_impl < 2 || ok, "fused decode kernel unsupported for this model: " + why);
+            AHA_REQUIRE(decode_impl != 3 || tp_world == 1, "the grid-barrier twin of the fused kernel is single-GPU only");
             fused = ok && decode_impl != 1;
-            ksplit = fused && (decode_impl == 3 || decode_impl == 5);
-            kosplit = fused && (decode_impl == 4 || decode_impl == 5);
-            AHA_REQUIRE(!kosplit || !layers[0].o.b, "K-split o_proj variant: o_proj bias is not supported");
-            AHA_REQUIRE(!ksplit || (I_l + ctx->num_sms - 1) / ctx->num_sms + 2 <= kFusedMaxHs, "K-split variant: more SwiGLU outputs per SM than it keeps in shared memory");
+            fused_ll = fused && decode_impl != 3;
         }
         num_pages = ceil_div(max_ctx, kPage);
         page_stride = (size_t)2 * nkv_l * kPage * cfg.hd;
@@ -448,29 +447,24 @@ struct TextModel {
             std::vector<FusedLayer> fl(cfg.L);
             for (int l = 0; l < cfg.L; ++l) {
                 TextLayer& T = layers[l];
-                fl[l] = FusedLayer{T.qkv.w, T.o.w, T.gu.w, T.down.w, T.qkv.b, T.o.b, T.ln1, T.ln2, T.qn, T.kn, nullptr, nullptr};
-                if (kosplit) {   // Wo as nkv column blocks [H][G*hd]: the slice a CTA of kv group g multiplies becomes contiguous rows
-                    const int Kp = (nh_l / nkv_l) * cfg.hd, Kt = nh_l * cfg.hd;
-                    __half* og = c.alloc<__half>((size_t)cfg.H * Kt);
-                    const size_t n = (size_t)cfg.H * Kt;
-                    split_columns_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(T.o.w, og, cfg.H, Kt, Kp);
-                    AHA_CUDA_CHECK(cudaGetLastError());
-                    fl[l].o_g = og;
-                }
-                if (ksplit) {   // Wdown^T [I][H]: the k-rows a CTA needs become contiguous 2*H-byte rows
-                    __half* wt = c.alloc<__half>((size_t)I_l * cfg.H);
-                    transpose_f16_kernel<<<dim3((unsigned)ceil_div(I_l, 32), (unsigned)ceil_div(cfg.H, 32)), dim3(32, 8), 0, c.stream>>>(T.down.w, wt, cfg.H, I_l);
-                    AHA_CUDA_CHECK(cudaGetLastError());
-                    fl[l].down_t = wt;
-                }
-            }
-            if (kosplit) xo = c.alloc<float>((size_t)2 * cfg.H);
-            if (ksplit) {
-                acc2 = c.alloc<float>((size_t)2 * cfg.H);
-                AHA_CUDA_CHECK(cudaMemsetAsync(acc2, 0, (size_t)2 * cfg.H * sizeof(float), c.stream));
-                AHA_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+                fl[l] = FusedLayer{T.qkv.w, T.o.w, T.gu.w, T.down.w, T.qkv.b, T.o.b, T.ln1, T.ln2, T.qn, T.kn};
             }
             d_fused_layers = upload(c, fl);
+            if (fused_ll) {
+                auto zalloc = [&](size_t n) { LLPk* p = c.alloc<LLPk>(n); AHA_CUDA_CHECK(cudaMemset(p, 0, n * sizeof(LLPk))); return p; };
+                ll_qkv = zalloc((size_t)qkv_dim);
+                ll_pb = zalloc((size_t)nh_l * fused_nsplit * kFusedPartialStride);
+                ll_att = zalloc((size_t)nh_l * cfg.hd);
+                ll_h = zalloc((size_t)I_l);
+                void* sym = nullptr;   // its own allocation: the IPC handle of a pointer covers the whole cudaMalloc block
+                AHA_CUDA_CHECK(cudaMalloc(&sym, ll_sym_packets() * sizeof(LLPk)));
+                c.allocs.push_back(sym);
+                AHA_CUDA_CHECK(cudaMemset(sym, 0, ll_sym_packets() * sizeof(LLPk)));
+                ll_sym = reinterpret_cast<LLPk*>(sym);
+                ll_peer_sym[tp_rank] = ll_sym;
+                d_ll_abort = c.alloc<int>(1);
+                AHA_CUDA_CHECK(cudaMemset(d_ll_abort, 0, sizeof(int)));
+            }
             d_ftrace = c.alloc<unsigned long long>(kFusedTraceWords);
             AHA_CUDA_CHECK(cudaMemset(d_ftrace, 0, kFusedTraceWords * sizeof(unsigned long long)));
             switch (nh_l / nkv_l) {
@@ -533,6 +527,34 @@ struct TextModel {
         NcclApi::unique_id id;
         std::memcpy(&id, unique_id, sizeof(id));
         n.check(n.CommInitRank(&comm, tp_world, id, tp_rank), "ncclCommInitRank");
+        if (!fused_ll) return;
+        // Map every rank's packet block into this process (CUDA IPC; NVLink / NVSwitch peer access): the handles travel
+        // through the communicator itself, so the C ABI needs nothing beyond the unique id it already takes.
+        cudaIpcMemHandle_t mine;
+        AHA_CUDA_CHECK(cudaIpcGetMemHandle(&mine, ll_sym));
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+        char* d_h = ctx->alloc<char>((size_t)64 * tp_world);
+        AHA_CUDA_CHECK(cudaMemcpyAsync(d_h + (size_t)64 * tp_rank, &mine, 64, cudaMemcpyHostToDevice, ctx->stream));
+        n.check(n.AllGather(d_h + (size_t)64 * tp_rank, d_h, 64, NcclApi::kInt8, comm, ctx->stream), "ncclAllGather(ipc handles)");
+        std::vector<cudaIpcMemHandle_t> all(tp_world);
+        AHA_CUDA_CHECK(cudaMemcpyAsync(all.data(), d_h, (size_t)64 * tp_world, cudaMemcpyDeviceToHost, ctx->stream));
+        AHA_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // every rank zeroed its block before it entered the all-gather
+        for (int w = 0; w < tp_world; ++w) {
+            if (w == tp_rank) continue;
+            void* p = nullptr;
+            AHA_CUDA_CHECK(cudaIpcOpenMemHandle(&p, all[w], cudaIpcMemLazyEnablePeerAccess));
+            ll_peer_sym[w] = reinterpret_cast<LLPk*>(p);
+        }
+    }
+    // a wait inside the fused kernel timed out (a peer GPU / CTA died): surface it instead of returning garbage
+    void check_ll_abort() {
+        if (!d_ll_abort) return;
+        int flag = 0;
+        AHA_CUDA_CHECK(cudaMemcpy(&flag, d_ll_abort, sizeof(int), cudaMemcpyDeviceToHost));
+        if (flag) {
+            cudaMemset(d_ll_abort, 0, sizeof(int));
+            throw std::runtime_error("fused decode step: a packet never arrived (tensor-parallel peer not running the same step?)");
+        }
     }
     // all-reduce(sum) of a partial projection over the tensor-parallel ranks, then x += sum (the residual add)
     void tp_reduce_add(float* partial, float* xdst, size_t n) {
@@ -655,9 +677,24 @@ struct TextModel {
         { const char* e = getenv("AHA_FUSED_DBG"); fa.dbg = e ? atoi(e) : 0; }
         fa.trace = d_ftrace;
         { const char* e = getenv("AHA_FUSED_STAGES"); fa.stages = e ? std::max(2, std::min(kFusedStages, atoi(e))) : fused_stages; }
+        fa.tp_rank = tp_rank; fa.tp_world = tp_world;
+        fa.v0 = (int)(((long long)cfg.V * tp_rank) / tp_world);
+        fa.V_l = (int)(((long long)cfg.V * (tp_rank + 1)) / tp_world) - fa.v0;
+        if (fused_ll) {
+            fa.ll_qkv = ll_qkv; fa.ll_pb = ll_pb; fa.ll_att = ll_att; fa.ll_h = ll_h; fa.ll_abort = d_ll_abort;
+            for (int w = 0; w < tp_world; ++w) {
+                AHA_REQUIRE(ll_peer_sym[w] != nullptr, "tensor-parallel peers are not attached");
+                fa.ll_xp[0][w] = ll_peer_sym[w];
+                fa.ll_xp[1][w] = ll_peer_sym[w] + (size_t)tp_world * cfg.H;
+                fa.ll_cand[w] = ll_peer_sym[w] + (size_t)2 * tp_world * cfg.H;
+            }
+            ll_launches += 1;
+            fa.ll_tag = ll_launches * 64u;   // layer l -> tag + l (L <= 62); 0 is the "never written" tag of the zeroed buffers
+            AHA_REQUIRE(cfg.L <= 62, "fused decode kernel: more than 62 layers");
+        } else {
+            fa.v0 = 0; fa.V_l = cfg.V;
+        }
         AHA_CUDA_CHECK(cudaMemsetAsync(d_sync, 0, sync_words * sizeof(unsigned), c.stream));
-        fa.acc2 = acc2; fa.xo = xo; fa.gsync = reinterpret_cast<unsigned*>(counters);
-        if (ksplit) AHA_CUDA_CHECK(cudaMemsetAsync(acc2, 0, (size_t)2 * cfg.H * sizeof(float), c.stream));
         switch (nh_l / nkv_l) {
             case 1: launch_fused<1>(fa); break;
             case 2: launch_fused<2>(fa); break;
@@ -666,9 +703,12 @@ struct TextModel {
         c.cnt.kernels++;
         step_graph_kernels = 1;
     }
-    void decode_step() {
+    // full_logits: the caller will read the whole logits row.  Under tensor parallelism the fused kernel multiplies only this
+    // rank's vocabulary shard (the winner is exchanged, not the row), so such a step takes the per-op path, whose lm_head
+    // is replicated.
+    void decode_step(bool full_logits = false) {
         Ctx& c = *ctx;
-        if (fused) { decode_step_fused(); return; }
+        if (fused && !(full_logits && tp_world > 1)) { decode_step_fused(); return; }
         if (!use_graph) { decode_step_launches(); return; }
         if (!step_graph) {
             const uint64_t k0 = c.cnt.kernels;
@@ -691,6 +731,8 @@ struct TextModel {
         AHA_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // `s` is a stack temporary
     }
     void destroy() {
+        for (int w = 0; w < kFusedMaxTp; ++w)
+            if (ll_peer_sym[w] && w != tp_rank) { cudaIpcCloseMemHandle(ll_peer_sym[w]); ll_peer_sym[w] = nullptr; }
         if (step_graph) { cudaGraphExecDestroy(step_graph); step_graph = nullptr; }
         if (comm) { NcclApi::get().CommDestroy(comm); comm = nullptr; }
     }

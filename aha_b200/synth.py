@@ -199,6 +199,14 @@ def make_weights(kind, cfg, seed=0):
 
 
 # ----------------------------------------------------------------------------- synthetic inputs
+# BASELINE.json's full-size workloads (configs 3, 2, 4); tests/golden/make_golden_full.py, tests/test_fullsize_gpu.py and
+# bench.py all build their inputs from these
+FULL_VL2_IMAGE = (1088, 1920)    # img_smart_resize(1080, 1920, 32, ...) -- SURVEY 8c known answer
+FULL_VL2_TEXT = 512
+FULL_Q06_PROMPT = 1920
+FULL_ASR_SECONDS = 30.0
+
+
 def synth_text_ids(n, vocab, seed, avoid=()):
     """Uniform ids in [0, vocab) avoiding the given special ids."""
     rng = np.random.default_rng(seed)

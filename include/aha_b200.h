@@ -66,9 +66,8 @@ typedef struct aha_options {
     int32_t max_patches;   /* largest ViT patch count (0 = 16384); Qwen3-VL only */
     int32_t max_frames;    /* largest mel frame count (0 = 3000); Qwen3-ASR only */
     int32_t use_graph;     /* 1 = replay the decode step from a CUDA graph (default), 0 = eager launches */
-    int32_t decode_impl;   /* 0 = auto, 1 = per-op kernels, 2 = persistent fused step kernel,
-                            * 3 / 4 / 5 = experimental variants of the fused kernel (K-split down projection / K-split o_proj behind a
-                            * kv-group barrier / both): fp32 atomics, run-dependent summation order, not validated on hardware yet */
+    int32_t decode_impl;   /* 0 = auto (fused where the model shape allows), 1 = per-op kernels under a CUDA graph (validation
+                            * twin), 2 = persistent fused step kernel required */
     int32_t gemm_impl;     /* 0 = auto, 1 = SIMT fp32, 2 = tcgen05 (split-fp16, fp32-exact) */
     const void* tp_comm;   /* opaque: ncclUniqueId bytes (128) when tp_world > 1, else NULL */
     int32_t reserved[8];   /* reserved[0]: prefill attention, 0 = tensor-core (mma, split-fp16) kernel, 1 = fp32 SIMT twin */

@@ -108,3 +108,107 @@ def test_asr06_config4_30s_audio():
         assert float(np.abs(a - b).max()) <= TOL
     finally:
         m.close()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Parity at BASELINE.json's own shapes: the CUDA path against ONE oracle forward per configuration, computed on the CPU of
+# the build container by tests/golden/make_golden_full.py and committed as tests/golden/full_*.npz (weights and inputs are
+# re-derived from the same seeds here).  Tolerance: north_star's 1e-3 on every logit; greedy ids must equal the oracle's
+# wherever the oracle's top-1/top-2 gap exceeds 10x the measured error.
+import os
+
+from conftest import GOLDEN
+
+
+def _golden(name):
+    p = os.path.join(GOLDEN, name)
+    assert os.path.exists(p), f"{p} is missing: run python tests/golden/make_golden_full.py in the build container"
+    return np.load(p)
+
+
+def _check_chain(m, g, S, prefill_logits, label):
+    """prefill logits, then the oracle's greedy ids teacher-forced for 8 steps; returns the largest |dlogit| seen."""
+    worst = float(np.abs(prefill_logits - g["prefill_logits"]).max())
+    assert worst <= TOL, f"{label}: prefill logits differ from the oracle by {worst}"
+    gaps, forced, sub = g["gaps"], g["forced"], int(g["sub_stride"])
+    ids_checked = 0
+    if gaps[0] > 10 * max(worst, 1e-6):
+        assert int(np.argmax(prefill_logits)) == int(forced[0]), f"{label}: first greedy id differs"
+        ids_checked += 1
+    n = len(forced)
+    for i in range(n):
+        l = m.forward_step(np.array([forced[i]], np.uint32), S + i)[0, 0]
+        e = float(np.abs(l[::sub] - g["step_logits_sub"][i]).max())
+        e = max(e, float(np.abs(l[g["step_top_ids"][i]] - g["step_top_vals"][i]).max()))
+        if i == n - 1:
+            e = max(e, float(np.abs(l - g["step_last_logits"]).max()))
+        assert e <= TOL, f"{label}: decode step {i} differs from the oracle by {e}"
+        worst = max(worst, e)
+        if gaps[i + 1] > 10 * max(e, 1e-6):
+            assert m.last_argmax == int(g["step_top_ids"][i][0]), f"{label}: greedy id at step {i} differs"
+            ids_checked += 1
+    print(f"\n{label}: max |dlogit| vs the full-size oracle golden = {worst:.2e} over prefill + {n} steps; {ids_checked}/{n + 1} greedy ids compared (min gap {gaps.min():.3f})")
+    return worst
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+def test_vl2_1080p_matches_the_full_size_oracle_golden(vl2, impl):
+    cfg, m0, m1 = vl2
+    m = m1 if impl == 1 else m0
+    g = _golden("full_vl2.npz")
+    VL2_IMAGE, VL2_TEXT = synth.FULL_VL2_IMAGE, synth.FULL_VL2_TEXT
+    m.clear_cache()
+    pv, grid = m.image_patchify(synth.synth_image(*VL2_IMAGE, seed=1))
+    assert grid.tolist() == g["grid"].tolist() and abs(float(pv.astype(np.float64).sum()) - float(g["pixel_sum"])) <= 1e-3 * abs(float(g["pixel_sum"])) + 1.0
+    ids = synth.vl_prompt_ids(cfg, grid, VL2_TEXT)
+    assert len(ids) == int(g["n_ids"]) and int(ids.astype(np.int64).sum()) == int(g["ids_crc"])
+    logits = m.forward_initial(ids, 0, [pv, grid, None, None, None])[0, 0]
+    assert int(m.debug_read("rope_delta", 0, 1)[0]) == int(g["rope_delta"])
+    ne = 2040 * 2048
+    for i in range(4):   # the four image-embed tensors (main merger + 3 deepstack): sampled rows + checksums
+        t = m.debug_read("image_embeds", i, ne).reshape(2040, 2048)
+        e = float(np.abs(t[g[f"embeds{i}_rows"]] - g[f"embeds{i}_sample"]).max())
+        assert e <= TOL, f"image_embeds[{i}] differs from the oracle by {e}"
+        assert abs(float(np.abs(t.astype(np.float64)).sum()) - float(g[f"embeds{i}_abs"])) <= 1e-5 * float(g[f"embeds{i}_abs"])
+    _check_chain(m, g, len(ids), logits, f"VL2 1080p+512 (decode_impl={impl})")
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+def test_q06_2k_matches_the_full_size_oracle_golden(impl):
+    Q06_PROMPT = synth.FULL_Q06_PROMPT
+    g = _golden("full_q06.npz")
+    cfg = synth.get_config("qwen3", "q0.6")
+    w = synth.make_weights("qwen3", cfg, 0)
+    m = B200Model("qwen3", cfg, w, eos_ids=[], max_ctx=2048, max_prefill=2048, decode_impl=impl)
+    del w
+    try:
+        ids = synth.synth_text_ids(Q06_PROMPT, 151000, 21)
+        assert int(ids.astype(np.int64).sum()) == int(g["ids_crc"])
+        logits = m.forward_initial(ids, 0)[0, 0]
+        _check_chain(m, g, len(ids), logits, f"Q0.6 1920-token prompt (decode_impl={impl})")
+    finally:
+        m.close()
+
+
+def test_asr06_30s_matches_the_full_size_oracle_golden():
+    ASR_SECONDS = synth.FULL_ASR_SECONDS
+    g = _golden("full_asr06.npz")
+    cfg = synth.get_config("qwen3_asr", "asr0.6")
+    w = synth.make_weights("qwen3_asr", cfg, 0)
+    m = B200Model("qwen3_asr", cfg, w, eos_ids=[], max_ctx=1024, max_frames=3000)
+    del w
+    try:
+        mel = m.mel_spectrogram(synth.synth_audio(ASR_SECONDS))
+        assert list(mel.shape) == g["mel_shape"].tolist()
+        assert abs(float(mel.astype(np.float64).sum()) - float(g["mel_sum"])) <= 1e-4 * abs(float(g["mel_sum"])) + 1.0
+        ids = synth.asr_prompt_ids(cfg, int(g["n_audio_tokens"]))
+        assert int(ids.astype(np.int64).sum()) == int(g["ids_crc"])
+        logits = m.forward_initial(ids, 0, [mel])[0, 0]
+        n_tok = int(g["n_audio_tokens"])
+        feat = m.debug_read("audio_embeds", 0, n_tok * 1024).reshape(n_tok, 1024)
+        e = float(np.abs(feat[g["audio_rows"]] - g["audio_sample"]).max())
+        assert e <= TOL, f"audio tower output differs from the oracle by {e}"
+        assert abs(float(np.abs(feat.astype(np.float64)).sum()) - float(g["audio_abs"])) <= 1e-5 * float(g["audio_abs"])
+        _check_chain(m, g, len(ids), logits, "ASR-0.6 30 s")
+    finally:
+        m.close()

@@ -351,3 +351,28 @@ def test_asr_errors(asr):
     m.clear_cache()
     with pytest.raises(B200Error, match="not equal to audio_feature len"):
         m.forward_initial(ids, 0, [mel])
+
+
+def _rand_ids(n, vocab, seed):
+    return np.random.default_rng(seed).integers(0, min(vocab, 1000), n).astype(np.uint32)
+
+
+# GQA groups other than 2 (every shipped Qwen3 size has nh / nkv = 2): MHA and a group of 4, fused and per-op decode
+@pytest.mark.parametrize("preset", ["tiny-g1", "tiny-g4"])
+@pytest.mark.parametrize("impl", [1, 2])
+def test_decode_with_other_gqa_groups(preset, impl):
+    cfg, w, m = make_model("qwen3", preset, max_ctx=512, decode_impl=impl)
+    o = make_oracle("qwen3", cfg, w)
+    try:
+        ids = _rand_ids(70, cfg["vocab_size"], 11)
+        got = m.forward_initial(ids, 0)[0, 0]
+        want = o.forward_initial(ids.reshape(1, -1), 0)[0, 0]
+        assert np.abs(got - want).max() <= TOL
+        tok = int(np.argmax(want))
+        for step in range(16):
+            lg = m.forward_step(np.array([tok], np.uint32), 70 + step)[0, 0]
+            lo = o.forward_step(np.array([[tok]]), 70 + step)[0, 0]
+            assert np.abs(lg - lo).max() <= TOL, (step, np.abs(lg - lo).max())
+            tok = int(np.argmax(lo))
+    finally:
+        m.close()

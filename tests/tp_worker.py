@@ -18,13 +18,19 @@ def main():
     dist.init_process_group("gloo")
     from aha_b200 import B200Model, nccl_unique_id, synth
     from oracle.qwen3 import Qwen3Model
+    for preset in ("tiny", "mid"):
+        run(preset, rank, world, local, dist, torch, B200Model, synth, Qwen3Model, nccl_unique_id)
+    dist.destroy_process_group()
+
+
+def run(preset, rank, world, local, dist, torch, B200Model, synth, Qwen3Model, nccl_unique_id):
     uid = [nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
-    cfg = synth.get_config("qwen3", "tiny")
+    cfg = synth.get_config("qwen3", preset)
     w = synth.make_weights("qwen3", cfg, 0)
     m = B200Model("qwen3", cfg, w, device=local, max_ctx=256, tp_rank=rank, tp_world=world, tp_unique_id=uid[0])
     o = Qwen3Model(cfg, w)
-    ids = synth.synth_text_ids(70, cfg["vocab_size"] - 8, 3)
+    ids = synth.synth_text_ids(70, min(cfg["vocab_size"], 1000) - 8, 3)
     S = 64
     got = m.forward_initial(ids[:S], 0)[0, 0]
     want = o.forward_initial(ids[:S].reshape(1, -1), 0)[0, 0]
@@ -41,14 +47,22 @@ def main():
     dist.all_gather(gathered, mine)
     for g in gathered:
         assert torch.equal(g, gathered[0]), "ranks disagree"
+    # greedy decode through the fused kernel: partial sums and argmax candidates cross NVLink as tagged packets; the
+    # tokens must equal the oracle's greedy continuation and agree on every rank
     toks = m.decode_steps(5, S + 6, 8)
+    assert m.stats()["kernels_per_decode_step"] == 1, "tensor-parallel decode did not take the fused kernel"
+    want_toks, tok = [], 5
+    for i in range(8):
+        lo = o.forward_step(np.array([[tok]]), S + 6 + i)[0, 0]
+        tok = int(np.argmax(lo))
+        want_toks.append(tok)
+    assert list(toks) == want_toks, (toks, want_toks)
     tl = [None] * world
     dist.all_gather_object(tl, toks)
     assert all(t == tl[0] for t in tl)
     if rank == 0:
-        print(f"TP{world} ok: max abs logit err {max(errs):.2e}, kernels/step {m.stats()['kernels_per_decode_step']}")
+        print(f"TP{world} {preset} ok: max abs logit err {max(errs):.2e}, kernels/step {m.stats()['kernels_per_decode_step']}")
     m.close()
-    dist.destroy_process_group()
 
 
 if __name__ == "__main__":
