@@ -30,7 +30,16 @@ class Options(C.Structure):
 
 class GenParams(C.Structure):
     _fields_ = [("temperature", C.c_float), ("repeat_penalty", C.c_float), ("repeat_last_n", C.c_int32),
-                ("max_tokens", C.c_uint32), ("seed", C.c_uint64)]
+                ("max_tokens", C.c_uint32), ("seed", C.c_uint64), ("top_p", C.c_float), ("top_k", C.c_int32),
+                ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+GEN_EOS_ON_FIRST, GEN_CONTINUE_RNG = 1, 2
+TOKEN_CALLBACK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_uint32)
+
+
+class AsrChunk(C.Structure):
+    _fields_ = [("ids", C.POINTER(C.c_uint32)), ("seq_len", C.c_size_t), ("input_features", TensorDesc)]
 
 
 class Usage(C.Structure):
@@ -58,8 +67,20 @@ SYMBOLS = {
     "aha_b200_stop_token_ids": (C.c_size_t, [_P, _U32P, C.c_size_t]),
     "aha_b200_generate": (C.c_int, [_P, _U32P, C.c_size_t, C.POINTER(MM), C.POINTER(GenParams), _U32P, C.c_size_t,
                                     C.POINTER(C.c_size_t), C.POINTER(Usage)]),
+    "aha_b200_generate_stream": (C.c_int, [_P, _U32P, C.c_size_t, C.POINTER(MM), C.POINTER(GenParams), TOKEN_CALLBACK, C.c_void_p,
+                                           C.POINTER(Usage)]),
+    "aha_b200_asr_generate": (C.c_int, [_P, C.POINTER(AsrChunk), C.c_size_t, C.POINTER(GenParams), _U32P, C.c_size_t,
+                                        C.POINTER(C.c_size_t), TOKEN_CALLBACK, C.c_void_p, C.POINTER(Usage)]),
+    "aha_b200_debug_sample": (C.c_int, [_P, _F32P, C.POINTER(GenParams), _U32P, C.c_size_t, C.c_uint32, _U32P]),
     "aha_b200_mel_spectrogram": (C.c_int, [_P, _F32P, C.c_size_t, _F32P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "aha_b200_image_patchify": (C.c_int, [_P, C.POINTER(C.c_uint8), C.c_size_t, C.c_size_t, _F32P, C.c_size_t, _U32P]),
+    "aha_b200_img_smart_resize": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _U32P, _U32P]),
+    "aha_b200_image_resize": (C.c_int, [_P, C.POINTER(C.c_uint8), C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(C.c_uint8)]),
+    "aha_b200_image_preprocess": (C.c_int, [_P, C.POINTER(C.c_uint8), C.c_size_t, C.c_size_t, C.c_uint32, C.c_uint32, _F32P, C.c_size_t, _U32P]),
+    "aha_b200_expand_placeholders": (C.c_int, [_U32P, C.c_size_t, C.c_uint32, _U32P, C.c_size_t, _U32P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "aha_b200_feat_extract_output_length": (C.c_size_t, [C.c_size_t]),
+    "aha_b200_float_range_normalize": (C.c_int, [_F32P, C.c_size_t]),
+    "aha_b200_split_audio_into_chunks": (C.c_int, [C.c_size_t, C.c_uint32, C.c_float, C.POINTER(C.c_size_t), C.c_size_t, C.POINTER(C.c_size_t)]),
     "aha_b200_embed": (C.c_int, [_P, _U32P, C.c_size_t, _F32P]),
     "aha_b200_rerank": (C.c_int, [_P, _U32P, C.c_size_t, _U32P, C.POINTER(C.c_size_t), C.c_size_t, _F32P]),
     "aha_b200_nccl_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),

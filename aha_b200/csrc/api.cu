@@ -4,9 +4,11 @@
 // Qwen3ASRModel (qwen3_asr/model.rs:308-425) and generate_generic (common/generate.rs:115-159).
 #include <array>
 #include <chrono>
+#include <functional>
 #include <mutex>
 
 #include "audio_model.cuh"
+#include "preprocess.cuh"
 #include "text_model.cuh"
 #include "vision_model.cuh"
 
@@ -34,8 +36,10 @@ struct aha_model {
     int max_scatter = 0;
     double last_vision_secs = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    // pinned staging for the host<->device scalars of a step
+    // pinned staging for the host<->device scalars of a step / the tokens of a burst
     uint32_t* h_pin = nullptr;
+    static constexpr int kStreamBurst = 8;   // streaming: steps the device may run ahead of the token being delivered
+    cudaEvent_t ev_tok[kStreamBurst] = {};
 };
 
 namespace {
@@ -219,7 +223,7 @@ void forward_prefill(aha_model* m, const uint32_t* ids, size_t S, size_t offset,
             for (float* p : m->vision.ds_out) deepstack.push_back(p);
         }
         // positions: first call -> get_rope_index, later -> arange + offset + rope_deltas (model.rs:1226-1264)
-        if (!m->have_rope_delta) {
+        if (!m->have_rope_delta || (initial && offset == 0)) {   // cache_position[0] == 0 recomputes get_rope_index even when rope_deltas is set (model.rs:1228)
             int delta = 0;
             get_rope_index(ids, (int)S, grid, m->vision.cfg.merge, m->image_token_id, m->vision_start_token_id, pos3, delta);
             m->rope_delta = delta; m->have_rope_delta = true;
@@ -275,6 +279,7 @@ void forward_any(aha_model* m, const uint32_t* ids, size_t S, size_t offset, con
         AHA_REQUIRE(offset == 0, "seq_len > 1 with seqlen_offset > 0 is not supported (the reference's mask shape rejects it too)");
         forward_prefill(m, ids, S, offset, mm, initial);
         T.finish_argmax(0);
+        T.sample(0);   // device sampler of generate(): penalty / temperature / top-k / top-p on the prefill logits (no-op for plain ArgMax)
     }
     fetch_outputs(m, logits_out, argmax_out);
     if (m->kind != aha_model::QWEN3 && has_mm) {
@@ -315,7 +320,8 @@ int aha_b200_create(const char* kind, const char* config_json, const aha_tensor_
         AHA_CUDA_CHECK(cudaStreamCreateWithFlags(&m->ctx.stream, cudaStreamNonBlocking));
         AHA_CUDA_CHECK(cudaEventCreate(&m->ev0));
         AHA_CUDA_CHECK(cudaEventCreate(&m->ev1));
-        AHA_CUDA_CHECK(cudaMallocHost(&m->h_pin, 64));
+        AHA_CUDA_CHECK(cudaMallocHost(&m->h_pin, 64 * sizeof(uint32_t)));
+        for (auto& e : m->ev_tok) AHA_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         gemv_init();
         gemm_tc_init();
         const std::string k = kind;
@@ -397,62 +403,172 @@ size_t aha_b200_stop_token_ids(aha_model* m, uint32_t* out, size_t cap) {
     return m->stop_ids.size();
 }
 
+namespace {
+
+// get_logit_processor (sample.rs:7-38): which Sampling the request's parameters select
+int sampling_mode(const aha_gen_params& p) {
+    const bool has_t = !(p.temperature < 1e-7f);
+    const bool has_k = p.top_k > 0, has_p = p.top_p > 0.f;
+    if (!has_t) return SAMPLE_ARGMAX;
+    if (!has_k) return has_p ? SAMPLE_TOPP : SAMPLE_ALL;
+    return has_p ? SAMPLE_TOPK_TOPP : SAMPLE_TOPK;
+}
+
+struct GenSink {   // receives every generated token in order; returns true to stop the request (client went away)
+    std::function<bool(uint32_t token, size_t index)> push;
+};
+
+// generate_generic / generate_stream_generic (common/generate.rs:115-159, 231-368) with the loop on the device:
+// forward_initial + sample, then decode steps chained through DecodeState (token, position, history, RNG draw index all
+// live in HBM); the host only looks at the tokens, a burst behind the device.  `stream`: tokens are handed to the sink one
+// by one as their step completes (per-step event) while the device keeps running ahead inside the burst.
+void generate_impl(aha_model* m, const uint32_t* ids, size_t seq_len, const aha_mm* mm, const aha_gen_params& params, const GenSink& sink, bool stream,
+                   aha_usage* usage, size_t* n_generated) {
+    TextModel& T = m->text;
+    const size_t sample_len = std::max<size_t>(params.max_tokens, 1);   // `for _ in 1..sample_len`: sample_len 0 and 1 both yield exactly one token
+    AHA_REQUIRE(seq_len + sample_len <= (size_t)T.max_ctx,
+                "prompt + max_tokens exceeds max_ctx (the handle's KV capacity, aha_options.max_ctx; the reference's cache is unbounded)");
+    using clk = std::chrono::steady_clock;
+    const bool eos_on_first = (params.flags & AHA_GEN_EOS_ON_FIRST) != 0;
+    struct Reset {   // model.clear_cache() (generate.rs:147) -- also on the error path, so that a failed request never leaves rope_delta / pages behind
+        aha_model* m;
+        ~Reset() { m->text.reset_pages(); m->have_rope_delta = false; m->rope_delta = 0; m->text.clear_sampler(); }
+    } reset{m};
+    const int mode = sampling_mode(params);
+    uint32_t draws0 = 0;
+    if ((params.flags & AHA_GEN_CONTINUE_RNG) != 0) {   // one LogitsProcessor across the chunks of a request: keep its stream position
+        DecodeState cur;
+        AHA_CUDA_CHECK(cudaMemcpy(&cur, T.d_state, sizeof(cur), cudaMemcpyDeviceToHost));
+        draws0 = cur.n_draws;
+    }
+    T.set_sampler(mode, params.temperature, params.top_p, params.top_k, params.repeat_penalty, params.repeat_last_n, params.seed);
+    T.set_state(0, 0, 0, 0, draws0);    // empty history: the first token sees no repeat-penalty context
+    auto is_eos = [&](uint32_t t) { for (uint32_t e : m->stop_ids) if (e == t) return true; return false; };
+    const auto t0 = clk::now();
+    uint32_t tok = 0;
+    forward_any(m, ids, seq_len, 0, mm, true, nullptr, &tok);   // forward_initial + sample_and_push
+    T.check_sample_error();
+    const auto t1 = clk::now();
+    const double vision_secs = m->last_vision_secs;
+    size_t done = 1;
+    bool stop = sink.push(tok, 0) || (eos_on_first && is_eos(tok));   // generate_generic never EOS-checks the first token; the ASR loop does
+    if (sample_len > 1 && !stop) {
+        T.ensure_tokens((int)(seq_len + sample_len));
+        DecodeState cur;
+        AHA_CUDA_CHECK(cudaMemcpy(&cur, T.d_state, sizeof(cur), cudaMemcpyDeviceToHost));
+        T.set_state(tok, (int)seq_len, m->kind == aha_model::QWEN3VL ? m->rope_delta : 0, 1, cur.n_draws);
+        AHA_CUDA_CHECK(cudaMemcpy(T.d_history, &tok, sizeof(uint32_t), cudaMemcpyHostToDevice));   // history[0] = first token (penalty context)
+        const size_t burst_max = stream ? (size_t)aha_model::kStreamBurst : 32;
+        while (done < sample_len && !stop) {
+            const size_t n = std::min<size_t>(burst_max, sample_len - done);
+            for (size_t i = 0; i < n; ++i) {
+                T.decode_step();
+                if (stream) {
+                    AHA_CUDA_CHECK(cudaMemcpyAsync(m->h_pin + i, T.d_history + done + i, sizeof(uint32_t), cudaMemcpyDeviceToHost, m->ctx.stream));
+                    AHA_CUDA_CHECK(cudaEventRecord(m->ev_tok[i], m->ctx.stream));
+                }
+            }
+            if (!stream) {
+                AHA_CUDA_CHECK(cudaMemcpyAsync(m->h_pin, T.d_history + done, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, m->ctx.stream));
+                AHA_CUDA_CHECK(cudaStreamSynchronize(m->ctx.stream));
+            }
+            for (size_t i = 0; i < n && !stop; ++i) {
+                if (stream) AHA_CUDA_CHECK(cudaEventSynchronize(m->ev_tok[i]));
+                const uint32_t t = m->h_pin[i];
+                ++done;
+                stop = sink.push(t, done - 1) || is_eos(t);   // an EOS token is pushed before the break (generate.rs:139-141)
+            }
+            AHA_CUDA_CHECK(cudaStreamSynchronize(m->ctx.stream));
+            T.check_ll_abort();
+            T.check_sample_error();
+        }
+    }
+    const auto t2 = clk::now();
+    if (n_generated) *n_generated = done;
+    if (usage) {
+        usage->prompt_tokens += (uint32_t)seq_len;
+        usage->completion_tokens += (uint32_t)done;
+        usage->prompt_secs += std::chrono::duration<double>(t1 - t0).count();
+        usage->completion_secs += std::chrono::duration<double>(t2 - t1).count();
+        usage->vision_secs += vision_secs;
+    }
+}
+
+}  // namespace
+
 int aha_b200_generate(aha_model* m, const uint32_t* ids, size_t seq_len, const aha_mm* mm, const aha_gen_params* params, uint32_t* out_tokens,
                       size_t cap, size_t* n_out, aha_usage* usage) {
     return guarded(m, [&] {
         AHA_REQUIRE(params && out_tokens && n_out, "params, out_tokens and n_out are required");
-        AHA_REQUIRE(params->temperature < 1e-7f, "only the ArgMax sampler (temperature < 1e-7) is implemented");
-        AHA_REQUIRE(params->repeat_penalty == 1.0f || params->repeat_penalty == 0.0f || params->repeat_last_n == 0,
-                    "repeat_penalty != 1.0 is not implemented on the device loop");
+        AHA_REQUIRE(cap >= std::max<size_t>(params->max_tokens, 1), "out_tokens capacity is smaller than max_tokens");
+        if (usage) *usage = aha_usage{};
+        size_t n = 0;
+        GenSink sink{[&](uint32_t t, size_t i) { out_tokens[i] = t; n = i + 1; return false; }};
+        generate_impl(m, ids, seq_len, mm, *params, sink, false, usage, nullptr);
+        *n_out = n;
+    });
+}
+
+int aha_b200_generate_stream(aha_model* m, const uint32_t* ids, size_t seq_len, const aha_mm* mm, const aha_gen_params* params,
+                             aha_token_callback on_token, void* user, aha_usage* usage) {
+    return guarded(m, [&] {
+        AHA_REQUIRE(params && on_token, "params and on_token are required");
+        if (usage) *usage = aha_usage{};
+        GenSink sink{[&](uint32_t t, size_t i) { return on_token(user, t, (uint32_t)i) != 0; }};
+        generate_impl(m, ids, seq_len, mm, *params, sink, true, usage, nullptr);
+    });
+}
+
+int aha_b200_asr_generate(aha_model* m, const aha_asr_chunk* chunks, size_t n_chunks, const aha_gen_params* params, uint32_t* out_tokens, size_t cap,
+                          size_t* n_out, aha_token_callback on_token, void* user, aha_usage* usage) {
+    return guarded(m, [&] {
+        AHA_REQUIRE(m->kind == aha_model::QWEN3_ASR, "asr_generate needs a qwen3_asr handle");
+        AHA_REQUIRE(chunks && n_chunks >= 1 && params && out_tokens && n_out, "chunks, params, out_tokens and n_out are required");
+        if (usage) *usage = aha_usage{};
+        // Qwen3AsrGenerateModel::generate (qwen3_asr/generate.rs:130-186): ONE LogitsProcessor for the whole request (its RNG
+        // stream runs on across the chunks), no repeat penalty, every token -- the first included -- is EOS-checked, the KV
+        // cache is cleared after every chunk, the token lists of the chunks are concatenated.
+        size_t total = 0;
+        for (size_t c = 0; c < n_chunks; ++c) {
+            aha_gen_params p = *params;
+            p.repeat_penalty = 1.0f;
+            p.top_k = 0;                                  // get_logit_processor(Some(temperature), top_p, None, seed)
+            p.flags |= AHA_GEN_EOS_ON_FIRST;
+            if (c > 0) p.flags |= AHA_GEN_CONTINUE_RNG;
+            AHA_REQUIRE(total + std::max<size_t>(p.max_tokens, 1) <= cap, "out_tokens capacity is smaller than n_chunks * max_tokens");
+            aha_mm mm{&chunks[c].input_features, 1};
+            const size_t base = total;
+            bool abort = false;
+            GenSink sink{[&](uint32_t t, size_t i) {
+                out_tokens[base + i] = t; total = base + i + 1;
+                if (on_token && on_token(user, t, (uint32_t)(base + i)) != 0) abort = true;
+                return abort;
+            }};
+            generate_impl(m, chunks[c].ids, chunks[c].seq_len, &mm, p, sink, on_token != nullptr, usage, nullptr);
+            if (abort) break;
+        }
+        *n_out = total;
+    });
+}
+
+int aha_b200_debug_sample(aha_model* m, const float* logits, const aha_gen_params* params, const uint32_t* context, size_t n_context,
+                          uint32_t draw_index, uint32_t* token_out) {
+    return guarded(m, [&] {
+        AHA_REQUIRE(logits && params && token_out && (context || n_context == 0), "logits, params and token_out are required");
         TextModel& T = m->text;
-        const size_t sample_len = params->max_tokens ? params->max_tokens : 1024;
-        AHA_REQUIRE(cap >= sample_len, "out_tokens capacity is smaller than max_tokens");
-        AHA_REQUIRE(seq_len + sample_len <= (size_t)T.max_ctx, "prompt + max_tokens exceeds max_ctx");
-        using clk = std::chrono::steady_clock;
-        std::vector<uint32_t> generated;
-        const auto t0 = clk::now();
-        uint32_t tok = 0;
-        forward_any(m, ids, seq_len, 0, mm, true, nullptr, &tok);   // forward_initial + sample (first token never EOS-checked)
-        generated.push_back(tok);
-        const auto t1 = clk::now();
-        const double vision_secs = m->last_vision_secs;
-        // decode loop on the device: token feedback through DecodeState, EOS inspected on the host once per burst
-        size_t done = 1;
-        bool stop = false;
-        if (sample_len > 1) {
-            T.ensure_tokens((int)(seq_len + sample_len));
-            T.set_state(tok, (int)seq_len, m->kind == aha_model::QWEN3VL ? m->rope_delta : 0, 0);
-            std::vector<uint32_t> burst;
-            while (done < sample_len && !stop) {
-                const size_t n = std::min<size_t>(32, sample_len - done);
-                for (size_t i = 0; i < n; ++i) T.decode_step();
-                burst.resize(n);
-                AHA_CUDA_CHECK(cudaMemcpyAsync(burst.data(), T.d_history + (done - 1), n * sizeof(uint32_t), cudaMemcpyDeviceToHost, m->ctx.stream));
-                AHA_CUDA_CHECK(cudaStreamSynchronize(m->ctx.stream));
-                T.check_ll_abort();
-                for (size_t i = 0; i < n; ++i) {
-                    generated.push_back(burst[i]);
-                    ++done;
-                    bool is_eos = false;
-                    for (uint32_t e : m->stop_ids) is_eos |= (e == burst[i]);
-                    if (is_eos) { stop = true; break; }  // EOS is pushed before the break (generate.rs:139-141)
-                }
-            }
-        }
-        const auto t2 = clk::now();
-        for (size_t i = 0; i < generated.size(); ++i) out_tokens[i] = generated[i];
-        *n_out = generated.size();
-        if (usage) {
-            usage->prompt_tokens = (uint32_t)seq_len;
-            usage->completion_tokens = (uint32_t)generated.size();
-            usage->prompt_secs = std::chrono::duration<double>(t1 - t0).count();
-            usage->completion_secs = std::chrono::duration<double>(t2 - t1).count();
-            usage->vision_secs = vision_secs;
-        }
-        // model.clear_cache() (generate.rs:147)
-        m->text.reset_pages();
-        m->have_rope_delta = false;
-        m->rope_delta = 0;
+        AHA_REQUIRE(n_context <= (size_t)T.hist_cap, "context longer than the history buffer");
+        const int mode = sampling_mode(*params);
+        T.set_sampler(mode, params->temperature, params->top_p, params->top_k, params->repeat_penalty, params->repeat_last_n, params->seed);
+        AHA_REQUIRE(T.samp_active, "plain ArgMax needs no sampler (temperature < 1e-7 and no repeat penalty)");
+        AHA_CUDA_CHECK(cudaMemcpyAsync(T.logits, logits, (size_t)T.cfg.V * sizeof(float), cudaMemcpyHostToDevice, m->ctx.stream));
+        if (n_context) AHA_CUDA_CHECK(cudaMemcpyAsync(T.d_history, context, n_context * sizeof(uint32_t), cudaMemcpyHostToDevice, m->ctx.stream));
+        T.set_state(0, 0, 0, (int)n_context, draw_index);
+        T.sample(0);
+        AHA_CUDA_CHECK(cudaMemcpyAsync(m->h_pin, T.d_argmax, sizeof(uint32_t), cudaMemcpyDeviceToHost, m->ctx.stream));
+        AHA_CUDA_CHECK(cudaStreamSynchronize(m->ctx.stream));
+        T.check_sample_error();
+        T.clear_sampler();
+        *token_out = m->h_pin[0];
     });
 }
 
@@ -558,6 +674,107 @@ int aha_b200_image_patchify(aha_model* m, const uint8_t* img_hwc, size_t h, size
         } catch (...) { cudaFree(d_img); throw; }
         cudaFree(d_img);
         grid_thw_out[0] = 1; grid_thw_out[1] = (uint32_t)gh; grid_thw_out[2] = (uint32_t)gw;
+    });
+}
+
+extern "C++" {
+namespace {
+template <typename F>
+int guarded_host(F&& f) {   // host-only entries (no handle): errors land in the create-error slot read by aha_b200_last_error(NULL)
+    try { f(); return 0; }
+    catch (const std::exception& e) { std::lock_guard<std::mutex> lk(g_err_mu); g_create_error = e.what(); return 1; }
+}
+// resize (h, w, 3) u8 on the device -> (nh, nw, 3) u8 on the device; both buffers owned by the caller
+void resize_on_device(aha_model* m, const uint8_t* d_in, int h, int w, uint8_t* d_out, int nh, int nw, float* d_tmp) {
+    if (nh == h && nw == w) {   // imageops::resize copies when the dimensions already match
+        AHA_CUDA_CHECK(cudaMemcpyAsync(d_out, d_in, (size_t)h * w * 3, cudaMemcpyDeviceToDevice, m->ctx.stream));
+        return;
+    }
+    AHA_REQUIRE(2.0f * std::max(1.0f, (float)h / nh) + 2 <= kResizeMaxTaps && 2.0f * std::max(1.0f, (float)w / nw) + 2 <= kResizeMaxTaps,
+                "image downscale factor beyond the resize kernel's tap window (15x)");
+    resize_vertical_kernel<<<nh, 256, 0, m->ctx.stream>>>(d_in, h, w, nh, d_tmp);
+    resize_horizontal_kernel<<<nw, 256, 0, m->ctx.stream>>>(d_tmp, nh, w, nw, d_out);
+    AHA_CUDA_CHECK(cudaGetLastError());
+    m->ctx.cnt.kernels += 2;
+}
+}  // namespace
+}  // extern "C++"
+
+int aha_b200_img_smart_resize(uint32_t img_h, uint32_t img_w, uint32_t factor, uint32_t min_pixels, uint32_t max_pixels, uint32_t* out_h, uint32_t* out_w) {
+    return guarded_host([&] {
+        AHA_REQUIRE(out_h && out_w, "out_h and out_w are required");
+        img_smart_resize(img_h, img_w, factor, min_pixels, max_pixels, *out_h, *out_w);
+    });
+}
+
+int aha_b200_image_resize(aha_model* m, const uint8_t* img_hwc, size_t h, size_t w, size_t new_h, size_t new_w, uint8_t* out_hwc) {
+    return guarded(m, [&] {
+        AHA_REQUIRE(img_hwc && out_hwc && h > 0 && w > 0 && new_h > 0 && new_w > 0, "images and positive sizes are required");
+        uint8_t *d_in = nullptr, *d_out = nullptr;
+        float* d_tmp = nullptr;
+        auto cleanup = [&] { cudaFree(d_in); cudaFree(d_out); cudaFree(d_tmp); };
+        try {
+            AHA_CUDA_CHECK(cudaMalloc(&d_in, h * w * 3)); AHA_CUDA_CHECK(cudaMalloc(&d_out, new_h * new_w * 3)); AHA_CUDA_CHECK(cudaMalloc(&d_tmp, new_h * w * 3 * sizeof(float)));
+            AHA_CUDA_CHECK(cudaMemcpyAsync(d_in, img_hwc, h * w * 3, cudaMemcpyHostToDevice, m->ctx.stream));
+            resize_on_device(m, d_in, (int)h, (int)w, d_out, (int)new_h, (int)new_w, d_tmp);
+            AHA_CUDA_CHECK(cudaMemcpyAsync(out_hwc, d_out, new_h * new_w * 3, cudaMemcpyDeviceToHost, m->ctx.stream));
+            AHA_CUDA_CHECK(cudaStreamSynchronize(m->ctx.stream));
+        } catch (...) { cleanup(); throw; }
+        cleanup();
+    });
+}
+
+int aha_b200_image_preprocess(aha_model* m, const uint8_t* img_hwc, size_t h, size_t w, uint32_t min_pixels, uint32_t max_pixels, float* pixel_values_out,
+                              size_t cap, uint32_t grid_thw_out[3]) {
+    return guarded(m, [&] {
+        AHA_REQUIRE(m->kind == aha_model::QWEN3VL, "image_preprocess needs a qwen3vl handle");
+        AHA_REQUIRE(img_hwc && pixel_values_out && grid_thw_out && h > 0 && w > 0, "image, outputs and positive sizes are required");
+        VisionModel& V = m->vision;
+        const int ps = V.cfg.patch, mg = V.cfg.merge;
+        uint32_t rh = 0, rw = 0;
+        img_smart_resize((uint32_t)h, (uint32_t)w, (uint32_t)(ps * mg), min_pixels, max_pixels, rh, rw);   // Qwen3VLProcessor::process_img
+        const int gh = (int)rh / ps, gw = (int)rw / ps, N = gh * gw;
+        AHA_REQUIRE(N <= V.max_patches, "image needs " + std::to_string(N) + " patches after img_smart_resize, max_patches is " + std::to_string(V.max_patches));
+        AHA_REQUIRE((size_t)N * V.patch_dim <= cap, "pixel_values_out too small");
+        uint8_t *d_in = nullptr, *d_rs = nullptr;
+        float* d_tmp = nullptr;
+        auto cleanup = [&] { cudaFree(d_in); cudaFree(d_rs); cudaFree(d_tmp); };
+        try {
+            AHA_CUDA_CHECK(cudaMalloc(&d_in, h * w * 3)); AHA_CUDA_CHECK(cudaMalloc(&d_rs, (size_t)rh * rw * 3)); AHA_CUDA_CHECK(cudaMalloc(&d_tmp, (size_t)rh * w * 3 * sizeof(float)));
+            AHA_CUDA_CHECK(cudaMemcpyAsync(d_in, img_hwc, h * w * 3, cudaMemcpyHostToDevice, m->ctx.stream));
+            resize_on_device(m, d_in, (int)h, (int)w, d_rs, (int)rh, (int)rw, d_tmp);
+            patchify_kernel<<<N, 256, 0, m->ctx.stream>>>(d_rs, (int)rh, (int)rw, ps, mg, V.cfg.tpatch, V.pix);   // img_transform + frame duplication + 9-D permute
+            m->ctx.cnt.kernels++;
+            AHA_CUDA_CHECK(cudaMemcpyAsync(pixel_values_out, V.pix, (size_t)N * V.patch_dim * sizeof(float), cudaMemcpyDeviceToHost, m->ctx.stream));
+            AHA_CUDA_CHECK(cudaStreamSynchronize(m->ctx.stream));
+        } catch (...) { cleanup(); throw; }
+        cleanup();
+        grid_thw_out[0] = 1; grid_thw_out[1] = (uint32_t)gh; grid_thw_out[2] = (uint32_t)gw;
+    });
+}
+
+int aha_b200_expand_placeholders(const uint32_t* ids, size_t n, uint32_t token_id, const uint32_t* counts, size_t n_counts, uint32_t* out, size_t cap,
+                                 size_t* n_out) {
+    return guarded_host([&] {
+        AHA_REQUIRE(ids && n_out && (counts || n_counts == 0), "ids and n_out are required");
+        const std::vector<uint32_t> r = expand_placeholders(ids, n, token_id, counts, n_counts);
+        *n_out = r.size();
+        if (out) { AHA_REQUIRE(r.size() <= cap, "out too small"); std::memcpy(out, r.data(), r.size() * sizeof(uint32_t)); }
+    });
+}
+
+size_t aha_b200_feat_extract_output_length(size_t n_frames) { return feat_extract_output_length(n_frames); }
+
+int aha_b200_float_range_normalize(float* wave, size_t n) {
+    return guarded_host([&] { AHA_REQUIRE(wave || n == 0, "wave is required"); float_range_normalize(wave, n); });
+}
+
+int aha_b200_split_audio_into_chunks(size_t total_len, uint32_t sample_rate, float max_chunk_sec, size_t* lens_out, size_t cap, size_t* n_out) {
+    return guarded_host([&] {
+        AHA_REQUIRE(n_out && sample_rate > 0 && max_chunk_sec > 0.f, "n_out, a positive sample rate and chunk length are required");
+        const std::vector<size_t> r = split_audio_into_chunks(total_len, sample_rate, max_chunk_sec);
+        *n_out = r.size();
+        if (lens_out) { AHA_REQUIRE(r.size() <= cap, "lens_out too small"); for (size_t i = 0; i < r.size(); ++i) lens_out[i] = r[i]; }
     });
 }
 
@@ -686,6 +903,7 @@ void aha_b200_destroy(aha_model* m) {
     if (m->h_pin) cudaFreeHost(m->h_pin);
     if (m->ev0) cudaEventDestroy(m->ev0);
     if (m->ev1) cudaEventDestroy(m->ev1);
+    for (auto& e : m->ev_tok) if (e) cudaEventDestroy(e);
     if (m->ctx.stream) cudaStreamDestroy(m->ctx.stream);
     delete m;
 }

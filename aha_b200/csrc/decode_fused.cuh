@@ -94,6 +94,11 @@ struct FusedArgs {
     LLPk* ll_h;        // [I]
     LLPk* ll_xp[2][kFusedMaxTp];   // [o_proj | down][destination rank] -> that rank's [tp_world][H] block of partial sums (own rank = local memory)
     LLPk* ll_cand[kFusedMaxTp];    // [destination rank] -> that rank's [tp_world][2] argmax candidates (value, index) of the vocabulary shards
+    // "data is out" flags, one word per producing CTA and vector kind: written (relaxed, after the CTA's packets) by thread 0,
+    // polled by ONE warp of a consumer that found packets missing -- the other 320 threads of every waiting CTA stay off the
+    // memory system (every thread polling its own packets slows the weight stream of the CTAs still working: measured).
+    uint32_t* ll_flag;             // [4][256]: qkv | attention partials | merged attention | h, indexed by blockIdx.x
+    uint32_t* ll_flag_xp[2][kFusedMaxTp];   // [o_proj | down][destination rank] -> that rank's [tp_world][256] flags of the partial sums
     uint32_t ll_tag;   // tag of layer 0 of this launch; layer l uses ll_tag + l, the final phase ll_tag + L (never 0, never reused)
     int tp_rank, tp_world;
     int v0, V_l;       // vocabulary shard [v0, v0 + V_l) of the lm_head this rank multiplies (tp_world == 1: the whole of it)
@@ -232,6 +237,44 @@ __device__ __forceinline__ float4 ll_wait4(const LLPk* p, uint32_t tag, int* abo
     if (a.y == tag && a.w == tag && b.y == tag && b.w == tag)
         return make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(b.x), __uint_as_float(b.z));
     return ll_spin4<SYS>(p, tag, abort_flag);
+}
+
+template <bool SYS>
+__device__ __forceinline__ void ll_flag_store(uint32_t* p, uint32_t tag) {
+    if (SYS) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(tag) : "memory");
+    else asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(tag) : "memory");
+}
+template <bool SYS>
+__device__ __forceinline__ uint32_t ll_flag_load(const uint32_t* p) {
+    uint32_t v;
+    if (SYS) asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    else asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// AND of a predicate over the consumer threads of the CTA (named barrier 1)
+__device__ __forceinline__ bool consumer_all(bool ok) {
+    uint32_t r;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.u32 p, %1, 0;\n\t"
+        "bar.red.and.pred q, 1, %2, p;\n\t"
+        "selp.u32 %0, 1, 0, q;\n\t}"
+        : "=r"(r)
+        : "r"((uint32_t)ok), "n"(kFusedConsumers * 32)
+        : "memory");
+    return r != 0;
+}
+// Warp 0 polls `rows` x `n` flags (row stride `stride`) until each carries `tag`; everybody meets at the CTA barrier after.
+template <bool SYS>
+__device__ __noinline__ void ll_wait_flags(const uint32_t* f, int rows, int stride, int n, uint32_t tag, int* abort_flag) {
+    if (threadIdx.x < 32) {
+        LLWait w{abort_flag};
+        for (int i = threadIdx.x; i < rows * n; i += 32) {
+            const uint32_t* q = f + (size_t)(i / n) * stride + (i % n);
+            while (ll_flag_load<SYS>(q) != tag && !w.giveup()) __nanosleep(40);
+        }
+    }
+    consumer_bar_sync();
 }
 
 // Lighter synchronisation primitives than __threadfence() (= MEMBAR.SC.GPU + CCTL.IVALL per call on sm_100): a release
@@ -473,24 +516,26 @@ struct Consumer {
     // they carry `tag`; all loads of a vector are issued before the first tag is looked at, and the common case (data already
     // there) costs one L2 round trip.  RESID: the sum is added into the residual stream this CTA keeps in shared memory
     // (fixed rank order r = 0, 1, ... -> every CTA of every GPU forms bit-identical sums).
+    // flags / nflag: the "data is out" words of the CTAs that produce vector r (row r of `flags`, row stride 256).
     template <bool SYS, bool RESID>
-    __device__ __forceinline__ void load_ll(int K, const LLPk* pk, int nvec, size_t vstride, uint32_t tag, const float* norm_w, float eps) {
+    __device__ __forceinline__ void load_ll(int K, const LLPk* pk, int nvec, size_t vstride, uint32_t tag, const float* norm_w, float eps, const uint32_t* flags, int nflag) {
         constexpr int kChunk = kFusedConsumers * 32 * 4;   // elements one pass of the consumer threads covers
-        if (K <= 2 * kChunk) load_ll_n<SYS, RESID, 2>(K, pk, nvec, vstride, tag, norm_w, eps);
-        else if (K <= 3 * kChunk) load_ll_n<SYS, RESID, 3>(K, pk, nvec, vstride, tag, norm_w, eps);
-        else load_ll_n<SYS, RESID, (kFusedMaxK + kChunk - 1) / kChunk>(K, pk, nvec, vstride, tag, norm_w, eps);
+        if (K <= 2 * kChunk) load_ll_n<SYS, RESID, RESID, 2>(K, pk, nvec, vstride, tag, norm_w, eps, flags, nflag);
+        else if (K <= 3 * kChunk) load_ll_n<SYS, RESID, RESID, 3>(K, pk, nvec, vstride, tag, norm_w, eps, flags, nflag);
+        else load_ll_n<SYS, RESID, RESID, (kFusedMaxK + kChunk - 1) / kChunk>(K, pk, nvec, vstride, tag, norm_w, eps, flags, nflag);
     }
-    template <bool SYS, bool RESID, int kPer>
-    __device__ void load_ll_n(int K, const LLPk* pk, int nvec, size_t vstride, uint32_t tag, const float* norm_w, float eps) {
+    // NORM: RMSNorm of the vector (the residual-stream loads: RESID and NORM always come together; the o_proj / down inputs take neither)
+    template <bool SYS, bool RESID, bool NORM, int kPer>
+    __device__ void load_ll_n(int K, const LLPk* pk, int nvec, size_t vstride, uint32_t tag, const float* norm_w, float eps, const uint32_t* flags, int nflag) {
         const int tid = threadIdx.x;
-        float4 v[kPer], w[kPer];
+        float4 v[kPer], w[NORM ? kPer : 1];
 #pragma unroll
         for (int j = 0; j < kPer; ++j) {
             const int e = (tid + j * kFusedConsumers * 32) * 4;
             v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            w[j] = v[j];
+            if (NORM) w[j] = v[j];
             if (e < K) {
-                if (norm_w) w[j] = *reinterpret_cast<const float4*>(norm_w + e);
+                if (NORM) w[j] = *reinterpret_cast<const float4*>(norm_w + e);
                 if (RESID) v[j] = *reinterpret_cast<const float4*>(xres + e);
             }
         }
@@ -502,6 +547,16 @@ struct Consumer {
                 const int e = (tid + j * kFusedConsumers * 32) * 4;
                 if (e < K) { pa[j] = ll_load2<SYS>(base + e); pb[j] = ll_load2<SYS>(base + e + 2); }
             }
+            bool ok = true;
+#pragma unroll
+            for (int j = 0; j < kPer; ++j) {
+                const int e = (tid + j * kFusedConsumers * 32) * 4;
+                if (e < K) ok = ok && pa[j].y == tag && pa[j].w == tag && pb[j].y == tag && pb[j].w == tag;
+            }
+            // fast path: every packet of every thread was there (one L2 round trip).  Otherwise ONE warp waits for the producers'
+            // flags and the stale packets are read again (a flag can overtake its packets: the re-read still checks the tags).
+            const bool all_ok = consumer_all(ok);
+            if (!all_ok) ll_wait_flags<SYS>(flags + (size_t)r * 256, 1, 0, nflag, tag, ll_abort);
 #pragma unroll
             for (int j = 0; j < kPer; ++j) {
                 const int e = (tid + j * kFusedConsumers * 32) * 4;
@@ -521,7 +576,7 @@ struct Consumer {
                 if (e < K) *reinterpret_cast<float4*>(xres + e) = v[j];
             }
         }
-        if (norm_w) {
+        if (NORM) {
             float ss = 0.f;
 #pragma unroll
             for (int j = 0; j < kPer; ++j) ss += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
@@ -690,6 +745,11 @@ struct Consumer {
         }
         it = i;
         consumer_bar_sync();
+        if (LL && threadIdx.x == 0) {   // every packet store of this CTA has been issued: raise its "data is out" flag
+            if (EPI == FE_QKV) ll_flag_store<false>(a.ll_flag + 0 * 256 + blockIdx.x, tag);
+            else if (EPI == FE_SWIGLU) ll_flag_store<false>(a.ll_flag + 3 * 256 + blockIdx.x, tag);
+            else if (EPI == FE_RESID) for (int w = 0; w < a.tp_world; ++w) ll_flag_store<true>(a.ll_flag_xp[par][w] + (size_t)a.tp_rank * 256 + blockIdx.x, tag);
+        }
     }
 };
 
@@ -714,6 +774,15 @@ __device__ void fused_attention(const FusedArgs& a, Consumer& c, AttnSmem<G>& s,
     const bool has_item = attn_item(a, ctx, kvh, split, hp0, hp1);
     if (!has_item || c.sync_only) return;  // this CTA's producer issued nothing for the phase either
     // ---- prologue: q heads (warps 0..G-1) and the new k (warp G): RMSNorm over hd then RoPE; v copy (warp G+1)
+    if (LL) {   // are this head's q / k / v rows out yet?  (fast path: yes; else one warp polls the qkv flags of the grid)
+        bool ok = true;
+        if (warp <= G + 1) {
+            const size_t src_off = (size_t)(warp < G ? (kvh * G + warp) : (warp == G ? (a.nh + kvh) : (a.nh + a.nkv + kvh))) * HD + lane * 4;
+            const uint4 pa = ll_load2<false>(a.ll_qkv + src_off), pb2 = ll_load2<false>(a.ll_qkv + src_off + 2);
+            ok = pa.y == tag && pa.w == tag && pb2.y == tag && pb2.w == tag;
+        }
+        if (!consumer_all(ok)) ll_wait_flags<false>(a.ll_flag, 1, 0, (int)gridDim.x, tag, c.ll_abort);
+    }
     if (warp <= G) {
         const bool is_q = warp < G;
         const size_t src_off = (size_t)(is_q ? (kvh * G + warp) : (a.nh + kvh)) * HD + lane * 4;
@@ -857,10 +926,21 @@ __device__ void fused_attention(const FusedArgs& a, Consumer& c, AttnSmem<G>& s,
     }
     // barrier mode: the split partials are merged by the consumers of the next phase (Consumer::load_attn), after the grid barrier
     if (!LL) return;
+    consumer_bar_sync();
+    const int item = kvh * a.nsplit + split;
+    if (tid == 0) ll_flag_store<false>(a.ll_flag + 1 * 256 + item, tag);
     // LL mode: the nsplit CTAs of this kv head merge the partials among themselves -- CTA `split` owns the dims
     // [d0, d1) of the group's G heads: warp g takes head g, lane s takes split s (all (m, l) pairs and value packets of a
     // pass are in flight together), and the merged values leave as packets of the attention vector that o_proj reads.
     // 150 KB of partials per reader (every CTA merging every head) becomes 2-3 KB here plus the 16 KB vector.
+    {   // fast path: the (m, l) packets of every split of the group are there
+        bool ok = true;
+        if (warp < G && lane < a.nsplit) {
+            const uint4 ml = ll_load2<false>(a.ll_pb + ((size_t)(kvh * G + warp) * a.nsplit + lane) * kFusedPartialStride + HD);
+            ok = ml.y == tag && ml.w == tag;
+        }
+        if (!consumer_all(ok)) ll_wait_flags<false>(a.ll_flag + 1 * 256 + kvh * a.nsplit, 1, 0, a.nsplit, tag, c.ll_abort);
+    }
     if (warp < G) {
         const int per = (HD + a.nsplit - 1) / a.nsplit;
         const int d0 = split * per, d1 = min(HD, d0 + per);
@@ -884,6 +964,8 @@ __device__ void fused_attention(const FusedArgs& a, Consumer& c, AttnSmem<G>& s,
             if (lane == 0) ll_store<false>(a.ll_att + (size_t)h * HD + d, O, tag);
         }
     }
+    consumer_bar_sync();
+    if (tid == 0) ll_flag_store<false>(a.ll_flag + 2 * 256 + item, tag);
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
@@ -988,7 +1070,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
             const LLPk* xp_d = a.ll_xp[1][a.tp_rank];
             // P1: qkv = Wqkv . rmsnorm(x); x = residual + the down partial sums of layer l - 1 (layer 0: the embedding row)
             if (first) c.load_x(a.H, nullptr, emb_row, Ly.ln1, a.eps, true);
-            else c.template load_ll<true, true>(a.H, xp_d, a.tp_world, (size_t)a.H, tag - 1u, Ly.ln1, a.eps);
+            else c.template load_ll<true, true>(a.H, xp_d, a.tp_world, (size_t)a.H, tag - 1u, Ly.ln1, a.eps, a.ll_flag_xp[1][a.tp_rank], (int)gridDim.x);
             CSTAMP();
             c.template gemv<FE_QKV, true>(a, a.qkv_dim, a.H, Ly.qkv_b, nullptr, best, bi, tag); CSTAMP();
             CSTAMP();
@@ -997,16 +1079,16 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
             fused_attention<G, true>(a, c, *as, cs, spages, l, Ly, t_new, tag); CSTAMP();
             CSTAMP();
             // P3: o_proj partial sums (this rank's heads) -> every rank
-            c.template load_ll<false, false>(a.nh * a.hd, a.ll_att, 1, 0, tag, nullptr, 0.f); CSTAMP();
+            c.template load_ll<false, false>(a.nh * a.hd, a.ll_att, 1, 0, tag, nullptr, 0.f, a.ll_flag + 2 * 256, a.nkv * a.nsplit); CSTAMP();
             c.template gemv<FE_RESID, true>(a, a.H, a.nh * a.hd, Ly.o_b, nullptr, best, bi, tag, 0); CSTAMP();
             CSTAMP();
             // P4: h = silu(gate) * up on rmsnorm(x), x = residual + sum over ranks of the o_proj partial sums
-            c.template load_ll<true, true>(a.H, xp_o, a.tp_world, (size_t)a.H, tag, Ly.ln2, a.eps);
+            c.template load_ll<true, true>(a.H, xp_o, a.tp_world, (size_t)a.H, tag, Ly.ln2, a.eps, a.ll_flag_xp[0][a.tp_rank], (int)gridDim.x);
             CSTAMP();
             c.template gemv<FE_SWIGLU, true>(a, 2 * a.I, a.H, nullptr, nullptr, best, bi, tag); CSTAMP();
             CSTAMP();
             // P5: down partial sums (this rank's slice of the intermediate dimension) -> every rank
-            c.template load_ll<false, false>(a.I, a.ll_h, 1, 0, tag, nullptr, 0.f); CSTAMP();
+            c.template load_ll<false, false>(a.I, a.ll_h, 1, 0, tag, nullptr, 0.f, a.ll_flag + 3 * 256, (int)gridDim.x); CSTAMP();
             c.template gemv<FE_RESID, true>(a, a.H, a.I, nullptr, nullptr, best, bi, tag, 1); CSTAMP();
             CSTAMP();
         } else {
@@ -1035,7 +1117,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
         }
     }
     // final: logits = lm_head . rmsnorm(x) over this rank's vocabulary shard, per-CTA argmax candidate
-    if constexpr (LL) c.template load_ll<true, true>(a.H, a.ll_xp[1][a.tp_rank], a.tp_world, (size_t)a.H, a.ll_tag + (uint32_t)a.L - 1u, a.final_norm, a.eps);
+    if constexpr (LL) c.template load_ll<true, true>(a.H, a.ll_xp[1][a.tp_rank], a.tp_world, (size_t)a.H, a.ll_tag + (uint32_t)a.L - 1u, a.final_norm, a.eps, a.ll_flag_xp[1][a.tp_rank], (int)gridDim.x);
     else c.load_x(a.H, a.x, nullptr, a.final_norm, a.eps);
     best = -INFINITY; bi = 0x7fffffff;
     c.template gemv<FE_LOGITS>(a, a.V_l, a.H, nullptr, a.logits + a.v0, best, bi, 0, 0, a.v0); CSTAMP();

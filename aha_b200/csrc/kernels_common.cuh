@@ -112,6 +112,8 @@ struct DecodeState {
     int32_t pos;         // seqlen_offset of the next step (= tokens already cached)
     int32_t rope_delta;  // Qwen3-VL rope_deltas (0 for text / ASR)
     int32_t n_hist;      // tokens written to history
+    uint32_t n_draws;    // random draws the request's sampler has consumed (index into its ChaCha12 stream)
+    uint32_t pad_[3];
 };
 __global__ void argmax_final_kernel(const float* __restrict__ pmax, const int* __restrict__ pidx, int n,
                                     uint32_t* __restrict__ argmax_out, DecodeState* __restrict__ st,
@@ -129,6 +131,7 @@ __global__ void argmax_final_kernel(const float* __restrict__ pmax, const int* _
         if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
     }
     if (threadIdx.x == 0) {
+        if (bi == 0x7fffffff) bi = 0;   // every candidate NaN: publish a valid id
         if (argmax_out) *argmax_out = (uint32_t)bi;
         if (advance && st) {
             st->token = (uint32_t)bi;

@@ -1,0 +1,158 @@
+// preprocess.cuh -- the host-facing processor pieces of the path: image resize on the GPU, and the integer / scalar host
+// routines of Qwen3VLProcessor and Qwen3AsrProcessor.
+//
+// Replaces (reference):
+//   img_smart_resize                       /root/reference/src/utils/img_utils.rs:297-331 (+ round/floor/ceil_by_factor, utils/mod.rs:392-405)
+//   img.resize_exact(w, h, CatmullRom)     src/models/qwen3vl/processor.rs:167 -> `image` crate 0.25 imageops::resize:
+//                                          vertical_sample into f32, then horizontal_sample back to u8 (third-party, not under
+//                                          /root/reference; restated from its published algorithm, see oracle/qwen3vl.py)
+//   <|image_pad|> / <|audio_pad|> expansion   qwen3vl/processor.rs:386-399, qwen3_asr/processor.rs:93-97 (on token ids here:
+//                                          the tokenizer is outside the path)
+//   float_range_normalize                  src/models/common/modules.rs:1353-1368
+//   split_audio_into_chunks                src/utils/audio_utils.rs:1743-1760
+//   get_feat_extract_output_lengths        src/models/qwen3_asr/processor.rs:187-195
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <stdexcept>
+#include <vector>
+
+#include "common.cuh"
+
+namespace aha {
+
+// ---------------------------------------------------------------------------------------------- img_smart_resize (host, f32 like the reference)
+inline uint32_t round_by_factor(float num, uint32_t factor) { return (uint32_t)std::round(num / (float)factor) * factor; }   // f32::round: half away from zero
+inline uint32_t floor_by_factor(float num, uint32_t factor) { return (uint32_t)std::floor(num / (float)factor) * factor; }
+inline uint32_t ceil_by_factor(float num, uint32_t factor) { return (uint32_t)std::ceil(num / (float)factor) * factor; }
+
+inline void img_smart_resize(uint32_t img_h, uint32_t img_w, uint32_t factor, uint32_t min_pixels, uint32_t max_pixels, uint32_t& h_bar, uint32_t& w_bar) {
+    AHA_REQUIRE(img_h > 0 && img_w > 0 && factor > 0, "img_smart_resize: empty image");
+    if (std::max(img_h, img_w) / std::min(img_h, img_w) > 200) throw std::runtime_error("absolute aspect ratio mush be smaller than 200");
+    h_bar = std::max(factor, round_by_factor((float)img_h, factor));
+    w_bar = std::max(factor, round_by_factor((float)img_w, factor));
+    if ((uint64_t)h_bar * w_bar > max_pixels) {
+        const float beta = std::sqrt((float)(img_h * img_w) / (float)max_pixels);
+        h_bar = std::max(factor, floor_by_factor((float)img_h / beta, factor));
+        w_bar = std::max(factor, floor_by_factor((float)img_w / beta, factor));
+    } else if ((uint64_t)h_bar * w_bar < min_pixels) {
+        const float beta = std::sqrt((float)min_pixels / (float)(img_h * img_w));
+        h_bar = ceil_by_factor((float)img_h * beta, factor);
+        w_bar = ceil_by_factor((float)img_w * beta, factor);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- CatmullRom resize (device)
+// bc_cubic_spline(x, b = 0, c = 0.5) / 6: the coefficients 9, -15, 6 and -3, 15, -24, 12 are what (12 - 9b - 6c) ... evaluate
+// to exactly in f32.  Every product and sum is rounded separately (__fmul_rn / __fadd_rn): the reference is Rust, which never
+// contracts a * b + c into an FMA, and the last bit decides a rounding to u8 now and then.
+__device__ __forceinline__ float catmullrom_kernel(float x) {
+    const float a = fabsf(x);
+    float k;
+    if (a < 1.0f) {
+        const float a2 = __fmul_rn(a, a), a3 = __fmul_rn(a2, a);
+        k = __fadd_rn(__fadd_rn(__fmul_rn(9.0f, a3), __fmul_rn(-15.0f, a2)), 6.0f);
+    } else if (a < 2.0f) {
+        const float a2 = __fmul_rn(a, a), a3 = __fmul_rn(a2, a);
+        k = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(-3.0f, a3), __fmul_rn(15.0f, a2)), __fmul_rn(-24.0f, a)), 12.0f);
+    } else k = 0.0f;
+    return __fdiv_rn(k, 6.0f);
+}
+
+constexpr int kResizeMaxTaps = 64;   // 2 * support * max(1, downscale ratio) + 2: covers a 15x downscale
+
+// One output coordinate of imageops::{vertical,horizontal}_sample: the input window [left, right) and its normalised weights.
+__device__ __forceinline__ void resize_taps(int out_i, int in_n, int out_n, int& left, int& right, float* ws) {
+    const float ratio = __fdiv_rn((float)in_n, (float)out_n);
+    const float sratio = ratio < 1.0f ? 1.0f : ratio;
+    const float src_support = __fmul_rn(2.0f, sratio);            // CatmullRom support = 2
+    float input = __fmul_rn(__fadd_rn((float)out_i, 0.5f), ratio);
+    long long l = (long long)floorf(__fsub_rn(input, src_support));
+    l = l < 0 ? 0 : (l > in_n - 1 ? in_n - 1 : l);
+    long long r = (long long)ceilf(__fadd_rn(input, src_support));
+    r = r < l + 1 ? l + 1 : (r > in_n ? in_n : r);
+    left = (int)l; right = (int)r;
+    input = __fsub_rn(input, 0.5f);
+    float sum = 0.0f;
+    const int n = min(right - left, kResizeMaxTaps);
+    for (int i = 0; i < n; ++i) {
+        const float w = catmullrom_kernel(__fdiv_rn(__fsub_rn((float)(left + i), input), sratio));
+        ws[i] = w;
+        sum = __fadd_rn(sum, w);
+    }
+    for (int i = 0; i < n; ++i) ws[i] = __fdiv_rn(ws[i], sum);
+    right = left + n;
+}
+
+// vertical_sample: u8 HWC (h, w, 3) -> f32 (new_h, w, 3); one block per output row
+__global__ void resize_vertical_kernel(const uint8_t* __restrict__ img, int h, int w, int new_h, float* __restrict__ tmp) {
+    __shared__ float ws[kResizeMaxTaps];
+    __shared__ int lr[2];
+    const int outy = blockIdx.x;
+    if (threadIdx.x == 0) { int l, r; resize_taps(outy, h, new_h, l, r, ws); lr[0] = l; lr[1] = r; }
+    __syncthreads();
+    const int left = lr[0], n = lr[1] - lr[0];
+    for (int xc = threadIdx.x; xc < w * 3; xc += blockDim.x) {
+        float t = 0.0f;
+        for (int i = 0; i < n; ++i) t = __fadd_rn(t, __fmul_rn((float)img[(size_t)(left + i) * w * 3 + xc], ws[i]));
+        tmp[(size_t)outy * w * 3 + xc] = t;
+    }
+}
+// horizontal_sample: f32 (h, w, 3) -> u8 (h, new_w, 3), clamp to [0, 255] and round half away from zero; one block per output column
+__global__ void resize_horizontal_kernel(const float* __restrict__ tmp, int h, int w, int new_w, uint8_t* __restrict__ out) {
+    __shared__ float ws[kResizeMaxTaps];
+    __shared__ int lr[2];
+    const int outx = blockIdx.x;
+    if (threadIdx.x == 0) { int l, r; resize_taps(outx, w, new_w, l, r, ws); lr[0] = l; lr[1] = r; }
+    __syncthreads();
+    const int left = lr[0], n = lr[1] - lr[0];
+    for (int yc = threadIdx.x; yc < h * 3; yc += blockDim.x) {
+        const int y = yc / 3, c = yc % 3;
+        float t = 0.0f;
+        for (int i = 0; i < n; ++i) t = __fadd_rn(t, __fmul_rn(tmp[((size_t)y * w + left + i) * 3 + c], ws[i]));
+        t = fminf(fmaxf(t, 0.0f), 255.0f);
+        out[((size_t)y * new_w + outx) * 3 + c] = (uint8_t)roundf(t);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- placeholder expansion / audio helpers (host)
+// the i-th occurrence of `token_id` becomes counts[i] copies of it; occurrences beyond n_counts stay single
+inline std::vector<uint32_t> expand_placeholders(const uint32_t* ids, size_t n, uint32_t token_id, const uint32_t* counts, size_t n_counts) {
+    std::vector<uint32_t> out;
+    out.reserve(n);
+    size_t k = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if (ids[i] == token_id && k < n_counts) out.insert(out.end(), counts[k++], token_id);
+        else out.push_back(ids[i]);
+    }
+    return out;
+}
+
+inline size_t feat_extract_output_length(size_t audio_len) {
+    const size_t leave = audio_len % 100;
+    if (leave > 0) {
+        const size_t feat = (leave - 1) / 2 + 1;
+        return ((feat - 1) / 2 + 1 - 1) / 2 + 1 + (audio_len / 100) * 13;
+    }
+    return (audio_len / 100) * 13;
+}
+
+inline void float_range_normalize(float* t, size_t n) {
+    float peak = 0.f;
+    for (size_t i = 0; i < n; ++i) peak = std::max(peak, std::fabs(t[i]));
+    if (peak == 0.0f) return;
+    if (peak > 1.0f) { const float mul = (float)(1.0 / (double)peak); for (size_t i = 0; i < n; ++i) t[i] = t[i] * mul; }   // affine(1 / peak as f64, 0)
+    for (size_t i = 0; i < n; ++i) t[i] = std::min(std::max(t[i], -1.0f), 1.0f);
+}
+
+// lengths of the chunks split_audio_into_chunks cuts (the last one is the remainder and may be 0, exactly like the reference)
+inline std::vector<size_t> split_audio_into_chunks(size_t total_len, size_t sr, float max_chunk_sec) {
+    const float total_sec = (float)total_len / (float)sr;
+    if (total_sec <= max_chunk_sec) return {total_len};
+    const size_t max_len = (size_t)std::round(max_chunk_sec * (float)sr);
+    std::vector<size_t> splits(total_len / max_len, max_len);
+    splits.push_back(total_len % max_len);
+    return splits;
+}
+
+}  // namespace aha

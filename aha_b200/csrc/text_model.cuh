@@ -20,6 +20,7 @@
 #include "json.hpp"
 #include "kernels_common.cuh"
 #include "nccl_shim.h"
+#include "sampling.cuh"
 
 namespace aha {
 
@@ -300,7 +301,8 @@ struct TextModel {
     LLPk* ll_peer_sym[kFusedMaxTp] = {};            // the same block of every rank (own entry = ll_sym)
     int* d_ll_abort = nullptr;
     uint32_t ll_launches = 0;
-    size_t ll_sym_packets() const { return (size_t)2 * tp_world * cfg.H + (size_t)tp_world * 2; }
+    uint32_t* ll_flag = nullptr;                    // [4][256] local "data is out" flags
+    size_t ll_sym_packets() const { return (size_t)2 * tp_world * cfg.H + (size_t)tp_world * 2 + (size_t)tp_world * 256; }   // + [2][W][256] u32 flags = W * 256 packets
     FusedLayer* d_fused_layers = nullptr;
     unsigned* d_sync = nullptr;   // [0] grid barrier, [1] final ticket, then kv tickets [nkv]
     unsigned long long* d_ftrace = nullptr;
@@ -308,6 +310,12 @@ struct TextModel {
     int fused_stages = kFusedStages;   // ring depth: re-measured on the final kernel of round 1, 11 slots 773 tok/s vs 8 slots 762 (profiles/README.md)
     int fused_grid = 0, fused_nsplit = 0;
     size_t fused_smem = 0;
+
+    // sampler of the device loop (sampling.cuh); inactive = plain ArgMax, which the step kernels compute themselves
+    bool samp_active = false;
+    SampleArgs samp{};
+    float* sample_work = nullptr;
+    int* d_sample_err = nullptr;
 
     // tracing (tests)
     bool trace = false;
@@ -419,7 +427,9 @@ struct TextModel {
             AHA_REQUIRE(decode_impl < 2 || ok, "fused decode kernel unsupported for this model: " + why);
             AHA_REQUIRE(decode_impl != 3 || tp_world == 1, "the grid-barrier twin of the fused kernel is single-GPU only");
             fused = ok && decode_impl != 1;
-            fused_ll = fused && decode_impl != 3;
+            // auto: one GPU -> the grid-barrier kernel (measured faster there: 774 vs 611 tok/s on the Qwen3-VL-2B stack, profiles/README.md);
+            // tensor parallel -> the packet kernel, whose exchange needs no cross-GPU barrier
+            fused_ll = fused && (decode_impl == 2 || (decode_impl == 0 && tp_world > 1));
         }
         num_pages = ceil_div(max_ctx, kPage);
         page_stride = (size_t)2 * nkv_l * kPage * cfg.hd;
@@ -462,6 +472,9 @@ struct TextModel {
                 AHA_CUDA_CHECK(cudaMemset(sym, 0, ll_sym_packets() * sizeof(LLPk)));
                 ll_sym = reinterpret_cast<LLPk*>(sym);
                 ll_peer_sym[tp_rank] = ll_sym;
+                ll_flag = c.alloc<uint32_t>(4 * 256);
+                AHA_CUDA_CHECK(cudaMemset(ll_flag, 0, 4 * 256 * sizeof(uint32_t)));
+                AHA_REQUIRE(c.num_sms <= 256, "more than 256 SMs");
                 d_ll_abort = c.alloc<int>(1);
                 AHA_CUDA_CHECK(cudaMemset(d_ll_abort, 0, sizeof(int)));
             }
@@ -687,7 +700,11 @@ struct TextModel {
                 fa.ll_xp[0][w] = ll_peer_sym[w];
                 fa.ll_xp[1][w] = ll_peer_sym[w] + (size_t)tp_world * cfg.H;
                 fa.ll_cand[w] = ll_peer_sym[w] + (size_t)2 * tp_world * cfg.H;
+                uint32_t* fl = reinterpret_cast<uint32_t*>(ll_peer_sym[w] + (size_t)2 * tp_world * cfg.H + (size_t)tp_world * 2);
+                fa.ll_flag_xp[0][w] = fl;
+                fa.ll_flag_xp[1][w] = fl + (size_t)tp_world * 256;
             }
+            fa.ll_flag = ll_flag;
             ll_launches += 1;
             fa.ll_tag = ll_launches * 64u;   // layer l -> tag + l (L <= 62); 0 is the "never written" tag of the zeroed buffers
             AHA_REQUIRE(cfg.L <= 62, "fused decode kernel: more than 62 layers");
@@ -707,6 +724,10 @@ struct TextModel {
     // rank's vocabulary shard (the winner is exchanged, not the row), so such a step takes the per-op path, whose lm_head
     // is replicated.
     void decode_step(bool full_logits = false) {
+        decode_step_argmax(full_logits || samp_active);
+        sample(1);
+    }
+    void decode_step_argmax(bool full_logits) {
         Ctx& c = *ctx;
         if (fused && !(full_logits && tp_world > 1)) { decode_step_fused(); return; }
         if (!use_graph) { decode_step_launches(); return; }
@@ -725,8 +746,55 @@ struct TextModel {
         c.cnt.graphs++;
         c.cnt.kernels += step_graph_kernels;
     }
-    void set_state(uint32_t token, int pos, int rope_delta, int n_hist) {
-        DecodeState s{token, pos, rope_delta, n_hist};
+    // ---- sampler.  mode / parameters follow get_logit_processor (sample.rs:7-38); `seed` keys the ChaCha12 stream.
+    void set_sampler(int mode, float temperature, float top_p, int top_k, float penalty, int last_n, uint64_t seed) {
+        const bool pen = !(penalty == 1.0f || last_n == 0);
+        samp_active = mode != SAMPLE_ARGMAX || pen;
+        if (!samp_active) return;
+        AHA_REQUIRE(cfg.V <= kSampleThreads * kSampleChunk, "vocabulary too large for the device sampler");
+        AHA_REQUIRE(!(mode == SAMPLE_TOPK || mode == SAMPLE_TOPK_TOPP) || top_k >= 1, "top_k must be >= 1");
+        AHA_REQUIRE(!(mode == SAMPLE_TOPK || mode == SAMPLE_TOPK_TOPP) || top_k >= cfg.V || top_k <= kSampleMaxTopK,
+                    "top_k > 1024 is not supported by the device sampler");
+        if (!sample_work) {
+            sample_work = ctx->alloc<float>((size_t)cfg.V);
+            d_sample_err = ctx->alloc<int>(1);
+            AHA_CUDA_CHECK(cudaMemset(d_sample_err, 0, sizeof(int)));
+        }
+        samp = SampleArgs{};
+        samp.logits = logits; samp.work = sample_work; samp.V = cfg.V; samp.mode = mode;
+        samp.inv_temp = mode == SAMPLE_ARGMAX ? 1.0f : (float)(1.0 / (double)temperature);
+        samp.top_p = top_p; samp.top_k = top_k; samp.penalty = penalty; samp.last_n = last_n;
+        // rand_core::SeedableRng::seed_from_u64: eight PCG32 outputs fill the 32-byte ChaCha seed
+        uint64_t stt = seed;
+        for (int i = 0; i < 8; ++i) {
+            stt = stt * 6364136223846793005ull + 11634580027462260723ull;
+            const uint32_t xs = (uint32_t)(((stt >> 18) ^ stt) >> 27);
+            const uint32_t rot = (uint32_t)(stt >> 59);
+            samp.key[i] = (xs >> rot) | (xs << ((32u - rot) & 31u));
+        }
+        samp.st = d_state; samp.history = d_history; samp.hist_cap = hist_cap; samp.token_out = d_argmax; samp.error = d_sample_err;
+    }
+    void clear_sampler() { samp_active = false; }
+    // overwrite = 1: the step kernel has already pushed its ArgMax token; the sampled token replaces it
+    void sample(int overwrite) {
+        if (!samp_active) return;
+        SampleArgs a = samp;
+        a.overwrite = overwrite;
+        sample_kernel<<<1, kSampleThreads, 0, ctx->stream>>>(a);
+        AHA_CUDA_CHECK(cudaGetLastError());
+        ctx->cnt.kernels++;
+    }
+    void check_sample_error() {
+        if (!d_sample_err || !samp_active) return;
+        int e = 0;
+        AHA_CUDA_CHECK(cudaMemcpy(&e, d_sample_err, sizeof(int), cudaMemcpyDeviceToHost));
+        if (e) {
+            cudaMemset(d_sample_err, 0, sizeof(int));
+            throw std::runtime_error("sampler: the token weights are all zero or not finite (rand::distr::weighted::WeightedIndex::new fails in the reference)");
+        }
+    }
+    void set_state(uint32_t token, int pos, int rope_delta, int n_hist, uint32_t n_draws = 0) {
+        DecodeState s{token, pos, rope_delta, n_hist, n_draws, {0, 0, 0}};
         AHA_CUDA_CHECK(cudaMemcpyAsync(d_state, &s, sizeof(s), cudaMemcpyHostToDevice, ctx->stream));
         AHA_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // `s` is a stack temporary
     }

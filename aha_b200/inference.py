@@ -141,23 +141,86 @@ class B200Model:
         self._lib.aha_b200_stop_token_ids(self._h, out, n)
         return [int(out[i]) for i in range(n)]
 
-    # ------------------------------------------------------------------ generate_generic
-    def generate(self, input_ids, data=None, max_tokens=1024, temperature=0.0, repeat_penalty=1.0, repeat_last_n=64,
-                 seed=299792458):
-        """-> (generated ids, usage dict).  Greedy (ArgMax) only, like `temperature: 0` requests."""
+    # ------------------------------------------------------------------ generate_generic / generate_stream_generic
+    @staticmethod
+    def _gen_params(max_tokens, temperature, top_p, top_k, repeat_penalty, repeat_last_n, seed, flags=0):
+        return L.GenParams(temperature=temperature or 0.0, repeat_penalty=repeat_penalty, repeat_last_n=repeat_last_n,
+                           max_tokens=max_tokens, seed=seed, top_p=top_p or 0.0, top_k=top_k or 0, flags=flags)
+
+    @staticmethod
+    def _usage(u):
+        return dict(prompt_tokens=u.prompt_tokens, completion_tokens=u.completion_tokens, prompt_secs=u.prompt_secs,
+                    completion_secs=u.completion_secs, vision_secs=u.vision_secs)
+
+    def generate(self, input_ids, data=None, max_tokens=1024, temperature=0.0, top_p=None, top_k=None, repeat_penalty=1.0,
+                 repeat_last_n=64, seed=299792458, flags=0):
+        """-> (generated ids, usage dict).  temperature < 1e-7: ArgMax; else the device sampler (TopK / TopKThenTopP / TopP /
+        All exactly as get_logit_processor picks them from temperature, top_p, top_k)."""
         ids = self._ids(input_ids)
         mm, _keep = self._mm(data)
-        p = L.GenParams(temperature=temperature, repeat_penalty=repeat_penalty, repeat_last_n=repeat_last_n,
-                        max_tokens=max_tokens, seed=seed)
-        out = (C.c_uint32 * max_tokens)()
+        p = self._gen_params(max_tokens, temperature, top_p, top_k, repeat_penalty, repeat_last_n, seed, flags)
+        cap = max(max_tokens, 1)
+        out = (C.c_uint32 * cap)()
         n = C.c_size_t(0)
         u = L.Usage()
         self._check(self._lib.aha_b200_generate(self._h, ids.ctypes.data_as(C.POINTER(C.c_uint32)), ids.size,
-                                                C.byref(mm) if mm is not None else None, C.byref(p), out, max_tokens,
+                                                C.byref(mm) if mm is not None else None, C.byref(p), out, cap,
                                                 C.byref(n), C.byref(u)))
-        usage = dict(prompt_tokens=u.prompt_tokens, completion_tokens=u.completion_tokens, prompt_secs=u.prompt_secs,
-                     completion_secs=u.completion_secs, vision_secs=u.vision_secs)
-        return [int(out[i]) for i in range(n.value)], usage
+        return [int(out[i]) for i in range(n.value)], self._usage(u)
+
+    def generate_stream(self, input_ids, on_token, data=None, max_tokens=1024, temperature=0.0, top_p=None, top_k=None,
+                        repeat_penalty=1.0, repeat_last_n=64, seed=299792458):
+        """generate_stream_generic: on_token(token, index) is called per generated token as its step completes; a truthy
+        return value ends the request.  -> usage dict."""
+        ids = self._ids(input_ids)
+        mm, _keep = self._mm(data)
+        p = self._gen_params(max_tokens, temperature, top_p, top_k, repeat_penalty, repeat_last_n, seed)
+        err = []
+
+        def _cb(_user, token, index):
+            try:
+                return 1 if on_token(int(token), int(index)) else 0
+            except Exception as e:  # never unwind through the C ABI
+                err.append(e)
+                return 1
+        cb = L.TOKEN_CALLBACK(_cb)
+        u = L.Usage()
+        self._check(self._lib.aha_b200_generate_stream(self._h, ids.ctypes.data_as(C.POINTER(C.c_uint32)), ids.size,
+                                                       C.byref(mm) if mm is not None else None, C.byref(p), cb, None, C.byref(u)))
+        if err:
+            raise err[0]
+        return self._usage(u)
+
+    def asr_generate(self, chunks, max_tokens=1024, temperature=0.0, top_p=None, seed=34562, on_token=None):
+        """Qwen3AsrGenerateModel::generate: chunks = [(ids, mel), ...] (one AudioData each).  -> (ids of all chunks, usage)."""
+        keep = []
+        arr = (L.AsrChunk * len(chunks))()
+        for i, (ids, mel) in enumerate(chunks):
+            ids = self._ids(ids)
+            mel = np.ascontiguousarray(mel, np.float32)
+            keep += [ids, mel]
+            arr[i].ids = ids.ctypes.data_as(C.POINTER(C.c_uint32))
+            arr[i].seq_len = ids.size
+            arr[i].input_features = L.make_desc(mel)
+        p = self._gen_params(max_tokens, temperature, top_p, None, 1.0, 64, seed)
+        cap = max(max_tokens, 1) * len(chunks)
+        out = (C.c_uint32 * cap)()
+        n = C.c_size_t(0)
+        u = L.Usage()
+        cb = L.TOKEN_CALLBACK((lambda _u, t, i: 1 if on_token(int(t), int(i)) else 0) if on_token else 0)
+        self._check(self._lib.aha_b200_asr_generate(self._h, arr, len(chunks), C.byref(p), out, cap, C.byref(n), cb, None, C.byref(u)))
+        return [int(out[i]) for i in range(n.value)], self._usage(u)
+
+    def debug_sample(self, logits, context=(), draw_index=0, temperature=0.0, top_p=None, top_k=None, repeat_penalty=1.0,
+                     repeat_last_n=64, seed=299792458):
+        """The device sampler on a given logits row (tests)."""
+        lg = np.ascontiguousarray(logits, np.float32).reshape(-1)
+        ctx = np.ascontiguousarray(np.asarray(list(context), dtype=np.uint32))
+        p = self._gen_params(1, temperature, top_p, top_k, repeat_penalty, repeat_last_n, seed)
+        tok = C.c_uint32(0)
+        self._check(self._lib.aha_b200_debug_sample(self._h, lg.ctypes.data_as(C.POINTER(C.c_float)), C.byref(p),
+                                                    ctx.ctypes.data_as(C.POINTER(C.c_uint32)), ctx.size, int(draw_index), C.byref(tok)))
+        return int(tok.value)
 
     # ------------------------------------------------------------------ Qwen3-Embedding / Qwen3-Reranker
     def embed(self, input_ids):
@@ -201,6 +264,29 @@ class B200Model:
         grid = (C.c_uint32 * 3)()
         self._check(self._lib.aha_b200_image_patchify(self._h, img.ctypes.data_as(C.POINTER(C.c_uint8)), h, w,
                                                       out.ctypes.data_as(C.POINTER(C.c_float)), out.size, grid))
+        return out, np.array([[grid[0], grid[1], grid[2]]], dtype=np.uint32)
+
+    def image_resize(self, img_u8_hwc, new_h, new_w):
+        """DynamicImage::resize_exact(new_w, new_h, CatmullRom) on the GPU."""
+        img = np.ascontiguousarray(img_u8_hwc, dtype=np.uint8)
+        h, w, _ = img.shape
+        out = np.empty((new_h, new_w, 3), np.uint8)
+        self._check(self._lib.aha_b200_image_resize(self._h, img.ctypes.data_as(C.POINTER(C.c_uint8)), h, w, new_h, new_w,
+                                                    out.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out
+
+    def image_preprocess(self, img_u8_hwc, min_pixels=65536, max_pixels=16777216):
+        """Qwen3VLProcessor::process_img + process_vision_tensor for an image of any size -> (pixel_values, grid_thw)."""
+        img = np.ascontiguousarray(img_u8_hwc, dtype=np.uint8)
+        h, w, _ = img.shape
+        vc = self.config["vision_config"]
+        from . import processors
+        rh, rw = processors.img_smart_resize(h, w, vc["patch_size"] * vc["spatial_merge_size"], min_pixels, max_pixels)
+        feat = vc["in_channels"] * vc["temporal_patch_size"] * vc["patch_size"] ** 2
+        out = np.empty(((rh // vc["patch_size"]) * (rw // vc["patch_size"]), feat), np.float32)
+        grid = (C.c_uint32 * 3)()
+        self._check(self._lib.aha_b200_image_preprocess(self._h, img.ctypes.data_as(C.POINTER(C.c_uint8)), h, w, min_pixels, max_pixels,
+                                                        out.ctypes.data_as(C.POINTER(C.c_float)), out.size, grid))
         return out, np.array([[grid[0], grid[1], grid[2]]], dtype=np.uint32)
 
     # ------------------------------------------------------------------ introspection (tests / bench)

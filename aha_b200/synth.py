@@ -246,6 +246,14 @@ def vl_prompt_ids(cfg, grid_thw, n_text, seed=3):
     return np.asarray(ids, dtype=np.uint32)
 
 
+def asr_audio_tokens(n_frames):
+    """Audio tokens of `n_frames` log-mel frames: 13 per full 100-frame chunk + three stride-2 convolutions over the rest
+    (get_feat_extract_output_lengths, /root/reference/src/models/qwen3_asr/processor.rs:187-195)."""
+    leave = n_frames % 100
+    tail = ((((leave - 1) // 2 + 1) - 1) // 2 + 1 - 1) // 2 + 1 if leave > 0 else 0
+    return tail + (n_frames // 100) * 13
+
+
 def asr_prompt_ids(cfg, n_audio_tokens, n_text=8, seed=4):
     tk = cfg["thinker_config"]
     special = (tk["audio_token_id"], tk["audio_start_token_id"], tk["audio_end_token_id"])

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define AHA_B200_ABI_VERSION 1
+#define AHA_B200_ABI_VERSION 2
 
 typedef struct aha_model aha_model;
 
@@ -66,20 +66,37 @@ typedef struct aha_options {
     int32_t max_patches;   /* largest ViT patch count (0 = 16384); Qwen3-VL only */
     int32_t max_frames;    /* largest mel frame count (0 = 3000); Qwen3-ASR only */
     int32_t use_graph;     /* 1 = replay the decode step from a CUDA graph (default), 0 = eager launches */
-    int32_t decode_impl;   /* 0 = auto (fused where the model shape allows), 1 = per-op kernels under a CUDA graph (validation
-                            * twin), 2 = persistent fused step kernel required */
+    int32_t decode_impl;   /* 0 = auto (persistent fused step kernel where the model shape allows: grid-barrier version on one GPU,
+                            * tagged-packet version under tensor parallelism), 1 = per-op kernels under a CUDA graph (validation twin),
+                            * 2 = fused, tagged-packet (data-flow) version, 3 = fused, grid-barrier version (single GPU only) */
     int32_t gemm_impl;     /* 0 = auto, 1 = SIMT fp32, 2 = tcgen05 (split-fp16, fp32-exact) */
     const void* tp_comm;   /* opaque: ncclUniqueId bytes (128) when tp_world > 1, else NULL */
     int32_t reserved[8];   /* reserved[0]: prefill attention, 0 = tensor-core (mma, split-fp16) kernel, 1 = fp32 SIMT twin */
 } aha_options;
 
-typedef struct aha_gen_params {      /* ChatCompletionParameters subset used by generate_generic */
-    float temperature;     /* < 1e-7 => ArgMax (sample.rs:13).  Non-greedy is not implemented: error. */
-    float repeat_penalty;  /* 1.0 = off (sample.rs:46) */
-    int32_t repeat_last_n; /* default 64 (generate.rs:47) */
-    uint32_t max_tokens;   /* sample_len (default 1024, generate.rs:408-409) */
-    uint64_t seed;         /* unused for ArgMax */
+typedef struct aha_gen_params {      /* ChatCompletionParameters subset used by generate_generic / GenerationContext::new (generate.rs:32-52) */
+    float temperature;     /* < 1e-7 => Sampling::ArgMax (sample.rs:13), else softmax(logits / temperature) is sampled on the device */
+    float repeat_penalty;  /* 1.0 = off (sample.rs:46); applied to the distinct tokens among the last repeat_last_n generated ones */
+    int32_t repeat_last_n; /* default 64 (generate.rs:47); 0 = off */
+    uint32_t max_tokens;   /* sample_len, already resolved by the caller (default 1024, generate.rs:408-409); 0 and 1 both yield one token */
+    uint64_t seed;         /* StdRng::seed_from_u64(seed) (default 299792458 / 34562 for ASR) */
+    float top_p;           /* <= 0 = None; with top_k: Sampling::TopKThenTopP, without: TopP */
+    int32_t top_k;         /* <= 0 = None; <= 1024 on the device sampler */
+    uint32_t flags;        /* AHA_GEN_* */
+    uint32_t reserved;
 } aha_gen_params;
+#define AHA_GEN_EOS_ON_FIRST 1u  /* the first token ends the request too if it is a stop id (the ASR loop, qwen3_asr/generate.rs:152-168) */
+#define AHA_GEN_CONTINUE_RNG 2u  /* keep drawing from the previous request's random stream (one LogitsProcessor across audio chunks) */
+
+/* generate_stream: called once per generated token, in order, as soon as its step has completed (the device keeps running a few
+ * steps ahead); a non-zero return ends the request (the reference's stream is dropped when the client goes away). */
+typedef int (*aha_token_callback)(void* user, uint32_t token, uint32_t index);
+
+typedef struct aha_asr_chunk {       /* one AudioData of Qwen3AsrProcessor::process_info (qwen3_asr/processor.rs:181-184) */
+    const uint32_t* ids;             /* prompt with the <|audio_pad|> run already expanded */
+    size_t seq_len;
+    aha_tensor_desc input_features;  /* log-mel (num_mel_bins, frames) */
+} aha_asr_chunk;
 
 typedef struct aha_usage {           /* Usage timing split (generate.rs:126-145) */
     uint32_t prompt_tokens;
@@ -133,6 +150,16 @@ int aha_b200_generate(aha_model* m, const uint32_t* ids, size_t seq_len, const a
 /* WhisperFeatureExtractor::call (/root/reference/src/models/feature_extractor/
  * feature_extraction_whisper.rs:65-115): wave (n) f32 host -> log-mel (n_mels, n_frames) f32 host.
  * Returns frames through *n_frames.  Qwen3-ASR handles only. */
+/* generate_stream_generic (common/generate.rs:231-368) minus tokenizer / SSE framing: tokens are delivered through on_token. */
+int aha_b200_generate_stream(aha_model* m, const uint32_t* ids, size_t seq_len, const aha_mm* mm,
+                             const aha_gen_params* params, aha_token_callback on_token, void* user, aha_usage* usage);
+
+/* Qwen3AsrGenerateModel::generate / generate_stream (qwen3_asr/generate.rs:130-268): per-chunk loop, stop on either EOS id
+ * (the handle's stop ids), KV cache cleared per chunk, one sampler for the whole request.  on_token may be NULL. */
+int aha_b200_asr_generate(aha_model* m, const aha_asr_chunk* chunks, size_t n_chunks, const aha_gen_params* params,
+                          uint32_t* out_tokens, size_t cap, size_t* n_out, aha_token_callback on_token, void* user,
+                          aha_usage* usage);
+
 int aha_b200_mel_spectrogram(aha_model* m, const float* wave, size_t n_samples,
                              float* mel_out, size_t mel_cap, size_t* n_frames);
 
@@ -145,6 +172,28 @@ int aha_b200_image_patchify(aha_model* m, const uint8_t* img_hwc, size_t h, size
 /* Qwen3Embedding::embed_one (/root/reference/src/models/qwen3_embedding/mod.rs:50-64): forward_hidden over the ids
  * (offset 0), last-token hidden state after the final RMSNorm, L2-normalised (x / sqrt(sum x^2 + 1e-6),
  * src/models/common/modules.rs:1287-1294); the cache is cleared afterwards.  out: hidden_size floats.  "qwen3" handles. */
+/* ---- processors (host side of Qwen3VLProcessor / Qwen3AsrProcessor; the *_resize / *_preprocess entries run on the GPU) ---- */
+/* img_smart_resize (src/utils/img_utils.rs:297-331): (h, w) -> multiples of `factor` inside the pixel budget.  Host only. */
+int aha_b200_img_smart_resize(uint32_t img_h, uint32_t img_w, uint32_t factor, uint32_t min_pixels, uint32_t max_pixels,
+                              uint32_t* out_h, uint32_t* out_w);
+/* DynamicImage::resize_exact(w, h, FilterType::CatmullRom) of an RGB8 image (qwen3vl/processor.rs:167) */
+int aha_b200_image_resize(aha_model* m, const uint8_t* img_hwc, size_t h, size_t w, size_t new_h, size_t new_w, uint8_t* out_hwc);
+/* Qwen3VLProcessor::process_img + process_vision_tensor for one image of ANY size (qwen3vl/processor.rs:151-251):
+ * img_smart_resize -> CatmullRom resize -> img_transform -> frame duplication -> merge-block patch order */
+int aha_b200_image_preprocess(aha_model* m, const uint8_t* img_hwc, size_t h, size_t w, uint32_t min_pixels, uint32_t max_pixels,
+                              float* pixel_values_out, size_t cap, uint32_t grid_thw_out[3]);
+/* <|image_pad|> / <|audio_pad|> expansion on token ids (qwen3vl/processor.rs:386-399, qwen3_asr/processor.rs:93-97): the i-th
+ * occurrence of token_id becomes counts[i] copies.  out may be NULL to query n_out.  Host only. */
+int aha_b200_expand_placeholders(const uint32_t* ids, size_t n, uint32_t token_id, const uint32_t* counts, size_t n_counts,
+                                 uint32_t* out, size_t cap, size_t* n_out);
+/* get_feat_extract_output_lengths (qwen3_asr/processor.rs:187-195).  Host only. */
+size_t aha_b200_feat_extract_output_length(size_t n_frames);
+/* float_range_normalize (common/modules.rs:1353-1368), in place.  Host only. */
+int aha_b200_float_range_normalize(float* wave, size_t n);
+/* split_audio_into_chunks (utils/audio_utils.rs:1743-1760): chunk lengths in samples.  Host only. */
+int aha_b200_split_audio_into_chunks(size_t total_len, uint32_t sample_rate, float max_chunk_sec, size_t* lens_out, size_t cap,
+                                     size_t* n_out);
+
 int aha_b200_embed(aha_model* m, const uint32_t* ids, size_t seq_len, float* out);
 /* Qwen3Reranker::rerank (/root/reference/src/models/qwen3_reranker/mod.rs:23-31): cosine score of the query embedding
  * against each document embedding (cosine_similarity_no_l2 on unit vectors).  doc_ids holds the documents back to back,
@@ -189,6 +238,9 @@ int aha_b200_decode_steps(aha_model* m, uint32_t first_token, size_t seqlen_offs
 /* Time one kernel of the decode step in isolation (CUDA events on the launching stream), cycling over the
  * layers' weights so that consecutive launches never hit L2.  which = "gemv_gate_up" | "gemv_qkv" |
  * "gemv_down" | "gemv_o" | "gemv_lm_head" | "decode_attn".  bytes_per_launch = algorithmic bytes. */
+/* the device sampler on a given logits row (tests): context = tokens generated so far, draw_index = draws already consumed */
+int aha_b200_debug_sample(aha_model* m, const float* logits, const aha_gen_params* params, const uint32_t* context,
+                          size_t n_context, uint32_t draw_index, uint32_t* token_out);
 int aha_b200_bench_kernel(aha_model* m, const char* which, int iters, double* avg_ms, uint64_t* bytes_per_launch);
 /* Run ONE Linear layer y = epilogue(x W^T + b) through the library's GEMM dispatch on host data (unit tests of the
  * tcgen05 and SIMT kernels against numpy): impl 1 = SIMT fp32, 2 = tcgen05 split-fp16; epi 0 = store, 1 = residual

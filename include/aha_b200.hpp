@@ -204,7 +204,8 @@ public:
     }
     // The whole request with the decode loop on the device (generate_generic semantics, aha_b200_generate).
     std::vector<uint32_t> generate(const std::vector<uint32_t>& ids, const MultiModalData* data, const GenerationContext& ctx, Usage* usage = nullptr) {
-        aha_gen_params p{0.f, ctx.repeat_penalty, (int32_t)ctx.repeat_last_n, (uint32_t)ctx.sample_len, 0};
+        aha_gen_params p{};
+        p.temperature = 0.f; p.repeat_penalty = ctx.repeat_penalty; p.repeat_last_n = (int32_t)ctx.repeat_last_n; p.max_tokens = (uint32_t)ctx.sample_len;
         std::vector<uint32_t> out(ctx.sample_len);
         size_t n = 0;
         aha_usage u{};

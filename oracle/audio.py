@@ -78,7 +78,7 @@ def float_range_normalize(t):
     if peak == 0:
         return t
     if peak > 1.0:
-        t = (t.astype(np.float64) * (1.0 / np.float64(peak))).astype(F32)
+        t = (t.astype(F32) * F32(1.0 / np.float64(peak))).astype(F32)      # Tensor::affine(1 / peak as f64, 0): mul is converted to f32, then v * mul + add in f32
     return np.clip(t, -1.0, 1.0).astype(F32)
 
 
@@ -108,6 +108,16 @@ class WhisperFeatureExtractor:
         if sampling_rate != self.sr:
             raise ValueError("sampling rate mismatch")
         return self.extract_fbank_features(raw_speech)
+
+
+def split_audio_into_chunks(total_len, sr, max_chunk_sec):
+    """audio_utils.rs:1743-1760 -> chunk lengths in samples.  The remainder is pushed even when it is 0 (as in the reference)."""
+    total_sec = F32(total_len) / F32(sr)
+    if total_sec <= F32(max_chunk_sec):
+        return [total_len]
+    q = F32(max_chunk_sec) * F32(sr)
+    max_len = int(np.floor(q + F32(0.5)))           # f32::round on a positive value
+    return [max_len] * (total_len // max_len) + [total_len % max_len]
 
 
 def get_feat_extract_output_lengths(audio_len):

@@ -47,6 +47,71 @@ def img_transform(img_u8_hwc, mean, std):
     return ((x - np.asarray(mean, F32).reshape(3, 1, 1)) / np.asarray(std, F32).reshape(3, 1, 1)).astype(F32)
 
 
+def _catmullrom_kernel(x):
+    """`image` crate 0.25 imageops::sample::catmullrom_kernel = bc_cubic_spline(x, 0.0, 0.5): all f32, no FMA."""
+    a = np.abs(np.asarray(x, F32))
+    a2 = (a * a).astype(F32)
+    a3 = (a2 * a).astype(F32)
+    near = ((F32(9.0) * a3).astype(F32) + (F32(-15.0) * a2).astype(F32)).astype(F32) + F32(6.0)
+    far = (((F32(-3.0) * a3).astype(F32) + (F32(15.0) * a2).astype(F32)).astype(F32) + (F32(-24.0) * a).astype(F32)).astype(F32) + F32(12.0)
+    k = np.where(a < 1, near, np.where(a < 2, far, F32(0))).astype(F32)
+    return (k / F32(6.0)).astype(F32)
+
+
+def _resize_taps(out_i, in_n, out_n, support=2.0):
+    """one output coordinate of imageops::{vertical,horizontal}_sample: (left, normalised weights)."""
+    ratio = F32(in_n) / F32(out_n)
+    sratio = F32(1.0) if ratio < 1 else ratio
+    src_support = F32(support) * sratio
+    inp = (F32(out_i) + F32(0.5)) * ratio
+    left = int(min(max(int(np.floor(inp - src_support)), 0), in_n - 1))
+    right = int(min(max(int(np.ceil(inp + src_support)), left + 1), in_n))
+    inp = F32(inp - F32(0.5))
+    ws = _catmullrom_kernel(((np.arange(left, right, dtype=F32) - inp) / sratio).astype(F32))
+    s = F32(0)
+    for w in ws:
+        s = F32(s + w)
+    return left, (ws / s).astype(F32)
+
+
+def resize_exact_catmullrom(img_u8_hwc, new_h, new_w):
+    """DynamicImage::resize_exact(new_w, new_h, FilterType::CatmullRom) for an RGB8 image (qwen3vl/processor.rs:167).
+    THIRD-PARTY arithmetic (`image` 0.25.10, not under /root/reference), restated from imageops::resize: a copy when the size
+    already matches, else vertical_sample into f32 followed by horizontal_sample back to u8 (clamp to [0, 255], round half away
+    from zero); taps accumulate left to right in f32."""
+    img = np.asarray(img_u8_hwc, np.uint8)
+    h, w, _ = img.shape
+    if (new_h, new_w) == (h, w):
+        return img.copy()
+    tmp = np.zeros((new_h, w, 3), F32)
+    for oy in range(new_h):
+        left, ws = _resize_taps(oy, h, new_h)
+        t = np.zeros((w, 3), F32)
+        for i, wt in enumerate(ws):
+            t = (t + (img[left + i].astype(F32) * wt).astype(F32)).astype(F32)
+        tmp[oy] = t
+    out = np.zeros((new_h, new_w, 3), np.uint8)
+    for ox in range(new_w):
+        left, ws = _resize_taps(ox, w, new_w)
+        t = np.zeros((new_h, 3), F32)
+        for i, wt in enumerate(ws):
+            t = (t + (tmp[:, left + i].astype(F32) * wt).astype(F32)).astype(F32)
+        t = np.clip(t, F32(0), F32(255))
+        out[:, ox] = np.floor(t + F32(0.5)).astype(np.uint8)      # t >= 0: round half away from zero == floor(t + 0.5)
+    return out
+
+
+def expand_placeholders(ids, token_id, counts):
+    """processor.rs:386-399 / qwen3_asr/processor.rs:93-97 on token ids: the i-th occurrence of the pad token becomes counts[i] copies."""
+    out, k = [], 0
+    for t in np.asarray(ids).reshape(-1).tolist():
+        if t == token_id and k < len(counts):
+            out += [t] * int(counts[k]); k += 1
+        else:
+            out.append(t)
+    return np.asarray(out, np.uint32)
+
+
 def process_vision_tensor(img_tchw, patch_size=16, temporal_patch_size=2, merge_size=2):
     """processor.rs:174-227: (t,c,h,w) -> (grid_t*grid_h*grid_w, c*tp*p*p), grid_thw (1,3)."""
     t = img_tchw.shape[0]
@@ -66,13 +131,12 @@ def process_vision_tensor(img_tchw, patch_size=16, temporal_patch_size=2, merge_
 
 def process_image(img_u8_hwc, mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5), patch_size=16, temporal_patch_size=2,
                   merge_size=2, min_pixels=65536, max_pixels=16777216):
-    """processor.rs:151-172,229-251 for one image whose size already satisfies img_smart_resize
-    (the CatmullRom `resize_exact` of the `image` crate is then the identity; non-identity resize is
-    out of scope).  The frame is duplicated (T=2) -- processor.rs:240."""
+    """processor.rs:151-172,229-251 for one image: img_smart_resize -> CatmullRom resize_exact -> img_transform; the frame
+    is duplicated (T=2) -- processor.rs:240."""
     h, w = img_u8_hwc.shape[:2]
     rh, rw = img_smart_resize(h, w, patch_size * merge_size, min_pixels, max_pixels)
     if (rh, rw) != (h, w):
-        raise ValueError(f"oracle requires pre-resized input: {(h, w)} -> {(rh, rw)}")
+        img_u8_hwc = resize_exact_catmullrom(img_u8_hwc, rh, rw)
     x = img_transform(img_u8_hwc, mean, std)[None]
     x = np.concatenate([x, x], axis=0)
     return process_vision_tensor(x, patch_size, temporal_patch_size, merge_size)

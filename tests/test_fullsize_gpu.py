@@ -169,11 +169,11 @@ def test_vl2_1080p_matches_the_full_size_oracle_golden(vl2, impl):
         t = m.debug_read("image_embeds", i, ne).reshape(2040, 2048)
         e = float(np.abs(t[g[f"embeds{i}_rows"]] - g[f"embeds{i}_sample"]).max())
         assert e <= TOL, f"image_embeds[{i}] differs from the oracle by {e}"
-        assert abs(float(np.abs(t.astype(np.float64)).sum()) - float(g[f"embeds{i}_abs"])) <= 1e-5 * float(g[f"embeds{i}_abs"])
+        assert abs(float(np.abs(t.astype(np.float64)).sum()) - float(g[f"embeds{i}_abs"])) <= 1e-4 * float(g[f"embeds{i}_abs"])
     _check_chain(m, g, len(ids), logits, f"VL2 1080p+512 (decode_impl={impl})")
 
 
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1, 2])
 def test_q06_2k_matches_the_full_size_oracle_golden(impl):
     Q06_PROMPT = synth.FULL_Q06_PROMPT
     g = _golden("full_q06.npz")
@@ -208,7 +208,7 @@ def test_asr06_30s_matches_the_full_size_oracle_golden():
         feat = m.debug_read("audio_embeds", 0, n_tok * 1024).reshape(n_tok, 1024)
         e = float(np.abs(feat[g["audio_rows"]] - g["audio_sample"]).max())
         assert e <= TOL, f"audio tower output differs from the oracle by {e}"
-        assert abs(float(np.abs(feat.astype(np.float64)).sum()) - float(g["audio_abs"])) <= 1e-5 * float(g["audio_abs"])
+        assert abs(float(np.abs(feat.astype(np.float64)).sum()) - float(g["audio_abs"])) <= 1e-4 * float(g["audio_abs"])
         _check_chain(m, g, len(ids), logits, "ASR-0.6 30 s")
     finally:
         m.close()
