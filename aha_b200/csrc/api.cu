@@ -315,7 +315,7 @@ int aha_b200_create(const char* kind, const char* config_json, const aha_tensor_
         m->ctx.device = o.device;
         m->ctx.num_sms = prop.multiProcessorCount;
         m->ctx.gemm_impl = o.gemm_impl;
-        m->ctx.attn_impl = o.reserved[0];   // 0 = tensor-core flash attention, 1 = fp32 SIMT twin
+        m->ctx.attn_impl = o.reserved[0];   // 0 = tensor-core flash attention (tcgen05 for head_dim 64), 1 = fp32 SIMT twin, 2 = mma.sync kernel everywhere
         AHA_CUDA_CHECK(cudaSetDevice(o.device));
         AHA_CUDA_CHECK(cudaStreamCreateWithFlags(&m->ctx.stream, cudaStreamNonBlocking));
         AHA_CUDA_CHECK(cudaEventCreate(&m->ev0));
@@ -324,6 +324,7 @@ int aha_b200_create(const char* kind, const char* config_json, const aha_tensor_
         for (auto& e : m->ev_tok) AHA_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         gemv_init();
         gemm_tc_init();
+        flash_attn_tc_init();
         const std::string k = kind;
         const std::string cfg_text = config_json;
         Json root = JsonParser(cfg_text).parse();

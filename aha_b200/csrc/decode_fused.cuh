@@ -290,6 +290,11 @@ __device__ __forceinline__ unsigned atom_acq_rel_add(unsigned* p, unsigned v) {
     return old;
 }
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
 // Grid barrier joined by the consumer threads only: one arrival counter in L2 (zeroed by the host before every
 // launch), polled by consumer thread 0 with relaxed loads; activations are always read with ld.global.cg.
@@ -311,9 +316,15 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& seq, i
             AHA_SYNC_STAMP(sy, seq, 2, 8);
             const unsigned target = (seq + 1u) * gridDim.x;
             unsigned polls = 0;
+#ifdef AHA_BARRIER_LDACQ
+            // A/B variant: acquire loads in the poll instead of a relaxed poll + fence.acq_rel (0.4 us per barrier in the anatomy trace)
+            while (ld_acquire_u32(counter) < target) { ++polls; }
+            AHA_SYNC_STAMP(sy, seq, 3, 8);
+#else
             while (ld_relaxed_u32(counter) < target) { ++polls; }
             AHA_SYNC_STAMP(sy, seq, 3, 8);
             fence_acq_rel_gpu();
+#endif
             AHA_SYNC_STAMP(sy, seq, 4, 8);
 #ifdef AHA_STAGE_TRACE
             if (sy && seq < 400u) sy[(size_t)seq * 8 + 6] = polls;

@@ -12,6 +12,7 @@
 #include "../../include/aha_b200.h"
 #include "attention.cuh"
 #include "attention_mma.cuh"
+#include "attention_tc.cuh"
 #include "decode_fused.cuh"
 #include "common.cuh"
 #include "gemm_simt.cuh"
@@ -37,7 +38,7 @@ struct Ctx {  // per-handle launch context
     bool capturing = false;
     std::vector<void*> allocs;
     size_t alloc_bytes = 0;
-    int attn_impl = 0;            // 0 = auto (tensor-core flash attention), 1 = fp32 SIMT flash attention
+    int attn_impl = 0;            // 0 = auto (tcgen05 flash attention for head_dim 64, mma.sync for 128), 1 = fp32 SIMT flash attention, 2 = mma.sync everywhere
     int gemm_impl = 0;            // 0 = auto (tcgen05 where the shape tiles), 1 = SIMT fp32, 2 = tcgen05 required
     __half* split_ws = nullptr;   // [2][rows*K] hi | lo halves of the activation operand
     size_t split_cap = 0;         // halfs per half-buffer
@@ -151,6 +152,7 @@ struct LinearW {
 template <int HD>
 inline void flash_dispatch(Ctx& c, const FlashArgs& a, int nheads, bool causal) {
     if (c.attn_impl == 1) flash_attn<HD>(c.stream, a, nheads, causal);
+    else if (HD == 64 && c.attn_impl == 0) { flash_attn_tc(c.stream, a, nheads, causal, c.split_buf((flash_tc_ws_halfs(a, nheads) + 1) / 2)); c.cnt.kernels++; }
     else { flash_attn_mma<HD>(c.stream, a, nheads, causal, c.split_buf((flash_mma_ws_halfs<HD>(a, nheads) + 1) / 2)); c.cnt.kernels++; }
     c.cnt.kernels++;
 }

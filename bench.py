@@ -463,8 +463,8 @@ def main():
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 16, "d2h_bytes_per_step": 4,
                         "with_logits_d2h_tokens_per_s": 1.0 / r["e2e_logits_s"], "logits_bytes": 4 * tc["vocab_size"]},
                 "roofline": roof,
-                "decode_impl": ("fused persistent kernel, phases exchange tagged packets (no grid barrier)" if fused and args.decode_impl != 3 else
-                                "fused persistent kernel, grid barriers" if fused else "per-op kernels (CUDA graph)"),
+                "decode_impl": ("fused persistent kernel, phases exchange tagged packets (no grid barrier)" if fused and args.decode_impl == 2 else
+                                "fused persistent kernel, grid barriers between phases" if fused else "per-op kernels (CUDA graph)"),
                 "cpu_baseline": cpu_base}
         if tp_rec is not None:
             line["tp"] = tp_rec

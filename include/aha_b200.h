@@ -71,7 +71,7 @@ typedef struct aha_options {
                             * 2 = fused, tagged-packet (data-flow) version, 3 = fused, grid-barrier version (single GPU only) */
     int32_t gemm_impl;     /* 0 = auto, 1 = SIMT fp32, 2 = tcgen05 (split-fp16, fp32-exact) */
     const void* tp_comm;   /* opaque: ncclUniqueId bytes (128) when tp_world > 1, else NULL */
-    int32_t reserved[8];   /* reserved[0]: prefill attention, 0 = tensor-core (mma, split-fp16) kernel, 1 = fp32 SIMT twin */
+    int32_t reserved[8];   /* reserved[0]: prefill attention, 0 = tensor cores (tcgen05 kernel for head_dim 64, mma.sync for 128; split-fp16), 1 = fp32 SIMT twin, 2 = mma.sync kernel everywhere */
 } aha_options;
 
 typedef struct aha_gen_params {      /* ChatCompletionParameters subset used by generate_generic / GenerationContext::new (generate.rs:32-52) */

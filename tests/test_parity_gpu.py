@@ -267,6 +267,28 @@ def test_vl_vision_tower_blocks(vl):
     o.visual.trace = None
 
 
+def test_vl_attention_implementations_agree(vl):
+    """ViT attention: tcgen05 kernel (default for head_dim 64) == mma.sync kernel == fp32 SIMT twin on a two-image (varlen) prompt
+    whose segment lengths are not multiples of the 128-query / 64-key tiles."""
+    cfg, w, m, o = vl
+    pv, grid, ids = _vl_inputs(cfg, [(256, 320), (352, 288)], 5)
+    m.clear_cache()
+    m.forward_initial(ids, 0, [pv, grid, None, None, None])
+    n = pv.shape[0] // 4 * cfg["vision_config"]["out_hidden_size"]
+    base = m.debug_read("image_embeds", 0, n)
+    o.clear_cache()
+    want, _ = o.visual.forward(pv, grid)
+    assert np.abs(base - want.reshape(-1)).max() <= 1e-4
+    for impl in (1, 2):
+        _, _, m2 = make_model("qwen3vl", "tiny", max_ctx=1024, max_patches=2048, attn_impl=impl)
+        try:
+            m2.forward_initial(ids, 0, [pv, grid, None, None, None])
+            other = m2.debug_read("image_embeds", 0, n)
+            assert np.abs(base - other).max() <= 1e-4, impl
+        finally:
+            m2.close()
+
+
 def test_vl_text_only_prompt(vl):
     cfg, w, m, o = vl
     ids = _ids(12, 1000, 3)
