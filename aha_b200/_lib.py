@@ -119,8 +119,22 @@ def load():
     return lib
 
 
+class BF16(np.ndarray):
+    """uint16 array whose elements are bfloat16 bit patterns (numpy has no bf16 dtype): `arr.view(BF16)` marks it for make_desc."""
+
+
+def to_bf16(x):
+    """float32 -> bfloat16 bits (round to nearest even), tagged as BF16."""
+    u = np.ascontiguousarray(x, np.float32).view(np.uint32)
+    return ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint16).view(BF16)
+
+
 def make_desc(arr, name=None):
     """TensorDesc for a C-contiguous numpy array (the caller keeps `arr` alive)."""
+    if isinstance(arr, BF16):
+        d = make_desc(arr.view(np.ndarray).view(np.float16), name)     # same bytes; only the dtype tag differs
+        d.dtype = AHA_BF16
+        return d
     if arr.dtype not in _NP2AHA:
         raise TypeError(f"unsupported dtype {arr.dtype}")
     if not arr.flags["C_CONTIGUOUS"]:

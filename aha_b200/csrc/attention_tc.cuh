@@ -11,7 +11,9 @@
 // TMEM columns each) so that one CTA's tensor work overlaps the other's softmax:
 //   warp 4 (one elected lane): TMA loads (Q once; K and V^T tiles single-buffered, re-issued the moment the MMA that
 //     read them has completed) and all tcgen05.mma: S[128 x 64] = Q K^T (12 UMMA M128 N64 K16 = 4 k-steps x 3 products)
-//     into TMEM columns 0..63, then PV[128 x 64] = P V (12 more) into columns 64..127; tcgen05.commit -> mbarriers;
+//     into one of TWO S buffers in TMEM (S runs a tile ahead of the softmax), PV[128 x 64] = P V (12 more) into a third
+//     64-column buffer, issued as soon as P is complete so that it executes under the next tile's softmax;
+//     tcgen05.commit -> mbarriers;
 //   warps 0-3: one thread per query row (= TMEM lane): tcgen05.ld its S row, scale / mask / online softmax in fp32, split
 //     P into fp16 hi | lo and store it to shared memory in the K-major SWIZZLE_128B layout the MMA descriptors expect,
 //     fence.proxy.async + arrive; later tcgen05.ld the PV row and fold it into the fp32 output row kept in registers.
@@ -120,8 +122,8 @@ __global__ void __launch_bounds__(kFaThreads, 2) flash_attn_tc_kernel(const __gr
     uint8_t* Vh = Kl + kKBytes;       uint8_t* Vl = Vh + kVBytes;
     uint8_t* Ph = Vl + kVBytes;       uint8_t* Pl = Ph + kPBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(Pl + kPBytes);
-    uint64_t *bar_q = bars, *bar_k = bars + 1, *bar_v = bars + 2, *bar_s = bars + 3, *bar_o = bars + 4, *bar_p = bars + 5;
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 6);
+    uint64_t *bar_q = bars, *bar_k = bars + 1, *bar_v = bars + 2, *bar_o = bars + 3, *bar_p = bars + 4, *bar_s = bars + 5;   // bar_s[2]: one per S buffer
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 7);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int head = blockIdx.y, kvh = head / a.groups;
@@ -132,20 +134,21 @@ __global__ void __launch_bounds__(kFaThreads, 2) flash_attn_tc_kernel(const __gr
     const int ntiles = (kv_end + BKV - 1) / BKV;
 
     if (tid == 0) {
-        mbar_init(bar_q, 1); mbar_init(bar_k, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1); mbar_init(bar_p, BQ);
+        mbar_init(bar_q, 1); mbar_init(bar_k, 1); mbar_init(bar_v, 1); mbar_init(&bar_s[0], 1); mbar_init(&bar_s[1], 1); mbar_init(bar_o, 1); mbar_init(bar_p, BQ);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {   // TMEM: 64 columns for S + 64 for the PV tile
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "n"(128) : "memory");
+    if (warp == 4) {   // TMEM: 2 x 64 columns for the S buffers + 64 for the PV tile (256 allocated: a power of two; two CTAs fill the SM's 512)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "n"(256) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_s = *tmem_holder, tmem_o = tmem_s + 64u;
+    const uint32_t tmem_s = *tmem_holder, tmem_o = tmem_s + 128u;
 
     if (warp == 4) {
-        // ======================= control lane: TMA + MMA issue
+        // ======================= control lane: TMA + MMA issue.  S runs ONE TILE AHEAD of the softmax (two S buffers in TMEM) and
+        // PV(t - 1) is issued the moment P(t - 1) is complete, so both MMAs execute under the softmax threads' arithmetic.
         if (lane == 0) {
             const int qrow = head * a.Sq + qt0, krow = kvh * a.Skv, vrow = kvh * HD;
             mbar_expect_tx(bar_q, 2 * kQBytes);
@@ -160,43 +163,55 @@ __global__ void __launch_bounds__(kFaThreads, 2) flash_attn_tc_kernel(const __gr
             const uint32_t idesc = umma_idesc_f16(BQ, 64);
             const uint64_t d_qh = umma_desc_sw128(Qh), d_ql = umma_desc_sw128(Ql), d_kh = umma_desc_sw128(Kh), d_kl = umma_desc_sw128(Kl);
             const uint64_t d_vh = umma_desc_sw128(Vh), d_vl = umma_desc_sw128(Vl), d_ph = umma_desc_sw128(Ph), d_pl = umma_desc_sw128(Pl);
-            mbar_wait(bar_q, 0);
-            for (int t = 0; t < ntiles; ++t) {
-                const uint32_t ph = (uint32_t)(t & 1);
-                mbar_wait(bar_k, ph);
-                tc_fence_after();
+            auto issue_s = [&](int t) {                          // S(t) = Qh Kh^T + Qh Kl^T + Ql Kh^T into S buffer t & 1
+                const uint32_t dst = tmem_s + (uint32_t)((t & 1) * 64);
 #pragma unroll
-                for (int ks = 0; ks < HD / 16; ++ks) {           // S = Qh Kh^T + Qh Kl^T + Ql Kh^T
+                for (int ks = 0; ks < HD / 16; ++ks) {
                     const uint64_t adv = (uint64_t)((ks * 32) >> 4);
-                    umma_f16(tmem_s, d_qh + adv, d_kh + adv, idesc, ks > 0 ? 1u : 0u);
-                    umma_f16(tmem_s, d_qh + adv, d_kl + adv, idesc, 1u);
-                    umma_f16(tmem_s, d_ql + adv, d_kh + adv, idesc, 1u);
+                    umma_f16(dst, d_qh + adv, d_kh + adv, idesc, ks > 0 ? 1u : 0u);
+                    umma_f16(dst, d_qh + adv, d_kl + adv, idesc, 1u);
+                    umma_f16(dst, d_ql + adv, d_kh + adv, idesc, 1u);
                 }
-                umma_commit(bar_s);
-                mbar_wait(bar_s, ph);                            // the K tile has been read: fetch the next one under the softmax
-                if (t + 1 < ntiles) {
-                    mbar_expect_tx(bar_k, 2 * kKBytes);
-                    tma_load_2d(Kh, &tm_kh, 0, krow + (t + 1) * BKV, bar_k);
-                    tma_load_2d(Kl, &tm_kl, 0, krow + (t + 1) * BKV, bar_k);
-                }
-                mbar_wait(bar_p, ph);                            // P (hi | lo) of this tile is in shared memory
-                mbar_wait(bar_v, ph);
+                umma_commit(&bar_s[t & 1]);
+            };
+            auto issue_pv = [&](int t) {                         // PV(t) = Ph Vh + Ph Vl + Pl Vh   (B = V^T tile, K-major over the kv tokens)
+                mbar_wait(bar_p, (uint32_t)(t & 1));             // P(t) is in shared memory; S buffer (t + 1) & 1 ... and PV(t - 1) have been read
+                mbar_wait(bar_v, (uint32_t)(t & 1));
                 tc_fence_after();
 #pragma unroll
-                for (int ks = 0; ks < BKV / 16; ++ks) {          // PV = Ph Vh + Ph Vl + Pl Vh   (B = V^T tile, K-major over the kv tokens)
+                for (int ks = 0; ks < BKV / 16; ++ks) {
                     const uint64_t adv = (uint64_t)((ks * 32) >> 4);
                     umma_f16(tmem_o, d_ph + adv, d_vh + adv, idesc, ks > 0 ? 1u : 0u);
                     umma_f16(tmem_o, d_ph + adv, d_vl + adv, idesc, 1u);
                     umma_f16(tmem_o, d_pl + adv, d_vh + adv, idesc, 1u);
                 }
                 umma_commit(bar_o);
-                mbar_wait(bar_o, ph);                            // the V tile has been read
+            };
+            mbar_wait(bar_q, 0);
+            mbar_wait(bar_k, 0);
+            tc_fence_after();
+            issue_s(0);
+            for (int t = 0; t < ntiles; ++t) {
+                mbar_wait(&bar_s[t & 1], (uint32_t)((t >> 1) & 1));   // S(t) done: the K tile is free, fetch K(t + 1)
                 if (t + 1 < ntiles) {
+                    mbar_expect_tx(bar_k, 2 * kKBytes);
+                    tma_load_2d(Kh, &tm_kh, 0, krow + (t + 1) * BKV, bar_k);
+                    tma_load_2d(Kl, &tm_kl, 0, krow + (t + 1) * BKV, bar_k);
+                }
+                if (t >= 1) issue_pv(t - 1);                     // runs under the softmax of tile t
+                if (t + 1 < ntiles) {                            // S(t + 1) into the other buffer (its last reader, softmax(t - 1), has arrived at bar_p(t - 1))
+                    mbar_wait(bar_k, (uint32_t)((t + 1) & 1));
+                    tc_fence_after();
+                    issue_s(t + 1);
+                }
+                if (t >= 1) {
+                    mbar_wait(bar_o, (uint32_t)((t - 1) & 1));    // PV(t - 1) done: the V tile is free, fetch V(t)
                     mbar_expect_tx(bar_v, 2 * kVBytes);
-                    tma_load_2d(Vh, &tm_vh, (t + 1) * BKV, vrow, bar_v);
-                    tma_load_2d(Vl, &tm_vl, (t + 1) * BKV, vrow, bar_v);
+                    tma_load_2d(Vh, &tm_vh, t * BKV, vrow, bar_v);
+                    tma_load_2d(Vl, &tm_vl, t * BKV, vrow, bar_v);
                 }
             }
+            issue_pv(ntiles - 1);
         }
         __syncwarp();
     } else {
@@ -206,19 +221,20 @@ __global__ void __launch_bounds__(kFaThreads, 2) flash_attn_tc_kernel(const __gr
         float o[HD];
 #pragma unroll
         for (int c = 0; c < HD; ++c) o[c] = 0.f;
-        float m = -INFINITY, l = 0.f;
+        float m = -INFINITY, l = 0.f;                            // m in the log2 domain: exp(x) = 2^(x * log2 e)
+        const float scale_log2 = a.scaling * 1.4426950408889634f;
         uint8_t* prow_h = Ph + (size_t)row * 128;
         uint8_t* prow_l = Pl + (size_t)row * 128;
         for (int t = 0; t < ntiles; ++t) {
-            const uint32_t ph = (uint32_t)(t & 1);
             const int kt0 = t * BKV;
-            mbar_wait(bar_s, ph);
+            mbar_wait(&bar_s[t & 1], (uint32_t)((t >> 1) & 1));
             tc_fence_after();
             float s[BKV];
             {
+                const uint32_t src = tmem_s + (uint32_t)((t & 1) * 64) + lane_base;
                 float v0[32], v1[32];
-                tmem_ld32(tmem_s + lane_base, v0);
-                tmem_ld32(tmem_s + lane_base + 32u, v1);
+                tmem_ld32(src, v0);
+                tmem_ld32(src + 32u, v1);
 #pragma unroll
                 for (int c = 0; c < 32; ++c) { s[c] = v0[c]; s[32 + c] = v1[c]; }
             }
@@ -226,19 +242,28 @@ __global__ void __launch_bounds__(kFaThreads, 2) flash_attn_tc_kernel(const __gr
 #pragma unroll
             for (int c = 0; c < BKV; ++c) {
                 const int kj = kt0 + c;
-                float v = s[c] * a.scaling;
+                float v = s[c] * scale_log2;
                 if (kj >= a.Skv || (CAUSAL && kj > qi + causal_shift)) v = -INFINITY;
                 s[c] = v;
                 rmax = fmaxf(rmax, v);
             }
             const float mn = fmaxf(m, rmax);
             const float mu = (mn == -INFINITY) ? 0.f : mn;
-            const float alpha = expf(m - mu);
+            const float alpha = exp2f(m - mu);
             float rs = 0.f;
 #pragma unroll
-            for (int c = 0; c < BKV; ++c) { s[c] = expf(s[c] - mu); rs += s[c]; }
+            for (int c = 0; c < BKV; ++c) { s[c] = exp2f(s[c] - mu); rs += s[c]; }
             l = l * alpha + rs;
             m = mn;
+            if (t >= 1) {   // PV(t - 1) ran under the arithmetic above; it also has to be done before P(t) may overwrite P(t - 1)
+                mbar_wait(bar_o, (uint32_t)((t - 1) & 1));
+                tc_fence_after();
+                float v0[32], v1[32];
+                tmem_ld32(tmem_o + lane_base, v0);
+                tmem_ld32(tmem_o + lane_base + 32u, v1);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) { o[c] = (o[c] + v0[c]) * alpha; o[32 + c] = (o[32 + c] + v1[c]) * alpha; }
+            }
             // P row -> shared memory, K-major SWIZZLE_128B: 16-byte chunk j of row r sits at chunk (j ^ (r & 7))
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -251,17 +276,15 @@ __global__ void __launch_bounds__(kFaThreads, 2) flash_attn_tc_kernel(const __gr
             fence_proxy_async_smem();      // generic-proxy stores -> visible to the tensor core's async-proxy reads
             tc_fence_before();
             mbar_arrive(bar_p);
-#pragma unroll
-            for (int c = 0; c < HD; ++c) o[c] *= alpha;
-            mbar_wait(bar_o, ph);
+        }
+        {
+            mbar_wait(bar_o, (uint32_t)((ntiles - 1) & 1));
             tc_fence_after();
-            {
-                float v0[32], v1[32];
-                tmem_ld32(tmem_o + lane_base, v0);
-                tmem_ld32(tmem_o + lane_base + 32u, v1);
+            float v0[32], v1[32];
+            tmem_ld32(tmem_o + lane_base, v0);
+            tmem_ld32(tmem_o + lane_base + 32u, v1);
 #pragma unroll
-                for (int c = 0; c < 32; ++c) { o[c] += v0[c]; o[32 + c] += v1[c]; }
-            }
+            for (int c = 0; c < 32; ++c) { o[c] += v0[c]; o[32 + c] += v1[c]; }
             tc_fence_before();
         }
         if (qi < a.Sq) {
@@ -275,7 +298,7 @@ __global__ void __launch_bounds__(kFaThreads, 2) flash_attn_tc_kernel(const __gr
     __syncthreads();
     if (warp == 4) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_s), "n"(128) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_s), "n"(256) : "memory");
     }
 }
 

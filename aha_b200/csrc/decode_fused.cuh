@@ -316,8 +316,10 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& seq, i
             AHA_SYNC_STAMP(sy, seq, 2, 8);
             const unsigned target = (seq + 1u) * gridDim.x;
             unsigned polls = 0;
-#ifdef AHA_BARRIER_LDACQ
-            // A/B variant: acquire loads in the poll instead of a relaxed poll + fence.acq_rel (0.4 us per barrier in the anatomy trace)
+#ifndef AHA_BARRIER_FENCE
+            // acquire loads in the poll (release by the arriving CTAs' reductions -> acquire here -> bar.sync to the other threads)
+            // instead of a relaxed poll + fence.acq_rel: the fence alone was 0.4 us of every barrier in the anatomy trace; measured
+            // 793.8 vs 768.6 tok/s on the Qwen3-VL-2B stack (profiles/README.md)
             while (ld_acquire_u32(counter) < target) { ++polls; }
             AHA_SYNC_STAMP(sy, seq, 3, 8);
 #else
@@ -980,15 +982,19 @@ __device__ void fused_attention(const FusedArgs& a, Consumer& c, AttnSmem<G>& s,
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
-template <int G, bool LL>
+// MODE 0: grid barriers between all phases.  MODE 1: every phase exchanges tagged packets.  MODE 2 (hybrid): grid barriers around the
+// attention and between gate/up and down (their exchanges are large or need an extra hop as packets: measured slower), tagged
+// packets for the two residual-stream exchanges per layer -- the ones that cross GPUs under tensor parallelism.
+template <int G, int MODE>
 __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(FusedArgs a) {
+    constexpr bool LL = MODE == 1, PX = MODE != 0;   // PX: the residual stream lives in shared memory and its updates travel as packets
     extern __shared__ __align__(1024) uint8_t fused_smem_raw[];
     uint8_t* ringbuf = fused_smem_raw;
     uint64_t* full = reinterpret_cast<uint64_t*>(fused_smem_raw + (size_t)kFusedStages * kFusedStageBytes);
     uint64_t* empty = full + kFusedStages;
     float* red = reinterpret_cast<float*>(empty + kFusedStages);
     float* xown = red + 32;                                     // [kFusedMaxOwnRows] (barrier mode only: LL mode keeps the whole stream in xres)
-    float* cs = xown + (LL ? 0 : kFusedMaxOwnRows);             // [128] cos | sin of the step's rotary angles
+    float* cs = xown + (MODE != 0 ? 0 : kFusedMaxOwnRows);      // [128] cos | sin of the step's rotary angles
     float* xs = cs + 128;                                       // [kFusedMaxK] activations / attention scratch
     int* spages = reinterpret_cast<int*>(xs + kFusedMaxK);      // [kFusedMaxPages] page table copy
     float* xres = reinterpret_cast<float*>(spages + kFusedMaxPages);   // [kFusedMaxH] LL mode: the residual stream (not carved in barrier mode)
@@ -1065,7 +1071,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
     const __half* emb_row = a.embed + (size_t)token * a.H;
     int own_r0, own_r1;
     cta_rows(a.H, 1, own_r0, own_r1);
-    if (!LL && tid < own_r1 - own_r0) xown[tid] = __half2float(emb_row[own_r0 + tid]);   // the rows of the residual stream this CTA owns start as the embedding row
+    if (!PX && tid < own_r1 - own_r0) xown[tid] = __half2float(emb_row[own_r0 + tid]);   // the rows of the residual stream this CTA owns start as the embedding row
     int ce = 0;
 #define CSTAMP() do { if (tid == 0) AHA_STAMP(a, 0, ce); } while (0)
     CSTAMP();
@@ -1102,6 +1108,31 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
             c.template load_ll<false, false>(a.I, a.ll_h, 1, 0, tag, nullptr, 0.f, a.ll_flag + 3 * 256, (int)gridDim.x); CSTAMP();
             c.template gemv<FE_RESID, true>(a, a.H, a.I, nullptr, nullptr, best, bi, tag, 1); CSTAMP();
             CSTAMP();
+        } else if constexpr (MODE == 2) {
+            const uint32_t tag = a.ll_tag + (uint32_t)l;
+            // P1: x = residual + down partial sums of layer l - 1 (packets, all ranks); qkv leaves as plain floats
+            if (first) c.load_x(a.H, nullptr, emb_row, Ly.ln1, a.eps, true);
+            else c.template load_ll<true, true>(a.H, a.ll_xp[1][a.tp_rank], a.tp_world, (size_t)a.H, tag - 1u, Ly.ln1, a.eps, a.ll_flag_xp[1][a.tp_rank], (int)gridDim.x);
+            CSTAMP();
+            c.template gemv<FE_QKV>(a, a.qkv_dim, a.H, Ly.qkv_b, a.qkv1, best, bi); CSTAMP();
+            grid_barrier(&a.sync[0], seq, a.dbg, a.trace, sy); CSTAMP();
+            // P2: attention (split partials as plain floats)
+            CSTAMP();
+            fused_attention<G>(a, c, *as, cs, spages, l, Ly, t_new); CSTAMP();
+            grid_barrier(&a.sync[0], seq, a.dbg, a.trace, sy); CSTAMP();
+            // P3: merge the splits, o_proj partial sums -> packets to every rank (no barrier: P4 polls them)
+            c.load_attn(a); CSTAMP();
+            c.template gemv<FE_RESID, true>(a, a.H, a.nh * a.hd, Ly.o_b, nullptr, best, bi, tag, 0); CSTAMP();
+            CSTAMP();
+            // P4
+            c.template load_ll<true, true>(a.H, a.ll_xp[0][a.tp_rank], a.tp_world, (size_t)a.H, tag, Ly.ln2, a.eps, a.ll_flag_xp[0][a.tp_rank], (int)gridDim.x);
+            CSTAMP();
+            c.template gemv<FE_SWIGLU>(a, 2 * a.I, a.H, nullptr, a.h1, best, bi); CSTAMP();
+            grid_barrier(&a.sync[0], seq, a.dbg, a.trace, sy); CSTAMP();
+            // P5: down partial sums -> packets
+            c.load_x(a.I, a.h1, nullptr, nullptr, 0.f); CSTAMP();
+            c.template gemv<FE_RESID, true>(a, a.H, a.I, nullptr, nullptr, best, bi, tag, 1); CSTAMP();
+            CSTAMP();
         } else {
         // P1: qkv = Wqkv . rmsnorm(x)      (layer 0 reads the embedding row directly: Embedding::forward)
         c.load_x(a.H, a.x, first ? emb_row : nullptr, Ly.ln1, a.eps);
@@ -1128,7 +1159,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
         }
     }
     // final: logits = lm_head . rmsnorm(x) over this rank's vocabulary shard, per-CTA argmax candidate
-    if constexpr (LL) c.template load_ll<true, true>(a.H, a.ll_xp[1][a.tp_rank], a.tp_world, (size_t)a.H, a.ll_tag + (uint32_t)a.L - 1u, a.final_norm, a.eps, a.ll_flag_xp[1][a.tp_rank], (int)gridDim.x);
+    if constexpr (PX) c.template load_ll<true, true>(a.H, a.ll_xp[1][a.tp_rank], a.tp_world, (size_t)a.H, a.ll_tag + (uint32_t)a.L - 1u, a.final_norm, a.eps, a.ll_flag_xp[1][a.tp_rank], (int)gridDim.x);
     else c.load_x(a.H, a.x, nullptr, a.final_norm, a.eps);
     best = -INFINITY; bi = 0x7fffffff;
     c.template gemv<FE_LOGITS>(a, a.V_l, a.H, nullptr, a.logits + a.v0, best, bi, 0, 0, a.v0); CSTAMP();
@@ -1165,7 +1196,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
             const int oi = __shfl_xor_sync(0xffffffffu, gi, o);
             if (ov > gb || (ov == gb && oi < gi)) { gb = ov; gi = oi; }
         }
-        if (LL && a.tp_world > 1) {
+        if (PX && a.tp_world > 1) {
             // vocabulary shards: every rank publishes its (value, index) candidate to every rank and picks the same winner
             // (largest value, lowest index on ties)
             const uint32_t ftag = a.ll_tag + (uint32_t)a.L;

@@ -26,7 +26,11 @@
 
 namespace aha {
 
-constexpr int kTcBM = 128, kTcBN = 128, kTcBK = 64, kTcStages = 4;
+#ifndef AHA_TC_STAGES
+#define AHA_TC_STAGES 4      // 4-stage ring, 1 CTA per SM; 2 = two co-resident CTAs per SM (one's epilogue under the other's MMAs)
+#endif
+constexpr int kTcBM = 128, kTcBN = 128, kTcBK = 64, kTcStages = AHA_TC_STAGES;
+constexpr int kTcCtasPerSm = kTcStages <= 2 ? 2 : 1;
 constexpr int kTcTileBytes = kTcBM * kTcBK * 2;             // 16 KB
 constexpr int kTcStageBytes = 3 * kTcTileBytes;             // A_hi, A_lo, W
 constexpr int kTcThreads = 192;
@@ -134,7 +138,7 @@ struct GemmTcArgs {
 };
 
 template <int EPI>
-__global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+__global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                                                                const __grid_constant__ CUtensorMap tm_w, GemmTcArgs g) {
     extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment in the shared window: align by hand (1 KB of slack is allocated)

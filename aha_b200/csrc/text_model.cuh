@@ -119,8 +119,16 @@ struct WeightTable {
             const uint16_t* s = reinterpret_cast<const uint16_t*>(d.data);
             for (int64_t r = 0; r < nr; ++r) std::memcpy(reinterpret_cast<uint16_t*>(dst) + r * dst_ld, s + (r0 + r) * C + c0, (size_t)nc * 2);
         } else {
+            // bf16 / f32 checkpoints are narrowed to fp16 (8 -> 10 mantissa bits for bf16: exact inside fp16's normal range).  A value
+            // outside that range would silently become inf (|w| > 65504) or lose bits (|w| < 2^-14): refuse the checkpoint loudly.
             for (int64_t r = 0; r < nr; ++r)
-                for (int64_t c = 0; c < nc; ++c) dst[r * dst_ld + c] = __float2half_rn(at(d, (size_t)((r0 + r) * C + c0 + c)));
+                for (int64_t c = 0; c < nc; ++c) {
+                    const float v = at(d, (size_t)((r0 + r) * C + c0 + c));
+                    const float av = std::fabs(v);
+                    if (!(av <= 65504.0f)) throw std::runtime_error("weight '" + n + "' holds a value outside the fp16 range (|w| > 65504 or not finite): this build stores linear weights as fp16");
+                    if (d.dtype == AHA_BF16 && av != 0.0f && av < 6.103515625e-05f) throw std::runtime_error("weight '" + n + "' holds a bf16 value below fp16's normal range (|w| < 2^-14): it would lose bits as fp16");
+                    dst[r * dst_ld + c] = __float2half_rn(v);
+                }
         }
     }
     std::vector<float> vec_f32(const std::string& n, size_t expect_n) const {
@@ -294,7 +302,8 @@ struct TextModel {
     bool use_graph = true;
     // fused persistent decode kernel (decode_fused.cuh)
     bool fused = false;
-    bool fused_ll = false;               // packet (data-flow) version of the fused kernel; false = the grid-barrier twin (decode_impl = 3)
+    bool fused_ll = false;               // the fused kernel keeps the residual stream on chip and exchanges packets (modes 1 and 2)
+    int fused_mode = 0;                  // decode_fused.cuh MODE: 0 grid barriers, 1 packets everywhere, 2 hybrid
     int decode_impl = 0;
     // LL packet buffers.  The blocks a tensor-parallel peer writes (partial sums, argmax candidates) live in ONE separate
     // allocation per rank so that a single CUDA IPC handle maps them into the peers.
@@ -407,7 +416,9 @@ struct TextModel {
         return true;
     }
     template <int G>
-    void (*fused_kernel() const)(FusedArgs) { return fused_ll ? decode_step_fused_kernel<G, true> : decode_step_fused_kernel<G, false>; }
+    void (*fused_kernel() const)(FusedArgs) {
+        return fused_mode == 1 ? decode_step_fused_kernel<G, 1> : (fused_mode == 2 ? decode_step_fused_kernel<G, 2> : decode_step_fused_kernel<G, 0>);
+    }
     template <int G>
     void fused_prepare() {
         fused_smem = fused_smem_bytes<G>(fused_ll);
@@ -425,13 +436,14 @@ struct TextModel {
         {
             std::string why;
             const bool ok = fused_supported(&why);
-            AHA_REQUIRE(decode_impl >= 0 && decode_impl <= 3, "decode_impl must be 0 (auto), 1 (per-op kernels), 2 (fused persistent kernel) or 3 (fused, grid-barrier twin)");
+            AHA_REQUIRE(decode_impl >= 0 && decode_impl <= 4, "decode_impl must be 0 (auto), 1 (per-op kernels), 2 (fused, packets), 3 (fused, grid barriers) or 4 (fused, hybrid)");
             AHA_REQUIRE(decode_impl < 2 || ok, "fused decode kernel unsupported for this model: " + why);
             AHA_REQUIRE(decode_impl != 3 || tp_world == 1, "the grid-barrier twin of the fused kernel is single-GPU only");
             fused = ok && decode_impl != 1;
             // auto: one GPU -> the grid-barrier kernel (measured faster there: 774 vs 611 tok/s on the Qwen3-VL-2B stack, profiles/README.md);
             // tensor parallel -> the packet kernel, whose exchange needs no cross-GPU barrier
-            fused_ll = fused && (decode_impl == 2 || (decode_impl == 0 && tp_world > 1));
+            fused_mode = !fused ? 0 : (decode_impl == 2 ? 1 : (decode_impl == 4 ? 2 : (decode_impl == 3 ? 0 : (tp_world > 1 ? 1 : 0))));
+            fused_ll = fused && fused_mode != 0;
         }
         num_pages = ceil_div(max_ctx, kPage);
         page_stride = (size_t)2 * nkv_l * kPage * cfg.hd;

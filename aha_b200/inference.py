@@ -57,7 +57,8 @@ class B200Model:
         self.config = config
         cfg_json = json.dumps(config).encode()
         names = list(weights.keys())
-        arrs = [np.ascontiguousarray(weights[n]) for n in names]
+        arrs = [weights[n] if (isinstance(weights[n], np.ndarray) and weights[n].flags["C_CONTIGUOUS"]) else np.ascontiguousarray(weights[n])
+                for n in names]   # (a BF16-tagged view must keep its subclass)
         descs = (L.TensorDesc * len(names))(*[L.make_desc(a, n) for a, n in zip(arrs, names)])
         eos = np.asarray(list(eos_ids), dtype=np.uint32)
         opts = L.Options(device=device, tp_rank=tp_rank, tp_world=tp_world, max_ctx=max_ctx, max_prefill=max_prefill,

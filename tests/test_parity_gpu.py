@@ -87,7 +87,8 @@ def test_qwen3_decode_implementations_agree(q3):
     others = [make_model("qwen3", "tiny", max_ctx=512, decode_impl=1)[2],
               make_model("qwen3", "tiny", max_ctx=512, decode_impl=1, use_graph=False)[2],
               make_model("qwen3", "tiny", max_ctx=512, decode_impl=2)[2],
-              make_model("qwen3", "tiny", max_ctx=512, decode_impl=3)[2]]
+              make_model("qwen3", "tiny", max_ctx=512, decode_impl=3)[2],
+              make_model("qwen3", "tiny", max_ctx=512, decode_impl=4)[2]]
     try:
         ids = _ids(50, cfg["vocab_size"], 8)
         m.clear_cache()
@@ -107,7 +108,7 @@ def test_qwen3_decode_implementations_agree(q3):
             m2.close()
 
 
-@pytest.mark.parametrize("impl", [1, 2, 3])
+@pytest.mark.parametrize("impl", [1, 2, 3, 4])
 def test_qwen3_long_context_decode(impl):
     """decode far past the prompt: many KV pages, every split of the attention busy."""
     cfg, w, m = make_model("qwen3", "tiny", max_ctx=2048, decode_impl=impl)
@@ -125,7 +126,7 @@ def test_qwen3_long_context_decode(impl):
         m.close()
 
 
-@pytest.mark.parametrize("impl", [1, 2, 3])
+@pytest.mark.parametrize("impl", [1, 2, 3, 4])
 def test_qwen3_production_row_shapes(impl):
     """Qwen3-VL-2B text-stack row shapes (H=2048, I=6144; 2 layers): the 4-row / 1-row tensor-core stage paths of the
     fused kernel (impl 2) and the per-op kernels (impl 1) against the oracle, teacher-forced over page boundaries."""
@@ -383,7 +384,7 @@ def _rand_ids(n, vocab, seed):
 
 # GQA groups other than 2 (every shipped Qwen3 size has nh / nkv = 2): MHA and a group of 4, fused and per-op decode
 @pytest.mark.parametrize("preset", ["tiny-g1", "tiny-g4"])
-@pytest.mark.parametrize("impl", [1, 2, 3])
+@pytest.mark.parametrize("impl", [1, 2, 3, 4])
 def test_decode_with_other_gqa_groups(preset, impl):
     cfg, w, m = make_model("qwen3", preset, max_ctx=512, decode_impl=impl)
     o = make_oracle("qwen3", cfg, w)
@@ -400,3 +401,36 @@ def test_decode_with_other_gqa_groups(preset, impl):
             tok = int(np.argmax(lo))
     finally:
         m.close()
+
+
+def test_bf16_checkpoint_is_narrowed_exactly_or_refused():
+    """Shipped Qwen3 checkpoints are bf16: values inside fp16's normal range convert exactly (logits equal the oracle on the bf16
+    values); a value fp16 cannot hold makes create fail loudly instead of loading an inf."""
+    from aha_b200 import B200Model, synth
+    from aha_b200._lib import to_bf16
+    from aha_b200.inference import B200Error
+    cfg = synth.get_config("qwen3", "tiny")
+    w16 = synth.make_weights("qwen3", cfg, 0)
+    wb = {k: to_bf16(v.astype(np.float32)) for k, v in w16.items()}
+    as_f32 = {k: (v.view(np.ndarray).astype(np.uint32) << 16).view(np.float32).reshape(w16[k].shape) for k, v in wb.items()}
+    for k, v in as_f32.items():   # keep the test inside the exactly-representable range (tiny values would be refused)
+        small = (np.abs(v) < 6.2e-5) & (v != 0)
+        if small.any():
+            v[small] = 0.0
+            wb[k] = to_bf16(v)
+    m = B200Model("qwen3", cfg, {k: v.reshape(w16[k].shape) for k, v in wb.items()}, max_ctx=256)
+    try:
+        o = make_oracle("qwen3", cfg, as_f32)
+        ids = _rand_ids(40, cfg["vocab_size"], 2)
+        got = m.forward_initial(ids, 0)[0, 0]
+        want = o.forward_initial(ids.reshape(1, -1), 0)[0, 0]
+        assert np.abs(got - want).max() <= TOL
+    finally:
+        m.close()
+    bad = dict(wb)
+    big = as_f32["model.norm.weight"].copy()   # norm gains stay fp32 on the device: use a linear weight for the range check
+    k = "model.layers.0.mlp.down_proj.weight"
+    v = as_f32[k].copy(); v[0, 0] = 1e6
+    bad[k] = to_bf16(v).reshape(v.shape)
+    with pytest.raises(B200Error, match="fp16 range"):
+        B200Model("qwen3", cfg, {kk: vv.reshape(w16[kk].shape) for kk, vv in bad.items()}, max_ctx=256)
