@@ -51,11 +51,16 @@ constexpr int kFusedTraceWords = 2 * 4096 + 256 * 256;     // timing traces: CTA
 constexpr int kFusedMaxOwnRows = 64;                     // residual-stream rows owned by one CTA (H / grid, rounded up)
 constexpr int kFusedPartialStride = 128 + 4;             // floats per (head, split) attention partial: acc[128], m, l, pad (16-byte rows)
 constexpr int kFusedMergeChunk = 20;                     // splits merged per pass when the o_proj input is assembled
-constexpr int kFusedMaxPages = 512;                      // page-table entries staged in shared memory (16K tokens)
+constexpr int kFusedMaxPages = 1024;                     // page-table entries staged in shared memory as uint16 (32K tokens; physical page ids < 65536)
 constexpr int kFusedMaxH = 4096;                         // residual stream kept per CTA in shared memory (LL mode)
 constexpr int kFusedMaxTp = 8;                           // tensor-parallel ranks on one NVSwitch domain
 
 struct __align__(8) LLPk { float v; uint32_t tag; };     // one tagged packet: 8-byte stores / loads are single-copy atomic
+struct LLPeerTab {                                       // device-resident table of the symmetric blocks of every tensor-parallel rank
+    LLPk* xp[2][kFusedMaxTp];                            // [o_proj | down][destination rank] -> that rank's [tp_world][H] block of partial sums
+    LLPk* cand[kFusedMaxTp];                             // [destination rank] -> that rank's [tp_world][2] argmax candidates (value, index)
+    uint32_t* flag_xp[2][kFusedMaxTp];                   // [o_proj | down][destination rank] -> that rank's [tp_world][256] "data is out" flags
+};
 
 struct FusedLayer {
     const __half *qkv, *o, *gu, *down;
@@ -92,13 +97,17 @@ struct FusedArgs {
     LLPk* ll_pb;       // [nh][nsplit][kFusedPartialStride] split-KV attention partials (acc[128], m, l)
     LLPk* ll_att;      // [nh * hd] merged attention output
     LLPk* ll_h;        // [I]
-    LLPk* ll_xp[2][kFusedMaxTp];   // [o_proj | down][destination rank] -> that rank's [tp_world][H] block of partial sums (own rank = local memory)
-    LLPk* ll_cand[kFusedMaxTp];    // [destination rank] -> that rank's [tp_world][2] argmax candidates (value, index) of the vocabulary shards
+    // Per-peer pointers live in a DEVICE table, not in this struct: indexing a kernel-parameter array with a runtime value makes the
+    // compiler copy the whole parameter block to local memory, and then every `a.field` of the hot loops is a local load (measured:
+    // all phases of the packet modes 1.5-4 us slower until this was moved out).
+    const struct LLPeerTab* ll_peers;
+    LLPk* ll_xp_local[2];          // this rank's own [tp_world][H] blocks of o_proj | down partial sums
+    LLPk* ll_cand_local;           // this rank's own [tp_world][2] argmax candidates
     // "data is out" flags, one word per producing CTA and vector kind: written (relaxed, after the CTA's packets) by thread 0,
     // polled by ONE warp of a consumer that found packets missing -- the other 320 threads of every waiting CTA stay off the
     // memory system (every thread polling its own packets slows the weight stream of the CTAs still working: measured).
     uint32_t* ll_flag;             // [4][256]: qkv | attention partials | merged attention | h, indexed by blockIdx.x
-    uint32_t* ll_flag_xp[2][kFusedMaxTp];   // [o_proj | down][destination rank] -> that rank's [tp_world][256] flags of the partial sums
+    uint32_t* ll_flag_xp_local[2]; // this rank's own [tp_world][256] flags of the o_proj | down partial sums
     uint32_t ll_tag;   // tag of layer 0 of this launch; layer l uses ll_tag + l, the final phase ll_tag + L (never 0, never reused)
     int tp_rank, tp_world;
     int v0, V_l;       // vocabulary shard [v0, v0 + V_l) of the lm_head this rank multiplies (tp_world == 1: the whole of it)
@@ -403,7 +412,7 @@ struct Producer {
             ++it;
         }
     }
-    const int* pages = nullptr;   // page table staged in shared memory
+    const uint16_t* pages = nullptr;   // page table staged in shared memory
     __device__ void attn(const FusedArgs& a, int layer, int ctx) {
         int kvh, split, hp0, hp1;
         if (!attn_item(a, ctx, kvh, split, hp0, hp1)) return;
@@ -745,7 +754,8 @@ struct Consumer {
                     float y = mine;
                     if (bias) y += bias[row];
                     if (LL && EPI == FE_RESID) {
-                        for (int w = 0; w < a.tp_world; ++w) ll_store<true>(a.ll_xp[par][w] + (size_t)a.tp_rank * a.H + row, y, tag);
+                        if (a.tp_world == 1) ll_store<false>(a.ll_xp_local[par] + row, y, tag);   // one GPU: gpu-scope store, no pointer table
+                        else for (int w = 0; w < a.tp_world; ++w) ll_store<true>(a.ll_peers->xp[par][w] + (size_t)a.tp_rank * a.H + row, y, tag);
                     } else if (LL && EPI == FE_QKV) {
                         ll_store<false>(a.ll_qkv + row, y, tag);
                     } else {
@@ -761,7 +771,10 @@ struct Consumer {
         if (LL && threadIdx.x == 0) {   // every packet store of this CTA has been issued: raise its "data is out" flag
             if (EPI == FE_QKV) ll_flag_store<false>(a.ll_flag + 0 * 256 + blockIdx.x, tag);
             else if (EPI == FE_SWIGLU) ll_flag_store<false>(a.ll_flag + 3 * 256 + blockIdx.x, tag);
-            else if (EPI == FE_RESID) for (int w = 0; w < a.tp_world; ++w) ll_flag_store<true>(a.ll_flag_xp[par][w] + (size_t)a.tp_rank * 256 + blockIdx.x, tag);
+            else if (EPI == FE_RESID) {
+                if (a.tp_world == 1) ll_flag_store<false>(a.ll_flag_xp_local[par] + blockIdx.x, tag);
+                else for (int w = 0; w < a.tp_world; ++w) ll_flag_store<true>(a.ll_peers->flag_xp[par][w] + (size_t)a.tp_rank * 256 + blockIdx.x, tag);
+            }
         }
     }
 };
@@ -779,7 +792,7 @@ struct AttnSmem {
 };
 
 template <int G, bool LL = false>
-__device__ void fused_attention(const FusedArgs& a, Consumer& c, AttnSmem<G>& s, const float* cs, const int* spages, int layer, const FusedLayer& Ly, int t_new, uint32_t tag = 0) {
+__device__ void fused_attention(const FusedArgs& a, Consumer& c, AttnSmem<G>& s, const float* cs, const uint16_t* spages, int layer, const FusedLayer& Ly, int t_new, uint32_t tag = 0) {
     constexpr int HD = 128;
     const int ctx = t_new + 1;
     const int lane = c.lane, warp = c.warp, tid = threadIdx.x;
@@ -996,7 +1009,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
     float* xown = red + 32;                                     // [kFusedMaxOwnRows] (barrier mode only: LL mode keeps the whole stream in xres)
     float* cs = xown + (MODE != 0 ? 0 : kFusedMaxOwnRows);      // [128] cos | sin of the step's rotary angles
     float* xs = cs + 128;                                       // [kFusedMaxK] activations / attention scratch
-    int* spages = reinterpret_cast<int*>(xs + kFusedMaxK);      // [kFusedMaxPages] page table copy
+    uint16_t* spages = reinterpret_cast<uint16_t*>(xs + kFusedMaxK);   // [kFusedMaxPages] page table copy (physical page ids)
     float* xres = reinterpret_cast<float*>(spages + kFusedMaxPages);   // [kFusedMaxH] LL mode: the residual stream (not carved in barrier mode)
     AttnSmem<G>* as = reinterpret_cast<AttnSmem<G>*>(xs);
     static_assert(sizeof(AttnSmem<G>) <= kFusedMaxK * sizeof(float), "attention scratch must fit in the xs region");
@@ -1011,7 +1024,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
     const int rope_delta = a.st->rope_delta;
     const uint32_t token = min(a.st->token, (uint32_t)(a.V - 1));   // a NaN logit row publishes 0x7fffffff: never index the embedding table with it
     const int ctx = t_new + 1;
-    for (int i = tid; i < (ctx + kPage - 1) / kPage && i < kFusedMaxPages; i += kFusedThreads) spages[i] = a.page_table[i];
+    for (int i = tid; i < (ctx + kPage - 1) / kPage && i < kFusedMaxPages; i += kFusedThreads) spages[i] = (uint16_t)a.page_table[i];
     if (tid < 64) {   // RoPE angle of this step (same for every layer): cos/sin once per kernel
         const float ang = (float)(t_new + rope_delta) * a.inv_freq[tid];
         cs[tid] = cosf(ang);
@@ -1083,11 +1096,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
         if constexpr (LL) {
             // Data-flow version: every phase polls the packets it needs (tag of this layer), no grid barrier anywhere.
             const uint32_t tag = a.ll_tag + (uint32_t)l;
-            const LLPk* xp_o = a.ll_xp[0][a.tp_rank];     // this rank's [tp_world][H] blocks of o_proj / down partial sums
-            const LLPk* xp_d = a.ll_xp[1][a.tp_rank];
+            const LLPk* xp_o = a.ll_xp_local[0];     // this rank's [tp_world][H] blocks of o_proj / down partial sums
+            const LLPk* xp_d = a.ll_xp_local[1];
             // P1: qkv = Wqkv . rmsnorm(x); x = residual + the down partial sums of layer l - 1 (layer 0: the embedding row)
             if (first) c.load_x(a.H, nullptr, emb_row, Ly.ln1, a.eps, true);
-            else c.template load_ll<true, true>(a.H, xp_d, a.tp_world, (size_t)a.H, tag - 1u, Ly.ln1, a.eps, a.ll_flag_xp[1][a.tp_rank], (int)gridDim.x);
+            else if (a.tp_world == 1) c.template load_ll<false, true>(a.H, xp_d, a.tp_world, (size_t)a.H, tag - 1u, Ly.ln1, a.eps, a.ll_flag_xp_local[1], (int)gridDim.x); else c.template load_ll<true, true>(a.H, xp_d, a.tp_world, (size_t)a.H, tag - 1u, Ly.ln1, a.eps, a.ll_flag_xp_local[1], (int)gridDim.x);
             CSTAMP();
             c.template gemv<FE_QKV, true>(a, a.qkv_dim, a.H, Ly.qkv_b, nullptr, best, bi, tag); CSTAMP();
             CSTAMP();
@@ -1100,7 +1113,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
             c.template gemv<FE_RESID, true>(a, a.H, a.nh * a.hd, Ly.o_b, nullptr, best, bi, tag, 0); CSTAMP();
             CSTAMP();
             // P4: h = silu(gate) * up on rmsnorm(x), x = residual + sum over ranks of the o_proj partial sums
-            c.template load_ll<true, true>(a.H, xp_o, a.tp_world, (size_t)a.H, tag, Ly.ln2, a.eps, a.ll_flag_xp[0][a.tp_rank], (int)gridDim.x);
+            if (a.tp_world == 1) c.template load_ll<false, true>(a.H, xp_o, a.tp_world, (size_t)a.H, tag, Ly.ln2, a.eps, a.ll_flag_xp_local[0], (int)gridDim.x); else c.template load_ll<true, true>(a.H, xp_o, a.tp_world, (size_t)a.H, tag, Ly.ln2, a.eps, a.ll_flag_xp_local[0], (int)gridDim.x);
             CSTAMP();
             c.template gemv<FE_SWIGLU, true>(a, 2 * a.I, a.H, nullptr, nullptr, best, bi, tag); CSTAMP();
             CSTAMP();
@@ -1112,7 +1125,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
             const uint32_t tag = a.ll_tag + (uint32_t)l;
             // P1: x = residual + down partial sums of layer l - 1 (packets, all ranks); qkv leaves as plain floats
             if (first) c.load_x(a.H, nullptr, emb_row, Ly.ln1, a.eps, true);
-            else c.template load_ll<true, true>(a.H, a.ll_xp[1][a.tp_rank], a.tp_world, (size_t)a.H, tag - 1u, Ly.ln1, a.eps, a.ll_flag_xp[1][a.tp_rank], (int)gridDim.x);
+            else if (a.tp_world == 1) c.template load_ll<false, true>(a.H, a.ll_xp_local[1], a.tp_world, (size_t)a.H, tag - 1u, Ly.ln1, a.eps, a.ll_flag_xp_local[1], (int)gridDim.x); else c.template load_ll<true, true>(a.H, a.ll_xp_local[1], a.tp_world, (size_t)a.H, tag - 1u, Ly.ln1, a.eps, a.ll_flag_xp_local[1], (int)gridDim.x);
             CSTAMP();
             c.template gemv<FE_QKV>(a, a.qkv_dim, a.H, Ly.qkv_b, a.qkv1, best, bi); CSTAMP();
             grid_barrier(&a.sync[0], seq, a.dbg, a.trace, sy); CSTAMP();
@@ -1125,7 +1138,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
             c.template gemv<FE_RESID, true>(a, a.H, a.nh * a.hd, Ly.o_b, nullptr, best, bi, tag, 0); CSTAMP();
             CSTAMP();
             // P4
-            c.template load_ll<true, true>(a.H, a.ll_xp[0][a.tp_rank], a.tp_world, (size_t)a.H, tag, Ly.ln2, a.eps, a.ll_flag_xp[0][a.tp_rank], (int)gridDim.x);
+            if (a.tp_world == 1) c.template load_ll<false, true>(a.H, a.ll_xp_local[0], a.tp_world, (size_t)a.H, tag, Ly.ln2, a.eps, a.ll_flag_xp_local[0], (int)gridDim.x); else c.template load_ll<true, true>(a.H, a.ll_xp_local[0], a.tp_world, (size_t)a.H, tag, Ly.ln2, a.eps, a.ll_flag_xp_local[0], (int)gridDim.x);
             CSTAMP();
             c.template gemv<FE_SWIGLU>(a, 2 * a.I, a.H, nullptr, a.h1, best, bi); CSTAMP();
             grid_barrier(&a.sync[0], seq, a.dbg, a.trace, sy); CSTAMP();
@@ -1159,7 +1172,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
         }
     }
     // final: logits = lm_head . rmsnorm(x) over this rank's vocabulary shard, per-CTA argmax candidate
-    if constexpr (PX) c.template load_ll<true, true>(a.H, a.ll_xp[1][a.tp_rank], a.tp_world, (size_t)a.H, a.ll_tag + (uint32_t)a.L - 1u, a.final_norm, a.eps, a.ll_flag_xp[1][a.tp_rank], (int)gridDim.x);
+    if constexpr (PX) if (a.tp_world == 1) c.template load_ll<false, true>(a.H, a.ll_xp_local[1], a.tp_world, (size_t)a.H, a.ll_tag + (uint32_t)a.L - 1u, a.final_norm, a.eps, a.ll_flag_xp_local[1], (int)gridDim.x); else c.template load_ll<true, true>(a.H, a.ll_xp_local[1], a.tp_world, (size_t)a.H, a.ll_tag + (uint32_t)a.L - 1u, a.final_norm, a.eps, a.ll_flag_xp_local[1], (int)gridDim.x);
     else c.load_x(a.H, a.x, nullptr, a.final_norm, a.eps);
     best = -INFINITY; bi = 0x7fffffff;
     c.template gemv<FE_LOGITS>(a, a.V_l, a.H, nullptr, a.logits + a.v0, best, bi, 0, 0, a.v0); CSTAMP();
@@ -1201,14 +1214,14 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
             // (largest value, lowest index on ties)
             const uint32_t ftag = a.ll_tag + (uint32_t)a.L;
             if (lane < a.tp_world) {
-                ll_store<true>(a.ll_cand[lane] + a.tp_rank * 2, gb, ftag);
-                ll_store<true>(a.ll_cand[lane] + a.tp_rank * 2 + 1, __int_as_float(gi), ftag);
+                ll_store<true>(a.ll_peers->cand[lane] + a.tp_rank * 2, gb, ftag);
+                ll_store<true>(a.ll_peers->cand[lane] + a.tp_rank * 2 + 1, __int_as_float(gi), ftag);
             }
             float cb = -INFINITY;
             int ci = 0x7fffffff;
             if (lane < a.tp_world) {
-                cb = ll_wait1<true>(a.ll_cand[a.tp_rank] + lane * 2, ftag, a.ll_abort);
-                ci = __float_as_int(ll_wait1<true>(a.ll_cand[a.tp_rank] + lane * 2 + 1, ftag, a.ll_abort));
+                cb = ll_wait1<true>(a.ll_cand_local + lane * 2, ftag, a.ll_abort);
+                ci = __float_as_int(ll_wait1<true>(a.ll_cand_local + lane * 2 + 1, ftag, a.ll_abort));
             }
             for (int o = 16; o > 0; o >>= 1) {
                 const float ov = __shfl_xor_sync(0xffffffffu, cb, o);
@@ -1232,7 +1245,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) decode_step_fused_kernel(Fus
 template <int G>
 inline size_t fused_smem_bytes(bool ll) {
     return (ll ? (size_t)kFusedMaxH * sizeof(float) : (size_t)kFusedMaxOwnRows * sizeof(float)) + (size_t)kFusedStages * kFusedStageBytes + 2 * kFusedStages * sizeof(uint64_t) + (32 + 128) * sizeof(float) + (size_t)kFusedMaxK * sizeof(float) +
-           (size_t)kFusedMaxPages * sizeof(int) + 64;
+           (size_t)kFusedMaxPages * sizeof(uint16_t) + 64;
 }
 
 }  // namespace aha

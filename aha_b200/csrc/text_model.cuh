@@ -313,6 +313,8 @@ struct TextModel {
     int* d_ll_abort = nullptr;
     uint32_t ll_launches = 0;
     uint32_t* ll_flag = nullptr;                    // [4][256] local "data is out" flags
+    LLPeerTab* d_ll_peers = nullptr;                // device copy of the per-peer pointer table (built once the peers are attached)
+    bool ll_peers_ready = false;
     size_t ll_sym_packets() const { return (size_t)2 * tp_world * cfg.H + (size_t)tp_world * 2 + (size_t)tp_world * 256; }   // + [2][W][256] u32 flags = W * 256 packets
     FusedLayer* d_fused_layers = nullptr;
     unsigned* d_sync = nullptr;   // [0] grid barrier, [1] final ticket, then kv tickets [nkv]
@@ -413,6 +415,7 @@ struct TextModel {
         if (cfg.attn_bias) return no("attention bias");
         if (nh_l / nkv_l > 4) return no("GQA group > 4");
         if (max_ctx_hint > kFusedMaxPages * kPage) return no("max_ctx beyond the page table staged in shared memory");
+        if (ceil_div(max_ctx_hint, kPage) > 65535) return no("more than 65535 KV pages");
         return true;
     }
     template <int G>
@@ -440,9 +443,10 @@ struct TextModel {
             AHA_REQUIRE(decode_impl < 2 || ok, "fused decode kernel unsupported for this model: " + why);
             AHA_REQUIRE(decode_impl != 3 || tp_world == 1, "the grid-barrier twin of the fused kernel is single-GPU only");
             fused = ok && decode_impl != 1;
-            // auto: one GPU -> the grid-barrier kernel (measured faster there: 774 vs 611 tok/s on the Qwen3-VL-2B stack, profiles/README.md);
-            // tensor parallel -> the packet kernel, whose exchange needs no cross-GPU barrier
-            fused_mode = !fused ? 0 : (decode_impl == 2 ? 1 : (decode_impl == 4 ? 2 : (decode_impl == 3 ? 0 : (tp_world > 1 ? 1 : 0))));
+            // auto: one GPU -> the grid-barrier kernel (measured fastest there: 794 vs 690 (hybrid) / 637 (packets) tok/s on the Qwen3-VL-2B
+            // stack, profiles/README.md); tensor parallel -> the hybrid kernel: local grid barriers inside the layer, NVLink packets for the
+            // two residual-stream exchanges (no cross-GPU barrier anywhere)
+            fused_mode = !fused ? 0 : (decode_impl == 2 ? 1 : (decode_impl == 4 ? 2 : (decode_impl == 3 ? 0 : (tp_world > 1 ? 2 : 0))));
             fused_ll = fused && fused_mode != 0;
         }
         num_pages = ceil_div(max_ctx, kPage);
@@ -489,6 +493,7 @@ struct TextModel {
                 ll_flag = c.alloc<uint32_t>(4 * 256);
                 AHA_CUDA_CHECK(cudaMemset(ll_flag, 0, 4 * 256 * sizeof(uint32_t)));
                 AHA_REQUIRE(c.num_sms <= 256, "more than 256 SMs");
+                d_ll_peers = c.alloc<LLPeerTab>(1);
                 d_ll_abort = c.alloc<int>(1);
                 AHA_CUDA_CHECK(cudaMemset(d_ll_abort, 0, sizeof(int)));
             }
@@ -709,14 +714,29 @@ struct TextModel {
         fa.V_l = (int)(((long long)cfg.V * (tp_rank + 1)) / tp_world) - fa.v0;
         if (fused_ll) {
             fa.ll_qkv = ll_qkv; fa.ll_pb = ll_pb; fa.ll_att = ll_att; fa.ll_h = ll_h; fa.ll_abort = d_ll_abort;
-            for (int w = 0; w < tp_world; ++w) {
-                AHA_REQUIRE(ll_peer_sym[w] != nullptr, "tensor-parallel peers are not attached");
-                fa.ll_xp[0][w] = ll_peer_sym[w];
-                fa.ll_xp[1][w] = ll_peer_sym[w] + (size_t)tp_world * cfg.H;
-                fa.ll_cand[w] = ll_peer_sym[w] + (size_t)2 * tp_world * cfg.H;
-                uint32_t* fl = reinterpret_cast<uint32_t*>(ll_peer_sym[w] + (size_t)2 * tp_world * cfg.H + (size_t)tp_world * 2);
-                fa.ll_flag_xp[0][w] = fl;
-                fa.ll_flag_xp[1][w] = fl + (size_t)tp_world * 256;
+            if (!ll_peers_ready) {
+                LLPeerTab tab{};
+                for (int w = 0; w < tp_world; ++w) {
+                    AHA_REQUIRE(ll_peer_sym[w] != nullptr, "tensor-parallel peers are not attached");
+                    tab.xp[0][w] = ll_peer_sym[w];
+                    tab.xp[1][w] = ll_peer_sym[w] + (size_t)tp_world * cfg.H;
+                    tab.cand[w] = ll_peer_sym[w] + (size_t)2 * tp_world * cfg.H;
+                    uint32_t* fl = reinterpret_cast<uint32_t*>(ll_peer_sym[w] + (size_t)2 * tp_world * cfg.H + (size_t)tp_world * 2);
+                    tab.flag_xp[0][w] = fl;
+                    tab.flag_xp[1][w] = fl + (size_t)tp_world * 256;
+                }
+                AHA_CUDA_CHECK(cudaMemcpyAsync(d_ll_peers, &tab, sizeof(tab), cudaMemcpyHostToDevice, c.stream));
+                AHA_CUDA_CHECK(cudaStreamSynchronize(c.stream));   // `tab` is a stack temporary
+                ll_peers_ready = true;
+            }
+            fa.ll_peers = d_ll_peers;
+            fa.ll_xp_local[0] = ll_sym;
+            fa.ll_xp_local[1] = ll_sym + (size_t)tp_world * cfg.H;
+            fa.ll_cand_local = ll_sym + (size_t)2 * tp_world * cfg.H;
+            {
+                uint32_t* fl = reinterpret_cast<uint32_t*>(ll_sym + (size_t)2 * tp_world * cfg.H + (size_t)tp_world * 2);
+                fa.ll_flag_xp_local[0] = fl;
+                fa.ll_flag_xp_local[1] = fl + (size_t)tp_world * 256;
             }
             fa.ll_flag = ll_flag;
             ll_launches += 1;
