@@ -48,20 +48,21 @@ struct SplitTcArgs {
     int nheads, nkv, skv_pad;
 };
 // blockIdx.y: 0 = q, 1 = k (one row per block, like split_qkv_kernel); 2 = v: 64-token tile per block, transposed through shared memory
+template <int HD>
 __global__ void split_qkv_tc_kernel(SplitTcArgs s) {
-    constexpr int HD = 64;
     const int which = blockIdx.y;
     if (which < 2) {
         const int S = which == 0 ? s.f.Sq : s.f.Skv, H = which == 0 ? s.nheads : s.nkv;
-        // 8 rows per pass of the 128 threads: 16 threads x float4 per row
-        for (size_t row = (size_t)blockIdx.x * 8 + threadIdx.x / 16; row < (size_t)S * H; row += (size_t)gridDim.x * 8) {
+        // HD / 4 threads x float4 per row, 512 / HD rows per pass of the 128 threads
+        constexpr int TPR = HD / 4, RPP = 128 / TPR;
+        for (size_t row = (size_t)blockIdx.x * RPP + threadIdx.x / TPR; row < (size_t)S * H; row += (size_t)gridDim.x * RPP) {
             const int head = (int)(row / S), tok = (int)(row % S);
             const float* src = which == 0 ? s.f.q + (size_t)(s.f.q0 + tok) * s.f.q_tok_stride + (size_t)head * s.f.q_head_stride
                                           : s.f.kv.k + s.f.kv.off(s.f.kv0 + tok, head);
             __half* hi = (which == 0 ? s.q_hi : s.k_hi) + row * HD;
             __half* lo = (which == 0 ? s.q_lo : s.k_lo) + row * HD;
             {
-                const int c4 = (threadIdx.x % 16) * 4;
+                const int c4 = (threadIdx.x % TPR) * 4;
                 const float4 v = *reinterpret_cast<const float4*>(src + c4);
                 uint32_t h0, l0, h1, l1;
                 split2(v.x, v.y, h0, l0);
@@ -109,12 +110,13 @@ __device__ __forceinline__ void pack8_split(const float* p, uint4& hi, uint4& lo
     split2(p[6], p[7], hi.w, lo.w);
 }
 
-template <bool CAUSAL>
-__global__ void __launch_bounds__(kFaThreads, 2) flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qh, const __grid_constant__ CUtensorMap tm_ql,
+template <int HD, bool CAUSAL>
+__global__ void __launch_bounds__(kFaThreads, HD == 64 ? 2 : 1) flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qh, const __grid_constant__ CUtensorMap tm_ql,
                                                                      const __grid_constant__ CUtensorMap tm_kh, const __grid_constant__ CUtensorMap tm_kl,
                                                                      const __grid_constant__ CUtensorMap tm_vh, const __grid_constant__ CUtensorMap tm_vl, FlashTcArgs a) {
-    constexpr int HD = 64, BQ = kFaBQ, BKV = kFaBKV;
-    constexpr int kQBytes = BQ * HD * 2, kKBytes = BKV * HD * 2, kVBytes = HD * BKV * 2, kPBytes = BQ * BKV * 2;   // 16, 8, 8, 16 KB
+    constexpr int BQ = kFaBQ, BKV = kFaBKV, KB = HD / 64;   // KB: 64-half k-blocks per head row (one TMA box each)
+    constexpr int kQBytes = BQ * HD * 2, kKBytes = BKV * HD * 2, kVBytes = HD * BKV * 2, kPBytes = BQ * BKV * 2;   // head_dim 64: 16, 8, 8, 16 KB
+    constexpr int kQBlk = BQ * 128, kKBlk = BKV * 128;       // bytes of one k-block of the Q / K tile
     extern __shared__ __align__(1024) uint8_t fa_tc_smem_raw[];
     uint8_t* base = fa_tc_smem_raw + ((1024u - (smem_u32(fa_tc_smem_raw) & 1023u)) & 1023u);
     uint8_t* Qh = base;               uint8_t* Ql = Qh + kQBytes;
@@ -151,26 +153,35 @@ __global__ void __launch_bounds__(kFaThreads, 2) flash_attn_tc_kernel(const __gr
         // PV(t - 1) is issued the moment P(t - 1) is complete, so both MMAs execute under the softmax threads' arithmetic.
         if (lane == 0) {
             const int qrow = head * a.Sq + qt0, krow = kvh * a.Skv, vrow = kvh * HD;
+            auto load_k = [&](int t) {
+                mbar_expect_tx(bar_k, 2 * kKBytes);
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb) {
+                    tma_load_2d(Kh + kb * kKBlk, &tm_kh, kb * 64, krow + t * BKV, bar_k);
+                    tma_load_2d(Kl + kb * kKBlk, &tm_kl, kb * 64, krow + t * BKV, bar_k);
+                }
+            };
             mbar_expect_tx(bar_q, 2 * kQBytes);
-            tma_load_2d(Qh, &tm_qh, 0, qrow, bar_q);
-            tma_load_2d(Ql, &tm_ql, 0, qrow, bar_q);
-            mbar_expect_tx(bar_k, 2 * kKBytes);
-            tma_load_2d(Kh, &tm_kh, 0, krow, bar_k);
-            tma_load_2d(Kl, &tm_kl, 0, krow, bar_k);
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb) {
+                tma_load_2d(Qh + kb * kQBlk, &tm_qh, kb * 64, qrow, bar_q);
+                tma_load_2d(Ql + kb * kQBlk, &tm_ql, kb * 64, qrow, bar_q);
+            }
+            load_k(0);
             mbar_expect_tx(bar_v, 2 * kVBytes);
             tma_load_2d(Vh, &tm_vh, 0, vrow, bar_v);
             tma_load_2d(Vl, &tm_vl, 0, vrow, bar_v);
-            const uint32_t idesc = umma_idesc_f16(BQ, 64);
+            const uint32_t idesc = umma_idesc_f16(BQ, 64), idesc_pv = umma_idesc_f16(BQ, HD);
             const uint64_t d_qh = umma_desc_sw128(Qh), d_ql = umma_desc_sw128(Ql), d_kh = umma_desc_sw128(Kh), d_kl = umma_desc_sw128(Kl);
             const uint64_t d_vh = umma_desc_sw128(Vh), d_vl = umma_desc_sw128(Vl), d_ph = umma_desc_sw128(Ph), d_pl = umma_desc_sw128(Pl);
             auto issue_s = [&](int t) {                          // S(t) = Qh Kh^T + Qh Kl^T + Ql Kh^T into S buffer t & 1
                 const uint32_t dst = tmem_s + (uint32_t)((t & 1) * 64);
 #pragma unroll
-                for (int ks = 0; ks < HD / 16; ++ks) {
-                    const uint64_t adv = (uint64_t)((ks * 32) >> 4);
-                    umma_f16(dst, d_qh + adv, d_kh + adv, idesc, ks > 0 ? 1u : 0u);
-                    umma_f16(dst, d_qh + adv, d_kl + adv, idesc, 1u);
-                    umma_f16(dst, d_ql + adv, d_kh + adv, idesc, 1u);
+                for (int ks = 0; ks < HD / 16; ++ks) {   // k-block ks / 4 of the tiles, 32 bytes per K = 16 step inside its 128-byte swizzle atom
+                    const uint64_t qa = (uint64_t)(((ks >> 2) * kQBlk + (ks & 3) * 32) >> 4), ka = (uint64_t)(((ks >> 2) * kKBlk + (ks & 3) * 32) >> 4);
+                    umma_f16(dst, d_qh + qa, d_kh + ka, idesc, ks > 0 ? 1u : 0u);
+                    umma_f16(dst, d_qh + qa, d_kl + ka, idesc, 1u);
+                    umma_f16(dst, d_ql + qa, d_kh + ka, idesc, 1u);
                 }
                 umma_commit(&bar_s[t & 1]);
             };
@@ -181,9 +192,9 @@ __global__ void __launch_bounds__(kFaThreads, 2) flash_attn_tc_kernel(const __gr
 #pragma unroll
                 for (int ks = 0; ks < BKV / 16; ++ks) {
                     const uint64_t adv = (uint64_t)((ks * 32) >> 4);
-                    umma_f16(tmem_o, d_ph + adv, d_vh + adv, idesc, ks > 0 ? 1u : 0u);
-                    umma_f16(tmem_o, d_ph + adv, d_vl + adv, idesc, 1u);
-                    umma_f16(tmem_o, d_pl + adv, d_vh + adv, idesc, 1u);
+                    umma_f16(tmem_o, d_ph + adv, d_vh + adv, idesc_pv, ks > 0 ? 1u : 0u);
+                    umma_f16(tmem_o, d_ph + adv, d_vl + adv, idesc_pv, 1u);
+                    umma_f16(tmem_o, d_pl + adv, d_vh + adv, idesc_pv, 1u);
                 }
                 umma_commit(bar_o);
             };
@@ -193,11 +204,7 @@ __global__ void __launch_bounds__(kFaThreads, 2) flash_attn_tc_kernel(const __gr
             issue_s(0);
             for (int t = 0; t < ntiles; ++t) {
                 mbar_wait(&bar_s[t & 1], (uint32_t)((t >> 1) & 1));   // S(t) done: the K tile is free, fetch K(t + 1)
-                if (t + 1 < ntiles) {
-                    mbar_expect_tx(bar_k, 2 * kKBytes);
-                    tma_load_2d(Kh, &tm_kh, 0, krow + (t + 1) * BKV, bar_k);
-                    tma_load_2d(Kl, &tm_kl, 0, krow + (t + 1) * BKV, bar_k);
-                }
+                if (t + 1 < ntiles) load_k(t + 1);
                 if (t >= 1) issue_pv(t - 1);                     // runs under the softmax of tile t
                 if (t + 1 < ntiles) {                            // S(t + 1) into the other buffer (its last reader, softmax(t - 1), has arrived at bar_p(t - 1))
                     mbar_wait(bar_k, (uint32_t)((t + 1) & 1));
@@ -258,11 +265,13 @@ __global__ void __launch_bounds__(kFaThreads, 2) flash_attn_tc_kernel(const __gr
             if (t >= 1) {   // PV(t - 1) ran under the arithmetic above; it also has to be done before P(t) may overwrite P(t - 1)
                 mbar_wait(bar_o, (uint32_t)((t - 1) & 1));
                 tc_fence_after();
-                float v0[32], v1[32];
-                tmem_ld32(tmem_o + lane_base, v0);
-                tmem_ld32(tmem_o + lane_base + 32u, v1);
 #pragma unroll
-                for (int c = 0; c < 32; ++c) { o[c] = (o[c] + v0[c]) * alpha; o[32 + c] = (o[32 + c] + v1[c]) * alpha; }
+                for (int c0 = 0; c0 < HD; c0 += 32) {
+                    float v0[32];
+                    tmem_ld32(tmem_o + lane_base + (uint32_t)c0, v0);
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) o[c0 + c] = (o[c0 + c] + v0[c]) * alpha;
+                }
             }
             // P row -> shared memory, K-major SWIZZLE_128B: 16-byte chunk j of row r sits at chunk (j ^ (r & 7))
 #pragma unroll
@@ -280,11 +289,13 @@ __global__ void __launch_bounds__(kFaThreads, 2) flash_attn_tc_kernel(const __gr
         {
             mbar_wait(bar_o, (uint32_t)((ntiles - 1) & 1));
             tc_fence_after();
-            float v0[32], v1[32];
-            tmem_ld32(tmem_o + lane_base, v0);
-            tmem_ld32(tmem_o + lane_base + 32u, v1);
 #pragma unroll
-            for (int c = 0; c < 32; ++c) { o[c] += v0[c]; o[32 + c] += v1[c]; }
+            for (int c0 = 0; c0 < HD; c0 += 32) {
+                float v0[32];
+                tmem_ld32(tmem_o + lane_base + (uint32_t)c0, v0);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) o[c0 + c] += v0[c];
+            }
             tc_fence_before();
         }
         if (qi < a.Sq) {
@@ -302,29 +313,32 @@ __global__ void __launch_bounds__(kFaThreads, 2) flash_attn_tc_kernel(const __gr
     }
 }
 
-inline size_t flash_tc_smem_bytes() { return (size_t)(2 * 16 + 4 * 8 + 2 * 16) * 1024 + 8 * sizeof(uint64_t) + 1024; }
+template <int HD>
+inline size_t flash_tc_smem_bytes() { return (size_t)(2 * kFaBQ * HD * 2 + 2 * kFaBKV * HD * 2 + 2 * HD * kFaBKV * 2 + 2 * kFaBQ * kFaBKV * 2) + 8 * sizeof(uint64_t) + 1024; }
 inline int flash_tc_skv_pad(int Skv) { return ceil_div(Skv, 64) * 64; }
-// workspace halfs: q hi|lo + k hi|lo ([head][token][64]) + v^T hi|lo ([head][64][skv_pad])
+// workspace halfs: q hi|lo + k hi|lo ([head][token][HD]) + v^T hi|lo ([head][HD][skv_pad])
+template <int HD>
 inline size_t flash_tc_ws_halfs(const FlashArgs& a, int nheads) {
     const int nkv = nheads / a.groups;
-    return 2 * ((size_t)nheads * a.Sq + (size_t)nkv * a.Skv + (size_t)nkv * flash_tc_skv_pad(a.Skv)) * 64;
+    return 2 * ((size_t)nheads * a.Sq + (size_t)nkv * a.Skv + (size_t)nkv * flash_tc_skv_pad(a.Skv)) * HD;
 }
 inline void flash_attn_tc_init() {
-    const int smem = (int)flash_tc_smem_bytes();
-    AHA_CUDA_CHECK(cudaFuncSetAttribute(flash_attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    AHA_CUDA_CHECK(cudaFuncSetAttribute(flash_attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    AHA_CUDA_CHECK(cudaFuncSetAttribute(flash_attn_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)flash_tc_smem_bytes<64>()));
+    AHA_CUDA_CHECK(cudaFuncSetAttribute(flash_attn_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)flash_tc_smem_bytes<64>()));
+    AHA_CUDA_CHECK(cudaFuncSetAttribute(flash_attn_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)flash_tc_smem_bytes<128>()));
+    AHA_CUDA_CHECK(cudaFuncSetAttribute(flash_attn_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)flash_tc_smem_bytes<128>()));
 }
-// head_dim 64 only (ViT, audio encoder).  `ws`: at least flash_tc_ws_halfs() halfs.
+// head_dim 64 (ViT, audio encoder: 2 CTAs per SM) and 128 (LLM prefill, causal, GQA, paged KV: 1 CTA per SM).  `ws`: at least flash_tc_ws_halfs<HD>() halfs.
+template <int HD>
 inline void flash_attn_tc(cudaStream_t st, const FlashArgs& a, int nheads, bool causal, __half* ws) {
     if (a.Sq == 0) return;
-    constexpr int HD = 64;
     const int nkv = nheads / a.groups, pad = flash_tc_skv_pad(a.Skv);
     SplitTcArgs sp;
     sp.f = a; sp.nheads = nheads; sp.nkv = nkv; sp.skv_pad = pad;
     const size_t nq = (size_t)nheads * a.Sq * HD, nk = (size_t)nkv * a.Skv * HD, nv = (size_t)nkv * HD * pad;
     sp.q_hi = ws; sp.q_lo = ws + nq; sp.k_hi = ws + 2 * nq; sp.k_lo = sp.k_hi + nk; sp.vt_hi = sp.k_lo + nk; sp.vt_lo = sp.vt_hi + nv;
-    const unsigned blocks = (unsigned)std::min<size_t>(std::max<size_t>(ceil_div((int)std::max((size_t)nheads * a.Sq, (size_t)nkv * a.Skv), 8), (size_t)nkv * (pad / 64)), 148 * 32);
-    split_qkv_tc_kernel<<<dim3(blocks, 3), 128, 0, st>>>(sp);
+    const unsigned blocks = (unsigned)std::min<size_t>(std::max<size_t>(ceil_div((int)std::max((size_t)nheads * a.Sq, (size_t)nkv * a.Skv), 512 / HD), (size_t)nkv * (pad / 64)), 148 * 32);
+    split_qkv_tc_kernel<HD><<<dim3(blocks, 3), 128, 0, st>>>(sp);
     const CUtensorMap tqh = make_tmap_f16_box(sp.q_hi, (uint64_t)nheads * a.Sq, HD, kFaBQ), tql = make_tmap_f16_box(sp.q_lo, (uint64_t)nheads * a.Sq, HD, kFaBQ);
     const CUtensorMap tkh = make_tmap_f16_box(sp.k_hi, (uint64_t)nkv * a.Skv, HD, kFaBKV), tkl = make_tmap_f16_box(sp.k_lo, (uint64_t)nkv * a.Skv, HD, kFaBKV);
     const CUtensorMap tvh = make_tmap_f16_box(sp.vt_hi, (uint64_t)nkv * HD, (uint64_t)pad, HD), tvl = make_tmap_f16_box(sp.vt_lo, (uint64_t)nkv * HD, (uint64_t)pad, HD);
@@ -332,9 +346,9 @@ inline void flash_attn_tc(cudaStream_t st, const FlashArgs& a, int nheads, bool 
     m.out = a.out; m.o_tok_stride = a.o_tok_stride; m.o_head_stride = a.o_head_stride;
     m.Sq = a.Sq; m.Skv = a.Skv; m.q0 = a.q0; m.groups = a.groups; m.scaling = a.scaling;
     dim3 grid(ceil_div(a.Sq, kFaBQ), nheads);
-    const size_t smem = flash_tc_smem_bytes();
-    if (causal) flash_attn_tc_kernel<true><<<grid, kFaThreads, smem, st>>>(tqh, tql, tkh, tkl, tvh, tvl, m);
-    else flash_attn_tc_kernel<false><<<grid, kFaThreads, smem, st>>>(tqh, tql, tkh, tkl, tvh, tvl, m);
+    const size_t smem = flash_tc_smem_bytes<HD>();
+    if (causal) flash_attn_tc_kernel<HD, true><<<grid, kFaThreads, smem, st>>>(tqh, tql, tkh, tkl, tvh, tvl, m);
+    else flash_attn_tc_kernel<HD, false><<<grid, kFaThreads, smem, st>>>(tqh, tql, tkh, tkl, tvh, tvl, m);
     AHA_CUDA_CHECK(cudaGetLastError());
 }
 

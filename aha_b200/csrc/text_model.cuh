@@ -160,7 +160,7 @@ struct LinearW {
 template <int HD>
 inline void flash_dispatch(Ctx& c, const FlashArgs& a, int nheads, bool causal) {
     if (c.attn_impl == 1) flash_attn<HD>(c.stream, a, nheads, causal);
-    else if (HD == 64 && c.attn_impl == 0) { flash_attn_tc(c.stream, a, nheads, causal, c.split_buf((flash_tc_ws_halfs(a, nheads) + 1) / 2)); c.cnt.kernels++; }
+    else if (c.attn_impl == 0) { flash_attn_tc<HD>(c.stream, a, nheads, causal, c.split_buf((flash_tc_ws_halfs<HD>(a, nheads) + 1) / 2)); c.cnt.kernels++; }
     else { flash_attn_mma<HD>(c.stream, a, nheads, causal, c.split_buf((flash_mma_ws_halfs<HD>(a, nheads) + 1) / 2)); c.cnt.kernels++; }
     c.cnt.kernels++;
 }

@@ -290,6 +290,26 @@ def test_vl_attention_implementations_agree(vl):
             m2.close()
 
 
+@pytest.mark.parametrize("S", [1, 63, 64, 65, 200, 257, 500])
+def test_llm_prefill_attention_implementations_agree(q3, S):
+    """Causal GQA prefill over the paged KV cache (head_dim 128): tcgen05 kernel (default) == mma.sync kernel == fp32 SIMT twin == oracle,
+    at prompt lengths around the 128-query / 64-key tile edges."""
+    cfg, w, m, o = q3
+    ids = _ids(S, cfg["vocab_size"], 31 + S)
+    m.clear_cache(); o.clear_cache()
+    base = m.forward_initial(ids, 0)[0, 0]
+    want = o.forward_initial(ids.reshape(1, -1), 0)[0, 0]
+    o.clear_cache()
+    assert np.abs(base - want).max() <= TOL
+    for impl in (1, 2):
+        _, _, m2 = make_model("qwen3", "tiny", max_ctx=1024, attn_impl=impl)
+        try:
+            other = m2.forward_initial(ids, 0)[0, 0]
+            assert np.abs(base - other).max() <= 1e-4, impl
+        finally:
+            m2.close()
+
+
 def test_vl_text_only_prompt(vl):
     cfg, w, m, o = vl
     ids = _ids(12, 1000, 3)
