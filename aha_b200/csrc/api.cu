@@ -362,6 +362,7 @@ int aha_b200_create(const char* kind, const char* config_json, const aha_tensor_
         }
         m->text.alloc_runtime(max_ctx, max_prefill, o.use_graph != 0, o.decode_impl);
         m->text.init_tp(o.tp_comm);
+        if (m->kind == aha_model::QWEN3VL) m->vision.set_tp(m->text.tp_rank, m->text.tp_world, m->text.comm);   // images sharded over the ranks
         m->max_scatter = max_prefill;
         m->d_scatter_idx = m->ctx.alloc<int>(max_prefill);
         for (size_t i = 0; i < n_eos; ++i) m->stop_ids.push_back(eos_ids[i]);

@@ -21,6 +21,7 @@ struct NcclApi {
     int (*CommDestroy)(comm_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int /*dtype*/, int /*op*/, comm_t, cudaStream_t) = nullptr;
     int (*AllGather)(const void*, void*, size_t /*sendcount*/, int /*dtype*/, comm_t, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t /*count*/, int /*dtype*/, int /*root*/, comm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
     void* handle = nullptr;
     static constexpr int kFloat32 = 7, kInt8 = 0, kSum = 0;
@@ -40,6 +41,7 @@ struct NcclApi {
             api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
             api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
             api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
+            api.Broadcast = reinterpret_cast<decltype(api.Broadcast)>(sym("ncclBroadcast"));
             api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
         }
         return api;

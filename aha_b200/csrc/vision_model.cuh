@@ -177,13 +177,51 @@ struct VisionModel {
         gemm(EPI_ACT, xn, Hm, m.fc1, nullptr, 0, mtmp, Hm, N / m2, ACT_GELU_ERF);  // Activation::Gelu = erf (model.rs:131)
         gemm(EPI_STORE, mtmp, Hm, m.fc2, nullptr, 0, out, cfg.out_hidden, N / m2);
     }
+    // Tensor parallelism (new design): every image (every cu_seqlens segment group) is independent through all blocks and
+    // mergers, so a request with several images is sharded BY IMAGE over the ranks -- image i runs on rank (i * world) / n_images --
+    // and the (tokens, out_hidden) embeddings + deepstack tensors are exchanged with one broadcast per owner.  A single image stays
+    // replicated (its rows would have to be split by heads: not built).
+    int tp_rank = 0, tp_world = 1;
+    NcclApi::comm_t comm = nullptr;
+    void set_tp(int rank, int world, NcclApi::comm_t cm) { tp_rank = rank; tp_world = world; comm = cm; }
+
     // pixel_values already in `pix` (N rows); grid: host (n_img x 3)
     void forward(int N, const std::vector<std::array<int, 3>>& grid) {
+        const int n_img = (int)grid.size();
+        if (tp_world <= 1 || n_img < 2 || comm == nullptr || trace) { forward_range(0, N, grid, N); return; }
+        const int m2 = cfg.merge * cfg.merge;
+        std::vector<int> first_patch(n_img + 1, 0);
+        for (int i = 0; i < n_img; ++i) first_patch[i + 1] = first_patch[i] + grid[i][0] * grid[i][1] * grid[i][2];
+        AHA_REQUIRE(first_patch[n_img] == N, "pixel_values rows do not match image_grid_thw");
+        std::vector<int> lo(tp_world + 1, 0);   // rank r owns images [lo[r], lo[r + 1]): image i belongs to rank (i * world) / n_images (non-decreasing in i)
+        for (int r = 0; r <= tp_world; ++r) {
+            int i = 0;
+            while (i < n_img && (int)(((long long)i * tp_world) / n_img) < r) ++i;
+            lo[r] = i;
+        }
+        {
+            const int a = lo[tp_rank], b = lo[tp_rank + 1];
+            if (b > a) forward_range(first_patch[a], first_patch[b] - first_patch[a], std::vector<std::array<int, 3>>(grid.begin() + a, grid.begin() + b), N);
+        }
+        NcclApi& api = NcclApi::get();
+        for (int r = 0; r < tp_world; ++r) {
+            const int a = lo[r], b = lo[r + 1];
+            if (b <= a) continue;
+            const size_t off = (size_t)(first_patch[a] / m2) * cfg.out_hidden, cnt = (size_t)((first_patch[b] - first_patch[a]) / m2) * cfg.out_hidden;
+            api.check(api.Broadcast(image_embeds + off, image_embeds + off, cnt, NcclApi::kFloat32, r, comm, ctx->stream), "ncclBroadcast(image embeds)");
+            for (float* d : ds_out) api.check(api.Broadcast(d + off, d + off, cnt, NcclApi::kFloat32, r, comm, ctx->stream), "ncclBroadcast(deepstack)");
+        }
+        last_N = N;
+    }
+    // the tower on patches [p_start, p_start + N) of `pix` (whole images `grid`); outputs land at their global token offsets
+    void forward_range(int p_start, int N, const std::vector<std::array<int, 3>>& grid, int N_total) {
         Ctx& c = *ctx;
         cudaStream_t st = c.stream;
         const int Hv = cfg.H;
-        AHA_REQUIRE(N <= max_patches, "image needs " + std::to_string(N) + " patches, max_patches is " + std::to_string(max_patches));
-        gemm(EPI_STORE, pix, patch_dim, patch, nullptr, 0, x, Hv, N);
+        const int m2_ = cfg.merge * cfg.merge;
+        AHA_REQUIRE(N_total <= max_patches, "image needs " + std::to_string(N_total) + " patches, max_patches is " + std::to_string(max_patches));
+        float* const emb_out = image_embeds + (size_t)(p_start / m2_) * cfg.out_hidden;
+        gemm(EPI_STORE, pix + (size_t)p_start * patch_dim, patch_dim, patch, nullptr, 0, x, Hv, N);
         int p0 = 0;
         std::vector<std::pair<int, int>> segs;  // (start, len) -- cu_seqlens = cumsum(h*w repeated t), model.rs:709-720
         for (auto& g : grid) {
@@ -219,10 +257,10 @@ struct VisionModel {
             gemm(EPI_RESID, h, cfg.I, b.fc2, x, Hv, x, Hv, N);
             if (trace) AHA_CUDA_CHECK(cudaMemcpyAsync(trace_buf + (size_t)(i + 1) * max_patches * Hv, x, (size_t)N * Hv * sizeof(float), cudaMemcpyDeviceToDevice, st));
             for (size_t k = 0; k < cfg.deepstack.size(); ++k)
-                if (cfg.deepstack[k] == i) run_merger(ds_mergers[k], x, N, ds_out[k]);
+                if (cfg.deepstack[k] == i) run_merger(ds_mergers[k], x, N, ds_out[k] + (size_t)(p_start / m2_) * cfg.out_hidden);
         }
-        run_merger(merger, x, N, image_embeds);
-        last_N = N;
+        run_merger(merger, x, N, emb_out);
+        last_N = N_total;
         AHA_CUDA_CHECK(cudaGetLastError());
     }
 };

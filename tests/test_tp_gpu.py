@@ -19,4 +19,4 @@ def test_tp2_matches_oracle():
            os.path.join(ROOT, "tests", "tp_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    assert "TP2 tiny ok" in r.stdout and "TP2 mid ok" in r.stdout, r.stdout[-2000:]
+    assert "TP2 tiny ok" in r.stdout and "TP2 mid ok" in r.stdout and "TP2 vl ok" in r.stdout, r.stdout[-2000:]

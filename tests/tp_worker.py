@@ -20,7 +20,43 @@ def main():
     from oracle.qwen3 import Qwen3Model
     for preset in ("tiny", "mid"):
         run(preset, rank, world, local, dist, torch, B200Model, synth, Qwen3Model, nccl_unique_id)
+    run_vl(rank, world, local, dist, torch, B200Model, synth, nccl_unique_id)
     dist.destroy_process_group()
+
+
+def run_vl(rank, world, local, dist, torch, B200Model, synth, nccl_unique_id):
+    """Qwen3-VL with three images under tensor parallelism: the ViT is sharded by image over the ranks (embeddings broadcast by
+    their owners), the text stack by heads; prefill + decode logits against the single-GPU oracle on every rank."""
+    from oracle.qwen3vl import Qwen3VLModel, process_image
+    uid = [nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    cfg = synth.get_config("qwen3vl", "tiny")
+    w = synth.make_weights("qwen3vl", cfg, 0)
+    m = B200Model("qwen3vl", cfg, w, device=local, max_ctx=1024, max_patches=2048, tp_rank=rank, tp_world=world, tp_unique_id=uid[0])
+    o = Qwen3VLModel(cfg, w)
+    pvs, grids = zip(*[process_image(synth.synth_image(h, w_, 40 + i)) for i, (h, w_) in enumerate([(256, 320), (320, 256), (192, 256)])])
+    pv, grid = np.concatenate(pvs, 0), np.concatenate(grids, 0)
+    ids = synth.vl_prompt_ids(cfg, grid, 7)
+    data = [pv, grid, None, None, None]
+    got = m.forward_initial(ids, 0, data)[0, 0]
+    want = o.forward_initial(ids.reshape(1, -1), 0, data)[0, 0]
+    err = float(np.abs(got - want).max())
+    assert err <= 1e-3, err
+    n = pv.shape[0] // 4 * cfg["vision_config"]["out_hidden_size"]
+    emb = m.debug_read("image_embeds", 0, n)
+    want_emb, _ = o.visual.forward(pv, grid)
+    assert float(np.abs(emb - want_emb.reshape(-1)).max()) <= 1e-4
+    S = len(ids)
+    g2 = m.forward_step(np.array([5], np.uint32), S)[0, 0]
+    w2 = o.forward_step(np.array([[5]]), S)[0, 0]
+    assert float(np.abs(g2 - w2).max()) <= 1e-3
+    mine = torch.from_numpy(np.stack([got, g2]))
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    assert all(torch.equal(g, gathered[0]) for g in gathered), "ranks disagree"
+    if rank == 0:
+        print(f"TP{world} vl ok: 3 images sharded over {world} ranks, max abs logit err {err:.2e}")
+    m.close()
 
 
 def run(preset, rank, world, local, dist, torch, B200Model, synth, Qwen3Model, nccl_unique_id):
