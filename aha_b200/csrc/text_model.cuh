@@ -39,7 +39,9 @@ struct Ctx {  // per-handle launch context
     std::vector<void*> allocs;
     size_t alloc_bytes = 0;
     int attn_impl = 0;            // 0 = auto (tcgen05 flash attention for head_dim 64, mma.sync for 128), 1 = fp32 SIMT flash attention, 2 = mma.sync everywhere
-    int gemm_impl = 0;            // 0 = auto (tcgen05 where the shape tiles), 1 = SIMT fp32, 2 = tcgen05 required
+    int gemm_impl = 0;            // 0 = auto (tcgen05 where the shape tiles), 1 = SIMT fp32, 2 = tcgen05 128 x 128 required, 3 = tcgen05 persistent 128 x 256 required
+    bool gemm_wide = true;        // auto: the persistent 128 x 256 kernel where N >= 256 (15-26 % faster than 128 x 128 on every prefill shape, profiles/r02_gemm_sweep.txt; AHA_GEMM_WIDE=0 turns it off)
+    int gemm_group_m = 8;         // row blocks per band of the persistent kernel's tile walk (AHA_GEMM_GROUP)
     __half* split_ws = nullptr;   // [2][rows*K] hi | lo halves of the activation operand
     size_t split_cap = 0;         // halfs per half-buffer
     __half* split_buf(size_t halfs) {
@@ -154,6 +156,8 @@ struct LinearW {
     int N = 0, K = 0;
     CUtensorMap tmap;     // TMA descriptor of w (128 x 64 boxes, SWIZZLE_128B) when has_tmap
     bool has_tmap = false;
+    CUtensorMap tmap256;  // the same with 256-row boxes (persistent 128 x 256 GEMM)
+    bool has_tmap256 = false;
 };
 
 // Prefill attention dispatch: tensor-core kernel (attention_mma.cuh) unless the exact SIMT twin is requested.
@@ -170,7 +174,7 @@ inline void flash_dispatch(Ctx& c, const FlashArgs& a, int nheads, bool causal) 
 inline void linear_gemm(Ctx& c, int epi, const float* A, int lda, LinearW& W, const float* resid, int ldr, float* C, int ldc, int M, int act = ACT_NONE) {
     if (M == 0) return;
     const bool tc_ok = gemm_tc_supported(M, W.N, W.K) && lda % 4 == 0;
-    AHA_REQUIRE(c.gemm_impl != 2 || tc_ok, "gemm_impl=2 (tcgen05) requested but the shape does not tile (K % 64, N % 32)");
+    AHA_REQUIRE(c.gemm_impl < 2 || tc_ok, "gemm_impl=2/3/4 (tcgen05) requested but the shape does not tile (K % 64, N % 32)");
     if (c.gemm_impl == 1 || !tc_ok || (c.gemm_impl == 0 && M < 32)) {
         GemmArgs g;
         g.A = A; g.lda = lda; g.W = W.w; g.bias = W.b; g.resid = resid; g.ldr = ldr; g.C = C; g.ldc = ldc; g.M = M; g.N = W.N; g.K = W.K; g.act = act;
@@ -186,7 +190,15 @@ inline void linear_gemm(Ctx& c, int epi, const float* A, int lda, LinearW& W, co
     split_f32_to_f16x2_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, c.stream>>>(A, lda, hi, lo, M, W.K);
     GemmTcArgs g;
     g.bias = W.b; g.resid = resid; g.ldr = ldr; g.C = C; g.ldc = ldc; g.M = M; g.N = W.N; g.K = W.K; g.act = act;
-    gemm_tc_launch(c.stream, epi, hi, lo, W.tmap, g);
+    g.group_m = std::max(1, c.gemm_group_m);
+    if (c.gemm_impl == 4) {
+        gemm_tc3_launch(c.stream, epi, hi, lo, W.tmap, g, c.num_sms);
+    } else if (c.gemm_impl == 3 || (c.gemm_impl == 0 && c.gemm_wide && W.N >= 256)) {
+        if (!W.has_tmap256) { W.tmap256 = make_tmap_f16_rows(W.w, (uint64_t)W.N, (uint64_t)W.K, 256); W.has_tmap256 = true; }
+        gemm_tc2_launch(c.stream, epi, hi, lo, W.tmap256, g, c.num_sms);
+    } else {
+        gemm_tc_launch(c.stream, epi, hi, lo, W.tmap, g);
+    }
     c.cnt.kernels += 2;
 }
 
@@ -224,6 +236,36 @@ inline LinearW upload_linear(Ctx& c, const WeightTable& wt, const std::vector<Ro
             for (size_t i = 0; i < h; ++i) { bi[2 * i] = b[i]; bi[2 * i + 1] = b[h + i]; }
             b.swap(bi);
         }
+        L.b = upload(c, b);
+    }
+    return L;
+}
+
+// One matrix uploaded through row / column maps: destination row r is source row row_map[r] (or all zeros when -1), destination
+// column k is source column col_map[k] (or zero).  Used to pad shapes the tensor-core kernels do not tile (vision head_dim 72 ->
+// 128-wide head slots, intermediate 4304 -> 4352): zero rows / columns leave the product unchanged.
+inline LinearW upload_linear_mapped(Ctx& c, const WeightTable& wt, const std::string& name, int64_t N_src, int64_t K_src, const std::vector<int>& row_map,
+                                    const std::vector<int>& col_map, const std::string& bias_name) {
+    std::vector<__half> src((size_t)N_src * K_src);
+    wt.rows_to_half(name, N_src, K_src, 0, N_src, 0, K_src, src.data(), K_src);
+    const size_t N = row_map.size(), K = col_map.size();
+    std::vector<__half> stage(N * K, __float2half(0.f));
+    for (size_t r = 0; r < N; ++r) {
+        if (row_map[r] < 0) continue;
+        AHA_REQUIRE(row_map[r] < N_src, "row map out of range for " + name);
+        const __half* sr = src.data() + (size_t)row_map[r] * K_src;
+        __half* dr = stage.data() + r * K;
+        for (size_t k = 0; k < K; ++k)
+            if (col_map[k] >= 0) dr[k] = sr[col_map[k]];
+    }
+    LinearW L;
+    L.N = (int)N; L.K = (int)K;
+    L.w = upload(c, stage);
+    if (!bias_name.empty()) {
+        auto v = wt.vec_f32(bias_name, (size_t)N_src);
+        std::vector<float> b(N, 0.f);
+        for (size_t r = 0; r < N; ++r)
+            if (row_map[r] >= 0) b[r] = v[row_map[r]];
         L.b = upload(c, b);
     }
     return L;

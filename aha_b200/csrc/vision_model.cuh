@@ -64,11 +64,11 @@ __global__ void vit_pos_embed_kernel(float* __restrict__ x, const __half* __rest
     }
 }
 
-// 2-D RoPE on q and k in place.  qkv: [N, 3*Hv]; head dim HD=64; freq j<16 from the row, 16<=j<32 from the col
-// (table p * inv_freq(dim=32, theta=1e4), rope.rs:424-441); emb = cat(f, f); x*cos + rotate_half(x)*sin.
-__global__ void vit_rope_kernel(float* __restrict__ qkv, const int2* __restrict__ rowcol, const float* __restrict__ inv_freq,
+// 2-D RoPE on q and k in place.  qkv: [N, 3*Hv] with Hv = heads * HDP (head slots of HDP floats, the first HD are the head);
+// freq j < HD/4 from the row, HD/4 <= j < HD/2 from the col (table p * inv_freq(dim=HD/2, theta=1e4), rope.rs:424-441);
+// emb = cat(f, f); x*cos + rotate_half(x)*sin.
+__global__ void vit_rope_kernel(float* __restrict__ qkv, const int2* __restrict__ rowcol, const float* __restrict__ inv_freq, int HD, int HDP,
                                 int heads, int Hv) {
-    constexpr int HD = 64;
     const int p = blockIdx.x;
     const int2 rc = rowcol[p];
     for (int idx = threadIdx.x; idx < 2 * heads * (HD / 2); idx += blockDim.x) {
@@ -77,7 +77,7 @@ __global__ void vit_rope_kernel(float* __restrict__ qkv, const int2* __restrict_
         const int hh = rem / (HD / 2), j = rem % (HD / 2);
         const float ang = (j < HD / 4) ? (float)rc.x * inv_freq[j] : (float)rc.y * inv_freq[j - HD / 4];
         const float c = cosf(ang), s = sinf(ang);
-        float* base = qkv + (size_t)p * 3 * Hv + (size_t)which * Hv + (size_t)hh * HD;
+        float* base = qkv + (size_t)p * 3 * Hv + (size_t)which * Hv + (size_t)hh * HDP;
         const float x1 = base[j], x2 = base[j + HD / 2];
         base[j] = x1 * c - x2 * s;
         base[j + HD / 2] = x2 * c + x1 * s;
@@ -100,7 +100,9 @@ struct VisionModel {
     LinearW patch;         // [Hv, 1536] + bias
     __half* pos_embed = nullptr;
     int n_side = 0;
-    float* inv_freq = nullptr;  // 16 entries
+    float* inv_freq = nullptr;  // hd / 4 entries
+    int hd = 64, hdp = 64;      // head_dim and the width of a head slot in qkv / attn (64, or 128 when head_dim is not 64: zero padded)
+    int Hp = 0, Ip = 0;         // heads * hdp; intermediate size rounded up to a multiple of 64 (zero rows / columns)
     std::vector<VisionBlock> blocks;
     Merger merger;
     std::vector<Merger> ds_mergers;
@@ -128,9 +130,18 @@ struct VisionModel {
     }
     void load(Ctx& c, const VisionCfg& cf, const WeightTable& wt, const std::string& p, int max_patches_) {
         ctx = &c; cfg = cf; max_patches = max_patches_;
-        AHA_REQUIRE(cfg.H / cfg.heads == 64, "vision head_dim must be 64");
+        // head_dim 64 (Qwen3-VL-2B / 4B towers) runs as is; any other head_dim <= 128 (72 in the 8B / 32B towers) is laid out in
+        // 128-wide head slots whose tail is zero: the qkv rows and the proj columns are padded at upload, so every kernel downstream
+        // (RoPE, the tcgen05 attention, the GEMMs) sees a shape it tiles and the result is unchanged.  The same for an
+        // intermediate size that is not a multiple of 64 (4304 -> 4352).
+        AHA_REQUIRE(cfg.H % cfg.heads == 0, "vision hidden_size must be a multiple of num_heads");
+        hd = cfg.H / cfg.heads;
+        AHA_REQUIRE(hd % 4 == 0 && hd <= 128, "vision head_dim must be a multiple of 4 and at most 128");
+        hdp = hd == 64 ? 64 : 128;
+        Hp = cfg.heads * hdp;
+        Ip = (cfg.I + 63) / 64 * 64;
         patch_dim = cfg.in_ch * cfg.tpatch * cfg.patch * cfg.patch;
-        AHA_REQUIRE(patch_dim % 16 == 0 && cfg.H % 16 == 0 && cfg.I % 16 == 0, "vision sizes must be multiples of 16");
+        AHA_REQUIRE(patch_dim % 16 == 0 && cfg.H % 16 == 0, "vision patch and hidden sizes must be multiples of 16");   // the intermediate size is padded to 64
         patch = upload_linear(c, wt, {{p + "patch_embed.proj.weight", cfg.H, 0, cfg.H}}, patch_dim, 0, patch_dim, false, {p + "patch_embed.proj.bias"});
         {
             std::vector<__half> st((size_t)cfg.npos * cfg.H);
@@ -138,25 +149,41 @@ struct VisionModel {
             pos_embed = upload(c, st);
         }
         n_side = (int)sqrtf((float)cfg.npos);  // (num_position_embeddings as f32).sqrt() as u32, model.rs:395
-        std::vector<float> inv(16);
-        for (int j = 0; j < 16; ++j) inv[j] = 1.0f / powf(10000.0f, (float)(2 * j) / 32.0f);
+        std::vector<float> inv(hd / 4);
+        for (int j = 0; j < hd / 4; ++j) inv[j] = 1.0f / powf(10000.0f, (float)(2 * j) / (float)(hd / 2));
         inv_freq = upload(c, inv);
+        std::vector<int> id_H(cfg.H), id_I(cfg.I), slot_rows(3 * (size_t)Hp, -1), slot_cols((size_t)Hp, -1), pad_I((size_t)Ip, -1);
+        for (int i = 0; i < cfg.H; ++i) id_H[i] = i;
+        for (int i = 0; i < cfg.I; ++i) { id_I[i] = i; pad_I[i] = i; }
+        for (int w3 = 0; w3 < 3; ++w3)
+            for (int hh = 0; hh < cfg.heads; ++hh)
+                for (int d = 0; d < hd; ++d) slot_rows[(size_t)w3 * Hp + (size_t)hh * hdp + d] = w3 * cfg.H + hh * hd + d;
+        for (int hh = 0; hh < cfg.heads; ++hh)
+            for (int d = 0; d < hd; ++d) slot_cols[(size_t)hh * hdp + d] = hh * hd + d;
+        const bool padded = hdp != hd || Ip != cfg.I;
         blocks.resize(cfg.depth);
         for (int i = 0; i < cfg.depth; ++i) {
             const std::string bp = p + "blocks." + std::to_string(i) + ".";
             VisionBlock& b = blocks[i];
             b.n1w = upload_vec(c, wt, bp + "norm1.weight", cfg.H); b.n1b = upload_vec(c, wt, bp + "norm1.bias", cfg.H);
             b.n2w = upload_vec(c, wt, bp + "norm2.weight", cfg.H); b.n2b = upload_vec(c, wt, bp + "norm2.bias", cfg.H);
-            b.qkv = lin(c, wt, bp + "attn.qkv", 3 * cfg.H, cfg.H);
-            b.proj = lin(c, wt, bp + "attn.proj", cfg.H, cfg.H);
-            b.fc1 = lin(c, wt, bp + "mlp.linear_fc1", cfg.I, cfg.H);
-            b.fc2 = lin(c, wt, bp + "mlp.linear_fc2", cfg.H, cfg.I);
+            if (!padded) {
+                b.qkv = lin(c, wt, bp + "attn.qkv", 3 * cfg.H, cfg.H);
+                b.proj = lin(c, wt, bp + "attn.proj", cfg.H, cfg.H);
+                b.fc1 = lin(c, wt, bp + "mlp.linear_fc1", cfg.I, cfg.H);
+                b.fc2 = lin(c, wt, bp + "mlp.linear_fc2", cfg.H, cfg.I);
+            } else {
+                b.qkv = upload_linear_mapped(c, wt, bp + "attn.qkv.weight", 3 * cfg.H, cfg.H, slot_rows, id_H, bp + "attn.qkv.bias");
+                b.proj = upload_linear_mapped(c, wt, bp + "attn.proj.weight", cfg.H, cfg.H, id_H, slot_cols, bp + "attn.proj.bias");
+                b.fc1 = upload_linear_mapped(c, wt, bp + "mlp.linear_fc1.weight", cfg.I, cfg.H, pad_I, id_H, bp + "mlp.linear_fc1.bias");
+                b.fc2 = upload_linear_mapped(c, wt, bp + "mlp.linear_fc2.weight", cfg.H, cfg.I, id_H, pad_I, bp + "mlp.linear_fc2.bias");
+            }
         }
         merger = load_merger(c, wt, p + "merger.", false);
         for (size_t i = 0; i < cfg.deepstack.size(); ++i) ds_mergers.push_back(load_merger(c, wt, p + "deepstack_merger_list." + std::to_string(i) + ".", true));
         const size_t N = max_patches, Hv = cfg.H, m2 = (size_t)cfg.merge * cfg.merge;
         pix = c.alloc<float>(N * patch_dim); x = c.alloc<float>(N * Hv); xn = c.alloc<float>(N * Hv);
-        qkv = c.alloc<float>(N * 3 * Hv); attn = c.alloc<float>(N * Hv); h = c.alloc<float>(N * cfg.I); mtmp = c.alloc<float>(N * Hv);
+        qkv = c.alloc<float>(N * 3 * Hp); attn = c.alloc<float>(N * Hp); h = c.alloc<float>(N * Ip); mtmp = c.alloc<float>(N * Hv);
         image_embeds = c.alloc<float>(N / m2 * cfg.out_hidden);
         for (size_t i = 0; i < cfg.deepstack.size(); ++i) ds_out.push_back(c.alloc<float>(N / m2 * cfg.out_hidden));
         rowcol = c.alloc<int2>(N);
@@ -236,25 +263,26 @@ struct VisionModel {
         }
         AHA_REQUIRE(p0 == N, "pixel_values rows do not match image_grid_thw");
         if (trace) AHA_CUDA_CHECK(cudaMemcpyAsync(trace_buf, x, (size_t)N * Hv * sizeof(float), cudaMemcpyDeviceToDevice, st));
-        const float scaling = (float)(1.0 / std::sqrt(64.0));
+        const float scaling = (float)(1.0 / std::sqrt((double)hd));
         for (int i = 0; i < cfg.depth; ++i) {
             VisionBlock& b = blocks[i];
             layernorm_kernel<<<N, 256, 0, st>>>(x, b.n1w, b.n1b, 1e-6f, xn, Hv); c.cnt.kernels++;
-            gemm(EPI_STORE, xn, Hv, b.qkv, nullptr, 0, qkv, 3 * Hv, N);
-            vit_rope_kernel<<<N, 256, 0, st>>>(qkv, rowcol, inv_freq, cfg.heads, Hv); c.cnt.kernels++;
+            gemm(EPI_STORE, xn, Hv, b.qkv, nullptr, 0, qkv, 3 * Hp, N);
+            vit_rope_kernel<<<N, 256, 0, st>>>(qkv, rowcol, inv_freq, hd, hdp, cfg.heads, Hp); c.cnt.kernels++;
             for (auto& sg : segs) {
                 FlashArgs fa;
-                fa.q = qkv; fa.q_tok_stride = 3 * Hv; fa.q_head_stride = 64;
-                fa.kv.k = qkv + Hv; fa.kv.v = qkv + 2 * Hv; fa.kv.page_table = nullptr; fa.kv.page_shift = 0; fa.kv.page_stride = 0;
-                fa.kv.tok_stride = 3 * Hv; fa.kv.head_stride = 64;
-                fa.out = attn; fa.o_tok_stride = Hv; fa.o_head_stride = 64;
+                fa.q = qkv; fa.q_tok_stride = 3 * Hp; fa.q_head_stride = hdp;
+                fa.kv.k = qkv + Hp; fa.kv.v = qkv + 2 * Hp; fa.kv.page_table = nullptr; fa.kv.page_shift = 0; fa.kv.page_stride = 0;
+                fa.kv.tok_stride = 3 * Hp; fa.kv.head_stride = hdp;
+                fa.out = attn; fa.o_tok_stride = Hp; fa.o_head_stride = hdp;
                 fa.Sq = sg.second; fa.Skv = sg.second; fa.q0 = sg.first; fa.kv0 = sg.first; fa.groups = 1; fa.scaling = scaling;
-                flash_dispatch<64>(c, fa, cfg.heads, false);
+                if (hdp == 64) flash_dispatch<64>(c, fa, cfg.heads, false);
+                else flash_dispatch<128>(c, fa, cfg.heads, false);
             }
-            gemm(EPI_RESID, attn, Hv, b.proj, x, Hv, x, Hv, N);
+            gemm(EPI_RESID, attn, Hp, b.proj, x, Hv, x, Hv, N);
             layernorm_kernel<<<N, 256, 0, st>>>(x, b.n2w, b.n2b, 1e-6f, xn, Hv); c.cnt.kernels++;
-            gemm(EPI_ACT, xn, Hv, b.fc1, nullptr, 0, h, cfg.I, N, cfg.act);
-            gemm(EPI_RESID, h, cfg.I, b.fc2, x, Hv, x, Hv, N);
+            gemm(EPI_ACT, xn, Hv, b.fc1, nullptr, 0, h, Ip, N, cfg.act);   // padded rows: act(0 + 0) = 0 for gelu / silu, and fc2's padded columns are zero anyway
+            gemm(EPI_RESID, h, Ip, b.fc2, x, Hv, x, Hv, N);
             if (trace) AHA_CUDA_CHECK(cudaMemcpyAsync(trace_buf + (size_t)(i + 1) * max_patches * Hv, x, (size_t)N * Hv * sizeof(float), cudaMemcpyDeviceToDevice, st));
             for (size_t k = 0; k < cfg.deepstack.size(); ++k)
                 if (cfg.deepstack[k] == i) run_merger(ds_mergers[k], x, N, ds_out[k] + (size_t)(p_start / m2_) * cfg.out_hidden);

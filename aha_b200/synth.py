@@ -37,6 +37,9 @@ _VIS_2B = dict(deepstack_visual_indexes=[5, 11, 17], depth=24, hidden_act="gelu_
 _VIS_TINY = dict(deepstack_visual_indexes=[0, 2], depth=4, hidden_act="gelu_pytorch_tanh", hidden_size=128,
                  in_channels=3, intermediate_size=256, num_heads=2, num_position_embeddings=64,
                  out_hidden_size=256, patch_size=16, spatial_merge_size=2, temporal_patch_size=2)
+# the Qwen3-VL-8B / 32B tower: hidden 1152 over 16 heads = head_dim 72, intermediate 4304 (neither tiles the tensor-core kernels: the
+# library pads head slots to 128 and the intermediate to 4352 at upload, vision_model.cuh)
+_VIS_8B = dict(_VIS_2B, depth=27, deepstack_visual_indexes=[8, 16, 24], hidden_size=1152, intermediate_size=4304, out_hidden_size=4096)
 _VL_IDS = dict(image_token_id=151655, video_token_id=151656, vision_start_token_id=151652, vision_end_token_id=151653)
 
 QWEN3VL = {
@@ -44,18 +47,22 @@ QWEN3VL = {
                  tie_word_embeddings=True,
                  text_config=dict(_TEXT_TINY, rope_theta=5000000.0, rope_scaling=dict(_MROPE)),
                  vision_config=dict(_VIS_TINY)),
+    # head_dim 72 and an intermediate size that is not a multiple of 64, at test cost (K = 576 and the padded shapes tile the tcgen05 GEMM)
+    "tiny-hd72": dict(image_token_id=1001, video_token_id=1002, vision_start_token_id=1003, vision_end_token_id=1004,
+                      tie_word_embeddings=True,
+                      text_config=dict(_TEXT_TINY, rope_theta=5000000.0, rope_scaling=dict(_MROPE)),
+                      vision_config=dict(_VIS_TINY, depth=2, deepstack_visual_indexes=[0], hidden_size=576, num_heads=8,
+                                         intermediate_size=1080)),
     "vl2": dict(_VL_IDS, tie_word_embeddings=True,
                 text_config=dict(_TEXT_06, hidden_size=2048, intermediate_size=6144, rope_theta=5000000.0,
                                  rope_scaling=dict(_MROPE)),
                 vision_config=dict(_VIS_2B)),
-    # BASELINE.json config 5 says "7B"; the reference registry has 2B/4B/8B/32B only (model_mapping.rs:57-64) -> the 8B text stack
-    # (H 4096, 36 layers, 32 / 8 heads, I 12288).  Vision tower: the real 8B tower has hidden 1152 / 16 heads = head_dim 72, which
-    # this build's ViT attention does not cover (head_dim 64 only); the preset keeps the 2B tower's width (1024 / 16 = 64) at the 8B
-    # tower's depth and deepstack taps -- config 5 measures the tensor-parallel TEXT stack over a ~17k-token multimodal context.
+    # BASELINE.json config 5 says "7B"; the reference registry has 2B/4B/8B/32B only (model_mapping.rs:57-64) -> Qwen3-VL-8B: text stack
+    # H 4096, 36 layers, 32 / 8 heads, I 12288; vision tower 27 blocks of hidden 1152 / 16 heads (head_dim 72), intermediate 4304.
     "vl8": dict(_VL_IDS, tie_word_embeddings=False,
                 text_config=dict(_TEXT_06, hidden_size=4096, intermediate_size=12288, num_attention_heads=32,
                                  num_hidden_layers=36, rope_theta=5000000.0, rope_scaling=dict(_MROPE)),
-                vision_config=dict(_VIS_2B, depth=27, deepstack_visual_indexes=[8, 16, 24], out_hidden_size=4096)),
+                vision_config=dict(_VIS_8B)),
 }
 
 _AUD_06 = dict(activation_function="gelu", conv_chunksize=500, d_model=896, downsample_hidden_size=480,

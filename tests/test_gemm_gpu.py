@@ -36,7 +36,7 @@ def _ref(x, w16, bias, resid, epi, act):
     return y
 
 
-@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("impl", [1, 2, 3])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (200, 256, 128), (1, 128, 64), (333, 384, 512), (129, 160, 1024), (64, 96, 2048)])
 def test_gemm_store(m, impl, M, N, K):
     rng = np.random.default_rng(M * 7 + N + K)
@@ -47,7 +47,7 @@ def test_gemm_store(m, impl, M, N, K):
     assert np.abs(y - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
 
 
-@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("impl", [1, 2, 3])
 @pytest.mark.parametrize("epi,act", [(1, 0), (2, 1), (2, 2), (2, 3), (3, 0)])
 def test_gemm_epilogues(m, impl, epi, act):
     rng = np.random.default_rng(epi * 10 + act)

@@ -268,6 +268,28 @@ def test_vl_vision_tower_blocks(vl):
     o.visual.trace = None
 
 
+@pytest.mark.parametrize("attn_impl,gemm_impl", [(0, 0), (1, 1), (2, 0)])
+def test_vl_head_dim_72_tower(attn_impl, gemm_impl):
+    """The Qwen3-VL-8B / 32B tower shape class: head_dim 72 (laid out in zero-padded 128-wide head slots) and an intermediate size that
+    is not a multiple of 64 (zero-padded rows / columns): every block output, the merged embeddings and the prefill logits against the
+    oracle, on the tensor-core kernels and on the exact fp32 twins."""
+    cfg, w, m = make_model("qwen3vl", "tiny-hd72", max_ctx=1024, max_patches=2048, attn_impl=attn_impl, gemm_impl=gemm_impl)
+    try:
+        o = make_oracle("qwen3vl", cfg, w)
+        pv, grid, ids = _vl_inputs(cfg, [(256, 320), (160, 96)], 5)
+        m.set_trace(True)
+        o.visual.trace = []
+        got = m.forward_initial(ids, 0, [pv, grid, None, None, None])[0, 0]
+        want = o.forward_initial(ids.reshape(1, -1), 0, [pv, grid, None, None, None])[0, 0]
+        Hv, N = cfg["vision_config"]["hidden_size"], pv.shape[0]
+        for i, (name, x) in enumerate(o.visual.trace):
+            g = m.debug_read("vit", i, N * Hv).reshape(N, Hv)
+            assert np.abs(g - x).max() <= 1e-4, name
+        assert np.abs(got - want).max() <= TOL
+    finally:
+        m.close()
+
+
 def test_vl_attention_implementations_agree(vl):
     """ViT attention: tcgen05 kernel (default for head_dim 64) == mma.sync kernel == fp32 SIMT twin on a two-image (varlen) prompt
     whose segment lengths are not multiples of the 128-query / 64-key tiles."""
