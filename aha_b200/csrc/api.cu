@@ -317,6 +317,8 @@ int aha_b200_create(const char* kind, const char* config_json, const aha_tensor_
         m->ctx.gemm_impl = o.gemm_impl;
         { const char* e = getenv("AHA_GEMM_WIDE"); if (e) m->ctx.gemm_wide = atoi(e) != 0; }
         { const char* e = getenv("AHA_GEMM_GROUP"); if (e) m->ctx.gemm_group_m = atoi(e); }
+        { const char* e = getenv("AHA_GEMM_PAIR"); if (e) m->ctx.gemm_pair = atoi(e) != 0; }
+        { const char* e = getenv("AHA_PRESPLIT"); if (e) m->ctx.presplit = atoi(e) != 0; }
         m->ctx.attn_impl = o.reserved[0];   // 0 = tensor-core flash attention (tcgen05 for head_dim 64), 1 = fp32 SIMT twin, 2 = mma.sync kernel everywhere
         AHA_CUDA_CHECK(cudaSetDevice(o.device));
         AHA_CUDA_CHECK(cudaStreamCreateWithFlags(&m->ctx.stream, cudaStreamNonBlocking));

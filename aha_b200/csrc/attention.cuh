@@ -94,6 +94,8 @@ struct FlashArgs {
     int q0, kv0;       // first query / kv token index of the segment (varlen segments, ViT cu_seqlens)
     int groups;        // q heads per kv head
     float scaling;
+    __half* out_hi = nullptr;   // tcgen05 kernel only: write the output as fp16 hi + lo halves (same strides as `out`) for the GEMM
+    __half* out_lo = nullptr;   // that follows, instead of fp32 `out`
 };
 
 template <int HD, bool CAUSAL>

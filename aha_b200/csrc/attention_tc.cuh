@@ -96,6 +96,7 @@ __global__ void split_qkv_tc_kernel(SplitTcArgs s) {
 
 struct FlashTcArgs {
     float* out; size_t o_tok_stride, o_head_stride;
+    __half *out_hi, *out_lo;   // when set: the output goes out as fp16 hi + lo halves (operand format of the next GEMM) instead of fp32
     int Sq, Skv, q0, groups;
     float scaling;
 };
@@ -300,9 +301,23 @@ __global__ void __launch_bounds__(kFaThreads, HD == 64 ? 2 : 1) flash_attn_tc_ke
         }
         if (qi < a.Sq) {
             const float inv = 1.0f / l;
-            float* dst = a.out + (size_t)(a.q0 + qi) * a.o_tok_stride + (size_t)head * a.o_head_stride;
+            const size_t off = (size_t)(a.q0 + qi) * a.o_tok_stride + (size_t)head * a.o_head_stride;
+            if (a.out_hi) {
 #pragma unroll
-            for (int c = 0; c < HD; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(o[c] * inv, o[c + 1] * inv, o[c + 2] * inv, o[c + 3] * inv);
+                for (int c = 0; c < HD; c += 8) {
+                    float r[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) r[e] = o[c + e] * inv;
+                    uint4 hi, lo;
+                    pack8_split(r, hi, lo);
+                    *reinterpret_cast<uint4*>(a.out_hi + off + c) = hi;
+                    *reinterpret_cast<uint4*>(a.out_lo + off + c) = lo;
+                }
+            } else {
+                float* dst = a.out + off;
+#pragma unroll
+                for (int c = 0; c < HD; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(o[c] * inv, o[c + 1] * inv, o[c + 2] * inv, o[c + 3] * inv);
+            }
         }
     }
     tc_fence_before();
@@ -343,7 +358,7 @@ inline void flash_attn_tc(cudaStream_t st, const FlashArgs& a, int nheads, bool 
     const CUtensorMap tkh = make_tmap_f16_box(sp.k_hi, (uint64_t)nkv * a.Skv, HD, kFaBKV), tkl = make_tmap_f16_box(sp.k_lo, (uint64_t)nkv * a.Skv, HD, kFaBKV);
     const CUtensorMap tvh = make_tmap_f16_box(sp.vt_hi, (uint64_t)nkv * HD, (uint64_t)pad, HD), tvl = make_tmap_f16_box(sp.vt_lo, (uint64_t)nkv * HD, (uint64_t)pad, HD);
     FlashTcArgs m;
-    m.out = a.out; m.o_tok_stride = a.o_tok_stride; m.o_head_stride = a.o_head_stride;
+    m.out = a.out; m.o_tok_stride = a.o_tok_stride; m.o_head_stride = a.o_head_stride; m.out_hi = a.out_hi; m.out_lo = a.out_lo;
     m.Sq = a.Sq; m.Skv = a.Skv; m.q0 = a.q0; m.groups = a.groups; m.scaling = a.scaling;
     dim3 grid(ceil_div(a.Sq, kFaBQ), nheads);
     const size_t smem = flash_tc_smem_bytes<HD>();

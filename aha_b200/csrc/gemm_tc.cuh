@@ -135,8 +135,69 @@ struct GemmTcArgs {
     float* C; int ldc;
     int M, N, K;
     int act;
+    __half* out_hi = nullptr;   // when set, the result (after bias / activation / SwiGLU) is written as fp16 hi + lo halves [M, ldo] for the
+    __half* out_lo = nullptr;   // next GEMM instead of fp32 C (EPI_STORE / EPI_ACT / EPI_SWIGLU)
+    int ldo = 0;
     int group_m = 8;   // persistent kernel: tiles are walked in bands of group_m row blocks (n outer, m inner) so that one wave of CTAs shares few A and W tiles
 };
+
+// 8 floats -> 8 fp16 hi + 8 fp16 lo (one 16-byte store each)
+__device__ __forceinline__ void tc_store_split8(const float* v, __half* hi, __half* lo) {
+    __half h[8], l[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        h[e] = __float2half_rn(v[e]);
+        l[e] = __float2half_rn(v[e] - __half2float(h[e]));
+    }
+    *reinterpret_cast<uint4*>(hi) = *reinterpret_cast<const uint4*>(h);
+    *reinterpret_cast<uint4*>(lo) = *reinterpret_cast<const uint4*>(l);
+}
+// one thread's 32 consecutive accumulator columns [n, n + 32) of output row `row`: bias / residual / activation / SwiGLU, then fp32
+// stores -- or, when g.out_hi is set, the fp16 hi + lo halves the next GEMM reads
+template <int EPI>
+__device__ __forceinline__ void tc_epilogue_store(const GemmTcArgs& g, float (&v)[32], int row, int n) {
+    if (row >= g.M || n >= g.N) return;
+    if (g.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += g.bias[n + j];
+    }
+    if (EPI == EPI_SWIGLU) {
+        float r[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = silu_f(v[2 * j]) * v[2 * j + 1];
+        if (g.out_hi) {
+            const size_t o = (size_t)row * g.ldo + n / 2;
+            tc_store_split8(r, g.out_hi + o, g.out_lo + o);
+            tc_store_split8(r + 8, g.out_hi + o + 8, g.out_lo + o + 8);
+        } else {
+            float* out = g.C + (size_t)row * g.ldc + n / 2;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(out + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+        }
+        return;
+    }
+    if (EPI == EPI_ACT) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = apply_act(g.act, v[j]);
+    }
+    if (EPI == EPI_RESID) {
+        const float* rr = g.resid + (size_t)row * g.ldr + n;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 r4 = *reinterpret_cast<const float4*>(rr + j);
+            v[j] += r4.x; v[j + 1] += r4.y; v[j + 2] += r4.z; v[j + 3] += r4.w;
+        }
+    }
+    if (EPI != EPI_RESID && g.out_hi) {
+        const size_t o = (size_t)row * g.ldo + n;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) tc_store_split8(v + j, g.out_hi + o + j, g.out_lo + o + j);
+        return;
+    }
+    float* out = g.C + (size_t)row * g.ldc + n;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(out + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+}
 
 template <int EPI>
 __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
@@ -211,36 +272,7 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) gemm_tc_kernel(const
         for (int c0 = 0; c0 < kTcBN; c0 += 32) {
             float v[32];
             tmem_ld32(tmem_acc + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, v);
-            const int n = n0 + c0;
-            if (row < g.M && n < g.N) {
-                if (g.bias) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] += g.bias[n + j];
-                }
-                if (EPI == EPI_SWIGLU) {
-                    float* out = g.C + (size_t)row * g.ldc + n / 2;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8)
-                        *reinterpret_cast<float4*>(out + j / 2) = make_float4(silu_f(v[j]) * v[j + 1], silu_f(v[j + 2]) * v[j + 3], silu_f(v[j + 4]) * v[j + 5],
-                                                                             silu_f(v[j + 6]) * v[j + 7]);
-                } else {
-                    if (EPI == EPI_ACT) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = apply_act(g.act, v[j]);
-                    }
-                    if (EPI == EPI_RESID) {
-                        const float* rr = g.resid + (size_t)row * g.ldr + n;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 r4 = *reinterpret_cast<const float4*>(rr + j);
-                            v[j] += r4.x; v[j + 1] += r4.y; v[j + 2] += r4.z; v[j + 3] += r4.w;
-                        }
-                    }
-                    float* out = g.C + (size_t)row * g.ldc + n;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(out + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                }
-            }
+            tc_epilogue_store<EPI>(g, v, row, n0 + c0);
         }
     }
     tc_fence_before();
@@ -260,39 +292,6 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) gemm_tc_kernel(const
 constexpr int kTc2BN = 256, kTc2Stages = 3;
 constexpr int kTc2WBytes = kTc2BN * kTcBK * 2;                       // 32 KB
 constexpr int kTc2StageBytes = 2 * kTcTileBytes + kTc2WBytes;        // A_hi, A_lo, W: 64 KB
-
-// one thread's 32 consecutive accumulator columns [n, n + 32) of output row `row`: bias / residual / activation / SwiGLU, fp32 stores
-template <int EPI>
-__device__ __forceinline__ void tc_epilogue_store(const GemmTcArgs& g, float (&v)[32], int row, int n) {
-    if (row >= g.M || n >= g.N) return;
-    if (g.bias) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += g.bias[n + j];
-    }
-    if (EPI == EPI_SWIGLU) {
-        float* out = g.C + (size_t)row * g.ldc + n / 2;
-#pragma unroll
-        for (int j = 0; j < 32; j += 8)
-            *reinterpret_cast<float4*>(out + j / 2) = make_float4(silu_f(v[j]) * v[j + 1], silu_f(v[j + 2]) * v[j + 3], silu_f(v[j + 4]) * v[j + 5],
-                                                                 silu_f(v[j + 6]) * v[j + 7]);
-        return;
-    }
-    if (EPI == EPI_ACT) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = apply_act(g.act, v[j]);
-    }
-    if (EPI == EPI_RESID) {
-        const float* rr = g.resid + (size_t)row * g.ldr + n;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-            const float4 r4 = *reinterpret_cast<const float4*>(rr + j);
-            v[j] += r4.x; v[j + 1] += r4.y; v[j + 2] += r4.z; v[j + 3] += r4.w;
-        }
-    }
-    float* out = g.C + (size_t)row * g.ldc + n;
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(out + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-}
 
 // tile index -> (row block, column block): bands of `gm` row blocks, inside a band the column block is the slow index
 __device__ __forceinline__ void tc2_tile(int t, int tiles_m, int tiles_n, int gm, int& mb, int& nb) {

@@ -31,6 +31,47 @@ __global__ void rmsnorm_kernel(const float* __restrict__ x, const float* __restr
     for (int i = threadIdx.x; i < H; i += blockDim.x) out[(size_t)blockIdx.x * H + i] = xr[i] * inv * w[i];
 }
 
+// x = hi + lo with both halves fp16 (|lo| <= 2^-11 |hi|): the operand format of the tensor-core GEMMs (gemm_tc.cuh).  Producers that feed
+// a GEMM write the two halves directly instead of an fp32 tensor that a separate pass would have to read back and split.
+__device__ __forceinline__ void split_half(float x, __half& h, __half& l) {
+    h = __float2half_rn(x);
+    l = __float2half_rn(x - __half2float(h));
+}
+// rmsnorm_kernel with the split output: out_hi / out_lo [rows, H] fp16
+__global__ void rmsnorm_split_kernel(const float* __restrict__ x, const float* __restrict__ w, float eps, __half* __restrict__ out_hi,
+                                     __half* __restrict__ out_lo, int H) {
+    __shared__ float red[32];
+    const float* xr = x + (size_t)blockIdx.x * H;
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < H; i += blockDim.x) { float v = xr[i]; ss = fmaf(v, v, ss); }
+    ss = block_sum(ss, red);
+    const float inv = 1.0f / sqrtf(ss / (float)H + eps);
+    for (int i = threadIdx.x; i < H; i += blockDim.x) {
+        __half h, l;
+        split_half(xr[i] * inv * w[i], h, l);
+        out_hi[(size_t)blockIdx.x * H + i] = h;
+        out_lo[(size_t)blockIdx.x * H + i] = l;
+    }
+}
+// layernorm_kernel with the split output
+__global__ void layernorm_split_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, float eps,
+                                       __half* __restrict__ out_hi, __half* __restrict__ out_lo, int H) {
+    __shared__ float red[32];
+    const float* xr = x + (size_t)blockIdx.x * H;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < H; i += blockDim.x) s += xr[i];
+    const float mean = block_sum(s, red) / (float)H;
+    float v = 0.f;
+    for (int i = threadIdx.x; i < H; i += blockDim.x) { float d = xr[i] - mean; v = fmaf(d, d, v); }
+    const float inv = 1.0f / sqrtf(block_sum(v, red) / (float)H + eps);
+    for (int i = threadIdx.x; i < H; i += blockDim.x) {
+        __half h, l;
+        split_half((xr[i] - mean) * inv * w[i] + b[i], h, l);
+        out_hi[(size_t)blockIdx.x * H + i] = h;
+        out_lo[(size_t)blockIdx.x * H + i] = l;
+    }
+}
+
 // candle_nn LayerNorm (remove_mean, affine): (x-mean)/sqrt(var+eps)*w+b.  One block per row of length H.
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                  const float* __restrict__ b, float eps, float* __restrict__ out, int H) {

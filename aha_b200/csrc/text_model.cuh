@@ -39,8 +39,10 @@ struct Ctx {  // per-handle launch context
     std::vector<void*> allocs;
     size_t alloc_bytes = 0;
     int attn_impl = 0;            // 0 = auto (tcgen05 flash attention for head_dim 64, mma.sync for 128), 1 = fp32 SIMT flash attention, 2 = mma.sync everywhere
-    int gemm_impl = 0;            // 0 = auto (tcgen05 where the shape tiles), 1 = SIMT fp32, 2 = tcgen05 128 x 128 required, 3 = tcgen05 persistent 128 x 256 required
+    int gemm_impl = 0;            // 0 = auto (tcgen05 where the shape tiles), 1 = SIMT fp32, 2 / 3 / 4 = tcgen05 required: 128 x 128 tiles / persistent 128 x 256 / CTA-pair 256 x 256
     bool gemm_wide = true;        // auto: the persistent 128 x 256 kernel where N >= 256 (15-26 % faster than 128 x 128 on every prefill shape, profiles/r02_gemm_sweep.txt; AHA_GEMM_WIDE=0 turns it off)
+    bool gemm_pair = true;        // auto: the CTA-pair kernel (cta_group::2, 256 x 256 tile per cluster) for prefill-sized M (>= 1024) and N >= 256: 1-3 % over the
+                                  // single-CTA persistent kernel, bit-identical results (profiles/r02_gemm_sweep_pair.txt; AHA_GEMM_PAIR=0 turns it off)
     int gemm_group_m = 8;         // row blocks per band of the persistent kernel's tile walk (AHA_GEMM_GROUP)
     __half* split_ws = nullptr;   // [2][rows*K] hi | lo halves of the activation operand
     size_t split_cap = 0;         // halfs per half-buffer
@@ -51,6 +53,20 @@ struct Ctx {  // per-handle launch context
             split_cap = halfs;
         }
         return split_ws;
+    }
+
+    // Pre-split activations (two ping-pong buffers): a producer -- norm kernel, attention, GEMM epilogue -- writes the fp16 hi + lo
+    // halves the next tensor-core GEMM reads, instead of an fp32 tensor that linear_gemm would have to read back and split.
+    bool presplit = true;         // AHA_PRESPLIT=0: every GEMM splits its own fp32 input (the round-1 data flow; results are bit-identical)
+    __half* act_ws[2] = {nullptr, nullptr};
+    size_t act_cap[2] = {0, 0};
+    __half* act_split(int which, size_t halfs) {   // hi at the returned pointer, lo at + act_cap[which]
+        if (halfs > act_cap[which]) {
+            if (act_ws[which]) { AHA_CUDA_CHECK(cudaStreamSynchronize(stream)); cudaFree(act_ws[which]); }
+            AHA_CUDA_CHECK(cudaMalloc(&act_ws[which], 2 * halfs * sizeof(__half)));
+            act_cap[which] = halfs;
+        }
+        return act_ws[which];
     }
 
     template <typename T>
@@ -65,6 +81,8 @@ struct Ctx {  // per-handle launch context
         for (void* p : allocs) cudaFree(p);
         allocs.clear();
         if (split_ws) { cudaFree(split_ws); split_ws = nullptr; split_cap = 0; }
+        for (int i = 0; i < 2; ++i)
+            if (act_ws[i]) { cudaFree(act_ws[i]); act_ws[i] = nullptr; act_cap[i] = 0; }
     }
 };
 
@@ -171,6 +189,42 @@ inline void flash_dispatch(Ctx& c, const FlashArgs& a, int nheads, bool causal) 
 
 // y = x W^T with the fused epilogues of gemm_simt.cuh.  Dispatch: tcgen05 split-fp16 kernel (gemm_tc.cuh) when the
 // shape tiles (K % 64 == 0, N % 32 == 0) and there are enough rows to fill a tile, else the exact SIMT kernel.
+struct ActSplit {   // fp16 hi + lo halves of an activation tensor [rows, ld]
+    __half* hi = nullptr;
+    __half* lo = nullptr;
+    explicit operator bool() const { return hi != nullptr; }
+};
+inline ActSplit act_split(Ctx& c, int which, size_t halfs) {
+    ActSplit a;
+    a.hi = c.act_split(which, halfs);
+    a.lo = a.hi + c.act_cap[which];
+    return a;
+}
+// true when linear_gemm runs (M, W) on a tensor-core kernel: only then may a producer hand over pre-split activations
+inline bool gemm_on_tc(const Ctx& c, int M, const LinearW& W) {
+    return c.gemm_impl != 1 && gemm_tc_supported(M, W.N, W.K) && !(c.gemm_impl == 0 && M < 32);
+}
+// the tensor-core GEMM on activations that are already split ([M, K] contiguous halves); `out`: write the result split as well
+inline void linear_gemm_split(Ctx& c, int epi, const __half* hi, const __half* lo, LinearW& W, const float* resid, int ldr, float* C, int ldc, int M,
+                              int act = ACT_NONE, ActSplit out = ActSplit(), int ldo = 0) {
+    if (M == 0) return;
+    AHA_REQUIRE(gemm_on_tc(c, M, W), "linear_gemm_split: shape does not run on the tensor-core kernels");
+    AHA_REQUIRE(!out || epi != EPI_RESID, "linear_gemm_split: the residual epilogue writes fp32");
+    if (!W.has_tmap) { W.tmap = make_tmap_f16(W.w, (uint64_t)W.N, (uint64_t)W.K); W.has_tmap = true; }
+    GemmTcArgs g;
+    g.bias = W.b; g.resid = resid; g.ldr = ldr; g.C = C; g.ldc = ldc; g.M = M; g.N = W.N; g.K = W.K; g.act = act;
+    g.out_hi = out.hi; g.out_lo = out.lo; g.ldo = ldo;
+    g.group_m = std::max(1, c.gemm_group_m);
+    if (c.gemm_impl == 4 || (c.gemm_impl == 0 && c.gemm_pair && W.N >= 256 && M >= 1024)) {
+        gemm_tc3_launch(c.stream, epi, hi, lo, W.tmap, g, c.num_sms);
+    } else if (c.gemm_impl == 3 || (c.gemm_impl == 0 && c.gemm_wide && W.N >= 256)) {
+        if (!W.has_tmap256) { W.tmap256 = make_tmap_f16_rows(W.w, (uint64_t)W.N, (uint64_t)W.K, 256); W.has_tmap256 = true; }
+        gemm_tc2_launch(c.stream, epi, hi, lo, W.tmap256, g, c.num_sms);
+    } else {
+        gemm_tc_launch(c.stream, epi, hi, lo, W.tmap, g);
+    }
+    c.cnt.kernels++;
+}
 inline void linear_gemm(Ctx& c, int epi, const float* A, int lda, LinearW& W, const float* resid, int ldr, float* C, int ldc, int M, int act = ACT_NONE) {
     if (M == 0) return;
     const bool tc_ok = gemm_tc_supported(M, W.N, W.K) && lda % 4 == 0;
@@ -182,24 +236,13 @@ inline void linear_gemm(Ctx& c, int epi, const float* A, int lda, LinearW& W, co
         c.cnt.kernels++;
         return;
     }
-    if (!W.has_tmap) { W.tmap = make_tmap_f16(W.w, (uint64_t)W.N, (uint64_t)W.K); W.has_tmap = true; }
     const size_t halfs = (size_t)M * W.K;
     __half* hi = c.split_buf(halfs);
     __half* lo = hi + c.split_cap;
     const size_t n4 = halfs / 4;
     split_f32_to_f16x2_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, c.stream>>>(A, lda, hi, lo, M, W.K);
-    GemmTcArgs g;
-    g.bias = W.b; g.resid = resid; g.ldr = ldr; g.C = C; g.ldc = ldc; g.M = M; g.N = W.N; g.K = W.K; g.act = act;
-    g.group_m = std::max(1, c.gemm_group_m);
-    if (c.gemm_impl == 4) {
-        gemm_tc3_launch(c.stream, epi, hi, lo, W.tmap, g, c.num_sms);
-    } else if (c.gemm_impl == 3 || (c.gemm_impl == 0 && c.gemm_wide && W.N >= 256)) {
-        if (!W.has_tmap256) { W.tmap256 = make_tmap_f16_rows(W.w, (uint64_t)W.N, (uint64_t)W.K, 256); W.has_tmap256 = true; }
-        gemm_tc2_launch(c.stream, epi, hi, lo, W.tmap256, g, c.num_sms);
-    } else {
-        gemm_tc_launch(c.stream, epi, hi, lo, W.tmap, g);
-    }
-    c.cnt.kernels += 2;
+    c.cnt.kernels++;
+    linear_gemm_split(c, epi, hi, lo, W, resid, ldr, C, ldc, M, act);
 }
 
 // Upload `names` stacked along the output dimension ([sum N_i, K]); optional row interleave of two
@@ -651,8 +694,17 @@ struct TextModel {
         const float scaling = (float)(1.0 / std::sqrt((double)hd));
         for (int l = 0; l < cfg.L; ++l) {
             TextLayer& T = layers[l];
-            rmsnorm_kernel<<<S, 256, 0, st>>>(x, T.ln1, cfg.eps, xn, H); c.cnt.kernels++;
-            gemm(EPI_STORE, xn, H, T.qkv, nullptr, 0, qkv, qkv_dim, S);
+            // pre-split data flow (Ctx::presplit): norm -> [hi|lo] -> qkv GEMM; attention -> [hi|lo] -> o_proj; norm -> [hi|lo] -> gate/up
+            // GEMM, whose SwiGLU epilogue writes [hi|lo] -> down_proj.  No stand-alone split pass, no fp32 intermediates.
+            const bool ps = c.presplit && gemm_on_tc(c, S, T.qkv) && gemm_on_tc(c, S, T.o) && gemm_on_tc(c, S, T.gu) && gemm_on_tc(c, S, T.down) && c.attn_impl == 0;
+            if (ps) {
+                ActSplit n1 = act_split(c, 0, (size_t)S * H);
+                rmsnorm_split_kernel<<<S, 256, 0, st>>>(x, T.ln1, cfg.eps, n1.hi, n1.lo, H); c.cnt.kernels++;
+                linear_gemm_split(c, EPI_STORE, n1.hi, n1.lo, T.qkv, nullptr, 0, qkv, qkv_dim, S);
+            } else {
+                rmsnorm_kernel<<<S, 256, 0, st>>>(x, T.ln1, cfg.eps, xn, H); c.cnt.kernels++;
+                gemm(EPI_STORE, xn, H, T.qkv, nullptr, 0, qkv, qkv_dim, S);
+            }
             KVSrc kv = kv_src(l);
             qk_norm_rope_kv_kernel<128><<<dim3(S, nh_l + 2 * nkv_l), 128, 0, st>>>(qkv, T.qn, T.kn, cfg.eps, rp, const_cast<float*>(kv.k), const_cast<float*>(kv.v), kv, nh_l, nkv_l, pos0);
             c.cnt.kernels++;
@@ -660,13 +712,26 @@ struct TextModel {
             fa.q = qkv; fa.q_tok_stride = qkv_dim; fa.q_head_stride = hd; fa.kv = kv;
             fa.out = attn; fa.o_tok_stride = (size_t)nh_l * hd; fa.o_head_stride = hd;
             fa.Sq = S; fa.Skv = pos0 + S; fa.q0 = 0; fa.kv0 = 0; fa.groups = nh_l / nkv_l; fa.scaling = scaling;
-            flash_dispatch<128>(c, fa, nh_l, true);
-            if (tp_world > 1) { gemm(EPI_STORE, attn, nh_l * hd, T.o, nullptr, 0, tp_tmp, H, S); tp_reduce_add(tp_tmp, x, (size_t)S * H); }
-            else gemm(EPI_RESID, attn, nh_l * hd, T.o, x, H, x, H, S);
-            rmsnorm_kernel<<<S, 256, 0, st>>>(x, T.ln2, cfg.eps, xn, H); c.cnt.kernels++;
-            gemm(EPI_SWIGLU, xn, H, T.gu, nullptr, 0, hbuf, I_l, S);
-            if (tp_world > 1) { gemm(EPI_STORE, hbuf, I_l, T.down, nullptr, 0, tp_tmp, H, S); tp_reduce_add(tp_tmp, x, (size_t)S * H); }
-            else gemm(EPI_RESID, hbuf, I_l, T.down, x, H, x, H, S);
+            if (ps) {
+                ActSplit ao = act_split(c, 1, (size_t)S * std::max(nh_l * hd, I_l));
+                fa.out_hi = ao.hi; fa.out_lo = ao.lo;
+                flash_dispatch<128>(c, fa, nh_l, true);
+                if (tp_world > 1) { linear_gemm_split(c, EPI_STORE, ao.hi, ao.lo, T.o, nullptr, 0, tp_tmp, H, S); tp_reduce_add(tp_tmp, x, (size_t)S * H); }
+                else linear_gemm_split(c, EPI_RESID, ao.hi, ao.lo, T.o, x, H, x, H, S);
+                ActSplit n2 = act_split(c, 0, (size_t)S * H);
+                rmsnorm_split_kernel<<<S, 256, 0, st>>>(x, T.ln2, cfg.eps, n2.hi, n2.lo, H); c.cnt.kernels++;
+                linear_gemm_split(c, EPI_SWIGLU, n2.hi, n2.lo, T.gu, nullptr, 0, nullptr, 0, S, ACT_NONE, ao, I_l);
+                if (tp_world > 1) { linear_gemm_split(c, EPI_STORE, ao.hi, ao.lo, T.down, nullptr, 0, tp_tmp, H, S); tp_reduce_add(tp_tmp, x, (size_t)S * H); }
+                else linear_gemm_split(c, EPI_RESID, ao.hi, ao.lo, T.down, x, H, x, H, S);
+            } else {
+                flash_dispatch<128>(c, fa, nh_l, true);
+                if (tp_world > 1) { gemm(EPI_STORE, attn, nh_l * hd, T.o, nullptr, 0, tp_tmp, H, S); tp_reduce_add(tp_tmp, x, (size_t)S * H); }
+                else gemm(EPI_RESID, attn, nh_l * hd, T.o, x, H, x, H, S);
+                rmsnorm_kernel<<<S, 256, 0, st>>>(x, T.ln2, cfg.eps, xn, H); c.cnt.kernels++;
+                gemm(EPI_SWIGLU, xn, H, T.gu, nullptr, 0, hbuf, I_l, S);
+                if (tp_world > 1) { gemm(EPI_STORE, hbuf, I_l, T.down, nullptr, 0, tp_tmp, H, S); tp_reduce_add(tp_tmp, x, (size_t)S * H); }
+                else gemm(EPI_RESID, hbuf, I_l, T.down, x, H, x, H, S);
+            }
             if (l < (int)deepstack.size() && n_visual > 0) {
                 scatter_rows_kernel<<<n_visual, 256, 0, st>>>(d_visual_idx, deepstack[l], x, H, 1); c.cnt.kernels++;
             }

@@ -196,8 +196,18 @@ struct VisionModel {
         linear_gemm(*ctx, epi, A, lda, W, resid, ldr, C, ldc, M, act);
     }
     void run_merger(Merger& m, const float* in, int N, float* out) {
-        cudaStream_t st = ctx->stream;
-        const int m2 = cfg.merge * cfg.merge, Hm = cfg.H * m2;
+        Ctx& c = *ctx;
+        cudaStream_t st = c.stream;
+        const int m2 = cfg.merge * cfg.merge, Hm = cfg.H * m2, R = N / m2;
+        if (c.presplit && gemm_on_tc(c, R, m.fc1) && gemm_on_tc(c, R, m.fc2)) {   // norm -> [hi|lo] -> fc1 (GELU epilogue writes [hi|lo]) -> fc2
+            ActSplit n = act_split(c, 0, (size_t)R * Hm), hsp = act_split(c, 1, (size_t)R * Hm);
+            if (m.post) layernorm_split_kernel<<<R, 256, 0, st>>>(in, m.nw, m.nb, 1e-6f, n.hi, n.lo, Hm);
+            else layernorm_split_kernel<<<N, 256, 0, st>>>(in, m.nw, m.nb, 1e-6f, n.hi, n.lo, cfg.H);
+            c.cnt.kernels++;
+            linear_gemm_split(c, EPI_ACT, n.hi, n.lo, m.fc1, nullptr, 0, nullptr, 0, R, ACT_GELU_ERF, hsp, Hm);
+            linear_gemm_split(c, EPI_STORE, hsp.hi, hsp.lo, m.fc2, nullptr, 0, out, cfg.out_hidden, R);
+            return;
+        }
         if (m.post) layernorm_kernel<<<N / m2, 256, 0, st>>>(in, m.nw, m.nb, 1e-6f, xn, Hm);
         else layernorm_kernel<<<N, 256, 0, st>>>(in, m.nw, m.nb, 1e-6f, xn, cfg.H);
         ctx->cnt.kernels++;
@@ -266,8 +276,18 @@ struct VisionModel {
         const float scaling = (float)(1.0 / std::sqrt((double)hd));
         for (int i = 0; i < cfg.depth; ++i) {
             VisionBlock& b = blocks[i];
-            layernorm_kernel<<<N, 256, 0, st>>>(x, b.n1w, b.n1b, 1e-6f, xn, Hv); c.cnt.kernels++;
-            gemm(EPI_STORE, xn, Hv, b.qkv, nullptr, 0, qkv, 3 * Hp, N);
+            // pre-split data flow (Ctx::presplit): each producer writes the fp16 hi + lo halves its GEMM reads (see text_model.cuh prefill)
+            const bool ps = c.presplit && c.attn_impl == 0 && gemm_on_tc(c, N, b.qkv) && gemm_on_tc(c, N, b.proj) && gemm_on_tc(c, N, b.fc1) && gemm_on_tc(c, N, b.fc2);
+            ActSplit ao;
+            if (ps) {
+                ActSplit n1 = act_split(c, 0, (size_t)N * Hv);
+                layernorm_split_kernel<<<N, 256, 0, st>>>(x, b.n1w, b.n1b, 1e-6f, n1.hi, n1.lo, Hv); c.cnt.kernels++;
+                linear_gemm_split(c, EPI_STORE, n1.hi, n1.lo, b.qkv, nullptr, 0, qkv, 3 * Hp, N);
+                ao = act_split(c, 1, (size_t)N * std::max(Hp, Ip));
+            } else {
+                layernorm_kernel<<<N, 256, 0, st>>>(x, b.n1w, b.n1b, 1e-6f, xn, Hv); c.cnt.kernels++;
+                gemm(EPI_STORE, xn, Hv, b.qkv, nullptr, 0, qkv, 3 * Hp, N);
+            }
             vit_rope_kernel<<<N, 256, 0, st>>>(qkv, rowcol, inv_freq, hd, hdp, cfg.heads, Hp); c.cnt.kernels++;
             for (auto& sg : segs) {
                 FlashArgs fa;
@@ -275,14 +295,23 @@ struct VisionModel {
                 fa.kv.k = qkv + Hp; fa.kv.v = qkv + 2 * Hp; fa.kv.page_table = nullptr; fa.kv.page_shift = 0; fa.kv.page_stride = 0;
                 fa.kv.tok_stride = 3 * Hp; fa.kv.head_stride = hdp;
                 fa.out = attn; fa.o_tok_stride = Hp; fa.o_head_stride = hdp;
+                fa.out_hi = ao.hi; fa.out_lo = ao.lo;
                 fa.Sq = sg.second; fa.Skv = sg.second; fa.q0 = sg.first; fa.kv0 = sg.first; fa.groups = 1; fa.scaling = scaling;
                 if (hdp == 64) flash_dispatch<64>(c, fa, cfg.heads, false);
                 else flash_dispatch<128>(c, fa, cfg.heads, false);
             }
-            gemm(EPI_RESID, attn, Hp, b.proj, x, Hv, x, Hv, N);
-            layernorm_kernel<<<N, 256, 0, st>>>(x, b.n2w, b.n2b, 1e-6f, xn, Hv); c.cnt.kernels++;
-            gemm(EPI_ACT, xn, Hv, b.fc1, nullptr, 0, h, Ip, N, cfg.act);   // padded rows: act(0 + 0) = 0 for gelu / silu, and fc2's padded columns are zero anyway
-            gemm(EPI_RESID, h, Ip, b.fc2, x, Hv, x, Hv, N);
+            if (ps) {
+                linear_gemm_split(c, EPI_RESID, ao.hi, ao.lo, b.proj, x, Hv, x, Hv, N);
+                ActSplit n2 = act_split(c, 0, (size_t)N * Hv);
+                layernorm_split_kernel<<<N, 256, 0, st>>>(x, b.n2w, b.n2b, 1e-6f, n2.hi, n2.lo, Hv); c.cnt.kernels++;
+                linear_gemm_split(c, EPI_ACT, n2.hi, n2.lo, b.fc1, nullptr, 0, nullptr, 0, N, cfg.act, ao, Ip);
+                linear_gemm_split(c, EPI_RESID, ao.hi, ao.lo, b.fc2, x, Hv, x, Hv, N);
+            } else {
+                gemm(EPI_RESID, attn, Hp, b.proj, x, Hv, x, Hv, N);
+                layernorm_kernel<<<N, 256, 0, st>>>(x, b.n2w, b.n2b, 1e-6f, xn, Hv); c.cnt.kernels++;
+                gemm(EPI_ACT, xn, Hv, b.fc1, nullptr, 0, h, Ip, N, cfg.act);   // padded rows: act(0 + 0) = 0 for gelu / silu, and fc2's padded columns are zero anyway
+                gemm(EPI_RESID, h, Ip, b.fc2, x, Hv, x, Hv, N);
+            }
             if (trace) AHA_CUDA_CHECK(cudaMemcpyAsync(trace_buf + (size_t)(i + 1) * max_patches * Hv, x, (size_t)N * Hv * sizeof(float), cudaMemcpyDeviceToDevice, st));
             for (size_t k = 0; k < cfg.deepstack.size(); ++k)
                 if (cfg.deepstack[k] == i) run_merger(ds_mergers[k], x, N, ds_out[k] + (size_t)(p_start / m2_) * cfg.out_hidden);

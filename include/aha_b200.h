@@ -70,7 +70,7 @@ typedef struct aha_options {
                             * tagged-packet version under tensor parallelism), 1 = per-op kernels under a CUDA graph (validation twin),
                             * 2 = fused, tagged-packet (data-flow) version, 3 = fused, grid-barrier version (single GPU only), 4 = fused hybrid (grid
                             * barriers inside the layer, tagged packets for the two residual-stream exchanges) */
-    int32_t gemm_impl;     /* 0 = auto, 1 = SIMT fp32, 2 = tcgen05 128x128 tiles (split-fp16, fp32-exact), 3 = tcgen05 persistent 128x256 tiles */
+    int32_t gemm_impl;     /* 0 = auto, 1 = SIMT fp32, 2 = tcgen05 128x128 tiles (split-fp16, fp32-exact), 3 = tcgen05 persistent 128x256 tiles, 4 = tcgen05 CTA-pair (cta_group::2) 256x256 tiles */
     const void* tp_comm;   /* opaque: ncclUniqueId bytes (128) when tp_world > 1, else NULL */
     int32_t reserved[8];   /* reserved[0]: prefill attention, 0 = tensor cores (tcgen05 kernel for head_dim 64, mma.sync for 128; split-fp16), 1 = fp32 SIMT twin, 2 = mma.sync kernel everywhere */
 } aha_options;
