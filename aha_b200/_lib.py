@@ -80,6 +80,8 @@ SYMBOLS = {
     "aha_b200_expand_placeholders": (C.c_int, [_U32P, C.c_size_t, C.c_uint32, _U32P, C.c_size_t, _U32P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "aha_b200_feat_extract_output_length": (C.c_size_t, [C.c_size_t]),
     "aha_b200_float_range_normalize": (C.c_int, [_F32P, C.c_size_t]),
+    "aha_b200_resample": (C.c_int, [_P, _F32P, C.c_size_t, C.c_int64, C.c_int64, _F32P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "aha_b200_sinc_resample_bank": (C.c_int, [C.c_int64, C.c_int64, _F32P, C.c_size_t, C.POINTER(C.c_int32)]),
     "aha_b200_split_audio_into_chunks": (C.c_int, [C.c_size_t, C.c_uint32, C.c_float, C.POINTER(C.c_size_t), C.c_size_t, C.POINTER(C.c_size_t)]),
     "aha_b200_embed": (C.c_int, [_P, _U32P, C.c_size_t, _F32P]),
     "aha_b200_rerank": (C.c_int, [_P, _U32P, C.c_size_t, _U32P, C.POINTER(C.c_size_t), C.c_size_t, _F32P]),

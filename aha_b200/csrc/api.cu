@@ -775,6 +775,56 @@ int aha_b200_float_range_normalize(float* wave, size_t n) {
     return guarded_host([&] { AHA_REQUIRE(wave || n == 0, "wave is required"); float_range_normalize(wave, n); });
 }
 
+int aha_b200_resample(aha_model* m, const float* wave, size_t n, int64_t orig_freq, int64_t new_freq, float* out, size_t cap, size_t* n_out) {
+    return guarded(m, [&] {
+        AHA_REQUIRE(n_out, "n_out is required");
+        AHA_REQUIRE(wave || n == 0, "wave is required");
+        if (orig_freq == new_freq) {   // resample(): the waveform itself
+            AHA_REQUIRE(orig_freq > 0, "Frequencies must be positive");
+            *n_out = n;
+            if (!out) return;
+            AHA_REQUIRE(cap >= n, "output buffer too small");
+            std::memcpy(out, wave, n * sizeof(float));
+            return;
+        }
+        const SincBank B = sinc_resample_bank(orig_freq, new_freq);
+        const size_t len_out = sinc_resample_out_len(B, n);
+        *n_out = len_out;
+        if (!out) return;
+        AHA_REQUIRE(cap >= len_out, "output buffer too small");
+        AHA_REQUIRE(B.taps.size() * sizeof(float) <= 96 * 1024, "resample: the filter bank of this frequency pair does not fit in shared memory (reduce the ratio orig : new)");
+        if (len_out == 0) return;
+        float *d_w = nullptr, *d_t = nullptr, *d_o = nullptr;
+        auto cleanup = [&] { cudaFree(d_w); cudaFree(d_t); cudaFree(d_o); };
+        try {
+            cudaStream_t st = m->ctx.stream;
+            AHA_CUDA_CHECK(cudaMalloc(&d_w, std::max<size_t>(n, 1) * sizeof(float))); AHA_CUDA_CHECK(cudaMalloc(&d_t, B.taps.size() * sizeof(float)));
+            AHA_CUDA_CHECK(cudaMalloc(&d_o, len_out * sizeof(float)));
+            AHA_CUDA_CHECK(cudaMemcpyAsync(d_w, wave, n * sizeof(float), cudaMemcpyHostToDevice, st));
+            AHA_CUDA_CHECK(cudaMemcpyAsync(d_t, B.taps.data(), B.taps.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+            const size_t smem = B.taps.size() * sizeof(float);
+            if (smem > 48 * 1024) AHA_CUDA_CHECK(cudaFuncSetAttribute(sinc_resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            sinc_resample_kernel<<<(unsigned)((len_out + 255) / 256), 256, smem, st>>>(d_w, (long long)n, d_t, B.orig, B.fresh, B.width, B.K, d_o, (long long)len_out);
+            AHA_CUDA_CHECK(cudaGetLastError());
+            m->ctx.cnt.kernels++;
+            AHA_CUDA_CHECK(cudaMemcpyAsync(out, d_o, len_out * sizeof(float), cudaMemcpyDeviceToHost, st));
+            AHA_CUDA_CHECK(cudaStreamSynchronize(st));
+        } catch (...) { cleanup(); throw; }
+        cleanup();
+    });
+}
+
+int aha_b200_sinc_resample_bank(int64_t orig_freq, int64_t new_freq, float* taps_out, size_t cap, int32_t dims_out[4]) {
+    return guarded_host([&] {
+        AHA_REQUIRE(dims_out, "dims_out is required");
+        const SincBank B = sinc_resample_bank(orig_freq, new_freq);
+        dims_out[0] = B.fresh; dims_out[1] = B.K; dims_out[2] = B.width; dims_out[3] = B.orig;
+        if (!taps_out) return;
+        AHA_REQUIRE(cap >= B.taps.size(), "output buffer too small");
+        std::memcpy(taps_out, B.taps.data(), B.taps.size() * sizeof(float));
+    });
+}
+
 int aha_b200_split_audio_into_chunks(size_t total_len, uint32_t sample_rate, float max_chunk_sec, size_t* lens_out, size_t cap, size_t* n_out) {
     return guarded_host([&] {
         AHA_REQUIRE(n_out && sample_rate > 0 && max_chunk_sec > 0.f, "n_out, a positive sample rate and chunk length are required");

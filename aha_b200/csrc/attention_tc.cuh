@@ -101,6 +101,11 @@ struct FlashTcArgs {
     float scaling;
 };
 
+__device__ __forceinline__ float ex2_approx(float x) {   // 2^x on the MUFU, flush-to-zero (inputs here are <= 0; -inf -> 0)
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // 16 fp32 -> two 16-byte chunks (8 halfs hi, 8 halfs lo)
@@ -246,32 +251,45 @@ __global__ void __launch_bounds__(kFaThreads, HD == 64 ? 2 : 1) flash_attn_tc_ke
 #pragma unroll
                 for (int c = 0; c < 32; ++c) { s[c] = v0[c]; s[32 + c] = v1[c]; }
             }
+            // The softmax arithmetic is what bounds this kernel (the tensor pipe idles under it), so it is kept minimal: masking only on
+            // the tiles that can need it (the last one / the causal diagonal), the max on raw scores (scale > 0 commutes with max), scale
+            // and max subtraction in ONE fma feeding ex2.approx, and the rescale of O skipped while no row of the warp moved its max.
+            const bool mask_tile = (kt0 + BKV > a.Skv) || (CAUSAL && kt0 + BKV - 1 > qt0 + (int)(warp * 32) + causal_shift);
             float rmax = -INFINITY;
+            if (mask_tile) {
 #pragma unroll
-            for (int c = 0; c < BKV; ++c) {
-                const int kj = kt0 + c;
-                float v = s[c] * scale_log2;
-                if (kj >= a.Skv || (CAUSAL && kj > qi + causal_shift)) v = -INFINITY;
-                s[c] = v;
-                rmax = fmaxf(rmax, v);
+                for (int c = 0; c < BKV; ++c) {
+                    const int kj = kt0 + c;
+                    if (kj >= a.Skv || (CAUSAL && kj > qi + causal_shift)) s[c] = -INFINITY;
+                    rmax = fmaxf(rmax, s[c]);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < BKV; ++c) rmax = fmaxf(rmax, s[c]);
             }
-            const float mn = fmaxf(m, rmax);
+            const float mn = fmaxf(m, rmax * scale_log2);
             const float mu = (mn == -INFINITY) ? 0.f : mn;
-            const float alpha = exp2f(m - mu);
+            const float alpha = ex2_approx(m - mu);
             float rs = 0.f;
 #pragma unroll
-            for (int c = 0; c < BKV; ++c) { s[c] = exp2f(s[c] - mu); rs += s[c]; }
+            for (int c = 0; c < BKV; ++c) { s[c] = ex2_approx(fmaf(s[c], scale_log2, -mu)); rs += s[c]; }
             l = l * alpha + rs;
             m = mn;
             if (t >= 1) {   // PV(t - 1) ran under the arithmetic above; it also has to be done before P(t) may overwrite P(t - 1)
                 mbar_wait(bar_o, (uint32_t)((t - 1) & 1));
                 tc_fence_after();
+                const bool rescale = __any_sync(0xffffffffu, alpha != 1.0f);
 #pragma unroll
                 for (int c0 = 0; c0 < HD; c0 += 32) {
                     float v0[32];
                     tmem_ld32(tmem_o + lane_base + (uint32_t)c0, v0);
+                    if (rescale) {
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) o[c0 + c] = (o[c0 + c] + v0[c]) * alpha;
+                        for (int c = 0; c < 32; ++c) o[c0 + c] = (o[c0 + c] + v0[c]) * alpha;
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) o[c0 + c] += v0[c];
+                    }
                 }
             }
             // P row -> shared memory, K-major SWIZZLE_128B: 16-byte chunk j of row r sits at chunk (j ^ (r & 7))

@@ -11,6 +11,7 @@
 //   float_range_normalize                  src/models/common/modules.rs:1353-1368
 //   split_audio_into_chunks                src/utils/audio_utils.rs:1743-1760
 //   get_feat_extract_output_lengths        src/models/qwen3_asr/processor.rs:187-195
+//   resample_simple (sinc, Hann window)    src/utils/audio_utils.rs:66-255 (what load_audio_with_resample applies to bring any input to 16 kHz)
 #pragma once
 #include <cmath>
 #include <cstdint>
@@ -153,6 +154,64 @@ inline std::vector<size_t> split_audio_into_chunks(size_t total_len, size_t sr, 
     std::vector<size_t> splits(total_len / max_len, max_len);
     splits.push_back(total_len % max_len);
     return splits;
+}
+
+// ---------------------------------------------------------------------------------------------- sinc resampling
+// get_sinc_resample_kernel, SincInterpHann branch: filter bank [new][2 * width + orig] in the reference's f32 arithmetic (affine = x * (f32)mul).
+struct SincBank { std::vector<float> taps; int orig = 0, fresh = 0, width = 0, K = 0; };
+inline SincBank sinc_resample_bank(int64_t orig_freq, int64_t new_freq, int64_t lowpass_filter_width = 6, double rolloff = 0.99) {
+    if (orig_freq <= 0 || new_freq <= 0) throw std::runtime_error("Frequencies must be positive");
+    if (lowpass_filter_width <= 0) throw std::runtime_error("Low pass filter width should be positive");
+    int64_t a = orig_freq, b = new_freq;
+    while (b) { const int64_t r = a % b; a = b; b = r; }
+    SincBank B;
+    B.orig = (int)(orig_freq / a); B.fresh = (int)(new_freq / a);
+    const double base_freq = (double)std::min(B.orig, B.fresh) * rolloff;
+    B.width = (int)std::ceil((double)lowpass_filter_width * (double)B.orig / base_freq);
+    B.K = 2 * B.width + B.orig;
+    B.taps.resize((size_t)B.fresh * B.K);
+    const float inv_orig = (float)(1.0 / (double)B.orig), inv_new = (float)(1.0 / (double)B.fresh), bf = (float)base_freq;
+    const float lw = (float)lowpass_filter_width, warg = (float)(M_PI / (double)lowpass_filter_width / 2.0), pi = (float)M_PI;
+    const float scale = (float)(base_freq / (double)B.orig);
+    for (int j = 0; j < B.fresh; ++j) {
+        const float tj = (float)(-j) * inv_new + 0.0f;
+        for (int k = 0; k < B.K; ++k) {
+            const float idx = (float)(k - B.width) * inv_orig + 0.0f;
+            float t = (tj + idx) * bf + 0.0f;
+            t = std::min(std::max(t, -lw), lw);
+            const float c = std::cos(t * warg);
+            const float window = c * c;
+            const float ts = t * pi;
+            const float sinc = ts == 0.0f ? 1.0f : std::sin(ts) / ts;
+            B.taps[(size_t)j * B.K + k] = sinc * window * scale;
+        }
+    }
+    return B;
+}
+inline size_t sinc_resample_out_len(const SincBank& B, size_t length) {   // apply_sinc_resample_kernel: min(ceil(new * len / orig), conv frames * new)
+    const size_t frames = length / B.orig + 1;   // (len + 2w + orig - K) / orig + 1
+    const size_t target = (size_t)std::ceil((double)B.fresh * (double)length / (double)B.orig);
+    return std::min(target, frames * (size_t)B.fresh);
+}
+// out[i * new + j] = sum_k taps[j][k] * padded[i * orig + k],  padded = [width zeros | wave | width + orig zeros]; taps in order, f32
+__global__ void sinc_resample_kernel(const float* __restrict__ wave, long long length, const float* __restrict__ taps, int orig, int fresh, int width, int K,
+                                     float* __restrict__ out, long long n_out) {
+    extern __shared__ float s_taps[];
+    for (int i = threadIdx.x; i < fresh * K; i += blockDim.x) s_taps[i] = taps[i];
+    __syncthreads();
+    const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n_out) return;
+    const long long i = o / fresh;
+    const int j = (int)(o - i * fresh);
+    const long long p0 = i * orig - width;   // wave index of tap 0
+    const float* tj = s_taps + (size_t)j * K;
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) {
+        const long long p = p0 + k;
+        const float x = (p >= 0 && p < length) ? wave[p] : 0.f;
+        acc = __fadd_rn(acc, __fmul_rn(x, tj[k]));   // separate multiply and add like a scalar f32 convolution (no fma contraction)
+    }
+    out[o] = acc;
 }
 
 }  // namespace aha

@@ -276,6 +276,16 @@ class B200Model:
                                                     out.ctypes.data_as(C.POINTER(C.c_uint8))))
         return out
 
+    def resample(self, wave, orig_freq, new_freq):
+        """resample_simple (audio_utils.rs:245-255) of a mono f32 waveform on the GPU: windowed-sinc polyphase filter, width 6, rolloff 0.99."""
+        w = np.ascontiguousarray(wave, np.float32).reshape(-1)
+        n = C.c_size_t(0)
+        fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+        self._check(self._lib.aha_b200_resample(self._h, fp(w), w.size, int(orig_freq), int(new_freq), None, 0, C.byref(n)))
+        out = np.empty(n.value, np.float32)
+        self._check(self._lib.aha_b200_resample(self._h, fp(w), w.size, int(orig_freq), int(new_freq), fp(out), out.size, C.byref(n)))
+        return out[:n.value]
+
     def image_preprocess(self, img_u8_hwc, min_pixels=65536, max_pixels=16777216):
         """Qwen3VLProcessor::process_img + process_vision_tensor for an image of any size -> (pixel_values, grid_thw)."""
         img = np.ascontiguousarray(img_u8_hwc, dtype=np.uint8)

@@ -48,6 +48,16 @@ def float_range_normalize(wave):
     return w.reshape(np.shape(wave))
 
 
+def sinc_resample_bank(orig_freq, new_freq):
+    """get_sinc_resample_kernel (audio_utils.rs:66-151, Hann, width 6, rolloff 0.99) -> (taps [new/g, K], width)."""
+    lib = L.load()
+    dims = (C.c_int32 * 4)()
+    _check(lib.aha_b200_sinc_resample_bank(int(orig_freq), int(new_freq), None, 0, dims))
+    taps = np.empty((dims[0], dims[1]), np.float32)
+    _check(lib.aha_b200_sinc_resample_bank(int(orig_freq), int(new_freq), taps.ctypes.data_as(C.POINTER(C.c_float)), taps.size, dims))
+    return taps, int(dims[2])
+
+
 def split_audio_into_chunks(total_len, sample_rate, max_chunk_sec):
     n = C.c_size_t(0)
     lib = L.load()

@@ -191,6 +191,14 @@ int aha_b200_expand_placeholders(const uint32_t* ids, size_t n, uint32_t token_i
 size_t aha_b200_feat_extract_output_length(size_t n_frames);
 /* float_range_normalize (common/modules.rs:1353-1368), in place.  Host only. */
 int aha_b200_float_range_normalize(float* wave, size_t n);
+/* resample_simple (utils/audio_utils.rs:66-255: windowed-sinc polyphase filter, lowpass width 6, rolloff 0.99, Hann), the
+ * step load_audio_with_resample (audio_utils.rs:636-650) applies to bring a decoded mono waveform to the model's 16 kHz.  The filter bank
+ * is built on the host in the reference's f32 arithmetic, the strided convolution runs on the GPU.  out may be NULL to query n_out
+ * (= min(ceil(new * n / orig), frames * new) samples).  Equal frequencies return the waveform unchanged, like the reference. */
+int aha_b200_resample(aha_model* m, const float* wave, size_t n, int64_t orig_freq, int64_t new_freq, float* out, size_t cap, size_t* n_out);
+/* get_sinc_resample_kernel (audio_utils.rs:66-151) alone: taps_out[new/g][2*width + orig/g]; dims_out = {new/g, taps per phase, width, orig/g}.
+ * taps_out may be NULL to query dims_out.  Host only. */
+int aha_b200_sinc_resample_bank(int64_t orig_freq, int64_t new_freq, float* taps_out, size_t cap, int32_t dims_out[4]);
 /* split_audio_into_chunks (utils/audio_utils.rs:1743-1760): chunk lengths in samples.  Host only. */
 int aha_b200_split_audio_into_chunks(size_t total_len, uint32_t sample_rate, float max_chunk_sec, size_t* lens_out, size_t cap,
                                      size_t* n_out);

@@ -127,3 +127,57 @@ def get_feat_extract_output_lengths(audio_len):
         feat = (leave - 1) // 2 + 1
         return ((feat - 1) // 2 + 1 - 1) // 2 + 1 + (audio_len // 100) * 13
     return (audio_len // 100) * 13
+
+
+# ----------------------------------------------------------------------------- sinc resampling
+def get_sinc_resample_kernel(orig_freq, new_freq, gcd_val, lowpass_filter_width=6, rolloff=0.99):
+    """audio_utils.rs:66-151 (SincInterpHann branch): the (new_freq/gcd, 2*width + orig_freq/gcd) filter bank and `width`.
+    Candle's `affine(mul, add)` on an f32 tensor computes `x * (mul as f32) + (add as f32)`; every step below is f32."""
+    if orig_freq <= 0 or new_freq <= 0:
+        raise ValueError("Frequencies must be positive")
+    if lowpass_filter_width <= 0:
+        raise ValueError("Low pass filter width should be positive")
+    orig, new = orig_freq // gcd_val, new_freq // gcd_val
+    base_freq = float(min(orig, new)) * rolloff                                   # f64
+    width = int(np.ceil(float(lowpass_filter_width) * float(orig) / base_freq))
+    idx = np.arange(-width, width + orig, dtype=F32) * F32(1.0 / orig) + F32(0.0)
+    t0 = np.arange(0, -new, -1, dtype=F32) * F32(1.0 / new) + F32(0.0)            # arange_step(0, -new, -1)
+    t = ((t0[:, None] + idx[None, :]).astype(F32) * F32(base_freq) + F32(0.0)).astype(F32)
+    t = np.clip(t, F32(-lowpass_filter_width), F32(lowpass_filter_width))
+    window = np.cos((t * F32(np.pi / lowpass_filter_width / 2.0)).astype(F32)).astype(F32)
+    window = (window * window).astype(F32)
+    scale = base_freq / float(orig)
+    ts = (t * F32(np.pi)).astype(F32)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        sinc = np.where(ts == 0, F32(1.0), (np.sin(ts).astype(F32) / ts).astype(F32)).astype(F32)
+    kernels = ((sinc * window).astype(F32) * F32(scale)).astype(F32)
+    return kernels, width
+
+
+def resample(wave, orig_freq, new_freq, lowpass_filter_width=6, rolloff=0.99):
+    """audio_utils.rs:154-243: zero-pad (width, width + orig), strided conv1d with the filter bank, interleave the `new` phases, cut to
+    ceil(new * len / orig).  wave: (channels, len) f32.  The f32 accumulation order of candle's conv1d is an assumption (taps in order)."""
+    wave = np.asarray(wave, F32)
+    if orig_freq <= 0 or new_freq <= 0:
+        raise ValueError("Frequencies must be positive")
+    if orig_freq == new_freq:
+        return wave.copy()
+    g = int(np.gcd(orig_freq, new_freq))
+    kernels, width = get_sinc_resample_kernel(orig_freq, new_freq, g, lowpass_filter_width, rolloff)
+    orig, new = orig_freq // g, new_freq // g
+    ch, length = wave.shape
+    padded = np.concatenate([np.zeros((ch, width), F32), wave, np.zeros((ch, width + orig), F32)], axis=1)
+    K = kernels.shape[1]
+    n_out = (padded.shape[1] - K) // orig + 1
+    out = np.zeros((ch, n_out, new), F32)
+    starts = np.arange(n_out) * orig
+    for k in range(K):
+        out = (out + padded[:, starts + k][:, :, None] * kernels[None, None, :, k]).astype(F32)
+    flat = out.reshape(ch, n_out * new)
+    target = int(np.ceil(float(new) * float(length) / float(orig)))
+    return flat[:, :min(target, flat.shape[1])].copy()
+
+
+def resample_simple(wave, orig_freq, new_freq):
+    """audio_utils.rs:245-255."""
+    return resample(wave, orig_freq, new_freq, 6, 0.99)

@@ -46,6 +46,29 @@ def test_audio_helpers():
     assert P.split_audio_into_chunks(16000 * 2400, 16000, 1200.0) == [19200000, 19200000, 0]      # the reference pushes the empty remainder too
 
 
+def test_sinc_resample_bank_and_oracle_properties():
+    """The filter bank built by the library (host f32) against the oracle's restatement, and closed-form properties of the resampler:
+    a constant stays constant away from the edges, a low-frequency sine keeps its frequency and amplitude, lengths follow ceil(new * n / orig)."""
+    for orig, new in ((48000, 16000), (44100, 16000), (8000, 16000), (22050, 16000), (24000, 16000), (16000, 24000)):
+        taps, width = P.sinc_resample_bank(orig, new)
+        g = int(np.gcd(orig, new))
+        want, w2 = OA.get_sinc_resample_kernel(orig, new, g)
+        assert width == w2 and taps.shape == want.shape == (new // g, 2 * width + orig // g)
+        assert np.abs(taps - want).max() <= 2e-7          # libm cos / sin against numpy's, a few ulp of values <= 1
+    x = np.ones((1, 4800), np.float32)
+    y = OA.resample_simple(x, 48000, 16000)
+    assert y.shape == (1, 1600) and np.abs(y[0, 40:-40] - 1.0).max() < 2e-3
+    t = np.arange(44100, dtype=np.float64) / 44100.0
+    y = OA.resample_simple(np.sin(2 * np.pi * 440.0 * t).astype(np.float32)[None], 44100, 16000)
+    assert y.shape == (1, 16000)
+    ref = np.sin(2 * np.pi * 440.0 * np.arange(16000) / 16000.0)
+    assert np.abs(y[0, 100:-100] - ref[100:-100]).max() < 5e-3
+    assert OA.resample_simple(x, 16000, 16000).shape == x.shape
+    assert OA.resample_simple(np.zeros((1, 1001), np.float32), 44100, 16000).shape == (1, int(np.ceil(160 * 1001 / 441)))
+    with pytest.raises(P.ProcessorError, match="Frequencies must be positive"):
+        P.sinc_resample_bank(0, 16000)
+
+
 def test_oracle_resize_properties():
     """The CatmullRom restatement: identity at equal size, constant images stay constant, a 2x box-like downscale of a ramp stays monotone."""
     img = synth.synth_image(40, 56, 3)
@@ -74,5 +97,25 @@ def test_gpu_resize_and_image_preprocess_match_the_oracle():
             want_pv, want_grid = OV.process_image(img)
             assert grid.tolist() == want_grid.tolist() and pv.shape == want_pv.shape
             assert float(np.abs(pv - want_pv).max()) <= 1e-6
+    finally:
+        m.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("orig,new,n", [(48000, 16000, 48000), (44100, 16000, 30011), (8000, 16000, 4001), (22050, 16000, 22050), (16000, 16000, 100),
+                                        (24000, 16000, 7), (16000, 24000, 1), (44100, 16000, 0)])
+def test_gpu_resample_matches_the_oracle(orig, new, n):
+    """aha_b200_resample (filter bank on the host, strided convolution on the GPU) against the restated resample_simple: same f32 products
+    and the same tap order, so the only differences are the few-ulp libm differences of the taps."""
+    from conftest import make_model
+    cfg, w, m = make_model("qwen3_asr", "tiny", max_ctx=64, max_frames=100)
+    try:
+        rng = np.random.default_rng(orig + n)
+        x = (0.3 * rng.standard_normal(n)).astype(np.float32)
+        got = m.resample(x, orig, new)
+        want = OA.resample_simple(x[None], orig, new)[0]
+        assert got.shape == want.shape
+        if n:
+            assert np.abs(got - want).max() <= 2e-6
     finally:
         m.close()
