@@ -88,6 +88,8 @@ SYMBOLS = {
     "aha_b200_nccl_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
     "aha_b200_rope_index": (C.c_int, [_U32P, C.c_size_t, _U32P, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32,
                                       C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "aha_b200_rope_index_mm": (C.c_int, [_U32P, C.c_size_t, _U32P, C.c_size_t, _U32P, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                         C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "aha_b200_destroy": (None, [_P]),
     "aha_b200_last_error": (C.c_char_p, [_P]),
     "aha_b200_stream": (_P, [_P]),

@@ -98,10 +98,12 @@ std::vector<int64_t> desc_to_i64(const aha_tensor_desc& d) {
 // Qwen3VLModel::get_rope_index, image branch (/root/reference/src/models/qwen3vl/model.rs:901-1071,1072-1090):
 // text runs get equal t/h/w ids; an image of merged grid (t,h',w') gets t_idx = base, h_idx = base+0..h'-1,
 // w_idx = base+0..w'-1; the next run starts at max+1; rope_delta = max+1-S.  pos3 is [3][S].
-void get_rope_index(const uint32_t* ids, int S, const std::vector<std::array<int, 3>>& grid, int merge, int image_tok, int vstart_tok,
-                    std::vector<int>& pos3, int& delta) {
+// video_grid: video_grid_thw with every (t, h, w) row already expanded to t rows of (1, h, w) (model.rs:907-925): each frame group has
+// its own <|vision_start|><|video_pad|>... run in the prompt (timestamps sit between them).
+void get_rope_index(const uint32_t* ids, int S, const std::vector<std::array<int, 3>>& grid, const std::vector<std::array<int, 3>>& video_grid, int merge,
+                    int image_tok, int video_tok, int vstart_tok, std::vector<int>& pos3, int& delta) {
     pos3.assign((size_t)3 * S, 0);
-    if (grid.empty()) {
+    if (grid.empty() && video_grid.empty()) {
         for (int r = 0; r < 3; ++r) for (int i = 0; i < S; ++i) pos3[(size_t)r * S + i] = i;
         delta = 0;
         return;
@@ -110,7 +112,7 @@ void get_rope_index(const uint32_t* ids, int S, const std::vector<std::array<int
     int last_max = -1;      // max of the last pushed chunk
     bool any = false;
     int text_start = 0, text_end = 0;
-    size_t image_index = 0;
+    size_t image_index = 0, video_index = 0;
     std::array<int, 3> thw{0, 0, 0};
     bool have_thw = false;
     auto push_text = [&](int len) {
@@ -132,7 +134,13 @@ void get_rope_index(const uint32_t* ids, int S, const std::vector<std::array<int
             have_thw = true;
             text_end = j;
         }
-        if (!have_thw) throw std::runtime_error("vision_start not followed by an image token (video is out of scope)");
+        if ((int)ids[j] == video_tok && video_tok >= 0) {
+            if (video_index >= video_grid.size()) throw std::runtime_error("more video placeholder runs than video_grid_thw frames");
+            thw = video_grid[video_index++];
+            have_thw = true;
+            text_end = j;
+        }
+        if (!have_thw) throw std::runtime_error("vision_start not followed by an image or video token");
         const int gt = thw[0], gh = thw[1] / merge, gw = thw[2] / merge;
         const int text_len = text_end - text_start;
         if (out + text_len + gt * gh * gw > S) throw std::runtime_error("image placeholders exceed the prompt length");
@@ -194,38 +202,65 @@ void forward_prefill(aha_model* m, const uint32_t* ids, size_t S, size_t offset,
         if (initial) AHA_REQUIRE(mm && mm->n == 5, "Qwen3VL process data error, must have pixel_values, image_grid_thw, pixel_values_video, video_grid_thw, cache_position");
         const aha_tensor_desc* pv = initial ? mm_entry(mm, 0) : nullptr;
         const aha_tensor_desc* thw = initial ? mm_entry(mm, 1) : nullptr;
-        if (initial) AHA_REQUIRE(!mm_entry(mm, 2) && !mm_entry(mm, 3), "video inputs are out of scope of this build (SURVEY.md section 8)");
-        std::vector<std::array<int, 3>> grid;
-        if (pv && thw) {
-            auto g = desc_to_i64(*thw);
-            AHA_REQUIRE(g.size() % 3 == 0 && !g.empty(), "image_grid_thw must be (n, 3)");
+        const aha_tensor_desc* pvv = initial ? mm_entry(mm, 2) : nullptr;
+        const aha_tensor_desc* vthw = initial ? mm_entry(mm, 3) : nullptr;
+        if (!(pv && thw)) { pv = nullptr; thw = nullptr; }       // `if let Some(pixel_values) && let Some(image_grid_thw)` (model.rs:1150-1151)
+        if (!(pvv && vthw)) { pvv = nullptr; vthw = nullptr; }   // the same for the video pair (model.rs:1169-1170)
+        std::vector<std::array<int, 3>> grid, vgrid, vgrid_frames;
+        auto read_grid = [&](const aha_tensor_desc& d, std::vector<std::array<int, 3>>& out, const char* what) {
+            auto g = desc_to_i64(d);
+            AHA_REQUIRE(g.size() % 3 == 0 && !g.empty(), std::string(what) + " must be (n, 3)");
             int N = 0;
-            for (size_t i = 0; i < g.size(); i += 3) { grid.push_back({(int)g[i], (int)g[i + 1], (int)g[i + 2]}); N += (int)(g[i] * g[i + 1] * g[i + 2]); }
-            AHA_REQUIRE(pv->rank == 2 && pv->shape[0] == N && pv->shape[1] == m->vision.patch_dim, "pixel_values shape does not match image_grid_thw");
-            AHA_REQUIRE(N <= m->vision.max_patches, "image needs " + std::to_string(N) + " patches, max_patches is " + std::to_string(m->vision.max_patches));
-            // placeholder positions + count check (model.rs:1158-1164)
-            std::vector<int> idx;
-            for (size_t i = 0; i < S; ++i) if ((int)ids[i] == m->image_token_id) idx.push_back((int)i);
-            const int n_embed = N / (m->vision.cfg.merge * m->vision.cfg.merge);
-            if ((int)idx.size() != n_embed)
-                throw std::runtime_error("n_image_token num: " + std::to_string(idx.size()) + " not equal to image_embed len: " + std::to_string(n_embed));
-            // pixel_values -> HBM, ViT
-            if (pv->dtype == AHA_F32) AHA_CUDA_CHECK(cudaMemcpyAsync(m->vision.pix, pv->data, (size_t)N * m->vision.patch_dim * sizeof(float), cudaMemcpyHostToDevice, c.stream));
-            else { auto f = desc_to_f32(*pv); AHA_CUDA_CHECK(cudaMemcpyAsync(m->vision.pix, f.data(), f.size() * sizeof(float), cudaMemcpyHostToDevice, c.stream)); AHA_CUDA_CHECK(cudaStreamSynchronize(c.stream)); }
+            for (size_t i = 0; i < g.size(); i += 3) { out.push_back({(int)g[i], (int)g[i + 1], (int)g[i + 2]}); N += (int)(g[i] * g[i + 1] * g[i + 2]); }
+            return N;
+        };
+        if (pv || pvv) {
+            VisionModel& V = m->vision;
+            const int N_img = pv ? read_grid(*thw, grid, "image_grid_thw") : 0;
+            const int N_vid = pvv ? read_grid(*vthw, vgrid, "video_grid_thw") : 0;
+            for (auto& g : vgrid) for (int t = 0; t < g[0]; ++t) vgrid_frames.push_back({1, g[1], g[2]});
+            const int N = N_img + N_vid, m2 = V.cfg.merge * V.cfg.merge;
+            if (pv) AHA_REQUIRE(pv->rank == 2 && pv->shape[0] == N_img && pv->shape[1] == V.patch_dim, "pixel_values shape does not match image_grid_thw");
+            if (pvv) AHA_REQUIRE(pvv->rank == 2 && pvv->shape[0] == N_vid && pvv->shape[1] == V.patch_dim, "pixel_values_video shape does not match video_grid_thw");
+            AHA_REQUIRE(N <= V.max_patches, "image needs " + std::to_string(N) + " patches, max_patches is " + std::to_string(V.max_patches));
+            // placeholder positions + count checks (model.rs:1158-1164, 1176-1183: the video branch raises the same text); the scatter list is
+            // the image positions followed by the video positions, matching the row order of the tower's output below
+            std::vector<int> idx, vidx;
+            for (size_t i = 0; i < S; ++i) {
+                if (pv && (int)ids[i] == m->image_token_id) idx.push_back((int)i);
+                if (pvv && (int)ids[i] == m->video_token_id) vidx.push_back((int)i);
+            }
+            if (pv && (int)idx.size() != N_img / m2)
+                throw std::runtime_error("n_image_token num: " + std::to_string(idx.size()) + " not equal to image_embed len: " + std::to_string(N_img / m2));
+            if (pvv && (int)vidx.size() != N_vid / m2)
+                throw std::runtime_error("n_image_token num: " + std::to_string(vidx.size()) + " not equal to image_embed len: " + std::to_string(N_vid / m2));
+            idx.insert(idx.end(), vidx.begin(), vidx.end());
+            const int n_embed = N / m2;
+            // pixel rows -> HBM (images, then video frames), one pass of the tower over both: every grid entry is independent through all
+            // blocks and mergers, so this equals the reference's two get_vision_features calls
+            auto put = [&](const aha_tensor_desc& d, size_t row0, size_t rows) {
+                float* dst = V.pix + row0 * V.patch_dim;
+                if (d.dtype == AHA_F32) AHA_CUDA_CHECK(cudaMemcpyAsync(dst, d.data, rows * V.patch_dim * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+                else { auto f = desc_to_f32(d); AHA_CUDA_CHECK(cudaMemcpyAsync(dst, f.data(), f.size() * sizeof(float), cudaMemcpyHostToDevice, c.stream)); AHA_CUDA_CHECK(cudaStreamSynchronize(c.stream)); }
+            };
+            if (pv) put(*pv, 0, (size_t)N_img);
+            if (pvv) put(*pvv, (size_t)N_img, (size_t)N_vid);
+            std::vector<std::array<int, 3>> all = grid;
+            all.insert(all.end(), vgrid.begin(), vgrid.end());
             AHA_CUDA_CHECK(cudaEventRecord(m->ev0, c.stream));
-            m->vision.forward(N, grid);
+            V.forward(N, all);
             AHA_CUDA_CHECK(cudaEventRecord(m->ev1, c.stream));
             upload_scatter_idx(m, idx);
             embed_gather_kernel<<<(unsigned)S, 256, 0, c.stream>>>(T.d_ids, T.embed, T.x, (int)S, T.cfg.H, T.cfg.V); c.cnt.kernels++;
-            scatter_rows_kernel<<<n_embed, 256, 0, c.stream>>>(m->d_scatter_idx, m->vision.image_embeds, T.x, T.cfg.H, 0); c.cnt.kernels++;
+            scatter_rows_kernel<<<n_embed, 256, 0, c.stream>>>(m->d_scatter_idx, V.image_embeds, T.x, T.cfg.H, 0); c.cnt.kernels++;
             embeds_ready = true;
-            n_visual = n_embed;
-            for (float* p : m->vision.ds_out) deepstack.push_back(p);
+            n_visual = n_embed;   // deepstack: x[idx[r]] += ds[r] over the same list = the joint embedding of model.rs:1189-1225
+            for (float* p : V.ds_out) deepstack.push_back(p);
         }
         // positions: first call -> get_rope_index, later -> arange + offset + rope_deltas (model.rs:1226-1264)
         if (!m->have_rope_delta || (initial && offset == 0)) {   // cache_position[0] == 0 recomputes get_rope_index even when rope_deltas is set (model.rs:1228)
             int delta = 0;
-            get_rope_index(ids, (int)S, grid, m->vision.cfg.merge, m->image_token_id, m->vision_start_token_id, pos3, delta);
+            get_rope_index(ids, (int)S, grid, vgrid_frames, m->vision.cfg.merge, m->image_token_id, m->video_token_id, m->vision_start_token_id, pos3, delta);
             m->rope_delta = delta; m->have_rope_delta = true;
         } else {
             for (int r = 0; r < 3; ++r) for (size_t i = 0; i < S; ++i) pos3[(size_t)r * S + i] = (int)(i + offset) + m->rope_delta;
@@ -929,17 +964,21 @@ int aha_b200_nccl_unique_id(uint8_t out[128]) {
     }
 }
 
-int aha_b200_rope_index(const uint32_t* ids, size_t seq_len, const uint32_t* grid_thw, size_t n_images, uint32_t spatial_merge_size,
-                        uint32_t image_token_id, uint32_t vision_start_token_id, int32_t* pos3_out, int32_t* rope_delta_out) {
+int aha_b200_rope_index_mm(const uint32_t* ids, size_t seq_len, const uint32_t* grid_thw, size_t n_images, const uint32_t* video_grid_thw, size_t n_videos,
+                           uint32_t spatial_merge_size, uint32_t image_token_id, uint32_t video_token_id, uint32_t vision_start_token_id, int32_t* pos3_out,
+                           int32_t* rope_delta_out) {
     try {
         AHA_REQUIRE(ids != nullptr && seq_len > 0 && pos3_out != nullptr && rope_delta_out != nullptr, "ids, pos3_out and rope_delta_out are required");
         AHA_REQUIRE(n_images == 0 || grid_thw != nullptr, "grid_thw is required when n_images > 0");
+        AHA_REQUIRE(n_videos == 0 || video_grid_thw != nullptr, "video_grid_thw is required when n_videos > 0");
         AHA_REQUIRE(spatial_merge_size > 0 && seq_len < (size_t)1 << 30, "bad spatial_merge_size / seq_len");
-        std::vector<std::array<int, 3>> grid(n_images);
+        std::vector<std::array<int, 3>> grid(n_images), frames;
         for (size_t i = 0; i < n_images; ++i) grid[i] = {(int)grid_thw[3 * i], (int)grid_thw[3 * i + 1], (int)grid_thw[3 * i + 2]};
+        for (size_t i = 0; i < n_videos; ++i)
+            for (uint32_t t = 0; t < video_grid_thw[3 * i]; ++t) frames.push_back({1, (int)video_grid_thw[3 * i + 1], (int)video_grid_thw[3 * i + 2]});
         std::vector<int> pos3;
         int delta = 0;
-        get_rope_index(ids, (int)seq_len, grid, (int)spatial_merge_size, (int)image_token_id, (int)vision_start_token_id, pos3, delta);
+        get_rope_index(ids, (int)seq_len, grid, frames, (int)spatial_merge_size, (int)image_token_id, (int)video_token_id, (int)vision_start_token_id, pos3, delta);
         for (size_t i = 0; i < pos3.size(); ++i) pos3_out[i] = pos3[i];
         *rope_delta_out = delta;
         return 0;
@@ -948,6 +987,11 @@ int aha_b200_rope_index(const uint32_t* ids, size_t seq_len, const uint32_t* gri
         g_create_error = e.what();
         return 1;
     }
+}
+int aha_b200_rope_index(const uint32_t* ids, size_t seq_len, const uint32_t* grid_thw, size_t n_images, uint32_t spatial_merge_size,
+                        uint32_t image_token_id, uint32_t vision_start_token_id, int32_t* pos3_out, int32_t* rope_delta_out) {
+    return aha_b200_rope_index_mm(ids, seq_len, grid_thw, n_images, nullptr, 0, spatial_merge_size, image_token_id, 0xffffffffu, vision_start_token_id, pos3_out,
+                                  rope_delta_out);
 }
 
 void aha_b200_destroy(aha_model* m) {

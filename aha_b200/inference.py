@@ -33,17 +33,20 @@ def nccl_unique_id():
     return bytes(buf)
 
 
-def rope_index(ids, grid_thw, config):
+def rope_index(ids, grid_thw, config, video_grid_thw=None):
     """M-RoPE position ids (3, S) int32 and rope_delta of a Qwen3-VL prompt -- the host routine forward_initial runs
-    (Qwen3VLModel::get_rope_index, /root/reference/src/models/qwen3vl/model.rs:901-1133).  No device work."""
+    (Qwen3VLModel::get_rope_index, /root/reference/src/models/qwen3vl/model.rs:901-1133), image and video branches.  No device work."""
     lib = L.load()
     ids = np.ascontiguousarray(np.asarray(ids).reshape(-1), dtype=np.uint32)
     grid = np.ascontiguousarray(np.asarray(grid_thw if grid_thw is not None else [], dtype=np.uint32).reshape(-1, 3))
+    vgrid = np.ascontiguousarray(np.asarray(video_grid_thw if video_grid_thw is not None else [], dtype=np.uint32).reshape(-1, 3))
     pos = np.empty((3, ids.size), np.int32)
     delta = C.c_int32(0)
-    rc = lib.aha_b200_rope_index(ids.ctypes.data_as(C.POINTER(C.c_uint32)), ids.size, grid.ctypes.data_as(C.POINTER(C.c_uint32)), grid.shape[0],
-                                 int(config["vision_config"]["spatial_merge_size"]), int(config["image_token_id"]),
-                                 int(config["vision_start_token_id"]), pos.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(delta))
+    u32 = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint32))
+    rc = lib.aha_b200_rope_index_mm(u32(ids), ids.size, u32(grid), grid.shape[0], u32(vgrid), vgrid.shape[0],
+                                    int(config["vision_config"]["spatial_merge_size"]), int(config["image_token_id"]),
+                                    int(config.get("video_token_id", 0xffffffff)), int(config["vision_start_token_id"]),
+                                    pos.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(delta))
     if rc != 0:
         raise B200Error(lib.aha_b200_last_error(None).decode())
     return pos, int(delta.value)

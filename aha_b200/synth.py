@@ -261,6 +261,22 @@ def vl_prompt_ids(cfg, grid_thw, n_text, seed=3):
     return np.asarray(ids, dtype=np.uint32)
 
 
+def vl_video_prompt_ids(cfg, video_grid_thw, n_stamp=3, seed=5):
+    """One video the way Qwen3VLProcessor lays it out (qwen3vl/processor.rs:447-571): per temporal grid step a few timestamp text ids,
+    then <|vision_start|> + (h*w/merge^2) x <|video_pad|> + <|vision_end|>."""
+    m2 = cfg["vision_config"]["spatial_merge_size"] ** 2
+    special = (cfg["image_token_id"], cfg["video_token_id"], cfg["vision_start_token_id"], cfg["vision_end_token_id"])
+    V = cfg["text_config"]["vocab_size"]
+    ids = []
+    k = 0
+    for t, h, w in np.asarray(video_grid_thw).tolist():
+        for _ in range(t):
+            ids += synth_text_ids(n_stamp, min(V, 151000), seed + k, avoid=special).tolist()
+            ids += [cfg["vision_start_token_id"]] + [cfg["video_token_id"]] * (h * w // m2) + [cfg["vision_end_token_id"]]
+            k += 1
+    return np.asarray(ids, dtype=np.uint32)
+
+
 def asr_audio_tokens(n_frames):
     """Audio tokens of `n_frames` log-mel frames: 13 per full 100-frame chunk + three stride-2 convolutions over the rest
     (get_feat_extract_output_lengths, /root/reference/src/models/qwen3_asr/processor.rs:187-195)."""

@@ -128,7 +128,7 @@ def describe(wl, cfg, S, n_mm):
     tc = text_config(wl["kind"], cfg)
     if wl["kind"] == "qwen3vl":
         h, w_ = wl["image"]
-        name = "Qwen3-VL-8B text stack + head_dim-64 vision tower (see aha_b200/synth.py)" if wl["preset"] == "vl8" else "Qwen3-VL-2B shape"
+        name = "Qwen3-VL-8B shape (text H 4096 x 36 layers, 32/8 heads; vision tower 1152 / 16 heads = head_dim 72, 27 blocks)" if wl["preset"] == "vl8" else "Qwen3-VL-2B shape"
         return (f"{name} ({wl['preset']}), random-init fp16 weights (seed 0), {wl.get('n_images', 1)} synthetic {w_}x{h} image(s) "
                 f"({n_mm} image tokens) + {wl['n_text']} text ids, greedy decode at ctx {S}+")
     if wl["kind"] == "qwen3":

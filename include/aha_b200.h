@@ -225,6 +225,12 @@ void aha_b200_destroy(aha_model* m);
 int aha_b200_rope_index(const uint32_t* ids, size_t seq_len, const uint32_t* grid_thw, size_t n_images, uint32_t spatial_merge_size,
                         uint32_t image_token_id, uint32_t vision_start_token_id, int32_t* pos3_out, int32_t* rope_delta_out);
 
+/* The same with the video branch (model.rs:907-925, 973-981): every row (t, h, w) of video_grid_thw stands for t runs of
+ * <|vision_start|><|video_pad|>... in the prompt, each positioned as a (1, h, w) grid. */
+int aha_b200_rope_index_mm(const uint32_t* ids, size_t seq_len, const uint32_t* grid_thw, size_t n_images, const uint32_t* video_grid_thw, size_t n_videos,
+                           uint32_t spatial_merge_size, uint32_t image_token_id, uint32_t video_token_id, uint32_t vision_start_token_id, int32_t* pos3_out,
+                           int32_t* rope_delta_out);
+
 /* Last error message of the handle (or of the failed create / handle-less call when m == NULL). */
 const char* aha_b200_last_error(aha_model* m);
 

@@ -331,20 +331,23 @@ class Qwen3VLTextModel:
             l.clear_kv_cache()
 
 
-def get_rope_index(input_ids, image_grid_thw, cfg):
-    """model.rs:901-1133, image-only branch (video is out of scope), mask=None.
-    Returns (position_ids (3,1,S) int64, rope_delta int)."""
+def get_rope_index(input_ids, image_grid_thw, cfg, video_grid_thw=None):
+    """model.rs:901-1133, mask=None.  Every (t, h, w) row of video_grid_thw becomes t rows of (1, h, w) (model.rs:907-925): each frame
+    group has its own <|vision_start|><|video_pad|>... run in the prompt.  Returns (position_ids (3,1,S) int64, rope_delta int)."""
     ids = np.asarray(input_ids).reshape(-1)
     S = ids.shape[0]
-    if image_grid_thw is None:
+    if image_grid_thw is None and video_grid_thw is None:
         pos = np.broadcast_to(np.arange(S, dtype=np.int64)[None, None], (3, 1, S)).copy()
         return pos, 0
     merge = cfg["vision_config"]["spatial_merge_size"]
-    img_tok, vs_tok = cfg["image_token_id"], cfg["vision_start_token_id"]
-    g = np.asarray(image_grid_thw)
+    img_tok, vid_tok, vs_tok = cfg["image_token_id"], cfg.get("video_token_id"), cfg["vision_start_token_id"]
+    g = np.asarray(image_grid_thw) if image_grid_thw is not None else None
+    vg = None
+    if video_grid_thw is not None:
+        vg = [[1, int(h), int(w)] for t, h, w in np.asarray(video_grid_thw).tolist() for _ in range(int(t))]
     vis_next = np.nonzero(ids == vs_tok)[0] + 1  # get_vision_next_indices
     chunks = []
-    text_start, text_end, image_index = 0, 0, 0
+    text_start, text_end, image_index, video_index = 0, 0, 0, 0
     thw = None
     last_max = -1
     for j in vis_next.tolist():
@@ -352,6 +355,10 @@ def get_rope_index(input_ids, image_grid_thw, cfg):
         if tok == img_tok:
             thw = g[image_index].tolist()
             image_index += 1
+            text_end = j
+        if vid_tok is not None and tok == vid_tok:
+            thw = vg[video_index]
+            video_index += 1
             text_end = j
         if thw is None:
             continue
@@ -377,7 +384,7 @@ def get_rope_index(input_ids, image_grid_thw, cfg):
 
 
 class Qwen3VLModel:
-    """model.rs:837-1324 incl. `impl InferenceModel` (image path; video tensors must be None)."""
+    """model.rs:837-1324 incl. `impl InferenceModel` (image and video tensors; decoding a video file into frames is the processor's job)."""
 
     def __init__(self, cfg, w, eos_ids=()):
         self.cfg = cfg
@@ -388,20 +395,46 @@ class Qwen3VLModel:
         self.rope_deltas = None
         self._stop = list(eos_ids)
 
-    def forward(self, input_ids, pixel_values=None, image_grid_thw=None, seqlen_offset=0):
+    def forward(self, input_ids, pixel_values=None, image_grid_thw=None, seqlen_offset=0, pixel_values_video=None, video_grid_thw=None):
+        """model.rs:1135-1290."""
         ids = np.asarray(input_ids).reshape(1, -1)
         x = nn.embedding(ids, self.text.embed)
-        mask, deep = None, None
+        image_mask = video_mask = None
+        deep_img = deep_vid = None
         if pixel_values is not None and image_grid_thw is not None:
-            emb, deep = self.visual.forward(pixel_values, image_grid_thw)
-            mask = (ids == self.cfg["image_token_id"])
-            n_tok = int(mask.sum())
+            emb, deep_img = self.visual.forward(pixel_values, image_grid_thw)
+            image_mask = (ids == self.cfg["image_token_id"])
+            n_tok = int(image_mask.sum())
             if n_tok != emb.shape[0]:  # model.rs:1158-1164
                 raise ValueError(f"n_image_token num: {n_tok} not equal to image_embed len: {emb.shape[0]}")
             x = x.copy()
-            x[0, np.nonzero(mask[0])[0]] = emb  # masked_scatter_dim0
+            x[0, np.nonzero(image_mask[0])[0]] = emb  # masked_scatter_dim0
+        if pixel_values_video is not None and video_grid_thw is not None:
+            emb, deep_vid = self.visual.forward(pixel_values_video, video_grid_thw)
+            video_mask = (ids == self.cfg["video_token_id"])
+            n_tok = int(video_mask.sum())
+            if n_tok != emb.shape[0]:  # model.rs:1176-1183 (the same message)
+                raise ValueError(f"n_image_token num: {n_tok} not equal to image_embed len: {emb.shape[0]}")
+            x = x.copy()
+            x[0, np.nonzero(video_mask[0])[0]] = emb
+        mask, deep = None, None
+        if image_mask is not None and video_mask is not None:  # model.rs:1189-1218: joint embedding in visual-position order
+            mask = image_mask | video_mask
+            vis = np.nonzero(mask[0])[0]
+            img_joint = np.nonzero(image_mask[0][vis])[0]
+            vid_joint = np.nonzero(video_mask[0][vis])[0]
+            deep = []
+            for di, dv in zip(deep_img, deep_vid):
+                joint = np.zeros((vis.shape[0], di.shape[-1]), F32)
+                joint[img_joint] += di
+                joint[vid_joint] += dv
+                deep.append(joint)
+        elif image_mask is not None:
+            mask, deep = image_mask, deep_img
+        elif video_mask is not None:
+            mask, deep = video_mask, deep_vid
         if self.rope_deltas is None:
-            pos, delta = get_rope_index(ids, image_grid_thw, self.cfg)
+            pos, delta = get_rope_index(ids, image_grid_thw, self.cfg, video_grid_thw)
             self.rope_deltas = delta
         else:  # model.rs:1235-1264
             s = ids.shape[1]
@@ -414,9 +447,7 @@ class Qwen3VLModel:
         if data is None or len(data) != 5:  # model.rs:1292-1296
             raise ValueError("Qwen3VL process data error, must have pixel_values, image_grid_thw, "
                              "pixel_values_video, video_grid_thw, cache_position")
-        if data[2] is not None or data[3] is not None:
-            raise NotImplementedError("video path is out of scope (SURVEY.md section 8)")
-        return self.forward(input_ids, data[0], data[1], seqlen_offset)
+        return self.forward(input_ids, data[0], data[1], seqlen_offset, data[2], data[3])
 
     def forward_step(self, input_ids, seqlen_offset):
         return self.forward(input_ids, None, None, seqlen_offset)

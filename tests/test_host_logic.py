@@ -60,6 +60,27 @@ def test_rope_index_random_prompts(shapes, data):
     assert delta == int(pos.max()) + 1 - ids.size
 
 
+@pytest.mark.parametrize("grids,vgrids,order", [
+    ([], [[3, 4, 6]], "v"),                       # video only: three frame groups, each its own (1, h, w) run
+    ([[1, 4, 6]], [[2, 8, 2]], "iv"),             # image then video
+    ([[1, 2, 2]], [[2, 4, 4], [1, 6, 2]], "vi"),  # two videos then an image
+])
+def test_rope_index_video_branch_matches_oracle(grids, vgrids, order):
+    parts = {"i": [synth.vl_prompt_ids(CFG, [g], 0) for g in grids], "v": [synth.vl_video_prompt_ids(CFG, [g]) for g in vgrids]}
+    ids = [synth.synth_text_ids(4, 1000, 1)]
+    for k in order:
+        ids += parts[k] + [synth.synth_text_ids(2, 1000, 2)]
+    ids = np.concatenate(ids).astype(np.uint32)
+    pos, delta = rope_index(ids, grids or None, CFG, vgrids)
+    want, want_delta = get_rope_index(ids.astype(np.int64), np.asarray(grids) if grids else None, CFG, np.asarray(vgrids))
+    assert (pos == want[:, 0]).all() and delta == want_delta
+    assert delta == int(pos.max()) + 1 - ids.size
+    # a frame group is positioned as a (1, h, w) grid: its t row is constant
+    first = int(np.nonzero(ids == CFG["video_token_id"])[0][0])
+    n0 = vgrids[0][1] * vgrids[0][2] // 4
+    assert (pos[0, first:first + n0] == pos[0, first]).all()
+
+
 def test_rope_index_errors_are_reported_not_thrown():
     ids = build_prompt([[1, 4, 6], [1, 4, 6]], [2, 2, 2])
     with pytest.raises(B200Error, match="more image placeholders"):
@@ -69,3 +90,6 @@ def test_rope_index_errors_are_reported_not_thrown():
     tail = np.append(synth.synth_text_ids(4, 1000, 1), np.uint32(CFG["vision_start_token_id"]))
     with pytest.raises(B200Error, match="vision_start"):
         rope_index(tail, [[1, 4, 6]], CFG)
+    vid = synth.vl_video_prompt_ids(CFG, [[2, 4, 4]])
+    with pytest.raises(B200Error, match="more video placeholder runs"):
+        rope_index(vid, None, CFG, [[1, 4, 4]])                      # two frame groups in the prompt, one in video_grid_thw

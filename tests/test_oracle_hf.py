@@ -66,6 +66,43 @@ def test_qwen3vl_matches_hf():
     assert np.abs(got - out).max() < 1e-5
 
 
+def test_qwen3vl_video_branch_matches_hf():
+    """Image + video in one prompt: the video tensors through the same tower, scattered at <|video_pad|>, joint deepstack injection, M-RoPE
+    with every temporal step of the video as its own (1, h, w) grid (model.rs:907-925, 1169-1225) -- against HF's implementation."""
+    from transformers import Qwen3VLConfig, Qwen3VLForConditionalGeneration
+    from oracle.qwen3vl import Qwen3VLModel, get_rope_index, img_transform, process_image, process_vision_tensor
+    cfg = synth.get_config("qwen3vl", "tiny")
+    w = synth.make_weights("qwen3vl", cfg, 0)
+    hc = Qwen3VLConfig(text_config=dict(cfg["text_config"], max_position_embeddings=4096), vision_config=cfg["vision_config"],
+                       image_token_id=cfg["image_token_id"], video_token_id=cfg["video_token_id"],
+                       vision_start_token_id=cfg["vision_start_token_id"], vision_end_token_id=cfg["vision_end_token_id"],
+                       tie_word_embeddings=True)
+    for c in (hc, hc.vision_config, hc.text_config):
+        c._attn_implementation = "eager"
+    hf = Qwen3VLForConditionalGeneration(hc).float().eval()
+    sd = {k: torch.from_numpy(v.astype(np.float32)) for k, v in w.items()}
+    sd["lm_head.weight"] = sd["model.language_model.embed_tokens.weight"]
+    hf.load_state_dict(sd, strict=False)
+    frames = np.stack([img_transform(synth.synth_image(64, 96, 11 + i), (0.5,) * 3, (0.5,) * 3) for i in range(4)])
+    pvv, vgrid = process_vision_tensor(frames)                        # 4 frames -> video_grid_thw [[2, 4, 6]]
+    pv, grid = process_image(synth.synth_image(128, 96, 1))
+    ids = np.concatenate([synth.synth_text_ids(3, 1000, 9), synth.vl_prompt_ids(cfg, grid, 0), synth.vl_video_prompt_ids(cfg, vgrid),
+                          synth.synth_text_ids(6, 1000, 4)]).astype(np.int64)
+    _, delta = get_rope_index(ids, grid, cfg, vgrid)
+    mm = torch.from_numpy((ids == cfg["image_token_id"]).astype(np.int64) + 2 * (ids == cfg["video_token_id"]).astype(np.int64))[None]
+    kw = dict(input_ids=torch.from_numpy(ids)[None], pixel_values=torch.from_numpy(pv), image_grid_thw=torch.from_numpy(grid.astype(np.int64)),
+              pixel_values_videos=torch.from_numpy(pvv), video_grid_thw=torch.from_numpy(vgrid.astype(np.int64)))
+    with torch.no_grad():
+        try:
+            out = hf(**kw, mm_token_type_ids=mm).logits[0, -1].numpy()
+        except TypeError:
+            out = hf(**kw).logits[0, -1].numpy()
+    assert int(hf.model.rope_deltas.reshape(-1)[0]) == delta
+    m = Qwen3VLModel(cfg, w)
+    got = m.forward_initial(ids.reshape(1, -1), 0, [pv, grid, pvv, vgrid, None])[0, 0]
+    assert np.abs(got - out).max() < 1e-5
+
+
 def test_mel_filter_bank_matches_hf():
     from transformers.audio_utils import mel_filter_bank as hfmel
     from oracle.audio import mel_filter_bank

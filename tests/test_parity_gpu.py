@@ -332,6 +332,43 @@ def test_llm_prefill_attention_implementations_agree(q3, S):
             m2.close()
 
 
+def _video_inputs(cfg, n_frames, h, w_, seed):
+    from aha_b200 import synth
+    from oracle.qwen3vl import img_transform, process_vision_tensor
+    frames = np.stack([img_transform(synth.synth_image(h, w_, seed + i), (0.5, 0.5, 0.5), (0.5, 0.5, 0.5)) for i in range(n_frames)])
+    return process_vision_tensor(frames)     # pixel_values_video (t*h*w, 1536), video_grid_thw [[t, h/16, w/16]]
+
+
+@pytest.mark.parametrize("with_image", [False, True])
+def test_vl_video_prefill_and_decode(vl, with_image):
+    """The video branch of Qwen3VLModel::forward (model.rs:1169-1225): pixel_values_video / video_grid_thw through the same tower, scattered at
+    the <|video_pad|> positions, joint deepstack injection with the image embeddings, M-RoPE with one (1, h, w) grid per frame group."""
+    from aha_b200 import synth
+    cfg, w, m, o = vl
+    pvv, vgrid = _video_inputs(cfg, 4, 64, 96, 11)               # 4 frames -> 2 temporal steps of 4 x 6 patches
+    parts = [synth.synth_text_ids(3, 1000, 9), synth.vl_video_prompt_ids(cfg, vgrid)]
+    pv = grid = None
+    if with_image:
+        pv, grid, img_ids = _vl_inputs(cfg, [(128, 96)], 0)
+        parts = [img_ids] + parts
+    ids = np.concatenate(parts + [synth.synth_text_ids(6, 1000, 4)]).astype(np.uint32)
+    m.clear_cache(); o.clear_cache()
+    got = m.forward_initial(ids, 0, [pv, grid, pvv, vgrid, None])[0, 0]
+    want = o.forward_initial(ids.reshape(1, -1), 0, [pv, grid, pvv, vgrid, None])[0, 0]
+    assert np.abs(got - want).max() <= TOL
+    assert int(m.debug_read("rope_delta", 0, 1)[0]) == o.rope_deltas
+    S = len(ids)
+    for i, t in enumerate([5, 17]):
+        got = m.forward_step(np.array([t], np.uint32), S + i)[0, 0]
+        want = o.forward_step(np.array([[t]]), S + i)[0, 0]
+        assert np.abs(got - want).max() <= TOL
+    bad = np.concatenate([ids, [cfg["video_token_id"]]]).astype(np.uint32)
+    m.clear_cache()
+    with pytest.raises(Exception, match="n_image_token num"):
+        m.forward_initial(bad, 0, [pv, grid, pvv, vgrid, None])
+    m.clear_cache()
+
+
 def test_vl_text_only_prompt(vl):
     cfg, w, m, o = vl
     ids = _ids(12, 1000, 3)
