@@ -34,7 +34,7 @@ class GenParams(C.Structure):
                 ("flags", C.c_uint32), ("reserved", C.c_uint32)]
 
 
-GEN_EOS_ON_FIRST, GEN_CONTINUE_RNG = 1, 2
+GEN_EOS_ON_FIRST, GEN_CONTINUE_RNG, GEN_REUSE_PREFIX = 1, 2, 4
 TOKEN_CALLBACK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_uint32)
 
 
@@ -63,6 +63,10 @@ SYMBOLS = {
                                   C.POINTER(Options), C.POINTER(_P)]),
     "aha_b200_forward_initial": (C.c_int, [_P, _U32P, C.c_size_t, C.c_size_t, C.POINTER(MM), _F32P, _U32P]),
     "aha_b200_forward_step": (C.c_int, [_P, _U32P, C.c_size_t, C.c_size_t, _F32P, _U32P]),
+    "aha_b200_forward_extend": (C.c_int, [_P, _U32P, C.c_size_t, C.c_size_t, _F32P, _U32P]),
+    "aha_b200_last_prefix_hit": (C.c_size_t, [_P]),
+    "aha_b200_prefix_match": (C.c_size_t, [_U32P, C.c_size_t, _U32P, C.c_size_t, _U32P, C.c_size_t, C.c_int]),
+    "aha_b200_mm_fingerprint": (C.c_uint64, [C.POINTER(MM)]),
     "aha_b200_clear_cache": (C.c_int, [_P]),
     "aha_b200_stop_token_ids": (C.c_size_t, [_P, _U32P, C.c_size_t]),
     "aha_b200_generate": (C.c_int, [_P, _U32P, C.c_size_t, C.POINTER(MM), C.POINTER(GenParams), _U32P, C.c_size_t,

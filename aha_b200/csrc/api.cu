@@ -40,6 +40,12 @@ struct aha_model {
     uint32_t* h_pin = nullptr;
     static constexpr int kStreamBurst = 8;   // streaming: steps the device may run ahead of the token being delivered
     cudaEvent_t ev_tok[kStreamBurst] = {};
+    // KV reuse across requests (new design: the reference clears the cache after every request, common/generate.rs:147,
+    // and serialises requests behind one lock, server/api.rs:117).  A request that carries AHA_GEN_REUSE_PREFIX leaves its K/V in the paged
+    // cache; the next such request prefills only what follows the longest common prefix.
+    std::vector<uint32_t> cached_ids;   // tokens whose K/V occupy positions 0 .. n-1 of the paged cache
+    uint64_t cached_mm_fp = 0;          // fingerprint of the multimodal tensors those tokens were embedded with (0 = none)
+    size_t last_prefix_hit = 0;         // tokens the last generate call did not have to prefill
 };
 
 namespace {
@@ -188,6 +194,71 @@ void fetch_outputs(aha_model* m, float* logits_out, uint32_t* argmax_out) {
     if (argmax_out) *argmax_out = m->h_pin[0];
 }
 
+
+// ---- KV reuse across requests: which prefix of the new prompt is already in the cache --------------------------------------------
+// Longest prefix of `ids` whose K/V can be taken from a cache holding `cached`: the common prefix, cut to n - 1 (the last prompt token is
+// always run: its logits are the request's first output).  Placeholder tokens (<|image_pad|>, <|video_pad|>, <|audio_pad|>) stand for rows
+// of the multimodal tensors, so they only count when those tensors are the same (`same_mm`), and every placeholder of BOTH sequences must
+// lie inside the common prefix -- the suffix is then plain text whose M-RoPE positions are index + rope_delta (qwen3vl/model.rs:1250-1264).
+size_t prefix_match(const uint32_t* cached, size_t n_cached, const uint32_t* ids, size_t n, const uint32_t* mm_tokens, size_t n_mm_tokens, bool same_mm) {
+    if (n == 0 || n_cached == 0 || !same_mm) return 0;
+    size_t lcp = 0;
+    while (lcp < n && lcp < n_cached && cached[lcp] == ids[lcp]) ++lcp;
+    auto is_mm = [&](uint32_t t) { for (size_t i = 0; i < n_mm_tokens; ++i) if (mm_tokens[i] == t) return true; return false; };
+    for (size_t i = lcp; i < n; ++i) if (is_mm(ids[i])) return 0;
+    for (size_t i = lcp; i < n_cached; ++i) if (is_mm(cached[i])) return 0;
+    return std::min(lcp, n - 1);
+}
+
+// 64-bit fingerprint of a host buffer: four independent multiply-xorshift lanes over 8-byte words (memory-bound on one core;
+// ~10 ms for the 50 MB pixel_values of a 1080p image), folded with the length.  Not cryptographic: it guards a cache, not a boundary.
+uint64_t fingerprint_bytes(const void* data, size_t n, uint64_t seed) {
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    uint64_t h[4] = {seed ^ 0x9e3779b97f4a7c15ull, seed ^ 0xbf58476d1ce4e5b9ull, seed ^ 0x94d049bb133111ebull, seed ^ 0x2545f4914f6cdd1dull};
+    const uint64_t k = 0xff51afd7ed558ccdull;
+    size_t i = 0;
+    for (; i + 32 <= n; i += 32) {
+        uint64_t w[4];
+        std::memcpy(w, p + i, 32);
+        for (int l = 0; l < 4; ++l) { h[l] = (h[l] ^ w[l]) * k; h[l] ^= h[l] >> 29; }
+    }
+    uint64_t tail[4] = {0, 0, 0, 0};
+    std::memcpy(tail, p + i, n - i);
+    for (int l = 0; l < 4; ++l) { h[l] = (h[l] ^ tail[l]) * k; h[l] ^= h[l] >> 29; }
+    uint64_t r = (uint64_t)n * 0xc4ceb9fe1a85ec53ull;
+    for (int l = 0; l < 4; ++l) { r = (r ^ h[l]) * k; r ^= r >> 32; }
+    return r;
+}
+// fingerprint of a request's MultiModalData (0 when it carries no tensor): dtype, shape and bytes of every present entry
+uint64_t mm_fingerprint(const aha_mm* mm) {
+    uint64_t fp = 0;
+    for (size_t i = 0; mm && i < mm->n; ++i) {
+        const aha_tensor_desc* d = mm_entry(mm, i);
+        if (!d) continue;
+        size_t esz = 4;
+        switch (d->dtype) { case AHA_F16: case AHA_BF16: esz = 2; break; case AHA_I64: esz = 8; break; case AHA_U8: esz = 1; break; default: break; }
+        uint64_t meta[11] = {(uint64_t)i + 1, (uint64_t)d->dtype, (uint64_t)d->rank};
+        for (int r = 0; r < d->rank && r < 8; ++r) meta[3 + r] = (uint64_t)d->shape[r];
+        fp = fingerprint_bytes(meta, sizeof(meta), fp);
+        fp = fingerprint_bytes(d->data, WeightTable::numel(*d) * esz, fp);
+        if (fp == 0) fp = 1;
+    }
+    return fp;
+}
+std::vector<uint32_t> mm_token_ids(const aha_model* m) {
+    std::vector<uint32_t> t;
+    for (int v : {m->image_token_id, m->video_token_id, m->audio_token_id}) if (v >= 0) t.push_back((uint32_t)v);
+    return t;
+}
+// model.clear_cache(): pages, rope_deltas, and what the prefix cache remembered
+void drop_cache(aha_model* m) {
+    m->text.reset_pages();
+    m->have_rope_delta = false;  // qwen3vl/model.rs:1279-1282
+    m->rope_delta = 0;
+    m->cached_ids.clear();
+    m->cached_mm_fp = 0;
+}
+
 // The multi-token forward (prefill).  Mirrors Qwen3Model::forward / Qwen3VLModel::forward / Qwen3ASRThinker::forward.
 void forward_prefill(aha_model* m, const uint32_t* ids, size_t S, size_t offset, const aha_mm* mm, bool initial) {
     TextModel& T = m->text;
@@ -295,14 +366,17 @@ void forward_prefill(aha_model* m, const uint32_t* ids, size_t S, size_t offset,
     T.prefill((int)S, (int)offset, embeds_ready, m->d_scatter_idx, n_visual, deepstack);
 }
 
-void forward_any(aha_model* m, const uint32_t* ids, size_t S, size_t offset, const aha_mm* mm, bool initial, float* logits_out, uint32_t* argmax_out) {
+// `extend`: prefill continuation (new design) -- S >= 1 further tokens against a cache that already holds `offset` tokens; the causal mask is
+// the (S, offset + S) one the reference never builds (its (S, S) mask makes a multi-token call with a non-empty cache fail, qwen3/model.rs:164-175).
+void forward_any(aha_model* m, const uint32_t* ids, size_t S, size_t offset, const aha_mm* mm, bool initial, float* logits_out, uint32_t* argmax_out,
+                 bool extend = false) {
     TextModel& T = m->text;
     AHA_REQUIRE(ids != nullptr && S >= 1, "input_ids must hold at least one token");
     AHA_REQUIRE(offset + S <= (size_t)T.max_ctx, "context exceeds max_ctx");
     const bool has_mm = initial && mm && ((m->kind == aha_model::QWEN3VL && (mm_entry(mm, 0) || mm_entry(mm, 2))) || (m->kind == aha_model::QWEN3_ASR && mm_entry(mm, 0)));
     if (initial && m->kind == aha_model::QWEN3VL) AHA_REQUIRE(mm && mm->n == 5, "Qwen3VL process data error, must have pixel_values, image_grid_thw, pixel_values_video, video_grid_thw, cache_position");
     if (initial && m->kind == aha_model::QWEN3_ASR) AHA_REQUIRE(mm && mm->n == 1, "Qwen3 asr process data error, must have input_features");
-    if (S == 1 && !has_mm && (m->kind != aha_model::QWEN3VL || m->have_rope_delta)) {
+    if (S == 1 && !has_mm && !extend && (m->kind != aha_model::QWEN3VL || m->have_rope_delta)) {
         // decode step: single token against the cache
         AHA_REQUIRE(ids[0] < (uint32_t)T.cfg.V, "token id out of range");
         T.ensure_tokens((int)offset + 1);
@@ -311,8 +385,25 @@ void forward_any(aha_model* m, const uint32_t* ids, size_t S, size_t offset, con
     } else {
         // The reference builds an (S,S) causal mask with offset 0 for every multi-token call
         // (qwen3/model.rs:164-175); with a non-empty cache its broadcast_add against (S, off+S) scores fails.
-        AHA_REQUIRE(offset == 0, "seq_len > 1 with seqlen_offset > 0 is not supported (the reference's mask shape rejects it too)");
-        forward_prefill(m, ids, S, offset, mm, initial);
+        if (!extend) AHA_REQUIRE(offset == 0, "seq_len > 1 with seqlen_offset > 0 is not supported (the reference's mask shape rejects it too)");
+        else AHA_REQUIRE(offset <= (size_t)T.pages_mapped * kPage, "forward_extend: seqlen_offset is beyond the tokens in the cache");
+        // A prompt longer than the activation workspace (max_prefill) runs as consecutive chunks against the growing cache: the first chunk is
+        // the reference's call (multimodal rows are scattered there), the others are continuations.  Same K/V, same logits for the last token.
+        const size_t chunk = (size_t)T.max_prefill;
+        size_t done = 0;
+        while (done < S) {
+            const size_t n = std::min(chunk, S - done);
+            const bool first = done == 0;
+            if (first && !extend) {
+                if (n < S && has_mm) {   // every placeholder row must be embedded by the call that carries the tensors
+                    const auto mmt = mm_token_ids(m);
+                    for (size_t i = n; i < S; ++i) for (uint32_t t : mmt) AHA_REQUIRE(ids[i] != t, "prompt exceeds max_prefill before its last multimodal placeholder");
+                }
+                // (Qwen3-VL: get_rope_index over the first chunk yields the whole prompt's rope_delta, because only text follows the last placeholder)
+                forward_prefill(m, ids, n, offset, mm, initial);
+            } else forward_prefill(m, ids + done, n, offset + done, nullptr, false);
+            done += n;
+        }
         T.finish_argmax(0);
         T.sample(0);   // device sampler of generate(): penalty / temperature / top-k / top-p on the prefill logits (no-op for plain ArgMax)
     }
@@ -422,19 +513,31 @@ int aha_b200_create(const char* kind, const char* config_json, const aha_tensor_
 
 int aha_b200_forward_initial(aha_model* m, const uint32_t* ids, size_t seq_len, size_t seqlen_offset, const aha_mm* mm, float* logits_out,
                              uint32_t* argmax_out) {
-    return guarded(m, [&] { forward_any(m, ids, seq_len, seqlen_offset, mm, true, logits_out, argmax_out); });
+    return guarded(m, [&] { m->cached_ids.clear(); forward_any(m, ids, seq_len, seqlen_offset, mm, true, logits_out, argmax_out); });
 }
 
 int aha_b200_forward_step(aha_model* m, const uint32_t* ids, size_t seq_len, size_t seqlen_offset, float* logits_out, uint32_t* argmax_out) {
-    return guarded(m, [&] { forward_any(m, ids, seq_len, seqlen_offset, nullptr, false, logits_out, argmax_out); });
+    return guarded(m, [&] { m->cached_ids.clear(); forward_any(m, ids, seq_len, seqlen_offset, nullptr, false, logits_out, argmax_out); });
 }
+
+int aha_b200_forward_extend(aha_model* m, const uint32_t* ids, size_t seq_len, size_t seqlen_offset, float* logits_out, uint32_t* argmax_out) {
+    return guarded(m, [&] { m->cached_ids.clear(); forward_any(m, ids, seq_len, seqlen_offset, nullptr, false, logits_out, argmax_out, true); });
+}
+
+size_t aha_b200_last_prefix_hit(aha_model* m) { return m ? m->last_prefix_hit : 0; }
+
+size_t aha_b200_prefix_match(const uint32_t* cached, size_t n_cached, const uint32_t* ids, size_t n, const uint32_t* mm_token_ids, size_t n_mm_tokens,
+                             int same_mm) {
+    if ((!cached && n_cached) || (!ids && n) || (!mm_token_ids && n_mm_tokens)) return 0;
+    return prefix_match(cached, n_cached, ids, n, mm_token_ids, n_mm_tokens, same_mm != 0);
+}
+
+uint64_t aha_b200_mm_fingerprint(const aha_mm* mm) { return mm_fingerprint(mm); }
 
 int aha_b200_clear_cache(aha_model* m) {
     return guarded(m, [&] {
         AHA_CUDA_CHECK(cudaStreamSynchronize(m->ctx.stream));
-        m->text.reset_pages();
-        m->have_rope_delta = false;  // qwen3vl/model.rs:1279-1282
-        m->rope_delta = 0;
+        drop_cache(m);
     });
 }
 
@@ -471,9 +574,24 @@ void generate_impl(aha_model* m, const uint32_t* ids, size_t seq_len, const aha_
                 "prompt + max_tokens exceeds max_ctx (the handle's KV capacity, aha_options.max_ctx; the reference's cache is unbounded)");
     using clk = std::chrono::steady_clock;
     const bool eos_on_first = (params.flags & AHA_GEN_EOS_ON_FIRST) != 0;
+    // KV reuse (AHA_GEN_REUSE_PREFIX): how much of this prompt the cache already holds.  Every path that is not a hit starts from
+    // model.clear_cache(), exactly where the reference starts every request.
+    const bool reuse = (params.flags & AHA_GEN_REUSE_PREFIX) != 0;
+    size_t hit = 0;
+    uint64_t mm_fp = 0;
+    if (reuse) {
+        mm_fp = mm_fingerprint(mm);
+        const auto mmt = mm_token_ids(m);
+        hit = prefix_match(m->cached_ids.data(), m->cached_ids.size(), ids, seq_len, mmt.data(), mmt.size(), mm_fp == m->cached_mm_fp);
+    }
+    if (hit == 0) drop_cache(m);
+    m->cached_ids.clear();   // the cache is being written: nothing is reusable until this request has completed
+    m->last_prefix_hit = hit;
+    std::vector<uint32_t> produced;   // what the request generated (the K/V of all but the last token end up in the cache)
     struct Reset {   // model.clear_cache() (generate.rs:147) -- also on the error path, so that a failed request never leaves rope_delta / pages behind
         aha_model* m;
-        ~Reset() { m->text.reset_pages(); m->have_rope_delta = false; m->rope_delta = 0; m->text.clear_sampler(); }
+        bool keep = false;
+        ~Reset() { if (!keep) drop_cache(m); m->text.clear_sampler(); }
     } reset{m};
     const int mode = sampling_mode(params);
     uint32_t draws0 = 0;
@@ -487,11 +605,13 @@ void generate_impl(aha_model* m, const uint32_t* ids, size_t seq_len, const aha_
     auto is_eos = [&](uint32_t t) { for (uint32_t e : m->stop_ids) if (e == t) return true; return false; };
     const auto t0 = clk::now();
     uint32_t tok = 0;
-    forward_any(m, ids, seq_len, 0, mm, true, nullptr, &tok);   // forward_initial + sample_and_push
+    if (hit > 0) forward_any(m, ids + hit, seq_len - hit, hit, nullptr, false, nullptr, &tok, true);   // only the tokens the cache does not hold yet
+    else forward_any(m, ids, seq_len, 0, mm, true, nullptr, &tok);   // forward_initial + sample_and_push
     T.check_sample_error();
     const auto t1 = clk::now();
     const double vision_secs = m->last_vision_secs;
     size_t done = 1;
+    produced.push_back(tok);
     bool stop = sink.push(tok, 0) || (eos_on_first && is_eos(tok));   // generate_generic never EOS-checks the first token; the ASR loop does
     if (sample_len > 1 && !stop) {
         T.ensure_tokens((int)(seq_len + sample_len));
@@ -517,6 +637,7 @@ void generate_impl(aha_model* m, const uint32_t* ids, size_t seq_len, const aha_
                 if (stream) AHA_CUDA_CHECK(cudaEventSynchronize(m->ev_tok[i]));
                 const uint32_t t = m->h_pin[i];
                 ++done;
+                produced.push_back(t);
                 stop = sink.push(t, done - 1) || is_eos(t);   // an EOS token is pushed before the break (generate.rs:139-141)
             }
             AHA_CUDA_CHECK(cudaStreamSynchronize(m->ctx.stream));
@@ -525,6 +646,14 @@ void generate_impl(aha_model* m, const uint32_t* ids, size_t seq_len, const aha_
         }
     }
     const auto t2 = clk::now();
+    if (reuse) {
+        // the cache now holds the prompt and every generated token that was fed back (all but the last one): step j wrote the K/V of token j-1.
+        // Steps the device ran past an EOS inside a burst wrote positions beyond that; they are simply overwritten by the next request.
+        m->cached_ids.assign(ids, ids + seq_len);
+        m->cached_ids.insert(m->cached_ids.end(), produced.begin(), produced.end() - 1);
+        m->cached_mm_fp = mm_fp;
+        reset.keep = true;
+    }
     if (n_generated) *n_generated = done;
     if (usage) {
         usage->prompt_tokens += (uint32_t)seq_len;
@@ -618,6 +747,7 @@ int aha_b200_decode_steps(aha_model* m, uint32_t first_token, size_t seqlen_offs
         TextModel& T = m->text;
         AHA_REQUIRE(first_token < (uint32_t)T.cfg.V, "token id out of range");
         AHA_REQUIRE(seqlen_offset + n_steps <= (size_t)T.max_ctx, "context exceeds max_ctx");
+        m->cached_ids.clear();
         T.ensure_tokens((int)(seqlen_offset + n_steps));
         T.set_state(first_token, (int)seqlen_offset, m->kind == aha_model::QWEN3VL ? m->rope_delta : 0, 0);
         if (n_steps > 0 && !T.step_graph && T.use_graph) {  // build the graph outside the timed region (pos is restored below)
@@ -911,7 +1041,7 @@ void embed_one(aha_model* m, const uint32_t* ids, size_t S, float* out) {
     AHA_REQUIRE(m->kind == aha_model::QWEN3, "embeddings need a qwen3 handle (Qwen3-Embedding shares Qwen3Model)");
     AHA_REQUIRE(ids && S >= 1 && out, "ids, seq_len and out are required");
     TextModel& T = m->text;
-    m->text.reset_pages();
+    drop_cache(m);
     upload_ids(m, ids, S);
     std::vector<int> pos3((size_t)3 * S);
     for (int r = 0; r < 3; ++r) for (size_t i = 0; i < S; ++i) pos3[(size_t)r * S + i] = (int)i;
@@ -923,7 +1053,7 @@ void embed_one(aha_model* m, const uint32_t* ids, size_t S, float* out) {
     m->ctx.cnt.kernels += 2;
     AHA_CUDA_CHECK(cudaMemcpyAsync(out, T.xn + H, (size_t)H * sizeof(float), cudaMemcpyDeviceToHost, m->ctx.stream));
     AHA_CUDA_CHECK(cudaStreamSynchronize(m->ctx.stream));
-    m->text.reset_pages();   // clear_kv_cache()
+    drop_cache(m);   // clear_kv_cache()
 }
 }  // namespace
 

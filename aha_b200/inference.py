@@ -52,6 +52,24 @@ def rope_index(ids, grid_thw, config, video_grid_thw=None):
     return pos, int(delta.value)
 
 
+def prefix_match(cached_ids, ids, mm_token_ids=(), same_mm=True):
+    """The rule behind generate(reuse_prefix=True), host only: how many leading tokens of `ids` a KV cache holding `cached_ids`
+    can supply (see aha_b200_prefix_match in include/aha_b200.h)."""
+    lib = L.load()
+    a = np.ascontiguousarray(np.asarray(cached_ids, dtype=np.uint32).reshape(-1))
+    b = np.ascontiguousarray(np.asarray(ids, dtype=np.uint32).reshape(-1))
+    t = np.ascontiguousarray(np.asarray(list(mm_token_ids), dtype=np.uint32).reshape(-1))
+    u32 = lambda x: x.ctypes.data_as(C.POINTER(C.c_uint32))
+    return int(lib.aha_b200_prefix_match(u32(a), a.size, u32(b), b.size, u32(t), t.size, 1 if same_mm else 0))
+
+
+def mm_fingerprint(data):
+    """64-bit fingerprint of a MultiModalData list (0 = no tensor): what decides whether two requests carry the same images / audio."""
+    lib = L.load()
+    mm, _keep = B200Model._mm(None, data)
+    return int(lib.aha_b200_mm_fingerprint(C.byref(mm))) if mm is not None else 0
+
+
 class B200Model:
     def __init__(self, kind, config, weights, eos_ids=(), device=0, max_ctx=8192, max_prefill=0, max_patches=0,
                  max_frames=0, use_graph=True, decode_impl=0, gemm_impl=0, attn_impl=0, tp_rank=0, tp_world=1, tp_unique_id=None):
@@ -136,6 +154,22 @@ class B200Model:
         self.last_argmax = int(am.value)
         return logits.reshape(1, 1, -1) if want_logits else None
 
+    def forward_extend(self, input_ids, seqlen_offset, want_logits=True):
+        """Prefill continuation (new design; the reference's (S, S) mask rejects S > 1 with a non-empty cache): further prompt
+        tokens against the `seqlen_offset` tokens already in the cache -> logits of the last one."""
+        ids = self._ids(input_ids)
+        logits = np.empty(self.vocab_size, np.float32) if want_logits else None
+        am = C.c_uint32(0)
+        self._check(self._lib.aha_b200_forward_extend(
+            self._h, ids.ctypes.data_as(C.POINTER(C.c_uint32)), ids.size, int(seqlen_offset),
+            logits.ctypes.data_as(C.POINTER(C.c_float)) if want_logits else None, C.byref(am)))
+        self.last_argmax = int(am.value)
+        return logits.reshape(1, 1, -1) if want_logits else None
+
+    def last_prefix_hit(self):
+        """Prompt tokens the last generate call took from the KV cache (reuse_prefix=True) instead of prefilling them."""
+        return int(self._lib.aha_b200_last_prefix_hit(self._h))
+
     def clear_cache(self):
         self._check(self._lib.aha_b200_clear_cache(self._h))
 
@@ -157,11 +191,14 @@ class B200Model:
                     completion_secs=u.completion_secs, vision_secs=u.vision_secs)
 
     def generate(self, input_ids, data=None, max_tokens=1024, temperature=0.0, top_p=None, top_k=None, repeat_penalty=1.0,
-                 repeat_last_n=64, seed=299792458, flags=0):
+                 repeat_last_n=64, seed=299792458, flags=0, reuse_prefix=False):
         """-> (generated ids, usage dict).  temperature < 1e-7: ArgMax; else the device sampler (TopK / TopKThenTopP / TopP /
-        All exactly as get_logit_processor picks them from temperature, top_p, top_k)."""
+        All exactly as get_logit_processor picks them from temperature, top_p, top_k).  reuse_prefix: keep this request's K/V
+        and prefill only what follows the prefix shared with the cache (multi-turn chats; same tokens as without it)."""
         ids = self._ids(input_ids)
         mm, _keep = self._mm(data)
+        if reuse_prefix:
+            flags |= L.GEN_REUSE_PREFIX
         p = self._gen_params(max_tokens, temperature, top_p, top_k, repeat_penalty, repeat_last_n, seed, flags)
         cap = max(max_tokens, 1)
         out = (C.c_uint32 * cap)()
@@ -173,12 +210,13 @@ class B200Model:
         return [int(out[i]) for i in range(n.value)], self._usage(u)
 
     def generate_stream(self, input_ids, on_token, data=None, max_tokens=1024, temperature=0.0, top_p=None, top_k=None,
-                        repeat_penalty=1.0, repeat_last_n=64, seed=299792458):
+                        repeat_penalty=1.0, repeat_last_n=64, seed=299792458, reuse_prefix=False):
         """generate_stream_generic: on_token(token, index) is called per generated token as its step completes; a truthy
         return value ends the request.  -> usage dict."""
         ids = self._ids(input_ids)
         mm, _keep = self._mm(data)
-        p = self._gen_params(max_tokens, temperature, top_p, top_k, repeat_penalty, repeat_last_n, seed)
+        p = self._gen_params(max_tokens, temperature, top_p, top_k, repeat_penalty, repeat_last_n, seed,
+                             L.GEN_REUSE_PREFIX if reuse_prefix else 0)
         err = []
 
         def _cb(_user, token, index):

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define AHA_B200_ABI_VERSION 2
+#define AHA_B200_ABI_VERSION 3
 
 typedef struct aha_model aha_model;
 
@@ -88,6 +88,9 @@ typedef struct aha_gen_params {      /* ChatCompletionParameters subset used by 
 } aha_gen_params;
 #define AHA_GEN_EOS_ON_FIRST 1u  /* the first token ends the request too if it is a stop id (the ASR loop, qwen3_asr/generate.rs:152-168) */
 #define AHA_GEN_CONTINUE_RNG 2u  /* keep drawing from the previous request's random stream (one LogitsProcessor across audio chunks) */
+#define AHA_GEN_REUSE_PREFIX 4u  /* KV reuse across requests (the reference clears the cache after every request, generate.rs:147):
+                                  * leave this request's K/V in the paged cache and, at its start, prefill only what follows the longest prefix
+                                  * the prompt shares with the cache (same token ids and the same multimodal tensors).  Tokens are unchanged. */
 
 /* generate_stream: called once per generated token, in order, as soon as its step has completed (the device keeps running a few
  * steps ahead); a non-zero return ends the request (the reference's stream is dropped when the client goes away). */
@@ -134,6 +137,27 @@ int aha_b200_forward_initial(aha_model* m, const uint32_t* ids, size_t seq_len, 
 /* InferenceModel::forward_step (/root/reference/src/models/common/mod.rs:37-38). */
 int aha_b200_forward_step(aha_model* m, const uint32_t* ids, size_t seq_len, size_t seqlen_offset,
                           float* logits_out, uint32_t* argmax_out);
+
+/* Prefill continuation (new design -- the reference's (S, S) causal mask makes a multi-token call with a non-empty cache fail,
+ * qwen3/model.rs:164-175): seq_len >= 1 further prompt tokens against a cache that holds exactly seqlen_offset tokens, with the
+ * (S, offset + S) causal mask.  Text tokens only (multimodal rows belong to forward_initial; Qwen3-VL positions continue as
+ * index + rope_delta, model.rs:1250-1264).  forward_initial(ids[0..a]) + forward_extend(ids[a..S], a) produces the logits of
+ * forward_initial(ids[0..S]).  It is what aha_b200_generate runs after a prefix-cache hit, and what a prompt longer than
+ * aha_options.max_prefill is cut into. */
+int aha_b200_forward_extend(aha_model* m, const uint32_t* ids, size_t seq_len, size_t seqlen_offset,
+                            float* logits_out, uint32_t* argmax_out);
+
+/* Prompt tokens the last aha_b200_generate / _generate_stream call took from the cache instead of prefilling them
+ * (0 without AHA_GEN_REUSE_PREFIX).  usage.prompt_tokens keeps counting the whole prompt, as the reference reports it. */
+size_t aha_b200_last_prefix_hit(aha_model* m);
+
+/* The rule behind AHA_GEN_REUSE_PREFIX, host only: the longest prefix of ids[0..n) whose K/V a cache holding cached[0..n_cached) can
+ * supply = the common prefix, at most n - 1 (the last prompt token is always run), and 0 unless the multimodal tensors are the same
+ * (same_mm) and every placeholder token (mm_token_ids: <|image_pad|>, <|video_pad|>, <|audio_pad|>) of both sequences lies inside it. */
+size_t aha_b200_prefix_match(const uint32_t* cached, size_t n_cached, const uint32_t* ids, size_t n,
+                             const uint32_t* mm_token_ids, size_t n_mm_tokens, int same_mm);
+/* 64-bit fingerprint of a request's MultiModalData (dtype, shape and bytes of every present entry; 0 = no tensor).  Host only. */
+uint64_t aha_b200_mm_fingerprint(const aha_mm* mm);
 
 /* InferenceModel::clear_cache (mod.rs:41; Qwen3-VL also resets rope_deltas, model.rs:1279-1282). */
 int aha_b200_clear_cache(aha_model* m);

@@ -29,7 +29,7 @@ def test_python_bindings_cover_the_header(lib_built):
     from aha_b200 import _lib
     assert sorted(_lib.SYMBOLS) == header_symbols()
     lib = _lib.load()
-    assert lib.aha_b200_abi_version() == 2
+    assert lib.aha_b200_abi_version() == 3
 
 
 def test_no_torch_types_in_the_abi():

@@ -93,3 +93,59 @@ def test_rope_index_errors_are_reported_not_thrown():
     vid = synth.vl_video_prompt_ids(CFG, [[2, 4, 4]])
     with pytest.raises(B200Error, match="more video placeholder runs"):
         rope_index(vid, None, CFG, [[1, 4, 4]])                      # two frame groups in the prompt, one in video_grid_thw
+
+
+# ---- KV reuse across requests: the host rule behind AHA_GEN_REUSE_PREFIX (include/aha_b200.h: aha_b200_prefix_match) ----
+def _prefix_rule(cached, ids, mm_tokens, same_mm):
+    """Plain restatement: common prefix, cut to n - 1; placeholders of either sequence past it (or other tensors) => 0."""
+    if len(ids) == 0 or len(cached) == 0 or not same_mm:
+        return 0
+    lcp = 0
+    while lcp < min(len(ids), len(cached)) and cached[lcp] == ids[lcp]:
+        lcp += 1
+    if any(t in mm_tokens for t in ids[lcp:]) or any(t in mm_tokens for t in cached[lcp:]):
+        return 0
+    return min(lcp, len(ids) - 1)
+
+
+def test_prefix_match_known_answers():
+    from aha_b200.inference import prefix_match
+    IMG = 9
+    assert prefix_match([1, 2, 3, 4], [1, 2, 3, 4, 5, 6]) == 4                 # multi-turn: the whole conversation so far
+    assert prefix_match([1, 2, 3, 4], [1, 2, 3, 4]) == 3                       # the last prompt token is always run
+    assert prefix_match([1, 2, 3, 4], [1, 2, 7, 8]) == 2
+    assert prefix_match([], [1, 2]) == 0 and prefix_match([1, 2], []) == 0
+    assert prefix_match([5, IMG, IMG, 6, 7], [5, IMG, IMG, 6, 8], [IMG]) == 4   # same image, new question
+    assert prefix_match([5, IMG, IMG, 6, 7], [5, IMG, IMG, 6, 8], [IMG], same_mm=False) == 0
+    assert prefix_match([5, IMG, IMG, 6], [5, IMG, 6, 6], [IMG]) == 0           # diverges inside the image run
+    assert prefix_match([5, 6, IMG, IMG], [5, 7, IMG, IMG], [IMG]) == 0         # image rows would sit at other positions
+    assert prefix_match([5, 6, 7, IMG], [5, 6, 8], [IMG]) == 0                  # the cached tail still holds an image
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.lists(st.integers(0, 5), max_size=24), st.lists(st.integers(0, 5), max_size=24), st.booleans())
+def test_prefix_match_property(cached, ids, same_mm):
+    from aha_b200.inference import prefix_match
+    assert prefix_match(cached, ids, [4, 5], same_mm) == _prefix_rule(cached, ids, [4, 5], same_mm)
+
+
+def test_mm_fingerprint_separates_requests():
+    from aha_b200.inference import mm_fingerprint
+    rng = np.random.default_rng(0)
+    pv = rng.standard_normal((64, 1536)).astype(np.float32)
+    grid = np.array([[1, 8, 8]], np.uint32)
+    a = mm_fingerprint([pv, grid, None, None, None])
+    assert a != 0 and a == mm_fingerprint([pv.copy(), grid.copy(), None, None, None])
+    assert mm_fingerprint([None, None, None, None, None]) == 0 and mm_fingerprint(None) == 0
+    pv2 = pv.copy(); pv2[63, 1535] = np.nextafter(pv2[63, 1535], np.float32(10))   # one ulp in the last element
+    assert mm_fingerprint([pv2, grid, None, None, None]) != a
+    assert mm_fingerprint([pv, np.array([[1, 4, 16]], np.uint32), None, None, None]) != a
+    assert mm_fingerprint([None, None, pv, grid, None]) != a                        # the same bytes as a video are another request
+    assert mm_fingerprint([pv.reshape(128, 768), grid, None, None, None]) != a
+    for n in (0, 1, 7, 31, 32, 33, 100):                                             # every tail length of the 32-byte blocks
+        x = np.arange(n, dtype=np.uint8)
+        fp = mm_fingerprint([x])
+        assert fp == mm_fingerprint([x.copy()])
+        if n:
+            y = x.copy(); y[-1] ^= 1
+            assert mm_fingerprint([y]) != fp
