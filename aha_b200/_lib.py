@@ -82,6 +82,13 @@ SYMBOLS = {
     "aha_b200_image_resize": (C.c_int, [_P, C.POINTER(C.c_uint8), C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(C.c_uint8)]),
     "aha_b200_image_preprocess": (C.c_int, [_P, C.POINTER(C.c_uint8), C.c_size_t, C.c_size_t, C.c_uint32, C.c_uint32, _F32P, C.c_size_t, _U32P]),
     "aha_b200_expand_placeholders": (C.c_int, [_U32P, C.c_size_t, C.c_uint32, _U32P, C.c_size_t, _U32P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "aha_b200_video_smart_resize": (C.c_int, [C.c_uint32] * 8 + [_U32P, _U32P]),
+    "aha_b200_video_sample_frames": (C.c_int, [C.c_uint32] * 6 + [_U32P, _U32P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "aha_b200_video_timestamps": (C.c_int, [_U32P, C.c_size_t, C.c_float, C.c_uint32, _F32P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "aha_b200_format_timestamp": (C.c_int, [C.c_float, C.c_char_p, C.c_size_t]),
+    "aha_b200_video_preprocess": (C.c_int, [_P, C.POINTER(C.c_uint8), C.c_size_t, C.c_size_t, C.c_size_t, _F32P, C.c_size_t, _U32P]),
+    "aha_b200_expand_video_placeholders": (C.c_int, [_U32P, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, _U32P, C.c_size_t, C.c_uint32, _U32P, _U32P,
+                                                     C.c_size_t, _U32P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "aha_b200_feat_extract_output_length": (C.c_size_t, [C.c_size_t]),
     "aha_b200_float_range_normalize": (C.c_int, [_F32P, C.c_size_t]),
     "aha_b200_resample": (C.c_int, [_P, _F32P, C.c_size_t, C.c_int64, C.c_int64, _F32P, C.c_size_t, C.POINTER(C.c_size_t)]),

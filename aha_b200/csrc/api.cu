@@ -825,6 +825,52 @@ __global__ void patchify_kernel(const uint8_t* __restrict__ img, int H, int W, i
     }
 }
 
+// process_videos for one video (qwen3vl/processor.rs:253-280 + process_vision_tensor :174-227): T frames u8 (T, H, W, 3) -> rescale, normalise,
+// pad the frame count to a multiple of temporal_patch_size by repeating the last frame, merge-block patch order with features (c, frame in group, py, px)
+__global__ void video_patchify_kernel(const uint8_t* __restrict__ frames, int T, int H, int W, int patch, int merge, int tpatch, float* __restrict__ out) {
+    const int gw = W / patch, gh = H / patch;
+    const int per = gh * gw;
+    const int gt = blockIdx.x / per, p = blockIdx.x % per;   // temporal group, patch in merge-block order inside it
+    const int mw = gw / merge;
+    const int blk = p / (merge * merge), in = p % (merge * merge);
+    const int row = (blk / mw) * merge + in / merge, col = (blk % mw) * merge + in % merge;
+    const int pp = patch * patch, feat = 3 * tpatch * pp;
+    for (int f = threadIdx.x; f < feat; f += blockDim.x) {
+        const int c = f / (tpatch * pp), tt = (f / pp) % tpatch, rem = f % pp, py = rem / patch, px = rem % patch;
+        const int frame = min(gt * tpatch + tt, T - 1);
+        const uint8_t v = frames[(((size_t)frame * H + (row * patch + py)) * W + (col * patch + px)) * 3 + c];
+        const float x = (float)v * (1.0f / 255.0f);
+        out[(size_t)blockIdx.x * feat + f] = (x - 0.5f) / 0.5f;
+    }
+}
+
+int aha_b200_video_preprocess(aha_model* m, const uint8_t* frames_thwc, size_t n_frames, size_t h, size_t w, float* pixel_values_out, size_t cap,
+                              uint32_t grid_thw_out[3]) {
+    return guarded(m, [&] {
+        AHA_REQUIRE(m->kind == aha_model::QWEN3VL, "video_preprocess needs a qwen3vl handle");
+        AHA_REQUIRE(frames_thwc && pixel_values_out && grid_thw_out && n_frames > 0 && h > 0 && w > 0, "frames, outputs and positive sizes are required");
+        VisionModel& V = m->vision;
+        const int ps = V.cfg.patch, mg = V.cfg.merge, tp = V.cfg.tpatch;
+        AHA_REQUIRE(h % (ps * mg) == 0 && w % (ps * mg) == 0, "frame size must already be a multiple of patch_size*merge_size (video_smart_resize output)");
+        const int gt = ((int)n_frames + tp - 1) / tp, gh = (int)h / ps, gw = (int)w / ps;
+        const size_t N = (size_t)gt * gh * gw;
+        AHA_REQUIRE(N <= (size_t)V.max_patches, "video needs " + std::to_string(N) + " patches, max_patches is " + std::to_string(V.max_patches));
+        AHA_REQUIRE(N * V.patch_dim <= cap, "pixel_values_out too small");
+        uint8_t* d_in = nullptr;
+        const size_t bytes = n_frames * h * w * 3;
+        AHA_CUDA_CHECK(cudaMalloc(&d_in, bytes));
+        try {
+            AHA_CUDA_CHECK(cudaMemcpyAsync(d_in, frames_thwc, bytes, cudaMemcpyHostToDevice, m->ctx.stream));
+            video_patchify_kernel<<<(unsigned)N, 256, 0, m->ctx.stream>>>(d_in, (int)n_frames, (int)h, (int)w, ps, mg, tp, V.pix);
+            m->ctx.cnt.kernels++;
+            AHA_CUDA_CHECK(cudaMemcpyAsync(pixel_values_out, V.pix, N * V.patch_dim * sizeof(float), cudaMemcpyDeviceToHost, m->ctx.stream));
+            AHA_CUDA_CHECK(cudaStreamSynchronize(m->ctx.stream));
+        } catch (...) { cudaFree(d_in); throw; }
+        cudaFree(d_in);
+        grid_thw_out[0] = (uint32_t)gt; grid_thw_out[1] = (uint32_t)gh; grid_thw_out[2] = (uint32_t)gw;
+    });
+}
+
 int aha_b200_image_patchify(aha_model* m, const uint8_t* img_hwc, size_t h, size_t w, float* pixel_values_out, size_t cap, uint32_t grid_thw_out[3]) {
     return guarded(m, [&] {
         AHA_REQUIRE(m->kind == aha_model::QWEN3VL, "image_patchify needs a qwen3vl handle");
@@ -929,6 +975,56 @@ int aha_b200_expand_placeholders(const uint32_t* ids, size_t n, uint32_t token_i
     return guarded_host([&] {
         AHA_REQUIRE(ids && n_out && (counts || n_counts == 0), "ids and n_out are required");
         const std::vector<uint32_t> r = expand_placeholders(ids, n, token_id, counts, n_counts);
+        *n_out = r.size();
+        if (out) { AHA_REQUIRE(r.size() <= cap, "out too small"); std::memcpy(out, r.data(), r.size() * sizeof(uint32_t)); }
+    });
+}
+
+int aha_b200_video_smart_resize(uint32_t num_frames, uint32_t height, uint32_t width, uint32_t temporal_factor, uint32_t factor, uint32_t min_pixels,
+                                uint32_t max_pixels, uint32_t video_ratio, uint32_t* out_h, uint32_t* out_w) {
+    return guarded_host([&] {
+        AHA_REQUIRE(out_h && out_w, "out_h and out_w are required");
+        video_smart_resize(num_frames, height, width, temporal_factor, factor, min_pixels, max_pixels, video_ratio, *out_h, *out_w);
+    });
+}
+
+int aha_b200_video_sample_frames(uint32_t total_frames, uint32_t rate_num, uint32_t rate_den, uint32_t fps, uint32_t min_frames, uint32_t max_frames,
+                                 uint32_t* nframes_out, uint32_t* indices_out, size_t cap, size_t* n_out) {
+    return guarded_host([&] {
+        AHA_REQUIRE(n_out, "n_out is required");
+        uint32_t nframes = 0;
+        const std::vector<uint32_t> idx = video_sample_frames(total_frames, rate_num, rate_den, fps, min_frames, max_frames, nframes);
+        if (nframes_out) *nframes_out = nframes;
+        *n_out = idx.size();
+        if (indices_out) { AHA_REQUIRE(idx.size() <= cap, "indices_out too small"); std::memcpy(indices_out, idx.data(), idx.size() * sizeof(uint32_t)); }
+    });
+}
+
+int aha_b200_video_timestamps(const uint32_t* frame_indices, size_t n, float fps, uint32_t t_merge_size, float* stamps_out, size_t cap, size_t* n_out) {
+    return guarded_host([&] {
+        AHA_REQUIRE(frame_indices && n_out, "frame_indices and n_out are required");
+        const std::vector<float> st = video_timestamps(frame_indices, n, fps, t_merge_size);
+        *n_out = st.size();
+        if (stamps_out) { AHA_REQUIRE(st.size() <= cap, "stamps_out too small"); std::memcpy(stamps_out, st.data(), st.size() * sizeof(float)); }
+    });
+}
+
+int aha_b200_format_timestamp(float seconds, char* out, size_t cap) {
+    return guarded_host([&] {
+        AHA_REQUIRE(out && cap > 0, "out is required");
+        // format!("<{:.1} seconds>", t): both Rust and printf print the exactly rounded decimal (ties to even) of the f32 value
+        const int n = std::snprintf(out, cap, "<%.1f seconds>", (double)seconds);
+        AHA_REQUIRE(n > 0 && (size_t)n < cap, "out too small");
+    });
+}
+
+int aha_b200_expand_video_placeholders(const uint32_t* ids, size_t n, uint32_t video_token_id, uint32_t vision_start_token_id, uint32_t vision_end_token_id,
+                                       const uint32_t* video_grid_thw, size_t n_videos, uint32_t merge_size, const uint32_t* stamp_ids,
+                                       const uint32_t* stamp_lens, size_t n_stamps, uint32_t* out, size_t cap, size_t* n_out) {
+    return guarded_host([&] {
+        AHA_REQUIRE(ids && n_out && (video_grid_thw || n_videos == 0) && (stamp_lens || n_stamps == 0), "ids, video_grid_thw, stamp_lens and n_out are required");
+        const std::vector<uint32_t> r = expand_video_placeholders(ids, n, video_token_id, vision_start_token_id, vision_end_token_id, video_grid_thw, n_videos, merge_size,
+                                                                  stamp_ids, stamp_lens, n_stamps);
         *n_out = r.size();
         if (out) { AHA_REQUIRE(r.size() <= cap, "out too small"); std::memcpy(out, r.data(), r.size() * sizeof(uint32_t)); }
     });

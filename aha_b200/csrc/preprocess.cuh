@@ -129,6 +129,108 @@ inline std::vector<uint32_t> expand_placeholders(const uint32_t* ids, size_t n, 
     return out;
 }
 
+// ---------------------------------------------------------------------------------------------- video processor (host)
+// video_smart_resize (/root/reference/src/utils/video_utils.rs:9-59).  The pixel products are u32 like the reference's (a release build wraps).
+// video_ratio 0 = None; the reference passes Some(16): ffmpeg's scaler needs multiples of 16, so the factor becomes lcm(factor, 16).
+inline void video_smart_resize(uint32_t num_frames, uint32_t height, uint32_t width, uint32_t temporal_factor, uint32_t factor, uint32_t min_pixels,
+                               uint32_t max_pixels, uint32_t video_ratio, uint32_t& h_bar, uint32_t& w_bar) {
+    AHA_REQUIRE(temporal_factor > 0 && factor > 0, "video_smart_resize: zero factor");
+    if (num_frames < temporal_factor) throw std::runtime_error(std::to_string(num_frames) + " must be larger than temporal_factor " + std::to_string(temporal_factor));
+    if (height < factor || width < factor)
+        throw std::runtime_error("height:" + std::to_string(height) + " or width:" + std::to_string(width) + " must be larger than factor:" + std::to_string(factor));
+    const uint32_t ratio = std::max(height, width) / std::min(height, width);
+    if (ratio > 200) throw std::runtime_error("absolute aspect ratio mush be smaller than 200, got " + std::to_string(ratio));
+    uint32_t image_factor = factor;
+    if (video_ratio) {
+        uint32_t a = image_factor, b = video_ratio;
+        while (b) { const uint32_t t = a % b; a = b; b = t; }
+        image_factor = image_factor / a * video_ratio;   // lcm
+    }
+    h_bar = round_by_factor((float)height, image_factor);
+    w_bar = round_by_factor((float)width, image_factor);
+    const uint32_t t_bar = round_by_factor((float)num_frames, temporal_factor);
+    if (t_bar * h_bar * w_bar > max_pixels) {
+        const float beta = std::sqrt((float)(num_frames * height * width) / (float)max_pixels);
+        h_bar = std::max(image_factor, floor_by_factor((float)height / beta, image_factor));
+        w_bar = std::max(image_factor, floor_by_factor((float)width / beta, image_factor));
+    } else if (t_bar * h_bar * w_bar < min_pixels) {
+        const float beta = std::sqrt((float)min_pixels / (float)(num_frames * height * width));
+        h_bar = ceil_by_factor((float)height * beta, image_factor);
+        w_bar = ceil_by_factor((float)width * beta, image_factor);
+    }
+}
+
+// Frame sampling of get_video_data (qwen3vl/processor.rs:481-491, 526-527): `fps` frames per second of video, clamped to
+// [min_frames, max_frames] and to the frame count; every sample_interval-th decoded frame is kept.  nframes is what video_smart_resize
+// is called with -- the number of kept frames can differ from it (the reference has the same gap).
+inline std::vector<uint32_t> video_sample_frames(uint32_t total_frames, uint32_t rate_num, uint32_t rate_den, uint32_t fps, uint32_t min_frames, uint32_t max_frames,
+                                                 uint32_t& nframes) {
+    AHA_REQUIRE(total_frames > 0 && rate_num > 0 && rate_den > 0, "No frames extracted from video");
+    const float rate = (float)rate_num / (float)rate_den;
+    nframes = (uint32_t)std::round((float)total_frames / rate * (float)fps);
+    nframes = std::min(std::min(std::max(nframes, min_frames), max_frames), total_frames);
+    AHA_REQUIRE(nframes > 0, "video frame sampling: max_frames is 0");
+    const uint32_t interval = (uint32_t)std::round((float)total_frames / (float)nframes);
+    std::vector<uint32_t> idx;
+    for (uint32_t f = 0; f < total_frames; ++f) if (f % interval == 0) idx.push_back(f);
+    return idx;
+}
+
+// calculate_timestamps (qwen3vl/processor.rs:282-307): frame indices padded with the last one to a multiple of t_merge_size, seconds = index / fps
+// in f32, one stamp per group = the mean of its first and last frame's time
+inline std::vector<float> video_timestamps(const uint32_t* frame_indices, size_t n, float fps, uint32_t t_merge_size) {
+    AHA_REQUIRE(n > 0 && t_merge_size > 0, "calculate_timestamps: no frames");
+    std::vector<uint32_t> idx(frame_indices, frame_indices + n);
+    if (n % t_merge_size != 0) idx.insert(idx.end(), t_merge_size - n % t_merge_size, idx.back());
+    std::vector<float> stamps;
+    for (size_t i = 0; i < idx.size(); i += t_merge_size) stamps.push_back(((float)idx[i] / fps + (float)idx[i + t_merge_size - 1] / fps) / 2.0f);
+    return stamps;
+}
+
+// The video half of process_info (qwen3vl/processor.rs:404-437) on token ids.  For every <|video_pad|> left in the prompt, in order of
+// video index: t frame groups of [stamp text ids of "<{:.1} seconds>", <|vision_start|>, h*w/merge^2 x <|video_pad|>, <|vision_end|>] replace the
+// FIRST <|vision_start|><|video_pad|><|vision_end|> triple if the prompt holds one anywhere, else the first lone <|video_pad|> (text.replacen(.., 1)).
+// stamp_ids / stamp_lens: the tokenised timestamp strings of all frame groups of all videos, back to back (the tokenizer stays with the caller).
+inline std::vector<uint32_t> expand_video_placeholders(const uint32_t* ids, size_t n, uint32_t video_tok, uint32_t vstart_tok, uint32_t vend_tok,
+                                                       const uint32_t* grid_thw, size_t n_videos, uint32_t merge, const uint32_t* stamp_ids,
+                                                       const uint32_t* stamp_lens, size_t n_stamps) {
+    AHA_REQUIRE(merge > 0, "expand_video_placeholders: merge size 0");
+    // expanded runs are kept apart from unexpanded tokens (the reference writes "<|placeholder|>" and renames it at the end)
+    struct Tok { uint32_t id; bool done; };
+    std::vector<Tok> text(n);
+    for (size_t i = 0; i < n; ++i) text[i] = {ids[i], false};
+    size_t index = 0, stamp = 0, stamp_off = 0;
+    for (;;) {
+        size_t lone = text.size(), triple = text.size();
+        for (size_t i = 0; i < text.size(); ++i) {
+            if (text[i].done || text[i].id != video_tok) continue;
+            if (lone == text.size()) lone = i;
+            if (i > 0 && i + 1 < text.size() && !text[i - 1].done && text[i - 1].id == vstart_tok && !text[i + 1].done && text[i + 1].id == vend_tok) { triple = i; break; }
+        }
+        if (lone == text.size()) break;
+        if (index >= n_videos) throw std::runtime_error("more <|video_pad|> placeholders than video_grid_thw rows");
+        const uint32_t t = grid_thw[3 * index], h = grid_thw[3 * index + 1], w = grid_thw[3 * index + 2];
+        const uint32_t frame_seqlen = h * w / (merge * merge);
+        std::vector<Tok> rep;
+        for (uint32_t f = 0; f < t; ++f) {
+            if (stamp >= n_stamps) throw std::runtime_error("fewer timestamp token runs than video frame groups");
+            for (uint32_t k = 0; k < stamp_lens[stamp]; ++k) rep.push_back({stamp_ids[stamp_off + k], true});
+            stamp_off += stamp_lens[stamp++];
+            rep.push_back({vstart_tok, true});
+            rep.insert(rep.end(), frame_seqlen, Tok{video_tok, true});
+            rep.push_back({vend_tok, true});
+        }
+        size_t a = lone, b = lone + 1;
+        if (triple != text.size()) { a = triple - 1; b = triple + 2; }
+        text.erase(text.begin() + a, text.begin() + b);
+        text.insert(text.begin() + a, rep.begin(), rep.end());
+        ++index;
+    }
+    std::vector<uint32_t> out(text.size());
+    for (size_t i = 0; i < text.size(); ++i) out[i] = text[i].id;
+    return out;
+}
+
 inline size_t feat_extract_output_length(size_t audio_len) {
     const size_t leave = audio_len % 100;
     if (leave > 0) {

@@ -308,6 +308,21 @@ class B200Model:
                                                       out.ctypes.data_as(C.POINTER(C.c_float)), out.size, grid))
         return out, np.array([[grid[0], grid[1], grid[2]]], dtype=np.uint32)
 
+    def video_preprocess(self, frames_u8_thwc):
+        """Qwen3VLProcessor::process_videos for one clip: RGB24 frames (T, H, W, 3) at their video_smart_resize size ->
+        (pixel_values_video, video_grid_thw)."""
+        fr = np.ascontiguousarray(frames_u8_thwc, dtype=np.uint8)
+        t, h, w, _ = fr.shape
+        vc = self.config["vision_config"]
+        tp = vc["temporal_patch_size"]
+        feat = vc["in_channels"] * tp * vc["patch_size"] ** 2
+        n = ((t + tp - 1) // tp) * (h // vc["patch_size"]) * (w // vc["patch_size"])
+        out = np.empty((n, feat), np.float32)
+        grid = (C.c_uint32 * 3)()
+        self._check(self._lib.aha_b200_video_preprocess(self._h, fr.ctypes.data_as(C.POINTER(C.c_uint8)), t, h, w,
+                                                        out.ctypes.data_as(C.POINTER(C.c_float)), out.size, grid))
+        return out, np.array([[grid[0], grid[1], grid[2]]], dtype=np.uint32)
+
     def image_resize(self, img_u8_hwc, new_h, new_w):
         """DynamicImage::resize_exact(new_w, new_h, CatmullRom) on the GPU."""
         img = np.ascontiguousarray(img_u8_hwc, dtype=np.uint8)

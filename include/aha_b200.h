@@ -211,6 +211,35 @@ int aha_b200_image_preprocess(aha_model* m, const uint8_t* img_hwc, size_t h, si
  * occurrence of token_id becomes counts[i] copies.  out may be NULL to query n_out.  Host only. */
 int aha_b200_expand_placeholders(const uint32_t* ids, size_t n, uint32_t token_id, const uint32_t* counts, size_t n_counts,
                                  uint32_t* out, size_t cap, size_t* n_out);
+/* ---- video half of Qwen3VLProcessor (qwen3vl/processor.rs:253-307, 404-437, 447-571).  Decoding and scaling the file is ffmpeg's job in the
+ * reference (a cargo feature) and stays with the caller; everything computed around it is here. ---- */
+/* video_smart_resize (utils/video_utils.rs:9-59): frame size for a clip of num_frames frames inside the pixel budget; video_ratio = 16 as
+ * get_video_data passes it (0 = None).  Host only. */
+int aha_b200_video_smart_resize(uint32_t num_frames, uint32_t height, uint32_t width, uint32_t temporal_factor, uint32_t factor,
+                                uint32_t min_pixels, uint32_t max_pixels, uint32_t video_ratio, uint32_t* out_h, uint32_t* out_w);
+/* Frame sampling of get_video_data (processor.rs:481-491, 526-527): stream of total_frames frames at rate_num/rate_den per second, `fps` samples per
+ * second clamped to [min_frames, max_frames] (the processor's 2, 4, 768) -> nframes (what video_smart_resize is given) and the kept indices
+ * (every round(total/nframes)-th frame).  indices_out may be NULL to query n_out.  Host only. */
+int aha_b200_video_sample_frames(uint32_t total_frames, uint32_t rate_num, uint32_t rate_den, uint32_t fps, uint32_t min_frames,
+                                 uint32_t max_frames, uint32_t* nframes_out, uint32_t* indices_out, size_t cap, size_t* n_out);
+/* calculate_timestamps (processor.rs:282-307): one stamp (seconds) per group of t_merge_size sampled frames.  Host only. */
+int aha_b200_video_timestamps(const uint32_t* frame_indices, size_t n, float fps, uint32_t t_merge_size, float* stamps_out, size_t cap,
+                              size_t* n_out);
+/* format!("<{:.1} seconds>", stamp) (processor.rs:419): the text the caller tokenises for each frame group.  Host only. */
+int aha_b200_format_timestamp(float seconds, char* out, size_t cap);
+/* Qwen3VLProcessor::process_videos for one clip (processor.rs:253-280): n_frames RGB24 frames (T, H, W, 3) already at the size
+ * video_smart_resize chose -> rescale + normalise + process_vision_tensor (last frame repeated up to a multiple of temporal_patch_size)
+ * -> pixel_values_video (grid_t*grid_h*grid_w, 3*2*16*16) f32 host + video_grid_thw[3].  Runs on the GPU. */
+int aha_b200_video_preprocess(aha_model* m, const uint8_t* frames_thwc, size_t n_frames, size_t h, size_t w,
+                              float* pixel_values_out, size_t cap, uint32_t grid_thw_out[3]);
+/* <|video_pad|> expansion of process_info (processor.rs:404-437) on token ids: video i becomes grid_t runs of
+ * [stamp text ids, <|vision_start|>, h*w/merge^2 x <|video_pad|>, <|vision_end|>], replacing the first
+ * <|vision_start|><|video_pad|><|vision_end|> triple if the prompt holds one, else the first lone <|video_pad|>.  stamp_ids/stamp_lens:
+ * the tokenised "<x.x seconds>" strings of all frame groups of all videos, back to back.  out may be NULL to query n_out.  Host only. */
+int aha_b200_expand_video_placeholders(const uint32_t* ids, size_t n, uint32_t video_token_id, uint32_t vision_start_token_id,
+                                       uint32_t vision_end_token_id, const uint32_t* video_grid_thw, size_t n_videos,
+                                       uint32_t merge_size, const uint32_t* stamp_ids, const uint32_t* stamp_lens, size_t n_stamps,
+                                       uint32_t* out, size_t cap, size_t* n_out);
 /* get_feat_extract_output_lengths (qwen3_asr/processor.rs:187-195).  Host only. */
 size_t aha_b200_feat_extract_output_length(size_t n_frames);
 /* float_range_normalize (common/modules.rs:1353-1368), in place.  Host only. */

@@ -142,6 +142,87 @@ def process_image(img_u8_hwc, mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5), patch_s
     return process_vision_tensor(x, patch_size, temporal_patch_size, merge_size)
 
 
+# ----------------------------------------------------------------------------- video half of the processor
+def video_smart_resize(num_frames, height, width, temporal_factor, factor, min_pixels, max_pixels, video_ratio=None):
+    """utils/video_utils.rs:9-59; returns (height, width).  The pixel products are u32 in the reference (a release build wraps)."""
+    u32 = lambda v: int(v) & 0xFFFFFFFF
+    if num_frames < temporal_factor:
+        raise ValueError(f"{num_frames} must be larger than temporal_factor {temporal_factor}")
+    if height < factor or width < factor:
+        raise ValueError(f"height:{height} or width:{width} must be larger than factor:{factor}")
+    if max(height, width) // min(height, width) > 200:
+        raise ValueError("absolute aspect ratio mush be smaller than 200, got %d" % (max(height, width) // min(height, width)))
+    image_factor = factor
+    if video_ratio is not None:
+        image_factor = int(np.lcm(image_factor, video_ratio))
+    h_bar = round_by_factor(height, image_factor)
+    w_bar = round_by_factor(width, image_factor)
+    t_bar = round_by_factor(num_frames, temporal_factor)
+    if u32(t_bar * h_bar * w_bar) > max_pixels:
+        beta = np.sqrt(F32(u32(num_frames * height * width)) / F32(max_pixels), dtype=F32)
+        h_bar = max(image_factor, floor_by_factor(F32(height) / beta, image_factor))
+        w_bar = max(image_factor, floor_by_factor(F32(width) / beta, image_factor))
+    elif u32(t_bar * h_bar * w_bar) < min_pixels:
+        beta = np.sqrt(F32(min_pixels) / F32(u32(num_frames * height * width)), dtype=F32)
+        h_bar = ceil_by_factor(F32(height) * beta, image_factor)
+        w_bar = ceil_by_factor(F32(width) * beta, image_factor)
+    return h_bar, w_bar
+
+
+def _round_f32(x):
+    """f32::round (half away from zero) of a non-negative f32."""
+    return int(np.floor(float(F32(x)) + 0.5))   # exact in f64 for any f32 of this magnitude
+
+
+def video_sample_frames(total_frames, rate_num, rate_den, fps, min_frames, max_frames):
+    """get_video_data's sampling (processor.rs:481-491, 526-527): returns (nframes, kept frame indices)."""
+    rate = F32(rate_num) / F32(rate_den)
+    nframes = _round_f32(F32(total_frames) / rate * F32(fps))
+    nframes = min(min(max(nframes, min_frames), max_frames), total_frames)
+    interval = _round_f32(F32(total_frames) / F32(nframes))
+    return nframes, [f for f in range(total_frames) if f % interval == 0]
+
+
+def calculate_timestamps(frames_indices, fps, t_merge_size):
+    """processor.rs:282-307."""
+    idx = list(frames_indices)
+    if len(idx) % t_merge_size != 0:
+        idx += [idx[-1]] * (t_merge_size - len(idx) % t_merge_size)
+    ts = [F32(x) / F32(fps) for x in idx]
+    return [F32((ts[i] + ts[i + t_merge_size - 1]) / F32(2.0)) for i in range(0, len(ts), t_merge_size)]
+
+
+def format_timestamp(t):
+    """format!("<{:.1} seconds>", t): the exactly rounded decimal of the f32 value."""
+    return "<%.1f seconds>" % float(F32(t))
+
+
+def process_video(frames_u8_thwc, mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5), patch_size=16, temporal_patch_size=2, merge_size=2):
+    """process_videos for one clip (processor.rs:253-280): the (t, c, h, w) tensor get_video_data stacks from RGB24 frames,
+    * 1/255, (x - mean) / std, then process_vision_tensor."""
+    x = np.transpose(np.asarray(frames_u8_thwc), (0, 3, 1, 2)).astype(F32) * F32(1.0 / 255.0)
+    x = (x - np.asarray(mean, F32).reshape(1, 3, 1, 1)) / np.asarray(std, F32).reshape(1, 3, 1, 1)
+    return process_vision_tensor(x.astype(F32), patch_size, temporal_patch_size, merge_size)
+
+
+def expand_video_placeholders_text(text, video_grid_thw, stamps_per_video, merge_size=2, video_token="<|video_pad|>",
+                                   vision_start="<|vision_start|>", vision_end="<|vision_end|>"):
+    """processor.rs:404-437 verbatim, on the STRING the reference edits (stamps_per_video[i] = calculate_timestamps of video i)."""
+    merge_length = merge_size ** 2
+    index = 0
+    while video_token in text:
+        t, h, w = [int(v) for v in video_grid_thw[index]]
+        frame_seqlen = h * w // merge_length
+        ph = ""
+        for frame_idx in range(t):
+            ph += format_timestamp(stamps_per_video[index][frame_idx])
+            ph += vision_start + "<|placeholder|>" * frame_seqlen + vision_end
+        three = vision_start + video_token + vision_end
+        text = text.replace(three, ph, 1) if three in text else text.replace(video_token, ph, 1)
+        index += 1
+    return text.replace("<|placeholder|>", video_token)
+
+
 def linspace(start, end, steps):
     """tensor_utils.rs:354-365 (f32: start + i*step)."""
     if steps == 1:
