@@ -573,6 +573,7 @@ void generate_impl(aha_model* m, const uint32_t* ids, size_t seq_len, const aha_
     AHA_REQUIRE(seq_len + sample_len <= (size_t)T.max_ctx,
                 "prompt + max_tokens exceeds max_ctx (the handle's KV capacity, aha_options.max_ctx; the reference's cache is unbounded)");
     using clk = std::chrono::steady_clock;
+    const auto t0 = clk::now();   // prompt_secs covers everything up to the first token, the prefix lookup (fingerprint of the tensors) included
     const bool eos_on_first = (params.flags & AHA_GEN_EOS_ON_FIRST) != 0;
     // KV reuse (AHA_GEN_REUSE_PREFIX): how much of this prompt the cache already holds.  Every path that is not a hit starts from
     // model.clear_cache(), exactly where the reference starts every request.
@@ -603,7 +604,6 @@ void generate_impl(aha_model* m, const uint32_t* ids, size_t seq_len, const aha_
     T.set_sampler(mode, params.temperature, params.top_p, params.top_k, params.repeat_penalty, params.repeat_last_n, params.seed);
     T.set_state(0, 0, 0, 0, draws0);    // empty history: the first token sees no repeat-penalty context
     auto is_eos = [&](uint32_t t) { for (uint32_t e : m->stop_ids) if (e == t) return true; return false; };
-    const auto t0 = clk::now();
     uint32_t tok = 0;
     if (hit > 0) forward_any(m, ids + hit, seq_len - hit, hit, nullptr, false, nullptr, &tok, true);   // only the tokens the cache does not hold yet
     else forward_any(m, ids, seq_len, 0, mm, true, nullptr, &tok);   // forward_initial + sample_and_push

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(HD) qk_norm_rope_kv_kernel(float* __restrict__
     float* src = qkv + (size_t)s * row + (size_t)slot * HD;
     const float x = src[d];
     if (slot >= nh + nkv) {  // V: plain copy into the cache
-        vdst[kv.off(pos0 + s, slot - nh - nkv) + d] = x;
+        vdst[kv.off(pos0 + s, slot - nh - nkv) + d] = kv_store_round(x);
         return;
     }
     const bool is_q = slot < nh;
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(HD) qk_norm_rope_kv_kernel(float* __restrict__
     const float rot = (d < HD / 2) ? -xs[d + HD / 2] : xs[d - HD / 2];
     const float o = n * c + rot * sn;
     if (is_q) src[d] = o;
-    else kdst[kv.off(pos0 + s, slot - nh) + d] = o;
+    else kdst[kv.off(pos0 + s, slot - nh) + d] = kv_store_round(o);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -321,10 +321,12 @@ __global__ void __launch_bounds__(256) decode_attn_kernel(DecodeAttnArgs a) {
             o[e] = n[e] * cosf(ang) + rot * sinf(ang);
         }
         float* dst = is_q ? qs[warp] : knew;
+        if (!is_q) { for (int e = 0; e < 4; ++e) o[e] = kv_store_round(o[e]); }
         *reinterpret_cast<float4*>(dst + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);
     } else if (warp == G + 1) {
-        *reinterpret_cast<float4*>(vnew + lane * 4) =
-            *reinterpret_cast<const float4*>(a.qkv + (size_t)(a.nh + a.nkv + kvh) * HD + lane * 4);
+        float4 v = *reinterpret_cast<const float4*>(a.qkv + (size_t)(a.nh + a.nkv + kvh) * HD + lane * 4);
+        v = make_float4(kv_store_round(v.x), kv_store_round(v.y), kv_store_round(v.z), kv_store_round(v.w));
+        *reinterpret_cast<float4*>(vnew + lane * 4) = v;
     }
     __syncthreads();
 

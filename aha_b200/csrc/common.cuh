@@ -100,6 +100,14 @@ __device__ __forceinline__ float apply_act(int act, float x) {
     }
 }
 
+// Measurement build only (-DAHA_KV_ROUND_FP16, variants/kv16.so): every K / V value is rounded to fp16 precision on its way into the
+// (still fp32) cache, which is numerically what an fp16 KV cache would hold.  The default build compiles this to the identity.
+#ifdef AHA_KV_ROUND_FP16
+__device__ __forceinline__ float kv_store_round(float x) { return __half2float(__float2half_rn(x)); }
+#else
+__device__ __forceinline__ float kv_store_round(float x) { return x; }
+#endif
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 }  // namespace aha

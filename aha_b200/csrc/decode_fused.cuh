@@ -827,10 +827,17 @@ __device__ void fused_attention(const FusedArgs& a, Consumer& c, AttnSmem<G>& s,
             o[e] = n[e] * cs[j] + rot * cs[HD / 2 + j];
         }
         float* dst = is_q ? s.qs[warp] : s.knew;
+#ifdef AHA_KV_ROUND_FP16
+        if (!is_q) { for (int e = 0; e < 4; ++e) o[e] = kv_store_round(o[e]); }
+#endif
         *reinterpret_cast<float4*>(dst + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);
     } else if (warp == G + 1) {
         const size_t src_off = (size_t)(a.nh + a.nkv + kvh) * HD + lane * 4;
-        *reinterpret_cast<float4*>(s.vnew + lane * 4) = LL ? ll_wait4<false>(a.ll_qkv + src_off, tag, c.ll_abort) : __ldcg(reinterpret_cast<const float4*>(a.qkv1 + src_off));
+        float4 v = LL ? ll_wait4<false>(a.ll_qkv + src_off, tag, c.ll_abort) : __ldcg(reinterpret_cast<const float4*>(a.qkv1 + src_off));
+#ifdef AHA_KV_ROUND_FP16
+        v = make_float4(kv_store_round(v.x), kv_store_round(v.y), kv_store_round(v.z), kv_store_round(v.w));
+#endif
+        *reinterpret_cast<float4*>(s.vnew + lane * 4) = v;
     }
     consumer_bar_sync();
     const int hp_new = t_new / kHalfPage;

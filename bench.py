@@ -257,7 +257,23 @@ def make_inputs(m, wl, cfg, synth):
     return synth.asr_prompt_ids(cfg, synth.asr_audio_tokens(mel.shape[1])), [mel]
 
 
-def measure(m, wl, cfg, synth, K, W, reps, barrier, want_e2e=True):
+def measure_prefix_cache(m, synth, ids, data, n_new=32, n_gen=8):
+    """The second turn of a conversation about the same inputs: turn 2 = turn 1's prompt + its answer + n_new new ids.
+    cold = what the reference does (cache cleared per request: tower + full prefill again); warm = AHA_GEN_REUSE_PREFIX (only the new
+    tokens are prefilled, the tower is skipped).  Time to first token = usage.prompt_secs; the greedy tokens must be identical."""
+    a1, _ = m.generate(ids, data, max_tokens=n_gen, reuse_prefix=True)
+    p2 = np.concatenate([ids, np.asarray(a1, np.uint32), synth.synth_text_ids(n_new, 151000, 77)]).astype(np.uint32)
+    warm, uw = m.generate(p2, data, max_tokens=n_gen, reuse_prefix=True)
+    hit = m.last_prefix_hit()
+    m.clear_cache()
+    cold, uc = m.generate(p2, data, max_tokens=n_gen)
+    m.clear_cache()
+    return {"turn2_prompt_tokens": int(len(p2)), "hit_tokens": int(hit), "ttft_cold_ms": 1e3 * uc["prompt_secs"], "ttft_warm_ms": 1e3 * uw["prompt_secs"],
+            "tower_cold_ms": 1e3 * uc["vision_secs"], "tower_warm_ms": 1e3 * uw["vision_secs"], "tokens_equal": bool(warm == cold),
+            "note": "new design (SURVEY 8f rank 4): the reference clears its KV cache after every request"}
+
+
+def measure(m, wl, cfg, synth, K, W, reps, barrier, want_e2e=True, want_prefix=False):
     """prefill once, then time K fused decode steps (device-resident) and K forward_step calls (e2e)."""
     ids, data = make_inputs(m, wl, cfg, synth)
     S = len(ids)
@@ -294,6 +310,11 @@ def measure(m, wl, cfg, synth, K, W, reps, barrier, want_e2e=True):
         for i in range(n):   # the same with the full logits row returned to the host every step (what the reference's sampler consumes)
             m.forward_step(np.array([t], np.uint32), S + W + i, want_logits=True)
         res["e2e_logits_s"] = (time.perf_counter() - e0) / n
+    if want_prefix:
+        try:
+            res["prefix_cache"] = measure_prefix_cache(m, synth, ids, data)
+        except Exception as e:   # an extra record: it must never take the metric line down
+            res["prefix_cache"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     return res
 
 
@@ -381,7 +402,7 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.3)
-    r = measure(m, wl, cfg, synth, K, W, reps, barrier)
+    r = measure(m, wl, cfg, synth, K, W, reps, barrier, want_prefix=(world == 1))
     clocks = sampler.stop()
     assert r["S"] == S
     usage, st = r["usage"], r["stats"]
@@ -477,6 +498,8 @@ def main():
                 "cpu_baseline": cpu_base}
         if tp_rec is not None:
             line["tp"] = tp_rec
+        if r.get("prefix_cache") is not None:
+            line["prefix_cache"] = r["prefix_cache"]
         emit(line)
     if dist is not None:
         dist.destroy_process_group()

@@ -203,9 +203,13 @@ public:
         return out;
     }
     // The whole request with the decode loop on the device (generate_generic semantics, aha_b200_generate).
-    std::vector<uint32_t> generate(const std::vector<uint32_t>& ids, const MultiModalData* data, const GenerationContext& ctx, Usage* usage = nullptr) {
+    // reuse_prefix (new design; the reference clears the cache after every request, generate.rs:147): keep the K/V of this request and
+    // prefill only what follows the prefix the prompt shares with the cache -- same tokens, shorter time to the first one.
+    std::vector<uint32_t> generate(const std::vector<uint32_t>& ids, const MultiModalData* data, const GenerationContext& ctx, Usage* usage = nullptr,
+                                   bool reuse_prefix = false) {
         aha_gen_params p{};
         p.temperature = 0.f; p.repeat_penalty = ctx.repeat_penalty; p.repeat_last_n = (int32_t)ctx.repeat_last_n; p.max_tokens = (uint32_t)ctx.sample_len;
+        if (reuse_prefix) p.flags |= AHA_GEN_REUSE_PREFIX;
         std::vector<uint32_t> out(ctx.sample_len);
         size_t n = 0;
         aha_usage u{};
@@ -214,6 +218,13 @@ public:
         out.resize(n);
         if (usage) *usage = Usage{u.prompt_tokens, u.completion_tokens, u.prompt_secs, u.completion_secs, u.vision_secs};
         return out;
+    }
+    size_t last_prefix_hit() const { return aha_b200_last_prefix_hit(h_); }
+    // Prefill continuation (aha_b200_forward_extend): further prompt tokens against the `off` tokens already in the cache.
+    std::vector<float> forward_extend(const std::vector<uint32_t>& ids, size_t off) {
+        std::vector<float> logits(need_vocab());
+        check(aha_b200_forward_extend(h_, ids.data(), ids.size(), off, logits.data(), nullptr));
+        return logits;
     }
     aha_model* handle() const { return h_; }
 
@@ -226,6 +237,12 @@ private:
     aha_model* h_ = nullptr;
     size_t vocab_ = 0;
 };
+
+// How many leading tokens of `ids` a cache holding `cached` supplies (the rule behind AHA_GEN_REUSE_PREFIX, aha_b200_prefix_match).
+inline size_t prefix_match(const std::vector<uint32_t>& cached, const std::vector<uint32_t>& ids, const std::vector<uint32_t>& mm_token_ids = {},
+                           bool same_mm = true) {
+    return aha_b200_prefix_match(cached.data(), cached.size(), ids.data(), ids.size(), mm_token_ids.data(), mm_token_ids.size(), same_mm ? 1 : 0);
+}
 
 // Qwen3VLModel::get_rope_index on the host (aha_b200_rope_index): (3, S) position ids and rope_delta.
 inline std::pair<std::vector<int32_t>, int32_t> rope_index(const std::vector<uint32_t>& ids, const std::vector<uint32_t>& grid_thw, uint32_t spatial_merge_size,

@@ -82,6 +82,14 @@ int main(int argc, char** argv) {
         try { rope_index(bad, {1, 68, 120}, 2, IMG, VS); } catch (const Error& e) { threw = std::strstr(e.what(), "vision_start") != nullptr; }
         REQUIRE(threw);
     }
+    {   // the prefix-cache rule (host only): multi-turn reuse, the last prompt token always runs, placeholders must lie inside the prefix
+        const uint32_t IMG = 9;
+        REQUIRE(prefix_match({1, 2, 3, 4}, {1, 2, 3, 4, 5, 6}) == 4);
+        REQUIRE(prefix_match({1, 2, 3, 4}, {1, 2, 3, 4}) == 3);
+        REQUIRE(prefix_match({5, IMG, IMG, 6, 7}, {5, IMG, IMG, 6, 8}, {IMG}) == 4);
+        REQUIRE(prefix_match({5, IMG, IMG, 6, 7}, {5, IMG, IMG, 6, 8}, {IMG}, false) == 0);
+        REQUIRE(prefix_match({5, 6, IMG, IMG}, {5, 7, IMG, IMG}, {IMG}) == 0);
+    }
     if (argc > 1 && std::string(argv[1]) == "nogpu") {   // no CPU fallback: the constructor throws with the library's message
         bool threw = false;
         try {
