@@ -6,6 +6,7 @@
 #include <chrono>
 #include <functional>
 #include <mutex>
+#include <thread>
 
 #include "audio_model.cuh"
 #include "preprocess.cuh"
@@ -210,10 +211,10 @@ size_t prefix_match(const uint32_t* cached, size_t n_cached, const uint32_t* ids
     return std::min(lcp, n - 1);
 }
 
-// 64-bit fingerprint of a host buffer: four independent multiply-xorshift lanes over 8-byte words (memory-bound on one core;
-// ~10 ms for the 50 MB pixel_values of a 1080p image), folded with the length.  Not cryptographic: it guards a cache, not a boundary.
-uint64_t fingerprint_bytes(const void* data, size_t n, uint64_t seed) {
-    const unsigned char* p = static_cast<const unsigned char*>(data);
+// 64-bit fingerprint of a host buffer: four independent multiply-xorshift lanes over 8-byte words, folded with the length.  Buffers
+// beyond 1 MiB are cut into 1 MiB blocks hashed by up to 8 threads and folded in block order (the value does not depend on the thread
+// count).  Not cryptographic: it guards a cache, not a boundary.
+uint64_t fingerprint_block(const unsigned char* p, size_t n, uint64_t seed) {
     uint64_t h[4] = {seed ^ 0x9e3779b97f4a7c15ull, seed ^ 0xbf58476d1ce4e5b9ull, seed ^ 0x94d049bb133111ebull, seed ^ 0x2545f4914f6cdd1dull};
     const uint64_t k = 0xff51afd7ed558ccdull;
     size_t i = 0;
@@ -223,11 +224,25 @@ uint64_t fingerprint_bytes(const void* data, size_t n, uint64_t seed) {
         for (int l = 0; l < 4; ++l) { h[l] = (h[l] ^ w[l]) * k; h[l] ^= h[l] >> 29; }
     }
     uint64_t tail[4] = {0, 0, 0, 0};
-    std::memcpy(tail, p + i, n - i);
+    if (n > i) std::memcpy(tail, p + i, n - i);
     for (int l = 0; l < 4; ++l) { h[l] = (h[l] ^ tail[l]) * k; h[l] ^= h[l] >> 29; }
     uint64_t r = (uint64_t)n * 0xc4ceb9fe1a85ec53ull;
     for (int l = 0; l < 4; ++l) { r = (r ^ h[l]) * k; r ^= r >> 32; }
     return r;
+}
+uint64_t fingerprint_bytes(const void* data, size_t n, uint64_t seed) {
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    constexpr size_t kBlock = (size_t)1 << 20;
+    if (n <= kBlock) return fingerprint_block(p, n, seed);
+    const size_t nb = (n + kBlock - 1) / kBlock;
+    std::vector<uint64_t> hb(nb);
+    const unsigned nt = (unsigned)std::min<size_t>(std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency())), nb);
+    auto work = [&](unsigned t) { for (size_t b = t; b < nb; b += nt) hb[b] = fingerprint_block(p + b * kBlock, std::min(kBlock, n - b * kBlock), seed + b); };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+    return fingerprint_block(reinterpret_cast<const unsigned char*>(hb.data()), nb * sizeof(uint64_t), seed ^ (uint64_t)n);
 }
 // fingerprint of a request's MultiModalData (0 when it carries no tensor): dtype, shape and bytes of every present entry
 uint64_t mm_fingerprint(const aha_mm* mm) {
@@ -819,9 +834,10 @@ __global__ void patchify_kernel(const uint8_t* __restrict__ img, int H, int W, i
     for (int f = threadIdx.x; f < feat; f += blockDim.x) {
         const int c = f / (tpatch * patch * patch), rem = f % (patch * patch), py = rem / patch, px = rem % patch;
         const uint8_t v = img[((size_t)(row * patch + py) * W + (col * patch + px)) * 3 + c];
-        // img_transform: f32(v) * (1/255), (x - 0.5) / 0.5   (img_utils.rs:272-294 with mean = std = 0.5)
-        const float x = (float)v * (1.0f / 255.0f);
-        out[(size_t)p * feat + f] = (x - 0.5f) / 0.5f;
+        // img_transform: f32(v) * (1/255), (x - 0.5) / 0.5   (img_utils.rs:272-294 with mean = std = 0.5).  Each step rounded on its own
+        // (candle runs affine, broadcast_sub and broadcast_div as three kernels; a contracted v * (1/255) - 0.5 differs in the last bit)
+        const float x = __fmul_rn((float)v, 1.0f / 255.0f);
+        out[(size_t)p * feat + f] = __fdiv_rn(__fsub_rn(x, 0.5f), 0.5f);
     }
 }
 
@@ -839,8 +855,8 @@ __global__ void video_patchify_kernel(const uint8_t* __restrict__ frames, int T,
         const int c = f / (tpatch * pp), tt = (f / pp) % tpatch, rem = f % pp, py = rem / patch, px = rem % patch;
         const int frame = min(gt * tpatch + tt, T - 1);
         const uint8_t v = frames[(((size_t)frame * H + (row * patch + py)) * W + (col * patch + px)) * 3 + c];
-        const float x = (float)v * (1.0f / 255.0f);
-        out[(size_t)blockIdx.x * feat + f] = (x - 0.5f) / 0.5f;
+        const float x = __fmul_rn((float)v, 1.0f / 255.0f);   // affine, broadcast_sub, broadcast_div: three separately rounded steps
+        out[(size_t)blockIdx.x * feat + f] = __fdiv_rn(__fsub_rn(x, 0.5f), 0.5f);
     }
 }
 
@@ -1053,7 +1069,6 @@ int aha_b200_resample(aha_model* m, const float* wave, size_t n, int64_t orig_fr
         *n_out = len_out;
         if (!out) return;
         AHA_REQUIRE(cap >= len_out, "output buffer too small");
-        AHA_REQUIRE(B.taps.size() * sizeof(float) <= 96 * 1024, "resample: the filter bank of this frequency pair does not fit in shared memory (reduce the ratio orig : new)");
         if (len_out == 0) return;
         float *d_w = nullptr, *d_t = nullptr, *d_o = nullptr;
         auto cleanup = [&] { cudaFree(d_w); cudaFree(d_t); cudaFree(d_o); };
@@ -1062,10 +1077,19 @@ int aha_b200_resample(aha_model* m, const float* wave, size_t n, int64_t orig_fr
             AHA_CUDA_CHECK(cudaMalloc(&d_w, std::max<size_t>(n, 1) * sizeof(float))); AHA_CUDA_CHECK(cudaMalloc(&d_t, B.taps.size() * sizeof(float)));
             AHA_CUDA_CHECK(cudaMalloc(&d_o, len_out * sizeof(float)));
             AHA_CUDA_CHECK(cudaMemcpyAsync(d_w, wave, n * sizeof(float), cudaMemcpyHostToDevice, st));
-            AHA_CUDA_CHECK(cudaMemcpyAsync(d_t, B.taps.data(), B.taps.size() * sizeof(float), cudaMemcpyHostToDevice, st));
             const size_t smem = B.taps.size() * sizeof(float);
-            if (smem > 48 * 1024) AHA_CUDA_CHECK(cudaFuncSetAttribute(sinc_resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            sinc_resample_kernel<<<(unsigned)((len_out + 255) / 256), 256, smem, st>>>(d_w, (long long)n, d_t, B.orig, B.fresh, B.width, B.K, d_o, (long long)len_out);
+            const unsigned blocks = (unsigned)((len_out + 255) / 256);
+            if (smem <= 96 * 1024) {   // the whole bank in shared memory
+                AHA_CUDA_CHECK(cudaMemcpyAsync(d_t, B.taps.data(), smem, cudaMemcpyHostToDevice, st));
+                if (smem > 48 * 1024) AHA_CUDA_CHECK(cudaFuncSetAttribute(sinc_resample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                sinc_resample_kernel<true><<<blocks, 256, smem, st>>>(d_w, (long long)n, d_t, B.orig, B.fresh, B.width, B.K, d_o, (long long)len_out);
+            } else {                   // 44.1 kHz and friends: hundreds of KB of taps, read from a transposed copy through the caches
+                std::vector<float> tT(B.taps.size());
+                for (int j = 0; j < B.fresh; ++j) for (int k = 0; k < B.K; ++k) tT[(size_t)k * B.fresh + j] = B.taps[(size_t)j * B.K + k];
+                AHA_CUDA_CHECK(cudaMemcpyAsync(d_t, tT.data(), smem, cudaMemcpyHostToDevice, st));
+                AHA_CUDA_CHECK(cudaStreamSynchronize(st));   // tT is a temporary
+                sinc_resample_kernel<false><<<blocks, 256, 0, st>>>(d_w, (long long)n, d_t, B.orig, B.fresh, B.width, B.K, d_o, (long long)len_out);
+            }
             AHA_CUDA_CHECK(cudaGetLastError());
             m->ctx.cnt.kernels++;
             AHA_CUDA_CHECK(cudaMemcpyAsync(out, d_o, len_out * sizeof(float), cudaMemcpyDeviceToHost, st));

@@ -295,23 +295,28 @@ inline size_t sinc_resample_out_len(const SincBank& B, size_t length) {   // app
     const size_t target = (size_t)std::ceil((double)B.fresh * (double)length / (double)B.orig);
     return std::min(target, frames * (size_t)B.fresh);
 }
-// out[i * new + j] = sum_k taps[j][k] * padded[i * orig + k],  padded = [width zeros | wave | width + orig zeros]; taps in order, f32
+// out[i * new + j] = sum_k taps[j][k] * padded[i * orig + k],  padded = [width zeros | wave | width + orig zeros]; taps in order, f32.
+// SMEM: the whole bank [new][K] is staged in shared memory (48 -> 16 kHz: 15 KB).  Otherwise (44.1 -> 16 kHz: 160 x 477 taps = 305 KB; 22.05 -> 16 kHz:
+// 600 KB) the taps are read through L1 / L2 from a TRANSPOSED copy [K][new], so that the threads of a warp (consecutive j) read consecutive words.
+template <bool SMEM>
 __global__ void sinc_resample_kernel(const float* __restrict__ wave, long long length, const float* __restrict__ taps, int orig, int fresh, int width, int K,
                                      float* __restrict__ out, long long n_out) {
     extern __shared__ float s_taps[];
-    for (int i = threadIdx.x; i < fresh * K; i += blockDim.x) s_taps[i] = taps[i];
-    __syncthreads();
+    if (SMEM) {
+        for (int i = threadIdx.x; i < fresh * K; i += blockDim.x) s_taps[i] = taps[i];
+        __syncthreads();
+    }
     const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= n_out) return;
     const long long i = o / fresh;
     const int j = (int)(o - i * fresh);
     const long long p0 = i * orig - width;   // wave index of tap 0
-    const float* tj = s_taps + (size_t)j * K;
     float acc = 0.f;
     for (int k = 0; k < K; ++k) {
         const long long p = p0 + k;
         const float x = (p >= 0 && p < length) ? wave[p] : 0.f;
-        acc = __fadd_rn(acc, __fmul_rn(x, tj[k]));   // separate multiply and add like a scalar f32 convolution (no fma contraction)
+        const float t = SMEM ? s_taps[(size_t)j * K + k] : __ldg(taps + (size_t)k * fresh + j);
+        acc = __fadd_rn(acc, __fmul_rn(x, t));   // separate multiply and add like a scalar f32 convolution (no fma contraction)
     }
     out[o] = acc;
 }

@@ -142,6 +142,14 @@ def test_mm_fingerprint_separates_requests():
     assert mm_fingerprint([pv, np.array([[1, 4, 16]], np.uint32), None, None, None]) != a
     assert mm_fingerprint([None, None, pv, grid, None]) != a                        # the same bytes as a video are another request
     assert mm_fingerprint([pv.reshape(128, 768), grid, None, None, None]) != a
+    big = rng.integers(0, 256, 3 * (1 << 20) + 12345, dtype=np.uint8)               # beyond 1 MiB: blocks hashed by several threads, folded in order
+    fb = mm_fingerprint([big])
+    assert fb == mm_fingerprint([big.copy()])
+    for pos in (0, (1 << 20) - 1, 1 << 20, 2 * (1 << 20) + 77, big.size - 1):       # first / last byte of a block, the ragged tail
+        y = big.copy(); y[pos] ^= 0x80
+        assert mm_fingerprint([y]) != fb, pos
+    sw = big.copy(); sw[:1 << 20], sw[1 << 20:2 << 20] = big[1 << 20:2 << 20].copy(), big[:1 << 20].copy()
+    assert mm_fingerprint([sw]) != fb                                                # two blocks swapped: block order is part of the value
     for n in (0, 1, 7, 31, 32, 33, 100):                                             # every tail length of the 32-byte blocks
         x = np.arange(n, dtype=np.uint8)
         fp = mm_fingerprint([x])

@@ -398,7 +398,7 @@ def test_vl_image_patchify(vl):
     pv, grid = m.image_patchify(img)
     wpv, wgrid = process_image(img)
     assert grid.tolist() == wgrid.tolist()
-    assert np.abs(pv - wpv).max() <= 1e-6
+    assert np.array_equal(pv, wpv)    # affine, sub, div rounded one by one like the reference: bit-exact
 
 
 # ----------------------------------------------------------------------------- Qwen3-ASR
