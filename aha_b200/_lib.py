@@ -42,6 +42,10 @@ class AsrChunk(C.Structure):
     _fields_ = [("ids", C.POINTER(C.c_uint32)), ("seq_len", C.c_size_t), ("input_features", TensorDesc)]
 
 
+class BatchRequest(C.Structure):
+    _fields_ = [("ids", C.POINTER(C.c_uint32)), ("seq_len", C.c_size_t), ("mm", C.POINTER(MM)), ("params", GenParams)]
+
+
 class Usage(C.Structure):
     _fields_ = [("prompt_tokens", C.c_uint32), ("completion_tokens", C.c_uint32), ("prompt_secs", C.c_double),
                 ("completion_secs", C.c_double), ("vision_secs", C.c_double)]
@@ -71,6 +75,7 @@ SYMBOLS = {
     "aha_b200_stop_token_ids": (C.c_size_t, [_P, _U32P, C.c_size_t]),
     "aha_b200_generate": (C.c_int, [_P, _U32P, C.c_size_t, C.POINTER(MM), C.POINTER(GenParams), _U32P, C.c_size_t,
                                     C.POINTER(C.c_size_t), C.POINTER(Usage)]),
+    "aha_b200_generate_batch": (C.c_int, [_P, C.POINTER(BatchRequest), C.c_size_t, _U32P, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(Usage)]),
     "aha_b200_generate_stream": (C.c_int, [_P, _U32P, C.c_size_t, C.POINTER(MM), C.POINTER(GenParams), TOKEN_CALLBACK, C.c_void_p,
                                            C.POINTER(Usage)]),
     "aha_b200_asr_generate": (C.c_int, [_P, C.POINTER(AsrChunk), C.c_size_t, C.POINTER(GenParams), _U32P, C.c_size_t,

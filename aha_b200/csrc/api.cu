@@ -11,6 +11,7 @@
 #include "audio_model.cuh"
 #include "preprocess.cuh"
 #include "text_model.cuh"
+#include "batch_decode.cuh"
 #include "vision_model.cuh"
 
 using namespace aha;
@@ -47,6 +48,7 @@ struct aha_model {
     std::vector<uint32_t> cached_ids;   // tokens whose K/V occupy positions 0 .. n-1 of the paged cache
     uint64_t cached_mm_fp = 0;          // fingerprint of the multimodal tensors those tokens were embedded with (0 = none)
     size_t last_prefix_hit = 0;         // tokens the last generate call did not have to prefill
+    BatchDecoder batch;                 // several sequences decoded in lockstep (aha_b200_generate_batch); buffers allocated on first use
 };
 
 namespace {
@@ -384,14 +386,14 @@ void forward_prefill(aha_model* m, const uint32_t* ids, size_t S, size_t offset,
 // `extend`: prefill continuation (new design) -- S >= 1 further tokens against a cache that already holds `offset` tokens; the causal mask is
 // the (S, offset + S) one the reference never builds (its (S, S) mask makes a multi-token call with a non-empty cache fail, qwen3/model.rs:164-175).
 void forward_any(aha_model* m, const uint32_t* ids, size_t S, size_t offset, const aha_mm* mm, bool initial, float* logits_out, uint32_t* argmax_out,
-                 bool extend = false) {
+                 bool extend = false, bool force_prefill = false) {
     TextModel& T = m->text;
     AHA_REQUIRE(ids != nullptr && S >= 1, "input_ids must hold at least one token");
     AHA_REQUIRE(offset + S <= (size_t)T.max_ctx, "context exceeds max_ctx");
     const bool has_mm = initial && mm && ((m->kind == aha_model::QWEN3VL && (mm_entry(mm, 0) || mm_entry(mm, 2))) || (m->kind == aha_model::QWEN3_ASR && mm_entry(mm, 0)));
     if (initial && m->kind == aha_model::QWEN3VL) AHA_REQUIRE(mm && mm->n == 5, "Qwen3VL process data error, must have pixel_values, image_grid_thw, pixel_values_video, video_grid_thw, cache_position");
     if (initial && m->kind == aha_model::QWEN3_ASR) AHA_REQUIRE(mm && mm->n == 1, "Qwen3 asr process data error, must have input_features");
-    if (S == 1 && !has_mm && !extend && (m->kind != aha_model::QWEN3VL || m->have_rope_delta)) {
+    if (S == 1 && !has_mm && !extend && !force_prefill && (m->kind != aha_model::QWEN3VL || m->have_rope_delta)) {
         // decode step: single token against the cache
         AHA_REQUIRE(ids[0] < (uint32_t)T.cfg.V, "token id out of range");
         T.ensure_tokens((int)offset + 1);
@@ -680,6 +682,98 @@ void generate_impl(aha_model* m, const uint32_t* ids, size_t seq_len, const aha_
 }
 
 }  // namespace
+
+namespace {
+// Static batching: n independent requests, each prefilled on its own page table, then decoded in lockstep (batch_decode.cuh).  Every
+// request follows generate_generic's rules on its own (first token never EOS-checked, an EOS token is pushed and ends THAT request, its
+// own sampler / seed / repeat-penalty history) and so yields exactly the tokens aha_b200_generate would yield for it alone.
+void generate_batch_impl(aha_model* m, const aha_batch_request* reqs, size_t n, uint32_t* out_tokens, size_t cap, size_t* n_out, aha_usage* usage) {
+    TextModel& T = m->text;
+    AHA_REQUIRE(n >= 1 && n <= (size_t)kGemvBatchMax, "generate_batch: 1 to 8 requests");
+    AHA_REQUIRE(T.tp_world == 1, "generate_batch is single-GPU (run one batch per tensor-parallel group member instead)");
+    AHA_REQUIRE(T.max_prefill >= kGemvBatchMax, "generate_batch needs max_prefill >= 8");
+    using clk = std::chrono::steady_clock;
+    std::vector<size_t> sample_len(n);
+    size_t pages = 0;
+    for (size_t i = 0; i < n; ++i) {
+        AHA_REQUIRE(reqs[i].ids && reqs[i].seq_len >= 1, "generate_batch: every request needs input_ids");
+        sample_len[i] = std::max<size_t>(reqs[i].params.max_tokens, 1);
+        AHA_REQUIRE(cap >= sample_len[i], "out_tokens capacity (per request) is smaller than max_tokens");
+        AHA_REQUIRE((reqs[i].params.flags & (AHA_GEN_CONTINUE_RNG | AHA_GEN_REUSE_PREFIX)) == 0, "generate_batch: CONTINUE_RNG / REUSE_PREFIX are per-handle states of the single-request calls");
+        pages += (reqs[i].seq_len + sample_len[i] + kPage - 1) / kPage;
+        n_out[i] = 0;
+        if (usage) usage[i] = aha_usage{};
+    }
+    AHA_REQUIRE(pages <= (size_t)T.num_pages, "the requests of the batch need " + std::to_string(pages * kPage) + " tokens of KV capacity, max_ctx is " + std::to_string(T.max_ctx));
+    const bool simt = std::getenv("AHA_BATCH_GEMV") && std::atoi(std::getenv("AHA_BATCH_GEMV")) == 1;   // 1 = projections on the exact SIMT GEMM (validation twin)
+    BatchDecoder& B = m->batch;
+    drop_cache(m);
+    B.init(T, kGemvBatchMax);
+    for (auto& sl : B.slots) sl.mapped = 0;
+    B.table_for.clear();
+    int swapped = -1;
+    struct Reset {   // whatever happens, the handle is left as after clear_cache(), with its own page table in place
+        aha_model* m; BatchDecoder* B; int* swapped;
+        ~Reset() { if (*swapped >= 0) B->swap_table(*swapped); drop_cache(m); m->text.clear_sampler(); for (auto& sl : B->slots) sl.mapped = 0; }
+    } reset{m, &B, &swapped};
+    auto is_eos = [&](uint32_t t) { for (uint32_t e : m->stop_ids) if (e == t) return true; return false; };
+
+    // ---- prefill, one request after the other (each is the reference's forward_initial + sample_and_push)
+    std::vector<int> act;
+    std::vector<clk::time_point> t_first(n);
+    for (size_t i = 0; i < n; ++i) {
+        const aha_batch_request& r = reqs[i];
+        const auto t0 = clk::now();
+        B.swap_table((int)i); swapped = (int)i;
+        m->have_rope_delta = false; m->rope_delta = 0;
+        T.set_sampler(sampling_mode(r.params), r.params.temperature, r.params.top_p, r.params.top_k, r.params.repeat_penalty, r.params.repeat_last_n, r.params.seed);
+        T.set_state(0, 0, 0, 0, 0);
+        uint32_t tok = 0;
+        forward_any(m, r.ids, r.seq_len, 0, r.mm, true, nullptr, &tok, false, true);
+        T.check_sample_error();
+        T.ensure_tokens((int)(r.seq_len + sample_len[i]));       // every page the request can touch is mapped now (the step kernels only read the table)
+        DecodeState cur;
+        AHA_CUDA_CHECK(cudaMemcpy(&cur, T.d_state, sizeof(cur), cudaMemcpyDeviceToHost));
+        B.adopt((int)i, tok, (int)r.seq_len, m->kind == aha_model::QWEN3VL ? m->rope_delta : 0, cur.n_draws);
+        B.swap_table((int)i); swapped = -1;
+        t_first[i] = clk::now();
+        out_tokens[i * cap] = tok; n_out[i] = 1;
+        if (usage) {
+            usage[i].prompt_tokens = (uint32_t)r.seq_len;
+            usage[i].prompt_secs = std::chrono::duration<double>(t_first[i] - t0).count();
+            usage[i].vision_secs = m->last_vision_secs;
+        }
+        const bool stop = (r.params.flags & AHA_GEN_EOS_ON_FIRST) != 0 && is_eos(tok);
+        if (sample_len[i] > 1 && !stop) act.push_back((int)i);
+    }
+    // ---- decode in lockstep; a request leaves the batch at its EOS token or at max_tokens
+    const auto t_dec = clk::now();
+    std::vector<uint32_t> h_tok(kGemvBatchMax);
+    while (!act.empty()) {
+        B.step(act, simt);
+        AHA_CUDA_CHECK(cudaMemcpyAsync(h_tok.data(), B.d_tok, kGemvBatchMax * sizeof(uint32_t), cudaMemcpyDeviceToHost, m->ctx.stream));
+        AHA_CUDA_CHECK(cudaStreamSynchronize(m->ctx.stream));
+        T.check_sample_error();
+        std::vector<int> next;
+        for (int slot : act) {
+            const uint32_t t = h_tok[slot];
+            out_tokens[(size_t)slot * cap + n_out[slot]] = t;
+            n_out[slot] += 1;
+            if (!(is_eos(t) || n_out[slot] >= sample_len[slot])) next.push_back(slot);
+            else if (usage) usage[slot].completion_secs = std::chrono::duration<double>(clk::now() - t_dec).count();
+        }
+        act.swap(next);
+    }
+    if (usage) for (size_t i = 0; i < n; ++i) usage[i].completion_tokens = (uint32_t)n_out[i];
+}
+}  // namespace
+
+int aha_b200_generate_batch(aha_model* m, const aha_batch_request* reqs, size_t n, uint32_t* out_tokens, size_t cap, size_t* n_out, aha_usage* usage) {
+    return guarded(m, [&] {
+        AHA_REQUIRE(reqs && out_tokens && n_out, "reqs, out_tokens and n_out are required");
+        generate_batch_impl(m, reqs, n, out_tokens, cap, n_out, usage);
+    });
+}
 
 int aha_b200_generate(aha_model* m, const uint32_t* ids, size_t seq_len, const aha_mm* mm, const aha_gen_params* params, uint32_t* out_tokens,
                       size_t cap, size_t* n_out, aha_usage* usage) {
@@ -1138,6 +1232,31 @@ int aha_b200_debug_gemm(aha_model* m, int impl, int epi, int act, int M, int N, 
                 AHA_CUDA_CHECK(cudaMalloc(&dr, (size_t)M * N * 4)); AHA_CUDA_CHECK(cudaMemcpy(dr, resid, (size_t)M * N * 4, cudaMemcpyHostToDevice));
             }
             LinearW W; W.w = dw; W.b = db; W.N = N; W.K = K;
+            if (impl == 5) {   // the batched decode GEMV (gemv_batch.cuh): M <= 8 activation rows against every weight row
+                AHA_REQUIRE(M <= kGemvBatchMax && (epi == EPI_STORE || epi == EPI_RESID || epi == EPI_SWIGLU), "batched GEMV: M <= 8, epilogue store / residual / SwiGLU");
+                GemvBatchArgs a{};
+                a.W = dw; a.x = dx; a.ldx = K; a.bias = db; a.resid = dr; a.ldr = N; a.out = dy; a.ldo = Nout; a.N = N; a.K = K; a.nb = M; a.eps = 0.f;
+                const int gepi = epi == EPI_STORE ? GEPI_STORE : (epi == EPI_RESID ? GEPI_RESID : GEPI_SWIGLU);
+                const int pro = epi == EPI_SWIGLU ? PRO_RMSNORM : PRO_NONE;   // (the SwiGLU instantiation carries the RMSNorm prologue: unit gain here)
+                float* ones = nullptr;
+                if (pro == PRO_RMSNORM) {
+                    std::vector<float> h1((size_t)K, 1.0f);
+                    AHA_CUDA_CHECK(cudaMalloc(&ones, (size_t)K * 4)); AHA_CUDA_CHECK(cudaMemcpy(ones, h1.data(), (size_t)K * 4, cudaMemcpyHostToDevice));
+                    a.norm_w = ones; a.eps = 1e-6f;
+                }
+                try {
+                    gemv_batch(c.stream, pro, gepi, a);
+                    AHA_CUDA_CHECK(cudaEventRecord(m->ev0, c.stream));
+                    for (int i = 0; i < std::max(iters, 0); ++i) gemv_batch(c.stream, pro, gepi, a);
+                    AHA_CUDA_CHECK(cudaEventRecord(m->ev1, c.stream));
+                    AHA_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+                } catch (...) { cudaFree(ones); throw; }
+                cudaFree(ones);
+                if (device_ms) { float ms = 0.f; AHA_CUDA_CHECK(cudaEventElapsedTime(&ms, m->ev0, m->ev1)); *device_ms = ms; }
+                AHA_CUDA_CHECK(cudaMemcpy(out, dy, (size_t)M * Nout * 4, cudaMemcpyDeviceToHost));
+                cleanup();
+                return;
+            }
             const int saved = c.gemm_impl;
             c.gemm_impl = impl;
             try {

@@ -285,7 +285,7 @@ struct DecodeAttnArgs {
 };
 
 template <int HD, int G>
-__global__ void __launch_bounds__(256) decode_attn_kernel(DecodeAttnArgs a) {
+__device__ __forceinline__ void decode_attn_body(const DecodeAttnArgs& a, const int split, const int kvh) {
     static_assert(HD == 128, "decode attention is specialised for head_dim 128");
     constexpr int NW = 8;
     __shared__ __align__(16) float qs[G][HD];
@@ -294,7 +294,6 @@ __global__ void __launch_bounds__(256) decode_attn_kernel(DecodeAttnArgs a) {
     __shared__ float sm_m[NW][G], sm_l[NW][G];
     __shared__ __align__(16) float sm_acc[NW][G][HD];
     __shared__ int s_last;
-    const int split = blockIdx.x, kvh = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int t_new = a.st->pos;            // cache index of the current token
     const int ctx = t_new + 1;
@@ -420,6 +419,17 @@ __global__ void __launch_bounds__(256) decode_attn_kernel(DecodeAttnArgs a) {
         a.out[(size_t)(kvh * G + g) * HD + d] = O / L;
     }
     if (tid == 0) a.counters[kvh] = 0;
+}
+
+template <int HD, int G>
+__global__ void __launch_bounds__(256) decode_attn_kernel(DecodeAttnArgs a) { decode_attn_body<HD, G>(a, blockIdx.x, blockIdx.y); }
+
+// The same for a batch of sequences decoded in lockstep (batch_decode.cuh): grid = (nsplit, nkv, sequences); sequence z takes its
+// projections row, DecodeState, page table, partial / counter / output buffers from table[z].
+template <int HD, int G>
+__global__ void __launch_bounds__(256) decode_attn_batch_kernel(const DecodeAttnArgs* __restrict__ table) {
+    const DecodeAttnArgs a = table[blockIdx.z];
+    decode_attn_body<HD, G>(a, blockIdx.x, blockIdx.y);
 }
 
 }  // namespace aha

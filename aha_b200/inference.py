@@ -209,6 +209,30 @@ class B200Model:
                                                 C.byref(n), C.byref(u)))
         return [int(out[i]) for i in range(n.value)], self._usage(u)
 
+    def generate_batch(self, requests):
+        """Static batching (aha_b200_generate_batch): requests = [dict(input_ids=..., data=None, max_tokens=..., temperature=..., top_p=...,
+        top_k=..., repeat_penalty=..., repeat_last_n=..., seed=...), ...] (at most 8) decoded in lockstep on this handle.
+        -> [(generated ids, usage dict), ...]: per request exactly what generate() returns for it alone."""
+        n = len(requests)
+        arr = (L.BatchRequest * n)()
+        keep = []
+        cap = 1
+        for i, r in enumerate(requests):
+            ids = self._ids(r["input_ids"])
+            mm, k = self._mm(r.get("data"))
+            keep += [ids, mm, k]
+            arr[i].ids = ids.ctypes.data_as(C.POINTER(C.c_uint32))
+            arr[i].seq_len = ids.size
+            arr[i].mm = C.pointer(mm) if mm is not None else None
+            arr[i].params = self._gen_params(r.get("max_tokens", 1024), r.get("temperature", 0.0), r.get("top_p"), r.get("top_k"),
+                                             r.get("repeat_penalty", 1.0), r.get("repeat_last_n", 64), r.get("seed", 299792458), r.get("flags", 0))
+            cap = max(cap, r.get("max_tokens", 1024))
+        out = (C.c_uint32 * (n * cap))()
+        n_out = (C.c_size_t * n)()
+        us = (L.Usage * n)()
+        self._check(self._lib.aha_b200_generate_batch(self._h, arr, n, out, cap, n_out, us))
+        return [([int(out[i * cap + j]) for j in range(n_out[i])], self._usage(us[i])) for i in range(n)]
+
     def generate_stream(self, input_ids, on_token, data=None, max_tokens=1024, temperature=0.0, top_p=None, top_k=None,
                         repeat_penalty=1.0, repeat_last_n=64, seed=299792458, reuse_prefix=False):
         """generate_stream_generic: on_token(token, index) is called per generated token as its step completes; a truthy

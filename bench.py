@@ -273,6 +273,29 @@ def measure_prefix_cache(m, synth, ids, data, n_new=32, n_gen=8):
             "note": "new design (SURVEY 8f rank 4): the reference clears its KV cache after every request"}
 
 
+def measure_batch(m, wl, synth, n_req=8, n_prompt=128, n_gen=64):
+    """Static batching (aha_b200_generate_batch): n_req text-only requests decoded in lockstep on the same handle -- every weight is read once per
+    step for all of them.  tokens/s = decode tokens of all requests / wall time of the lockstep loop (host sync per step included); the same
+    requests one after the other through generate() give the single-stream rate beside it, and the ids of both must agree."""
+    none = [None] * 5 if wl["kind"] == "qwen3vl" else None
+    reqs = [dict(input_ids=synth.synth_text_ids(n_prompt + 3 * i, 151000, 500 + i), data=none, max_tokens=n_gen) for i in range(n_req)]
+    m.generate_batch(reqs[:2])                                   # warm-up (buffers, kernel attributes)
+    t0 = time.perf_counter()
+    res = m.generate_batch(reqs)
+    wall = time.perf_counter() - t0
+    dec_tokens = sum(len(t) - 1 for t, _ in res)
+    dec_secs = max(u["completion_secs"] for _, u in res)
+    singles, single_secs = [], 0.0
+    for r in reqs:
+        t, u = m.generate(r["input_ids"], r["data"], max_tokens=n_gen)
+        singles.append(t); single_secs += u["completion_secs"]
+    return {"requests": n_req, "prompt_tokens": [int(len(r["input_ids"])) for r in reqs], "max_tokens": n_gen,
+            "value": dec_tokens / dec_secs, "unit": UNIT, "ms_per_step": 1e3 * dec_secs / max(n_gen - 1, 1), "wall_s_incl_prefill": wall,
+            "one_by_one_tokens_per_s": dec_tokens / single_secs, "speedup_vs_one_by_one": (dec_tokens / dec_secs) / (dec_tokens / single_secs),
+            "tokens_equal": bool(all(a == b[0] for a, b in zip(singles, res))),
+            "note": "new design (SURVEY 8f rank 4): the reference serves one request at a time; per-op kernels, no CUDA graph yet"}
+
+
 def measure(m, wl, cfg, synth, K, W, reps, barrier, want_e2e=True, want_prefix=False):
     """prefill once, then time K fused decode steps (device-resident) and K forward_step calls (e2e)."""
     ids, data = make_inputs(m, wl, cfg, synth)
@@ -315,6 +338,11 @@ def measure(m, wl, cfg, synth, K, W, reps, barrier, want_e2e=True, want_prefix=F
             res["prefix_cache"] = measure_prefix_cache(m, synth, ids, data)
         except Exception as e:   # an extra record: it must never take the metric line down
             res["prefix_cache"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        if wl["kind"] in ("qwen3", "qwen3vl"):
+            try:
+                res["batch"] = measure_batch(m, wl, synth)
+            except Exception as e:
+                res["batch"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     return res
 
 
@@ -500,6 +528,8 @@ def main():
             line["tp"] = tp_rec
         if r.get("prefix_cache") is not None:
             line["prefix_cache"] = r["prefix_cache"]
+        if r.get("batch") is not None:
+            line["batch"] = r["batch"]
         emit(line)
     if dist is not None:
         dist.destroy_process_group()

@@ -172,6 +172,20 @@ int aha_b200_generate(aha_model* m, const uint32_t* ids, size_t seq_len, const a
                       const aha_gen_params* params, uint32_t* out_tokens, size_t cap, size_t* n_out,
                       aha_usage* usage);
 
+/* Static batching (new design, SURVEY 8f rank 4: the reference serves one request at a time, server/api.rs:117): up to 8 independent
+ * requests on one handle, each prefilled on its own page table of the shared paged KV pool, then decoded in LOCKSTEP -- one pass over the
+ * weights per step serves every sequence.  Each request obeys generate_generic on its own (own sampler / seed / repeat penalty, an EOS
+ * token ends that request only) and returns exactly the tokens aha_b200_generate returns for it alone.  out_tokens: [n][cap], n_out: [n],
+ * usage: [n] or NULL.  The sum of ceil((seq_len + max_tokens) / 32) pages over the requests must fit max_ctx.  Single GPU. */
+typedef struct aha_batch_request {
+    const uint32_t* ids;
+    size_t seq_len;
+    const aha_mm* mm;                /* NULL for text-only models / prompts */
+    aha_gen_params params;
+} aha_batch_request;
+int aha_b200_generate_batch(aha_model* m, const aha_batch_request* reqs, size_t n, uint32_t* out_tokens, size_t cap,
+                            size_t* n_out, aha_usage* usage);
+
 /* WhisperFeatureExtractor::call (/root/reference/src/models/feature_extractor/
  * feature_extraction_whisper.rs:65-115): wave (n) f32 host -> log-mel (n_mels, n_frames) f32 host.
  * Returns frames through *n_frames.  Qwen3-ASR handles only. */
@@ -311,7 +325,8 @@ int aha_b200_debug_sample(aha_model* m, const float* logits, const aha_gen_param
                           size_t n_context, uint32_t draw_index, uint32_t* token_out);
 int aha_b200_bench_kernel(aha_model* m, const char* which, int iters, double* avg_ms, uint64_t* bytes_per_launch);
 /* Run ONE Linear layer y = epilogue(x W^T + b) through the library's GEMM dispatch on host data (unit tests of the
- * tcgen05 and SIMT kernels against numpy): impl 1 = SIMT fp32, 2 = tcgen05 split-fp16; epi 0 = store, 1 = residual
+ * tcgen05 and SIMT kernels against numpy): impl 1 = SIMT fp32, 2 = tcgen05 split-fp16, 5 = the batched decode GEMV (M <= 8; its SwiGLU
+ * instantiation runs with a unit-gain RMSNorm prologue); epi 0 = store, 1 = residual
  * add (resid [M,N]), 2 = activation (act: 1 silu, 2 gelu-erf, 3 gelu-tanh), 3 = SwiGLU on interleaved columns
  * (out [M,N/2]).  x [M,K] f32, w [N,K] f16 bits, bias [N] f32 or NULL.  device_ms: CUDA-event time of `iters` runs. */
 int aha_b200_debug_gemm(aha_model* m, int impl, int epi, int act, int M, int N, int K, const float* x, const uint16_t* w,
