@@ -706,15 +706,17 @@ void generate_batch_impl(aha_model* m, const aha_batch_request* reqs, size_t n, 
     }
     AHA_REQUIRE(pages <= (size_t)T.num_pages, "the requests of the batch need " + std::to_string(pages * kPage) + " tokens of KV capacity, max_ctx is " + std::to_string(T.max_ctx));
     const bool simt = std::getenv("AHA_BATCH_GEMV") && std::atoi(std::getenv("AHA_BATCH_GEMV")) == 1;   // 1 = projections on the exact SIMT GEMM (validation twin)
+    const bool use_graph = !(std::getenv("AHA_BATCH_GRAPH") && std::atoi(std::getenv("AHA_BATCH_GRAPH")) == 0);   // 0 = eager launches (A/B twin of the per-composition graphs)
     BatchDecoder& B = m->batch;
     drop_cache(m);
     B.init(T, kGemvBatchMax);
     for (auto& sl : B.slots) sl.mapped = 0;
     B.table_for.clear();
+    B.clear_graphs();
     int swapped = -1;
     struct Reset {   // whatever happens, the handle is left as after clear_cache(), with its own page table in place
         aha_model* m; BatchDecoder* B; int* swapped;
-        ~Reset() { if (*swapped >= 0) B->swap_table(*swapped); drop_cache(m); m->text.clear_sampler(); for (auto& sl : B->slots) sl.mapped = 0; }
+        ~Reset() { if (*swapped >= 0) B->swap_table(*swapped); drop_cache(m); m->text.clear_sampler(); for (auto& sl : B->slots) sl.mapped = 0; B->clear_graphs(); }
     } reset{m, &B, &swapped};
     auto is_eos = [&](uint32_t t) { for (uint32_t e : m->stop_ids) if (e == t) return true; return false; };
 
@@ -750,7 +752,7 @@ void generate_batch_impl(aha_model* m, const aha_batch_request* reqs, size_t n, 
     const auto t_dec = clk::now();
     std::vector<uint32_t> h_tok(kGemvBatchMax);
     while (!act.empty()) {
-        B.step(act, simt);
+        B.step(act, simt, use_graph);
         AHA_CUDA_CHECK(cudaMemcpyAsync(h_tok.data(), B.d_tok, kGemvBatchMax * sizeof(uint32_t), cudaMemcpyDeviceToHost, m->ctx.stream));
         AHA_CUDA_CHECK(cudaStreamSynchronize(m->ctx.stream));
         T.check_sample_error();
@@ -1368,6 +1370,7 @@ void aha_b200_destroy(aha_model* m) {
     cudaSetDevice(m->ctx.device);
     if (m->ctx.stream) cudaStreamSynchronize(m->ctx.stream);
     m->text.destroy();
+    m->batch.clear_graphs();
     m->ctx.free_all();
     if (m->h_pin) cudaFreeHost(m->h_pin);
     if (m->ev0) cudaEventDestroy(m->ev0);

@@ -40,6 +40,14 @@ struct BatchDecoder {
     DecodeAttnArgs* d_attn = nullptr;    // [L][cap] attention arguments of the current active list
     std::vector<BatchSlot> slots;
     std::vector<int> table_for;          // active list the attention table was built for
+    // One CUDA graph per composition of the batch (the active list changes only when a request finishes): ~170 launches per step become one.
+    // The graphs hold the requests' sampler parameters by value, so they live for one generate_batch call.
+    struct StepGraph { std::vector<int> act; bool simt; cudaGraphExec_t exec; uint64_t kernels; };
+    std::vector<StepGraph> graphs;
+    void clear_graphs() {
+        for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+        graphs.clear();
+    }
 
     void init(TextModel& t, int n) {
         T = &t;
@@ -144,13 +152,36 @@ struct BatchDecoder {
     }
 
     // one decode step of the sequences in `act` (slot indices, at most cap); leaves every slot's next token in d_tok[slot] and its DecodeState advanced
-    void step(const std::vector<int>& act, bool simt) {
+    void step(const std::vector<int>& act, bool simt, bool use_graph) {
+        Ctx& c = *T->ctx;
+        AHA_REQUIRE(!act.empty() && (int)act.size() <= cap, "batch step: bad active list");
+        if (act != table_for) build_attn_table(act);
+        if (!use_graph) { launches(act, simt); return; }
+        StepGraph* g = nullptr;
+        for (auto& e : graphs) if (e.simt == simt && e.act == act) { g = &e; break; }
+        if (!g) {
+            const uint64_t k0 = c.cnt.kernels;
+            cudaGraph_t cg = nullptr;
+            AHA_CUDA_CHECK(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal));
+            try { launches(act, simt); } catch (...) { cudaStreamEndCapture(c.stream, &cg); if (cg) cudaGraphDestroy(cg); throw; }
+            AHA_CUDA_CHECK(cudaStreamEndCapture(c.stream, &cg));
+            StepGraph e{act, simt, nullptr, c.cnt.kernels - k0};
+            c.cnt.kernels = k0;
+            const cudaError_t err = cudaGraphInstantiate(&e.exec, cg, 0);
+            cudaGraphDestroy(cg);
+            AHA_CUDA_CHECK(err);
+            graphs.push_back(e);
+            g = &graphs.back();
+        }
+        AHA_CUDA_CHECK(cudaGraphLaunch(g->exec, c.stream));
+        c.cnt.graphs++;
+        c.cnt.kernels += g->kernels;
+    }
+    void launches(const std::vector<int>& act, bool simt) {
         Ctx& c = *T->ctx;
         cudaStream_t st = c.stream;
         const TextCfg& cf = T->cfg;
         const int nb = (int)act.size(), H = cf.H;
-        AHA_REQUIRE(nb >= 1 && nb <= cap, "batch step: bad active list");
-        if (act != table_for) build_attn_table(act);
         for (int j = 0; j < nb; ++j) { embed_gather_kernel<<<1, 256, 0, st>>>(&d_states[act[j]].token, T->embed, xb + (size_t)j * H, 1, H, cf.V); c.cnt.kernels++; }
         for (int l = 0; l < cf.L; ++l) {
             TextLayer& Ly = T->layers[l];

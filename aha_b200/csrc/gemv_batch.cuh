@@ -67,33 +67,44 @@ __global__ void __launch_bounds__(256) gemv_batch_kernel(GemvBatchArgs a) {
     for (int k0 = 0; k0 < K; k0 += kGemvBatchKC) {
         const int kc = min(kGemvBatchKC, K - k0);
         __syncthreads();   // the previous pass has been consumed
-        for (int b = 0; b < NB; ++b) {
-            if (b >= nb) break;
-            const float* xr = a.x + (size_t)b * a.ldx + k0;
-            const float inv = PRO == PRO_RMSNORM ? s_inv[b] : 1.0f;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {   // rows beyond nb are staged as zeros: the inner loop then needs no predicate (their results are never stored)
+            const float* xr = a.x + (size_t)(b < nb ? b : 0) * a.ldx + k0;
+            const float inv = (PRO == PRO_RMSNORM && b < nb) ? s_inv[b] : 1.0f;
             for (int i = tid * 4; i < kc; i += 256 * 4) {
-                float4 v = *reinterpret_cast<const float4*>(xr + i);
-                if (PRO == PRO_RMSNORM) {
-                    const float4 w = *reinterpret_cast<const float4*>(a.norm_w + k0 + i);
-                    v.x = v.x * inv * w.x; v.y = v.y * inv * w.y; v.z = v.z * inv * w.z; v.w = v.w * inv * w.w;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (b < nb) {
+                    v = *reinterpret_cast<const float4*>(xr + i);
+                    if (PRO == PRO_RMSNORM) {
+                        const float4 w = *reinterpret_cast<const float4*>(a.norm_w + k0 + i);
+                        v.x = v.x * inv * w.x; v.y = v.y * inv * w.y; v.z = v.z * inv * w.z; v.w = v.w * inv * w.w;
+                    }
                 }
                 *reinterpret_cast<float4*>(xs + (size_t)b * kGemvBatchKC + i) = v;
             }
         }
         __syncthreads();
         const int nchunk = kc >> 3;
-#pragma unroll 2
         for (int c = lane; c < nchunk; c += 32) {
-            uint4 w[RPW];
+            // the 8 weights of every row are widened to fp32 ONCE and then meet all NB sequences (dot8 would convert them again per sequence);
+            // per (row, sequence) the eight fmas run in dot8's order, so the sums are those of gemv_kernel bit for bit
+            float wf[RPW][8];
 #pragma unroll
-            for (int r = 0; r < RPW; ++r) w[r] = ldg_stream(wr[r] + k0 + c * 8);
+            for (int r = 0; r < RPW; ++r) {
+                const uint4 w = ldg_stream(wr[r] + k0 + c * 8);
+                const float2 p0 = h2_to_f2(w.x), p1 = h2_to_f2(w.y), p2 = h2_to_f2(w.z), p3 = h2_to_f2(w.w);
+                wf[r][0] = p0.x; wf[r][1] = p0.y; wf[r][2] = p1.x; wf[r][3] = p1.y; wf[r][4] = p2.x; wf[r][5] = p2.y; wf[r][6] = p3.x; wf[r][7] = p3.y;
+            }
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
-                if (b < nb) {
-                    const float4 x0 = *reinterpret_cast<const float4*>(xs + (size_t)b * kGemvBatchKC + c * 8);
-                    const float4 x1 = *reinterpret_cast<const float4*>(xs + (size_t)b * kGemvBatchKC + c * 8 + 4);
+                const float4 x0 = *reinterpret_cast<const float4*>(xs + (size_t)b * kGemvBatchKC + c * 8);
+                const float4 x1 = *reinterpret_cast<const float4*>(xs + (size_t)b * kGemvBatchKC + c * 8 + 4);
 #pragma unroll
-                    for (int r = 0; r < RPW; ++r) acc[r][b] = dot8(w[r], x0, x1, acc[r][b]);
+                for (int r = 0; r < RPW; ++r) {
+                    float s = acc[r][b];
+                    s = fmaf(wf[r][0], x0.x, s); s = fmaf(wf[r][1], x0.y, s); s = fmaf(wf[r][2], x0.z, s); s = fmaf(wf[r][3], x0.w, s);
+                    s = fmaf(wf[r][4], x1.x, s); s = fmaf(wf[r][5], x1.y, s); s = fmaf(wf[r][6], x1.z, s); s = fmaf(wf[r][7], x1.w, s);
+                    acc[r][b] = s;
                 }
             }
         }
@@ -145,8 +156,9 @@ inline void gemv_batch_launch_one(cudaStream_t st, const GemvBatchArgs& a) {
 
 template <int PRO, int EPI>
 inline void gemv_batch_launch(cudaStream_t st, const GemvBatchArgs& a) {
-    // rows per warp as in gemv.cuh: enough CTAs for the 148 SMs first, then reuse of the staged activations; SwiGLU needs row pairs
-    const int rpw = gemv_pick_rpw(a.N, EPI == GEPI_SWIGLU);
+    // rows per warp: with nb sequences every staged activation chunk costs nb shared-memory reads per weight chunk, so reuse across rows matters
+    // more than at batch 1 (call 21: 5.4 ms per step of 8 sequences with gemv.cuh's choice): 4 rows per warp from N = 4096 (128 CTAs), else 2
+    const int rpw = a.N >= 4096 ? 4 : 2;
     const bool small = a.nb <= 4;
     if (rpw >= 4) { if (small) gemv_batch_launch_one<4, 4, PRO, EPI>(st, a); else gemv_batch_launch_one<8, 4, PRO, EPI>(st, a); }
     else if (rpw == 2 || EPI == GEPI_SWIGLU) { if (small) gemv_batch_launch_one<4, 2, PRO, EPI>(st, a); else gemv_batch_launch_one<8, 2, PRO, EPI>(st, a); }

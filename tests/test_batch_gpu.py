@@ -62,19 +62,21 @@ def _requests(V, spec):
     return [dict(input_ids=_ids(S, V, 100 + i), max_tokens=n, **kw) for i, (S, n, kw) in enumerate(spec)]
 
 
-@pytest.mark.parametrize("twin", [False, True])
-def test_batch_of_greedy_requests_equals_single_requests(q3, twin):
+@pytest.mark.parametrize("twin,graph", [(False, True), (False, False), (True, True)])
+def test_batch_of_greedy_requests_equals_single_requests(q3, twin, graph):
     """8 prompts of different lengths and budgets (page boundaries crossed at different steps, requests leaving the batch one by one):
     every request's ids equal its own oracle run and the library's own single-request generate."""
     cfg, w, m, o = q3
     V = cfg["vocab_size"]
     spec = [(5, 40, {}), (33, 9, {}), (64, 70, {}), (1, 12, {}), (200, 33, {}), (97, 1, {}), (31, 64, {}), (150, 20, {})]
     reqs = _requests(V, spec)
-    os.environ["AHA_BATCH_GEMV"] = "1" if twin else "0"
+    os.environ["AHA_BATCH_GEMV"] = "1" if twin else "0"        # 1: projections on the exact SIMT GEMM instead of the batched GEMV
+    os.environ["AHA_BATCH_GRAPH"] = "1" if graph else "0"      # 0: eager launches instead of one CUDA graph per composition of the batch
     try:
         res = m.generate_batch(reqs)
     finally:
         os.environ.pop("AHA_BATCH_GEMV", None)
+        os.environ.pop("AHA_BATCH_GRAPH", None)
     for r, (toks, usage) in zip(reqs, res):
         want = _oracle_generate(o, r["input_ids"], None, r["max_tokens"])
         assert toks == want, (len(r["input_ids"]), r["max_tokens"])

@@ -23,7 +23,7 @@ def _oracle_generate(o, ids, data, n, **samp):
         ctx = GenerationContext(temperature=0.0, initial_seq_len=len(ids), max_tokens=n)
         return generate_generic(o, np.asarray(ids).reshape(1, -1), data, ctx)[0]
     from oracle.sample import Sampler
-    s = Sampler(samp["temperature"], samp.get("top_p"), samp.get("top_k"), samp.get("repeat_penalty", 1.0), samp.get("repeat_last_n", 64),
+    s = Sampler(samp.get("temperature"), samp.get("top_p"), samp.get("top_k"), samp.get("repeat_penalty", 1.0), samp.get("repeat_last_n", 64),
                 seed=samp.get("seed", 299792458))
     toks = []
     eos = o.stop_token_ids()
