@@ -296,7 +296,7 @@ def measure_batch(m, wl, synth, n_req=8, n_prompt=128, n_gen=64):
             "note": "new design (SURVEY 8f rank 4): the reference serves one request at a time; per-op kernels, no CUDA graph yet"}
 
 
-def measure(m, wl, cfg, synth, K, W, reps, barrier, want_e2e=True, want_prefix=False):
+def measure(m, wl, cfg, synth, K, W, reps, barrier, want_e2e=True):
     """prefill once, then time K fused decode steps (device-resident) and K forward_step calls (e2e)."""
     ids, data = make_inputs(m, wl, cfg, synth)
     S = len(ids)
@@ -333,17 +333,23 @@ def measure(m, wl, cfg, synth, K, W, reps, barrier, want_e2e=True, want_prefix=F
         for i in range(n):   # the same with the full logits row returned to the host every step (what the reference's sampler consumes)
             m.forward_step(np.array([t], np.uint32), S + W + i, want_logits=True)
         res["e2e_logits_s"] = (time.perf_counter() - e0) / n
-    if want_prefix:
-        try:
-            res["prefix_cache"] = measure_prefix_cache(m, synth, ids, data)
-        except Exception as e:   # an extra record: it must never take the metric line down
-            res["prefix_cache"] = {"error": f"{type(e).__name__}: {e}"[:300]}
-        if wl["kind"] in ("qwen3", "qwen3vl"):
-            try:
-                res["batch"] = measure_batch(m, wl, synth)
-            except Exception as e:
-                res["batch"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    res["inputs"] = (ids, data)
     return res
+
+
+def extra_records(m, wl, synth, r):
+    """The two records beyond the metric (KV reuse, static batching): measured last on the handle, each on its own, so that nothing they do can
+    reach the numbers of the line (already taken) -- a failure becomes an `error` entry."""
+    ids, data = r["inputs"]
+    try:
+        r["prefix_cache"] = measure_prefix_cache(m, synth, ids, data)
+    except Exception as e:
+        r["prefix_cache"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    if wl["kind"] in ("qwen3", "qwen3vl"):
+        try:
+            r["batch"] = measure_batch(m, wl, synth)
+        except Exception as e:
+            r["batch"] = {"error": f"{type(e).__name__}: {e}"[:300]}
 
 
 def main():
@@ -430,7 +436,7 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.3)
-    r = measure(m, wl, cfg, synth, K, W, reps, barrier, want_prefix=(world == 1))
+    r = measure(m, wl, cfg, synth, K, W, reps, barrier)
     clocks = sampler.stop()
     assert r["S"] == S
     usage, st = r["usage"], r["stats"]
@@ -451,6 +457,8 @@ def main():
     step_bytes = st["decode_bytes_per_step_fixed"] + st["kv_bytes_per_token"] * (avg_ctx + 1)
     kv_read = st["kv_bytes_per_token"] * avg_ctx
     single_tokens = r["tokens"]
+    if world == 1:
+        extra_records(m, wl, synth, r)
     m.close()
     del m
 
