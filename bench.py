@@ -293,7 +293,7 @@ def measure_batch(m, wl, synth, n_req=8, n_prompt=128, n_gen=64):
             "value": dec_tokens / dec_secs, "unit": UNIT, "ms_per_step": 1e3 * dec_secs / max(n_gen - 1, 1), "wall_s_incl_prefill": wall,
             "one_by_one_tokens_per_s": dec_tokens / single_secs, "speedup_vs_one_by_one": (dec_tokens / dec_secs) / (dec_tokens / single_secs),
             "tokens_equal": bool(all(a == b[0] for a, b in zip(singles, res))),
-            "note": "new design (SURVEY 8f rank 4): the reference serves one request at a time; per-op kernels, no CUDA graph yet"}
+            "note": "new design (SURVEY 8f rank 4): the reference serves one request at a time; batched CUDA-core GEMV + per-sequence decode attention, one CUDA graph per batch composition"}
 
 
 def measure(m, wl, cfg, synth, K, W, reps, barrier, want_e2e=True):

@@ -15,6 +15,7 @@
 //   aha::generate_generic          the reference's host loop over the trait (one forward_step call per token)
 //   aha::B200Model::generate       the same request with the decode loop on the device (aha_b200_generate)
 #pragma once
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -218,6 +219,33 @@ public:
         out.resize(n);
         if (usage) *usage = Usage{u.prompt_tokens, u.completion_tokens, u.prompt_secs, u.completion_secs, u.vision_secs};
         return out;
+    }
+    // Static batching (aha_b200_generate_batch): up to 8 requests decoded in lockstep; result i is what generate() returns for request i alone.
+    struct BatchRequest { std::vector<uint32_t> ids; const MultiModalData* data = nullptr; GenerationContext ctx; };
+    std::vector<std::vector<uint32_t>> generate_batch(const std::vector<BatchRequest>& reqs, std::vector<Usage>* usage = nullptr) {
+        const size_t n = reqs.size();
+        std::vector<aha_batch_request> r(n);
+        std::vector<aha_mm> mms(n);
+        size_t cap = 1;
+        for (size_t i = 0; i < n; ++i) {
+            if (reqs[i].data) mms[i] = reqs[i].data->view();
+            r[i].ids = reqs[i].ids.data(); r[i].seq_len = reqs[i].ids.size(); r[i].mm = reqs[i].data ? &mms[i] : nullptr;
+            r[i].params = aha_gen_params{};
+            r[i].params.repeat_penalty = reqs[i].ctx.repeat_penalty; r[i].params.repeat_last_n = (int32_t)reqs[i].ctx.repeat_last_n;
+            r[i].params.max_tokens = (uint32_t)reqs[i].ctx.sample_len;
+            cap = std::max(cap, reqs[i].ctx.sample_len);
+        }
+        std::vector<uint32_t> out(n * cap);
+        std::vector<size_t> n_out(n);
+        std::vector<aha_usage> us(n);
+        check(aha_b200_generate_batch(h_, r.data(), n, out.data(), cap, n_out.data(), us.data()));
+        std::vector<std::vector<uint32_t>> res(n);
+        for (size_t i = 0; i < n; ++i) res[i].assign(out.begin() + (std::ptrdiff_t)(i * cap), out.begin() + (std::ptrdiff_t)(i * cap + n_out[i]));
+        if (usage) {
+            usage->clear();
+            for (const aha_usage& u : us) usage->push_back(Usage{u.prompt_tokens, u.completion_tokens, u.prompt_secs, u.completion_secs, u.vision_secs});
+        }
+        return res;
     }
     size_t last_prefix_hit() const { return aha_b200_last_prefix_hit(h_); }
     // Prefill continuation (aha_b200_forward_extend): further prompt tokens against the `off` tokens already in the cache.
