@@ -49,6 +49,12 @@ struct aha_model {
     uint64_t cached_mm_fp = 0;          // fingerprint of the multimodal tensors those tokens were embedded with (0 = none)
     size_t last_prefix_hit = 0;         // tokens the last generate call did not have to prefill
     BatchDecoder batch;                 // several sequences decoded in lockstep (aha_b200_generate_batch); buffers allocated on first use
+    // Continuous batching (aha_b200_batch_open / _add / _step / _close): requests join and leave a running batch between steps
+    struct BatchSession {
+        bool open = false;
+        bool used[kGemvBatchMax] = {};
+        size_t budget[kGemvBatchMax] = {}, produced[kGemvBatchMax] = {};
+    } session;
 };
 
 namespace {
@@ -267,6 +273,11 @@ std::vector<uint32_t> mm_token_ids(const aha_model* m) {
     for (int v : {m->image_token_id, m->video_token_id, m->audio_token_id}) if (v >= 0) t.push_back((uint32_t)v);
     return t;
 }
+void require_no_session(aha_model* m) {
+    AHA_REQUIRE(!m->session.open, "a batch session is open on this handle: call aha_b200_batch_close first");
+}
+bool env_flag(const char* name, bool dflt) { const char* v = std::getenv(name); return v ? std::atoi(v) != 0 : dflt; }
+
 // model.clear_cache(): pages, rope_deltas, and what the prefix cache remembered
 void drop_cache(aha_model* m) {
     m->text.reset_pages();
@@ -530,15 +541,15 @@ int aha_b200_create(const char* kind, const char* config_json, const aha_tensor_
 
 int aha_b200_forward_initial(aha_model* m, const uint32_t* ids, size_t seq_len, size_t seqlen_offset, const aha_mm* mm, float* logits_out,
                              uint32_t* argmax_out) {
-    return guarded(m, [&] { m->cached_ids.clear(); forward_any(m, ids, seq_len, seqlen_offset, mm, true, logits_out, argmax_out); });
+    return guarded(m, [&] { require_no_session(m); m->cached_ids.clear(); forward_any(m, ids, seq_len, seqlen_offset, mm, true, logits_out, argmax_out); });
 }
 
 int aha_b200_forward_step(aha_model* m, const uint32_t* ids, size_t seq_len, size_t seqlen_offset, float* logits_out, uint32_t* argmax_out) {
-    return guarded(m, [&] { m->cached_ids.clear(); forward_any(m, ids, seq_len, seqlen_offset, nullptr, false, logits_out, argmax_out); });
+    return guarded(m, [&] { require_no_session(m); m->cached_ids.clear(); forward_any(m, ids, seq_len, seqlen_offset, nullptr, false, logits_out, argmax_out); });
 }
 
 int aha_b200_forward_extend(aha_model* m, const uint32_t* ids, size_t seq_len, size_t seqlen_offset, float* logits_out, uint32_t* argmax_out) {
-    return guarded(m, [&] { m->cached_ids.clear(); forward_any(m, ids, seq_len, seqlen_offset, nullptr, false, logits_out, argmax_out, true); });
+    return guarded(m, [&] { require_no_session(m); m->cached_ids.clear(); forward_any(m, ids, seq_len, seqlen_offset, nullptr, false, logits_out, argmax_out, true); });
 }
 
 size_t aha_b200_last_prefix_hit(aha_model* m) { return m ? m->last_prefix_hit : 0; }
@@ -554,6 +565,13 @@ uint64_t aha_b200_mm_fingerprint(const aha_mm* mm) { return mm_fingerprint(mm); 
 int aha_b200_clear_cache(aha_model* m) {
     return guarded(m, [&] {
         AHA_CUDA_CHECK(cudaStreamSynchronize(m->ctx.stream));
+        if (m->session.open) {   // clear_cache ends a batch session too: every sequence's K/V is gone
+            for (auto& sl : m->batch.slots) sl.mapped = 0;
+            m->batch.table_for.clear();
+            m->batch.clear_graphs();
+            m->session = aha_model::BatchSession{};
+            m->text.clear_sampler();
+        }
         drop_cache(m);
     });
 }
@@ -586,6 +604,7 @@ struct GenSink {   // receives every generated token in order; returns true to s
 void generate_impl(aha_model* m, const uint32_t* ids, size_t seq_len, const aha_mm* mm, const aha_gen_params& params, const GenSink& sink, bool stream,
                    aha_usage* usage, size_t* n_generated) {
     TextModel& T = m->text;
+    require_no_session(m);
     const size_t sample_len = std::max<size_t>(params.max_tokens, 1);   // `for _ in 1..sample_len`: sample_len 0 and 1 both yield exactly one token
     AHA_REQUIRE(seq_len + sample_len <= (size_t)T.max_ctx,
                 "prompt + max_tokens exceeds max_ctx (the handle's KV capacity, aha_options.max_ctx; the reference's cache is unbounded)");
@@ -684,11 +703,133 @@ void generate_impl(aha_model* m, const uint32_t* ids, size_t seq_len, const aha_
 }  // namespace
 
 namespace {
+// One request into slot `slot` of the batch decoder: the reference's forward_initial + sample_and_push on the slot's own page table (swapped into
+// the TextModel for the duration, so tower / M-RoPE / deepstack / sampler-on-prefill are the single-request code), then its decode state, history
+// and sampler move into the slot.  *swapped tells the caller's guard which table is swapped in if this throws.
+uint32_t batch_prefill_slot(aha_model* m, int slot, const aha_batch_request& r, size_t sample_len, int* swapped) {
+    TextModel& T = m->text;
+    BatchDecoder& B = m->batch;
+    B.swap_table(slot); *swapped = slot;
+    m->have_rope_delta = false; m->rope_delta = 0;
+    T.set_sampler(sampling_mode(r.params), r.params.temperature, r.params.top_p, r.params.top_k, r.params.repeat_penalty, r.params.repeat_last_n, r.params.seed);
+    T.set_state(0, 0, 0, 0, 0);
+    uint32_t tok = 0;
+    forward_any(m, r.ids, r.seq_len, 0, r.mm, true, nullptr, &tok, false, true);
+    T.check_sample_error();
+    T.ensure_tokens((int)(r.seq_len + sample_len));       // every page the request can touch is mapped now (the step kernels only read the table)
+    DecodeState cur;
+    AHA_CUDA_CHECK(cudaMemcpy(&cur, T.d_state, sizeof(cur), cudaMemcpyDeviceToHost));
+    B.adopt(slot, tok, (int)r.seq_len, m->kind == aha_model::QWEN3VL ? m->rope_delta : 0, cur.n_draws);
+    B.swap_table(slot); *swapped = -1;
+    return tok;
+}
+
+// ---- continuous batching: the same slots and the same step, with requests joining and leaving between steps -------------------------
+// (new design; the reference's server holds ONE request behind a write lock, server/api.rs:117.)  A finished request's pages go back to the
+// free list at once, so a waiting request can take its place while the others keep decoding.
+void session_release(aha_model* m, int slot) {
+    BatchSlot& sl = m->batch.slots[slot];
+    for (int k = 0; k < sl.mapped; ++k) m->text.free_pages.push_back(sl.h_table[k]);
+    sl.mapped = 0;
+    sl.samp_active = false;
+    m->session.used[slot] = false;
+    m->batch.table_for.clear();
+    m->batch.clear_graphs();       // the graphs of compositions holding this slot carry its sampler arguments by value
+}
+void session_close(aha_model* m) {
+    if (m->batch.cap) { for (auto& sl : m->batch.slots) sl.mapped = 0; m->batch.table_for.clear(); m->batch.clear_graphs(); }
+    m->session = aha_model::BatchSession{};
+    drop_cache(m);
+    m->text.clear_sampler();
+}
+void session_open(aha_model* m) {
+    TextModel& T = m->text;
+    require_no_session(m);
+    AHA_REQUIRE(T.tp_world == 1, "batch sessions are single-GPU");
+    AHA_REQUIRE(T.max_prefill >= kGemvBatchMax, "batch sessions need max_prefill >= 8");
+    drop_cache(m);
+    m->batch.init(T, kGemvBatchMax);
+    for (auto& sl : m->batch.slots) sl.mapped = 0;
+    m->batch.table_for.clear();
+    m->batch.clear_graphs();
+    m->session = aha_model::BatchSession{};
+    m->session.open = true;
+}
+void session_add(aha_model* m, const aha_batch_request& r, int* slot_out, uint32_t* first_token, int* finished, aha_usage* usage) {
+    TextModel& T = m->text;
+    AHA_REQUIRE(m->session.open, "no batch session is open (aha_b200_batch_open)");
+    AHA_REQUIRE(r.ids && r.seq_len >= 1, "batch_add: the request needs input_ids");
+    AHA_REQUIRE((r.params.flags & (AHA_GEN_CONTINUE_RNG | AHA_GEN_REUSE_PREFIX)) == 0, "batch_add: CONTINUE_RNG / REUSE_PREFIX are per-handle states of the single-request calls");
+    int slot = -1;
+    for (int i = 0; i < kGemvBatchMax; ++i) if (!m->session.used[i]) { slot = i; break; }
+    AHA_REQUIRE(slot >= 0, "batch_add: all 8 slots are decoding (step until one finishes)");
+    const size_t sample_len = std::max<size_t>(r.params.max_tokens, 1);
+    const size_t need = (r.seq_len + sample_len + kPage - 1) / kPage;
+    AHA_REQUIRE(need <= T.free_pages.size(), "batch_add: the request needs " + std::to_string(need * kPage) + " tokens of KV capacity, " +
+                                                  std::to_string(T.free_pages.size() * kPage) + " are free (max_ctx " + std::to_string(T.max_ctx) + ")");
+    using clk = std::chrono::steady_clock;
+    const auto t0 = clk::now();
+    int swapped = -1;
+    struct Guard {   // a failed prefill leaves the session as it was: own table back in place, the slot's pages back in the pool
+        aha_model* m; int slot; int* swapped; bool ok = false;
+        ~Guard() { if (ok) return; if (*swapped >= 0) m->batch.swap_table(*swapped); session_release(m, slot); m->have_rope_delta = false; m->rope_delta = 0; m->text.clear_sampler(); }
+    } guard{m, slot, &swapped};
+    m->session.used[slot] = true;
+    const uint32_t tok = batch_prefill_slot(m, slot, r, sample_len, &swapped);
+    guard.ok = true;
+    m->text.clear_sampler();
+    m->batch.table_for.clear();
+    m->batch.clear_graphs();
+    m->session.budget[slot] = sample_len;
+    m->session.produced[slot] = 1;
+    bool stop = sample_len == 1;
+    if ((r.params.flags & AHA_GEN_EOS_ON_FIRST) != 0) for (uint32_t e : m->stop_ids) if (e == tok) stop = true;
+    if (usage) {
+        *usage = aha_usage{};
+        usage->prompt_tokens = (uint32_t)r.seq_len; usage->completion_tokens = 1;
+        usage->prompt_secs = std::chrono::duration<double>(clk::now() - t0).count();
+        usage->vision_secs = m->last_vision_secs;
+    }
+    if (stop) session_release(m, slot);
+    *slot_out = slot; *first_token = tok; *finished = stop ? 1 : 0;
+}
+size_t session_step(aha_model* m, uint32_t* tokens_out, int32_t* status_out) {
+    AHA_REQUIRE(m->session.open, "no batch session is open (aha_b200_batch_open)");
+    std::vector<int> act;
+    for (int i = 0; i < kGemvBatchMax; ++i) { status_out[i] = 0; tokens_out[i] = 0; if (m->session.used[i]) act.push_back(i); }
+    if (act.empty()) return 0;
+    m->batch.step(act, env_flag("AHA_BATCH_GEMV", false), env_flag("AHA_BATCH_GRAPH", true));
+    uint32_t h_tok[kGemvBatchMax];
+    AHA_CUDA_CHECK(cudaMemcpyAsync(h_tok, m->batch.d_tok, sizeof(h_tok), cudaMemcpyDeviceToHost, m->ctx.stream));
+    AHA_CUDA_CHECK(cudaStreamSynchronize(m->ctx.stream));
+    // a request whose sampler failed (all-zero weights) poisons only the check below; the session is closed by the caller's error path
+    for (int slot : act) {
+        const uint32_t t = h_tok[slot];
+        tokens_out[slot] = t;
+        m->session.produced[slot] += 1;
+        bool stop = m->session.produced[slot] >= m->session.budget[slot];
+        for (uint32_t e : m->stop_ids) if (e == t) stop = true;     // an EOS token is delivered, then the request ends (generate.rs:139-141)
+        status_out[slot] = stop ? 2 : 1;
+    }
+    for (int slot : act) if (status_out[slot] == 2) session_release(m, slot);
+    // sampler errors surface after the bookkeeping so that the slots stay consistent
+    {
+        TextModel& T = m->text;
+        if (T.d_sample_err) {
+            int e = 0;
+            AHA_CUDA_CHECK(cudaMemcpy(&e, T.d_sample_err, sizeof(int), cudaMemcpyDeviceToHost));
+            if (e) { cudaMemset(T.d_sample_err, 0, sizeof(int)); throw std::runtime_error("sampler: the token weights are all zero or not finite (rand::distr::weighted::WeightedIndex::new fails in the reference)"); }
+        }
+    }
+    return act.size();
+}
+
 // Static batching: n independent requests, each prefilled on its own page table, then decoded in lockstep (batch_decode.cuh).  Every
 // request follows generate_generic's rules on its own (first token never EOS-checked, an EOS token is pushed and ends THAT request, its
 // own sampler / seed / repeat-penalty history) and so yields exactly the tokens aha_b200_generate would yield for it alone.
 void generate_batch_impl(aha_model* m, const aha_batch_request* reqs, size_t n, uint32_t* out_tokens, size_t cap, size_t* n_out, aha_usage* usage) {
     TextModel& T = m->text;
+    require_no_session(m);
     AHA_REQUIRE(n >= 1 && n <= (size_t)kGemvBatchMax, "generate_batch: 1 to 8 requests");
     AHA_REQUIRE(T.tp_world == 1, "generate_batch is single-GPU (run one batch per tensor-parallel group member instead)");
     AHA_REQUIRE(T.max_prefill >= kGemvBatchMax, "generate_batch needs max_prefill >= 8");
@@ -705,8 +846,8 @@ void generate_batch_impl(aha_model* m, const aha_batch_request* reqs, size_t n, 
         if (usage) usage[i] = aha_usage{};
     }
     AHA_REQUIRE(pages <= (size_t)T.num_pages, "the requests of the batch need " + std::to_string(pages * kPage) + " tokens of KV capacity, max_ctx is " + std::to_string(T.max_ctx));
-    const bool simt = std::getenv("AHA_BATCH_GEMV") && std::atoi(std::getenv("AHA_BATCH_GEMV")) == 1;   // 1 = projections on the exact SIMT GEMM (validation twin)
-    const bool use_graph = !(std::getenv("AHA_BATCH_GRAPH") && std::atoi(std::getenv("AHA_BATCH_GRAPH")) == 0);   // 0 = eager launches (A/B twin of the per-composition graphs)
+    const bool simt = env_flag("AHA_BATCH_GEMV", false);      // 1 = projections on the exact SIMT GEMM (validation twin)
+    const bool use_graph = env_flag("AHA_BATCH_GRAPH", true);   // 0 = eager launches (A/B twin of the per-composition graphs)
     BatchDecoder& B = m->batch;
     drop_cache(m);
     B.init(T, kGemvBatchMax);
@@ -726,18 +867,7 @@ void generate_batch_impl(aha_model* m, const aha_batch_request* reqs, size_t n, 
     for (size_t i = 0; i < n; ++i) {
         const aha_batch_request& r = reqs[i];
         const auto t0 = clk::now();
-        B.swap_table((int)i); swapped = (int)i;
-        m->have_rope_delta = false; m->rope_delta = 0;
-        T.set_sampler(sampling_mode(r.params), r.params.temperature, r.params.top_p, r.params.top_k, r.params.repeat_penalty, r.params.repeat_last_n, r.params.seed);
-        T.set_state(0, 0, 0, 0, 0);
-        uint32_t tok = 0;
-        forward_any(m, r.ids, r.seq_len, 0, r.mm, true, nullptr, &tok, false, true);
-        T.check_sample_error();
-        T.ensure_tokens((int)(r.seq_len + sample_len[i]));       // every page the request can touch is mapped now (the step kernels only read the table)
-        DecodeState cur;
-        AHA_CUDA_CHECK(cudaMemcpy(&cur, T.d_state, sizeof(cur), cudaMemcpyDeviceToHost));
-        B.adopt((int)i, tok, (int)r.seq_len, m->kind == aha_model::QWEN3VL ? m->rope_delta : 0, cur.n_draws);
-        B.swap_table((int)i); swapped = -1;
+        const uint32_t tok = batch_prefill_slot(m, (int)i, r, sample_len[i], &swapped);
         t_first[i] = clk::now();
         out_tokens[i * cap] = tok; n_out[i] = 1;
         if (usage) {
@@ -769,6 +899,29 @@ void generate_batch_impl(aha_model* m, const aha_batch_request* reqs, size_t n, 
     if (usage) for (size_t i = 0; i < n; ++i) usage[i].completion_tokens = (uint32_t)n_out[i];
 }
 }  // namespace
+
+int aha_b200_batch_open(aha_model* m) { return guarded(m, [&] { session_open(m); }); }
+
+int aha_b200_batch_add(aha_model* m, const aha_batch_request* req, int32_t* slot_out, uint32_t* first_token_out, int32_t* finished_out, aha_usage* usage) {
+    return guarded(m, [&] {
+        AHA_REQUIRE(req && slot_out && first_token_out && finished_out, "req, slot_out, first_token_out and finished_out are required");
+        int slot = -1, fin = 0;
+        session_add(m, *req, &slot, first_token_out, &fin, usage);
+        *slot_out = slot; *finished_out = fin;
+    });
+}
+
+int aha_b200_batch_step(aha_model* m, uint32_t* tokens_out, int32_t* status_out, size_t* n_stepped_out) {
+    return guarded(m, [&] {
+        AHA_REQUIRE(tokens_out && status_out, "tokens_out[8] and status_out[8] are required");
+        const size_t n = session_step(m, tokens_out, status_out);
+        if (n_stepped_out) *n_stepped_out = n;
+    });
+}
+
+int aha_b200_batch_close(aha_model* m) {
+    return guarded(m, [&] { AHA_CUDA_CHECK(cudaStreamSynchronize(m->ctx.stream)); session_close(m); });
+}
 
 int aha_b200_generate_batch(aha_model* m, const aha_batch_request* reqs, size_t n, uint32_t* out_tokens, size_t cap, size_t* n_out, aha_usage* usage) {
     return guarded(m, [&] {
@@ -858,6 +1011,7 @@ int aha_b200_decode_steps(aha_model* m, uint32_t first_token, size_t seqlen_offs
         TextModel& T = m->text;
         AHA_REQUIRE(first_token < (uint32_t)T.cfg.V, "token id out of range");
         AHA_REQUIRE(seqlen_offset + n_steps <= (size_t)T.max_ctx, "context exceeds max_ctx");
+        require_no_session(m);
         m->cached_ids.clear();
         T.ensure_tokens((int)(seqlen_offset + n_steps));
         T.set_state(first_token, (int)seqlen_offset, m->kind == aha_model::QWEN3VL ? m->rope_delta : 0, 0);
@@ -1279,6 +1433,7 @@ int aha_b200_debug_gemm(aha_model* m, int impl, int epi, int act, int M, int N, 
 namespace {
 // Qwen3Model::forward_hidden + l2_normalize for one text; result left in T.xn[0:H] and copied to `out`
 void embed_one(aha_model* m, const uint32_t* ids, size_t S, float* out) {
+    require_no_session(m);
     AHA_REQUIRE(m->kind == aha_model::QWEN3, "embeddings need a qwen3 handle (Qwen3-Embedding shares Qwen3Model)");
     AHA_REQUIRE(ids && S >= 1 && out, "ids, seq_len and out are required");
     TextModel& T = m->text;

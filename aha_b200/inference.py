@@ -233,6 +233,36 @@ class B200Model:
         self._check(self._lib.aha_b200_generate_batch(self._h, arr, n, out, cap, n_out, us))
         return [([int(out[i * cap + j]) for j in range(n_out[i])], self._usage(us[i])) for i in range(n)]
 
+    # ---- continuous batching: requests join / leave a running batch between steps (aha_b200_batch_open / _add / _step / _close)
+    def batch_open(self):
+        self._check(self._lib.aha_b200_batch_open(self._h))
+
+    def batch_add(self, input_ids, data=None, max_tokens=1024, temperature=0.0, top_p=None, top_k=None, repeat_penalty=1.0, repeat_last_n=64,
+                  seed=299792458, flags=0):
+        """Prefill one request into a free slot -> (slot, first token, finished)."""
+        ids = self._ids(input_ids)
+        mm, _keep = self._mm(data)
+        req = L.BatchRequest()
+        req.ids = ids.ctypes.data_as(C.POINTER(C.c_uint32))
+        req.seq_len = ids.size
+        req.mm = C.pointer(mm) if mm is not None else None
+        req.params = self._gen_params(max_tokens, temperature, top_p, top_k, repeat_penalty, repeat_last_n, seed, flags)
+        slot, fin, tok = C.c_int32(-1), C.c_int32(0), C.c_uint32(0)
+        u = L.Usage()
+        self._check(self._lib.aha_b200_batch_add(self._h, C.byref(req), C.byref(slot), C.byref(tok), C.byref(fin), C.byref(u)))
+        return int(slot.value), int(tok.value), bool(fin.value)
+
+    def batch_step(self):
+        """One decode step of every running request -> {slot: (token, finished)} (empty when nothing is running)."""
+        toks = (C.c_uint32 * 8)()
+        status = (C.c_int32 * 8)()
+        n = C.c_size_t(0)
+        self._check(self._lib.aha_b200_batch_step(self._h, toks, status, C.byref(n)))
+        return {i: (int(toks[i]), status[i] == 2) for i in range(8) if status[i] != 0}
+
+    def batch_close(self):
+        self._check(self._lib.aha_b200_batch_close(self._h))
+
     def generate_stream(self, input_ids, on_token, data=None, max_tokens=1024, temperature=0.0, top_p=None, top_k=None,
                         repeat_penalty=1.0, repeat_last_n=64, seed=299792458, reuse_prefix=False):
         """generate_stream_generic: on_token(token, index) is called per generated token as its step completes; a truthy

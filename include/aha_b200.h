@@ -186,6 +186,20 @@ typedef struct aha_batch_request {
 int aha_b200_generate_batch(aha_model* m, const aha_batch_request* reqs, size_t n, uint32_t* out_tokens, size_t cap,
                             size_t* n_out, aha_usage* usage);
 
+/* Continuous batching on the same slots and the same lockstep step (new design): requests join and leave a running batch BETWEEN steps.
+ *   batch_open                      clear_cache, enter batch mode (the single-request entries are refused until batch_close / clear_cache)
+ *   batch_add(req)                  prefill the request into a free slot (its own page table; pages come from the shared pool and go back the
+ *                                   moment the request finishes) -> slot id, its first token, finished = 1 if that was also its last one
+ *   batch_step(tokens[8], status[8]) one decode step for every running request: status 0 = slot idle, 1 = token delivered, request continues,
+ *                                   2 = token delivered and it was the request's last (EOS or max_tokens): the slot is free again
+ *   batch_close                     drop everything
+ * Each request still yields exactly the ids aha_b200_generate yields for it alone, whenever it joins and whatever runs beside it. */
+int aha_b200_batch_open(aha_model* m);
+int aha_b200_batch_add(aha_model* m, const aha_batch_request* req, int32_t* slot_out, uint32_t* first_token_out,
+                       int32_t* finished_out, aha_usage* usage /* prompt side only; may be NULL */);
+int aha_b200_batch_step(aha_model* m, uint32_t* tokens_out /* [8] */, int32_t* status_out /* [8] */, size_t* n_stepped_out /* may be NULL */);
+int aha_b200_batch_close(aha_model* m);
+
 /* WhisperFeatureExtractor::call (/root/reference/src/models/feature_extractor/
  * feature_extraction_whisper.rs:65-115): wave (n) f32 host -> log-mel (n_mels, n_frames) f32 host.
  * Returns frames through *n_frames.  Qwen3-ASR handles only. */

@@ -163,3 +163,94 @@ def test_batch_mixes_image_and_text_requests():
         assert toks == _oracle_generate(o, r["input_ids"], r["data"], r["max_tokens"], **kw)
         assert (usage["vision_secs"] > 0) == (r["data"][0] is not None)
     m.close()
+
+
+# ---- continuous batching: requests join and leave a running batch between steps (aha_b200_batch_open / _add / _step / _close) ----
+class _Session:
+    def __init__(self, m):
+        self.m, self.out, self.running, self.slot_of = m, {}, {}, {}
+        m.batch_open()
+
+    def add(self, name, ids, **kw):
+        slot, tok, fin = self.m.batch_add(ids, **kw)
+        self.out[name] = [tok]
+        self.slot_of[name] = slot
+        if not fin:
+            assert slot not in self.running
+            self.running[slot] = name
+        return slot
+
+    def step(self, n=1):
+        for _ in range(n):
+            res = self.m.batch_step()
+            assert sorted(res) == sorted(self.running)          # exactly the running requests produce a token
+            for slot, (tok, fin) in res.items():
+                self.out[self.running[slot]].append(tok)
+                if fin:
+                    del self.running[slot]
+
+    def drain(self):
+        while self.running:
+            self.step()
+
+
+def test_continuous_batching_requests_join_and_leave(q3):
+    """Requests are admitted while others are mid-generation and take over the slots (and KV pages) of finished ones; whatever the
+    schedule, every request's ids are those of its own oracle run."""
+    cfg, w, m, o = q3
+    V = cfg["vocab_size"]
+    m.clear_cache()
+    reqs = {"A": (_ids(40, V, 401), dict(max_tokens=30)),
+            "B": (_ids(90, V, 402), dict(max_tokens=12)),
+            "C": (_ids(15, V, 403), dict(max_tokens=25, temperature=0.8, top_p=0.9, top_k=20, repeat_penalty=1.1, repeat_last_n=8, seed=9)),
+            "D": (_ids(70, V, 404), dict(max_tokens=18)),
+            "E": (_ids(33, V, 405), dict(max_tokens=10, temperature=1.0, seed=2)),
+            "F": (_ids(5, V, 406), dict(max_tokens=1))}
+    s = _Session(m)
+    s.add("A", reqs["A"][0], **reqs["A"][1])
+    slot_b = s.add("B", reqs["B"][0], **reqs["B"][1])
+    s.step(5)
+    s.add("C", reqs["C"][0], **reqs["C"][1])                    # joins while A and B are decoding
+    while "B" in s.running.values():
+        s.step()
+    assert s.add("D", reqs["D"][0], **reqs["D"][1]) == slot_b   # takes over B's slot (and its pages)
+    s.step(3)
+    s.add("E", reqs["E"][0], **reqs["E"][1])
+    s.add("F", reqs["F"][0], **reqs["F"][1])                    # a one-token request is finished by its prefill and never occupies a step
+    assert "F" not in s.running.values()
+    s.drain()
+    assert m.batch_step() == {}
+    m.batch_close()
+    for name, (ids, kw) in reqs.items():
+        n = kw["max_tokens"]
+        samp = {k: v for k, v in kw.items() if k != "max_tokens"}
+        assert s.out[name] == _oracle_generate(o, ids, None, n, **samp), name
+    toks, _ = m.generate(reqs["A"][0], max_tokens=30)             # the handle serves single requests again
+    assert toks == s.out["A"]
+
+
+def test_batch_session_rules(q3):
+    from aha_b200 import B200Error
+    cfg, w, m, o = q3
+    V = cfg["vocab_size"]
+    m.clear_cache()
+    with pytest.raises(B200Error, match="no batch session is open"):
+        m.batch_add(_ids(4, V, 1), max_tokens=2)
+    m.batch_open()
+    with pytest.raises(B200Error, match="batch session is open"):
+        m.generate(_ids(4, V, 1), max_tokens=2)
+    with pytest.raises(B200Error, match="batch session is open"):
+        m.forward_initial(_ids(4, V, 1), 0)
+    with pytest.raises(B200Error, match="KV capacity"):
+        m.batch_add(_ids(1500, V, 2), max_tokens=1000)            # 2500 tokens > max_ctx 2048: refused, session intact
+    slots = [m.batch_add(_ids(10 + i, V, 20 + i), max_tokens=40)[0] for i in range(8)]
+    assert sorted(slots) == list(range(8))
+    with pytest.raises(B200Error, match="all 8 slots"):
+        m.batch_add(_ids(4, V, 3), max_tokens=2)
+    assert len(m.batch_step()) == 8
+    m.clear_cache()                                               # clear_cache ends the session
+    toks, _ = m.generate(_ids(10, V, 20), max_tokens=6)
+    assert toks == _oracle_generate(o, _ids(10, V, 20), None, 6)
+    m.batch_open(); m.batch_close()
+    with pytest.raises(B200Error, match="no batch session is open"):
+        m.batch_step()
