@@ -277,6 +277,10 @@ void require_no_session(aha_model* m) {
     AHA_REQUIRE(!m->session.open, "a batch session is open on this handle: call aha_b200_batch_close first");
 }
 bool env_flag(const char* name, bool dflt) { const char* v = std::getenv(name); return v ? std::atoi(v) != 0 : dflt; }
+int env_int(const char* name, int dflt) { const char* v = std::getenv(name); return v ? std::atoi(v) : dflt; }
+// projections of the batched step: 0 = batched GEMV with the weights in registers, 1 = exact SIMT GEMM (validation twin), 2 = batched GEMV with the
+// cp.async weight ring
+constexpr int kBatchGemvDefault = 0;
 
 // model.clear_cache(): pages, rope_deltas, and what the prefix cache remembered
 void drop_cache(aha_model* m) {
@@ -798,7 +802,7 @@ size_t session_step(aha_model* m, uint32_t* tokens_out, int32_t* status_out) {
     std::vector<int> act;
     for (int i = 0; i < kGemvBatchMax; ++i) { status_out[i] = 0; tokens_out[i] = 0; if (m->session.used[i]) act.push_back(i); }
     if (act.empty()) return 0;
-    m->batch.step(act, env_flag("AHA_BATCH_GEMV", false), env_flag("AHA_BATCH_GRAPH", true));
+    m->batch.step(act, env_int("AHA_BATCH_GEMV", kBatchGemvDefault), env_flag("AHA_BATCH_GRAPH", true));
     uint32_t h_tok[kGemvBatchMax];
     AHA_CUDA_CHECK(cudaMemcpyAsync(h_tok, m->batch.d_tok, sizeof(h_tok), cudaMemcpyDeviceToHost, m->ctx.stream));
     AHA_CUDA_CHECK(cudaStreamSynchronize(m->ctx.stream));
@@ -846,7 +850,7 @@ void generate_batch_impl(aha_model* m, const aha_batch_request* reqs, size_t n, 
         if (usage) usage[i] = aha_usage{};
     }
     AHA_REQUIRE(pages <= (size_t)T.num_pages, "the requests of the batch need " + std::to_string(pages * kPage) + " tokens of KV capacity, max_ctx is " + std::to_string(T.max_ctx));
-    const bool simt = env_flag("AHA_BATCH_GEMV", false);      // 1 = projections on the exact SIMT GEMM (validation twin)
+    const int simt = env_int("AHA_BATCH_GEMV", kBatchGemvDefault);
     const bool use_graph = env_flag("AHA_BATCH_GRAPH", true);   // 0 = eager launches (A/B twin of the per-composition graphs)
     BatchDecoder& B = m->batch;
     drop_cache(m);
@@ -1388,7 +1392,7 @@ int aha_b200_debug_gemm(aha_model* m, int impl, int epi, int act, int M, int N, 
                 AHA_CUDA_CHECK(cudaMalloc(&dr, (size_t)M * N * 4)); AHA_CUDA_CHECK(cudaMemcpy(dr, resid, (size_t)M * N * 4, cudaMemcpyHostToDevice));
             }
             LinearW W; W.w = dw; W.b = db; W.N = N; W.K = K;
-            if (impl == 5) {   // the batched decode GEMV (gemv_batch.cuh): M <= 8 activation rows against every weight row
+            if (impl == 5 || impl == 6) {   // the batched decode GEMV (gemv_batch.cuh; 6 = the cp.async ring version): M <= 8 activation rows against every weight row
                 AHA_REQUIRE(M <= kGemvBatchMax && (epi == EPI_STORE || epi == EPI_RESID || epi == EPI_SWIGLU), "batched GEMV: M <= 8, epilogue store / residual / SwiGLU");
                 GemvBatchArgs a{};
                 a.W = dw; a.x = dx; a.ldx = K; a.bias = db; a.resid = dr; a.ldr = N; a.out = dy; a.ldo = Nout; a.N = N; a.K = K; a.nb = M; a.eps = 0.f;
@@ -1401,9 +1405,9 @@ int aha_b200_debug_gemm(aha_model* m, int impl, int epi, int act, int M, int N, 
                     a.norm_w = ones; a.eps = 1e-6f;
                 }
                 try {
-                    gemv_batch(c.stream, pro, gepi, a);
+                    gemv_batch(c.stream, pro, gepi, a, impl == 6);
                     AHA_CUDA_CHECK(cudaEventRecord(m->ev0, c.stream));
-                    for (int i = 0; i < std::max(iters, 0); ++i) gemv_batch(c.stream, pro, gepi, a);
+                    for (int i = 0; i < std::max(iters, 0); ++i) gemv_batch(c.stream, pro, gepi, a, impl == 6);
                     AHA_CUDA_CHECK(cudaEventRecord(m->ev1, c.stream));
                     AHA_CUDA_CHECK(cudaStreamSynchronize(c.stream));
                 } catch (...) { cudaFree(ones); throw; }

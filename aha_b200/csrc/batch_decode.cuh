@@ -42,7 +42,7 @@ struct BatchDecoder {
     std::vector<int> table_for;          // active list the attention table was built for
     // One CUDA graph per composition of the batch (the active list changes only when a request finishes): ~170 launches per step become one.
     // The graphs hold the requests' sampler parameters by value, so they live for one generate_batch call.
-    struct StepGraph { std::vector<int> act; bool simt; cudaGraphExec_t exec; uint64_t kernels; };
+    struct StepGraph { std::vector<int> act; int simt; cudaGraphExec_t exec; uint64_t kernels; };
     std::vector<StepGraph> graphs;
     void clear_graphs() {
         for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -130,9 +130,9 @@ struct BatchDecoder {
         decode_attn_batch_kernel<128, G><<<dim3(kDecodeSplits, T->nkv_l, nb), 256, 0, T->ctx->stream>>>(d_attn + (size_t)l * cap);
     }
 
-    void proj(int pro, int epi, const LinearW& W, const float* x, int ldx, const float* norm_w, const float* resid, int ldr, float* out, int ldo, int nb, bool simt) {
+    void proj(int pro, int epi, const LinearW& W, const float* x, int ldx, const float* norm_w, const float* resid, int ldr, float* out, int ldo, int nb, int simt) {   // simt: 0 = batched GEMV (registers), 1 = exact SIMT GEMM twin, 2 = batched GEMV with the cp.async weight ring
         Ctx& c = *T->ctx;
-        if (simt) {   // validation twin: the exact fp32 SIMT GEMM over the nb rows (normalised beforehand when a prologue is asked for)
+        if (simt == 1) {   // validation twin: the exact fp32 SIMT GEMM over the nb rows (normalised beforehand when a prologue is asked for)
             const float* a = x; int lda = ldx;
             if (pro == PRO_RMSNORM) {
                 rmsnorm_kernel<<<nb, 256, 0, c.stream>>>(x, norm_w, T->cfg.eps, T->xn, W.K); c.cnt.kernels++;   // xn: [max_prefill >= 8][H] scratch of the prefill
@@ -147,12 +147,12 @@ struct BatchDecoder {
         GemvBatchArgs a{};
         a.W = W.w; a.x = x; a.ldx = ldx; a.norm_w = norm_w; a.eps = T->cfg.eps; a.bias = W.b; a.resid = resid; a.ldr = ldr; a.out = out; a.ldo = ldo;
         a.N = W.N; a.K = W.K; a.nb = nb;
-        gemv_batch(c.stream, pro, epi, a);
+        gemv_batch(c.stream, pro, epi, a, simt == 2);
         c.cnt.kernels++;
     }
 
     // one decode step of the sequences in `act` (slot indices, at most cap); leaves every slot's next token in d_tok[slot] and its DecodeState advanced
-    void step(const std::vector<int>& act, bool simt, bool use_graph) {
+    void step(const std::vector<int>& act, int simt, bool use_graph) {
         Ctx& c = *T->ctx;
         AHA_REQUIRE(!act.empty() && (int)act.size() <= cap, "batch step: bad active list");
         if (act != table_for) build_attn_table(act);
@@ -177,7 +177,7 @@ struct BatchDecoder {
         c.cnt.graphs++;
         c.cnt.kernels += g->kernels;
     }
-    void launches(const std::vector<int>& act, bool simt) {
+    void launches(const std::vector<int>& act, int simt) {
         Ctx& c = *T->ctx;
         cudaStream_t st = c.stream;
         const TextCfg& cf = T->cfg;

@@ -20,13 +20,13 @@ for r in reqs:
     t, u = m.generate(r["input_ids"], max_tokens=n_gen)
     singles.append(t); t_single += u["completion_secs"]
 print(f"one by one (fused step kernel): {sum(len(t) - 1 for t in singles) / t_single:.1f} tok/s")
-for graph in ("1", "0"):
-    os.environ["AHA_BATCH_GRAPH"] = graph
+for impl in ("0", "2"):
+    os.environ["AHA_BATCH_GEMV"] = impl
     for nb in (1, 2, 4, 8):
         m.generate_batch(reqs[:nb])
         res = m.generate_batch(reqs[:nb])
         dec = sum(len(t) - 1 for t, _ in res)
         secs = max(u["completion_secs"] for _, u in res)
         same = all(a == b[0] for a, b in zip(singles, res))
-        print(f"batch {nb} ({'one CUDA graph per composition' if graph == '1' else 'eager launches'}): {dec / secs:8.1f} tok/s aggregate, {1e3 * secs / (n_gen - 1):.3f} ms/step, ids equal to single runs: {same}")
+        print(f"batch {nb} ({'GEMV v1 (weights in registers)' if impl == '0' else 'GEMV v2 (cp.async weight ring)'}): {dec / secs:8.1f} tok/s aggregate, {1e3 * secs / (n_gen - 1):.3f} ms/step, ids equal to single runs: {same}")
 m.close()

@@ -46,8 +46,11 @@ def test_batched_gemv_matches_numpy_and_the_simt_gemm(q3, M, N, K):
     assert np.abs(got - (ref + bias)).max() <= 2e-4 * max(1.0, np.abs(ref).max())
     simt, _ = m.debug_gemm(x, W, bias=bias, impl=1, epi=0)
     assert np.abs(got - simt).max() <= 1e-4 * max(1.0, np.abs(ref).max())
+    ring, _ = m.debug_gemm(x, W, bias=bias, impl=6, epi=0)        # weights through the cp.async ring: the same fmas in the same order
+    assert np.array_equal(ring, got)
     got, _ = m.debug_gemm(x, W, resid=resid, impl=5, epi=1)
     assert np.abs(got - (ref + resid)).max() <= 2e-4 * max(1.0, np.abs(ref).max())
+    assert np.array_equal(m.debug_gemm(x, W, resid=resid, impl=6, epi=1)[0], got)
     if N % 2 == 0:   # SwiGLU on interleaved (gate, up) rows, behind a unit-gain RMSNorm prologue
         xn = x / np.sqrt((x.astype(np.float64) ** 2).mean(-1, keepdims=True) + 1e-6)
         r2 = xn @ W.astype(np.float64).T
@@ -56,13 +59,14 @@ def test_batched_gemv_matches_numpy_and_the_simt_gemm(q3, M, N, K):
         got, _ = m.debug_gemm(x, W, impl=5, epi=3)
         assert got.shape == (M, N // 2)
         assert np.abs(got - want).max() <= 2e-4 * max(1.0, np.abs(want).max())
+        assert np.array_equal(m.debug_gemm(x, W, impl=6, epi=3)[0], got)
 
 
 def _requests(V, spec):
     return [dict(input_ids=_ids(S, V, 100 + i), max_tokens=n, **kw) for i, (S, n, kw) in enumerate(spec)]
 
 
-@pytest.mark.parametrize("twin,graph", [(False, True), (False, False), (True, True)])
+@pytest.mark.parametrize("twin,graph", [(0, True), (0, False), (1, True), (2, True), (2, False)])
 def test_batch_of_greedy_requests_equals_single_requests(q3, twin, graph):
     """8 prompts of different lengths and budgets (page boundaries crossed at different steps, requests leaving the batch one by one):
     every request's ids equal its own oracle run and the library's own single-request generate."""
@@ -70,7 +74,7 @@ def test_batch_of_greedy_requests_equals_single_requests(q3, twin, graph):
     V = cfg["vocab_size"]
     spec = [(5, 40, {}), (33, 9, {}), (64, 70, {}), (1, 12, {}), (200, 33, {}), (97, 1, {}), (31, 64, {}), (150, 20, {})]
     reqs = _requests(V, spec)
-    os.environ["AHA_BATCH_GEMV"] = "1" if twin else "0"        # 1: projections on the exact SIMT GEMM instead of the batched GEMV
+    os.environ["AHA_BATCH_GEMV"] = str(twin)                   # 0 / 2: batched GEMV (weights in registers / through the cp.async ring), 1: exact SIMT GEMM
     os.environ["AHA_BATCH_GRAPH"] = "1" if graph else "0"      # 0: eager launches instead of one CUDA graph per composition of the batch
     try:
         res = m.generate_batch(reqs)
