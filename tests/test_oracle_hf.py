@@ -219,3 +219,34 @@ def test_get_rope_index_matches_hf_on_interleaved_images():
         assert delta == int(want_delta.reshape(-1)[0])
     pos, delta = get_rope_index(ids, grid, cfg)
     assert delta == -1980                               # max(34, 60) - 2040
+
+
+def test_video_processor_restatement_matches_hf():
+    """The video half of the processor restated from the reference (qwen3vl/processor.rs:253-280, utils/video_utils.rs:9-59) against HF's
+    Qwen3VLVideoProcessor: the patch tensor of a clip (odd frame counts pad with the last frame) and the resize target.  The reference multiplies
+    frames * height * width in u32: wherever that product fits, its answer is HF's; where it wraps, the restatement follows the wrap (documented)."""
+    import torch
+    from transformers.models.qwen3_vl import video_processing_qwen3_vl as V
+    from aha_b200 import synth
+    from oracle import qwen3vl as OV
+    vp = V.Qwen3VLVideoProcessor(patch_size=16, temporal_patch_size=2, merge_size=2, image_mean=[0.5] * 3, image_std=[0.5] * 3,
+                                 do_resize=False, do_sample_frames=False)
+    for T in (2, 3, 5, 8):
+        frames = np.stack([synth.synth_image(64, 96, 10 + i) for i in range(T)])
+        out = vp(videos=[torch.from_numpy(frames).permute(0, 3, 1, 2)], return_tensors="pt")
+        pv, grid = OV.process_video(frames)
+        assert out["video_grid_thw"].numpy().tolist() == grid.tolist() == [[(T + 1) // 2, 4, 6]]
+        assert np.abs(out["pixel_values_videos"].numpy() - pv).max() <= 2e-7
+    rng = np.random.default_rng(0)
+    n = 0
+    for _ in range(1500):
+        t, h, w = int(rng.integers(1, 400)) * 2, int(rng.integers(32, 2200)), int(rng.integers(32, 4000))
+        if max(h, w) / min(h, w) > 200 or (h / 32) % 1 == 0.5 or (w / 32) % 1 == 0.5 or t * h * w >= 1 << 32:
+            continue                                    # f32 round-half-away vs Python's round-half-even on exact halves; the u32 wrap
+        mn, mx = int(rng.choice([4096, 262144])), int(rng.choice([1 << 20, 25165824]))
+        assert OV.video_smart_resize(t, h, w, 2, 32, mn, mx, None) == V.smart_resize(t, h, w, 2, 32, mn, mx), (t, h, w, mn, mx)
+        n += 1
+    assert n > 1000
+    # the wrap itself: 628 frames of 2068 x 3853 is 5.0e9 pixels; the reference sees 5.0e9 mod 2^32 = 7.1e8 and scales less than HF would
+    assert OV.video_smart_resize(628, 2068, 3853, 2, 32, 262144, 25165824, None) == (384, 704)
+    assert V.smart_resize(628, 2068, 3853, 2, 32, 262144, 25165824) == (128, 256)
