@@ -268,3 +268,38 @@ def test_gpu_video_pipeline_matches_the_oracle(n_frames):
     with pytest.raises(Exception, match="multiple of patch_size"):
         m.video_preprocess(np.zeros((2, 70, 100, 3), np.uint8))
     m.close()
+
+
+def test_video_placeholder_expansion_property():
+    """Random prompts (text, lone <|video_pad|>, full <|vision_start|><|video_pad|><|vision_end|> triples, stray start / end tokens) and random
+    grids: the id-level expansion equals the tokenised result of the reference's string edit, every time."""
+    from hypothesis import assume, given, settings, strategies as st
+    VS, VP, VE = "<|vision_start|>", "<|video_pad|>", "<|vision_end|>"
+    special = {VS: 1, VP: 2, VE: 3}
+
+    def tok(text):
+        ids = []
+        while text:
+            for s, i in special.items():
+                if text.startswith(s):
+                    ids.append(i); text = text[len(s):]; break
+            else:
+                ids.append(1000 + ord(text[0])); text = text[1:]
+        return ids
+
+    piece = st.sampled_from(["a", "bc ", VP, VS + VP + VE, VS, VE, " ", VS + VP, VP + VE])
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.lists(piece, max_size=9), st.lists(st.tuples(st.integers(1, 3), st.sampled_from([2, 4]), st.sampled_from([2, 4, 6])), min_size=6, max_size=6))
+    def check(pieces, grids):
+        text = "".join(pieces)
+        n_videos = text.count(VP)
+        assume(n_videos <= len(grids))
+        grids_used = [list(g) for g in grids[:max(n_videos, 1)]]
+        stamps = [OV.calculate_timestamps(list(range(0, 2 * g[0] * 5, 5)), 25.0, 2) for g in grids_used]
+        want = tok(OV.expand_video_placeholders_text(text, grids_used, stamps)) if n_videos else tok(text)
+        runs = [tok(OV.format_timestamp(t)) for stm in stamps for t in stm]
+        got = P.expand_video_placeholders(tok(text), grids_used, runs, 2, 1, 3)
+        assert got.tolist() == want, text
+
+    check()
