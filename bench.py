@@ -206,9 +206,14 @@ def cpu_reference_rate(kind, cfg, wts, S, rope_delta, steps, warmup, budget_s=25
         actual = max([d.get("num_threads", 0) for d in threadpool_info() if d.get("user_api") == "blas"] or [best_n])
         if warmup:
             cpu_decode_steps(m, S, warmup)
-        dt = cpu_decode_steps(m, S + warmup, n_steps)
+        # exactly n_steps steps, timed in blocks of <= 8 so that a disturbed stretch of the (shared) host shows up as such in the record
+        dt, blocks, done = 0.0, [], 0
+        while done < n_steps:
+            nblk = min(8, n_steps - done)
+            d = cpu_decode_steps(m, S + warmup + done, nblk)
+            blocks.append(round(nblk / d, 4)); dt += d; done += nblk
     return dict(value=n_steps / dt, ms_per_step=1e3 * dt / n_steps, threads=int(actual), steps=n_steps, sweep_tok_s_by_blas_threads=sweep,
-                host_threads_available=avail)
+                host_threads_available=avail, block_tok_s=blocks)
 
 
 _REAL_STDOUT = None
@@ -397,7 +402,7 @@ def main():
         r = cpu_reference_rate(wl["kind"], cfg, wts, S, delta, K, W)
         sample = (f"{r['steps']} greedy decode steps of the oracle port (numpy fp32 + OpenBLAS, pool set to {r['threads']} threads = the fastest of the sweep "
                   f"{r['sweep_tok_s_by_blas_threads']} tok/s by pool size; {r['host_threads_available']} host threads available) of the reference's text stack at "
-                  f"ctx {S}+ with a synthetic KV cache; tower + prefill not in the sample; the reference itself (Rust/Candle) cannot be built here (no cargo/rustc)")
+                  f"ctx {S}+ with a synthetic KV cache (tok/s per block of <= 8 steps: {r['block_tok_s']}); tower + prefill not in the sample; the reference itself (Rust/Candle) cannot be built here (no cargo/rustc)")
         line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
                 "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": config,
@@ -502,7 +507,7 @@ def main():
         cpu_base = {"value": c["value"], "unit": UNIT, "cores": c["threads"], "kind": "port",
                     "sample": f"{c['steps']} greedy decode steps of the oracle port (numpy fp32 + OpenBLAS, {c['threads']} threads = fastest of the sweep "
                               f"{c['sweep_tok_s_by_blas_threads']}; {c['host_threads_available']} host threads available) of the text stack at ctx {S}+ with a synthetic "
-                              f"KV cache (tower + prefill excluded); Rust/Candle reference not buildable here"}
+                              f"KV cache (tower + prefill excluded; tok/s per block of <= 8 steps: {c['block_tok_s']}); Rust/Candle reference not buildable here"}
 
     if rank == 0:
         traffic, traffic_src = ncu_traffic(args.preset)
