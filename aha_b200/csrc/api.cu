@@ -6,6 +6,7 @@
 #include <chrono>
 #include <functional>
 #include <mutex>
+#include <system_error>
 #include <thread>
 
 #include "audio_model.cuh"
@@ -247,8 +248,12 @@ uint64_t fingerprint_bytes(const void* data, size_t n, uint64_t seed) {
     const unsigned nt = (unsigned)std::min<size_t>(std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency())), nb);
     auto work = [&](unsigned t) { for (size_t b = t; b < nb; b += nt) hb[b] = fingerprint_block(p + b * kBlock, std::min(kBlock, n - b * kBlock), seed + b); };
     std::vector<std::thread> th;
-    for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
+    unsigned started = 1;   // lane 0 is this thread
+    try {
+        for (unsigned t = 1; t < nt; ++t) { th.emplace_back(work, t); ++started; }
+    } catch (const std::system_error&) {}   // no more threads to be had: the lanes that did not start are hashed here (same blocks, same value)
     work(0);
+    for (unsigned t = started; t < nt; ++t) work(t);
     for (auto& x : th) x.join();
     return fingerprint_block(reinterpret_cast<const unsigned char*>(hb.data()), nb * sizeof(uint64_t), seed ^ (uint64_t)n);
 }
