@@ -250,3 +250,25 @@ def test_video_processor_restatement_matches_hf():
     # the wrap itself: 628 frames of 2068 x 3853 is 5.0e9 pixels; the reference sees 5.0e9 mod 2^32 = 7.1e8 and scales less than HF would
     assert OV.video_smart_resize(628, 2068, 3853, 2, 32, 262144, 25165824, None) == (384, 704)
     assert V.smart_resize(628, 2068, 3853, 2, 32, 262144, 25165824) == (128, 256)
+
+
+def test_catmullrom_resize_restatement_matches_pillow_bicubic():
+    """`image`'s resize(CatmullRom) restated in oracle/qwen3vl.py (qwen3vl/processor.rs:167) against an independent implementation of the same
+    filter: Pillow's BICUBIC is the a = -0.5 cubic with the same centre alignment and the same support scaling when shrinking.  Pillow keeps an 8-bit
+    intermediate between its two passes (the crate keeps f32), so the comparison is on images whose intermediate cannot clip -- smooth ones at any
+    scale, and noise when shrinking (averaging keeps it inside 0..255) -- and allows the LSB that Pillow's fixed-point coefficients cost (two on a handful of pixels when ~10 taps meet noise)."""
+    PIL = pytest.importorskip("PIL.Image")
+    from aha_b200 import synth
+    from oracle.qwen3vl import resize_exact_catmullrom
+    yy, xx = np.mgrid[0:300, 0:400]
+    smooth = np.stack([(127 + 100 * np.sin(xx / 17.0) * np.cos(yy / 23.0)).astype(np.uint8),
+                       (127 + 90 * np.cos(xx / 29.0 + yy / 41.0)).astype(np.uint8),
+                       ((xx + yy) % 256 // 2 + 60).astype(np.uint8)], -1)
+    cases = [(smooth, nh, nw) for nh, nw in ((128, 160), (600, 800), (300, 400), (77, 391), (512, 96))]
+    cases += [(synth.synth_image(h, w, h + w), nh, nw) for h, w, nh, nw in ((300, 200, 96, 64), (480, 640, 96, 160), (1080, 1920, 352, 640))]
+    for img, nh, nw in cases:
+        got = resize_exact_catmullrom(img, nh, nw)
+        want = np.asarray(PIL.fromarray(img).resize((nw, nh), PIL.BICUBIC))
+        d = np.abs(got.astype(int) - want.astype(int))
+        assert d.max() <= 2 and (d > 1).mean() < 1e-3, (img.shape, nh, nw, int(d.max()), float((d > 1).mean()))   # 2 only with ~10 taps per pixel
+        assert (d > 0).mean() < 0.35
