@@ -272,3 +272,39 @@ def test_catmullrom_resize_restatement_matches_pillow_bicubic():
         d = np.abs(got.astype(int) - want.astype(int))
         assert d.max() <= 2 and (d > 1).mean() < 1e-3, (img.shape, nh, nw, int(d.max()), float((d > 1).mean()))   # 2 only with ~10 taps per pixel
         assert (d > 0).mean() < 0.35
+
+
+def test_img_smart_resize_restatement_matches_hf():
+    """img_smart_resize (img_utils.rs:297-331) against HF's Qwen2-VL smart_resize: equal wherever no side rounds to zero (the reference clamps a
+    side to the factor BEFORE it compares the pixel count with the budget, HF after) and no side sits on an exact half (f32 round-half-away vs
+    Python's round-half-even)."""
+    from transformers.models.qwen2_vl.image_processing_qwen2_vl import smart_resize
+    from oracle.qwen3vl import img_smart_resize
+    rng = np.random.default_rng(1)
+    n = 0
+    for _ in range(3000):
+        h, w = int(rng.integers(16, 6000)), int(rng.integers(16, 6000))
+        if max(h, w) / min(h, w) > 200 or (h / 32) % 1 == 0.5 or (w / 32) % 1 == 0.5:
+            continue
+        mn, mx = int(rng.choice([3136, 65536, 262144])), int(rng.choice([1048576, 16777216]))
+        assert img_smart_resize(h, w, 32, mn, mx) == smart_resize(h, w, 32, mn, mx), (h, w, mn, mx)
+        n += 1
+    assert n > 2500
+    assert img_smart_resize(15, 1425, 32, 3136, 1048576) == (32, 1440) and smart_resize(15, 1425, 32, 3136, 1048576) == (32, 576)   # the clamp-first quirk
+
+
+def test_sinc_resampler_restatement_matches_torchaudio():
+    """resample_simple (audio_utils.rs:66-255) is torchaudio's sinc_interp_hann resampler (lowpass_filter_width 6, rolloff 0.99) in f32: the restatement
+    against torchaudio.functional.resample itself -- a few 1e-7 for small filter banks, a few 1e-5 where 477 f32 taps meet torchaudio's f64-built kernel."""
+    torch = pytest.importorskip("torch")
+    torchaudio = pytest.importorskip("torchaudio")
+    from oracle.audio import resample_simple
+    rng = np.random.default_rng(0)
+    for orig, new, n, tol in ((48000, 16000, 48000, 1e-6), (44100, 16000, 30011, 5e-5), (8000, 16000, 4001, 1e-6), (22050, 16000, 22050, 1e-4),
+                              (24000, 16000, 7, 1e-6), (16000, 24000, 1001, 1e-6)):
+        x = (0.3 * rng.standard_normal(n)).astype(np.float32)
+        got = resample_simple(x[None], orig, new)[0]
+        want = torchaudio.functional.resample(torch.from_numpy(x)[None], orig, new, lowpass_filter_width=6, rolloff=0.99,
+                                              resampling_method="sinc_interp_hann")[0].numpy()
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() <= tol, (orig, new, float(np.abs(got - want).max()))
